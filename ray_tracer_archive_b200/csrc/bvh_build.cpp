@@ -1,0 +1,371 @@
+// bvh_build.cpp — host builder of the compressed 8-wide BVH the `extend` kernel traverses.
+// Replaces the reference's binary BVHNode (bvh.rs:74-130), whose construction sorts the whole object vector instead
+// of the [start,end) range and so drops objects (bvh.rs:86,108) — it is not replicated.  Closest-hit semantics stay
+// those of the linear HittableList scan (hittable_list.rs:39-51); the BVH only culls.
+//
+// Pipeline: per primitive type a binned-SAH binary tree (leaves <= 3 primitives)  ->  collapse to 8-wide nodes by
+// repeatedly opening the child with the largest surface area  ->  children assigned to octant-ordered slots (so the
+// traversal visits near children first by XOR-ing the slot with the ray octant)  ->  child boxes quantised to 8 bits
+// per plane relative to the node origin with a power-of-two step, rounded outward (conservative).
+// The per-type trees hang under one root, so every node's leaf children share one primitive type.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "rtb_internal.hpp"
+
+namespace rtb {
+namespace {
+
+struct Box3 {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  void grow(const float l[3], const float h[3]) {
+    for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], l[a]); hi[a] = std::fmax(hi[a], h[a]); }
+  }
+  void grow(const Box3& b) { grow(b.lo, b.hi); }
+  void grow_pt(const float p[3]) { grow(p, p); }
+  float area() const {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+  }
+};
+
+struct BinNode {  // binary tree node
+  Box3 box;
+  int left = -1, right = -1;  // children, or -1 for a leaf
+  uint32_t first = 0, count = 0;
+};
+
+struct Builder {
+  const HostScene& hs;
+  std::vector<uint32_t> order;      // indices into hs.prims for the current type
+  std::vector<float> centroid;      // 3 per prim (indexed by prim index)
+  std::vector<BinNode> bin;
+
+  int build_range(uint32_t first, uint32_t count) {
+    int me = (int)bin.size();
+    bin.emplace_back();
+    Box3 box, cbox;
+    for (uint32_t i = first; i < first + count; ++i) {
+      const HostPrim& p = hs.prims[order[i]];
+      box.grow(p.lo, p.hi);
+      cbox.grow_pt(&centroid[3 * (size_t)order[i]]);
+    }
+    bin[me].box = box;
+    bin[me].first = first;
+    bin[me].count = count;
+    if (count <= 3) return me;
+    // binned SAH over the widest centroid axis first, all three axes evaluated
+    const int NB = 16;
+    float best_cost = INFINITY;
+    int best_axis = -1, best_bin = -1;
+    for (int a = 0; a < 3; ++a) {
+      float ext = cbox.hi[a] - cbox.lo[a];
+      if (!(ext > 0.f)) continue;
+      Box3 bb[NB];
+      uint32_t bc[NB] = {0};
+      float k = NB / ext;
+      for (uint32_t i = first; i < first + count; ++i) {
+        const HostPrim& p = hs.prims[order[i]];
+        int b = (int)((centroid[3 * (size_t)order[i] + a] - cbox.lo[a]) * k);
+        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+        bb[b].grow(p.lo, p.hi);
+        bc[b]++;
+      }
+      float right_area[NB];
+      uint32_t right_cnt[NB];
+      Box3 acc;
+      uint32_t cnt = 0;
+      for (int b = NB - 1; b > 0; --b) {
+        acc.grow(bb[b]);
+        cnt += bc[b];
+        right_area[b] = acc.area();
+        right_cnt[b] = cnt;
+      }
+      Box3 accl;
+      uint32_t cl = 0;
+      for (int b = 0; b < NB - 1; ++b) {
+        accl.grow(bb[b]);
+        cl += bc[b];
+        if (cl == 0 || right_cnt[b + 1] == 0) continue;
+        float cost = accl.area() * (float)cl + right_area[b + 1] * (float)right_cnt[b + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+      }
+    }
+    uint32_t mid;
+    if (best_axis < 0) {
+      mid = first + count / 2;  // all centroids coincide: split the range
+    } else {
+      float ext = cbox.hi[best_axis] - cbox.lo[best_axis];
+      float k = NB / ext;
+      float lo = cbox.lo[best_axis];
+      auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t pi) {
+        int b = (int)((centroid[3 * (size_t)pi + best_axis] - lo) * k);
+        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+        return b <= best_bin;
+      });
+      mid = (uint32_t)(it - order.begin());
+      if (mid == first || mid == first + count) mid = first + count / 2;
+    }
+    int l = build_range(first, mid - first);
+    int r = build_range(mid, first + count - mid);
+    bin[me].left = l;
+    bin[me].right = r;
+    return me;
+  }
+};
+
+struct WideChild {
+  Box3 box;
+  int bin_node;   // binary node index (leaf or internal) in the type's tree; -1 for typed-root links
+  int link_node;  // for the root joining node: wide node index to link to
+  bool leaf;
+};
+
+uint8_t exp_byte_for(float extent) {
+  // smallest power-of-two step s = 2^(e-127) with 255*s >= extent
+  if (!(extent > 0.f)) return 1;
+  int e;
+  std::frexp(extent / 255.0f, &e);  // extent/255 = m * 2^e, m in [0.5,1)  ->  2^e >= extent/255
+  int biased = e + 127;
+  if (biased < 1) biased = 1;
+  if (biased > 254) biased = 254;
+  return (uint8_t)biased;
+}
+float step_from_byte(uint8_t b) {
+  uint32_t bits = (uint32_t)b << 23;
+  float f;
+  std::memcpy(&f, &bits, 4);
+  return f;
+}
+
+struct Assembler {
+  const HostScene& hs;
+  HostBvh& out;
+  uint32_t max_depth = 0;
+
+  // quantise children into node `ni`
+  void quantise(Node8& n, const WideChild* ch, const int* slot_of, int nch) {
+    Box3 nb;
+    for (int i = 0; i < nch; ++i) nb.grow(ch[i].box);
+    n.ox = nb.lo[0]; n.oy = nb.lo[1]; n.oz = nb.lo[2];
+    uint8_t eb[3];
+    float step[3];
+    for (int a = 0; a < 3; ++a) {
+      eb[a] = exp_byte_for(nb.hi[a] - nb.lo[a]);
+      for (;;) {  // make sure 255 steps really cover the extent in float arithmetic
+        step[a] = step_from_byte(eb[a]);
+        if (nb.lo[a] + 255.f * step[a] >= nb.hi[a] || eb[a] >= 254) break;
+        ++eb[a];
+      }
+    }
+    n.ex = eb[0]; n.ey = eb[1]; n.ez = eb[2];
+    for (int s = 0; s < 8; ++s)
+      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = 255; n.qhi[a][s] = 0; }  // empty: inverted box, never hit
+    for (int i = 0; i < nch; ++i) {
+      int s = slot_of[i];
+      for (int a = 0; a < 3; ++a) {
+        double o = nb.lo[a], st = step[a];
+        int ql = (int)std::floor(((double)ch[i].box.lo[a] - o) / st);
+        int qh = (int)std::ceil(((double)ch[i].box.hi[a] - o) / st);
+        ql = ql < 0 ? 0 : (ql > 255 ? 255 : ql);
+        qh = qh < 0 ? 0 : (qh > 255 ? 255 : qh);
+        // verify in float, the arithmetic the device uses (o + q*step is exact or rounded; widen if needed)
+        while (ql > 0 && nb.lo[a] + (float)ql * step[a] > ch[i].box.lo[a]) --ql;
+        while (qh < 255 && nb.lo[a] + (float)qh * step[a] < ch[i].box.hi[a]) ++qh;
+        n.qlo[a][s] = (uint8_t)ql;
+        n.qhi[a][s] = (uint8_t)qh;
+      }
+    }
+  }
+
+  // octant-ordered slot assignment: slot bit a set = child lies on the + side of axis a
+  void assign_slots(const WideChild* ch, int nch, int* slot_of) {
+    Box3 nb;
+    for (int i = 0; i < nch; ++i) nb.grow(ch[i].box);
+    float pc[3];
+    for (int a = 0; a < 3; ++a) pc[a] = 0.5f * (nb.lo[a] + nb.hi[a]);
+    float cost[8][8];
+    for (int i = 0; i < nch; ++i) {
+      float d[3];
+      for (int a = 0; a < 3; ++a) d[a] = 0.5f * (ch[i].box.lo[a] + ch[i].box.hi[a]) - pc[a];
+      for (int s = 0; s < 8; ++s)
+        cost[i][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+    }
+    bool child_done[8] = {false}, slot_used[8] = {false};
+    for (int i = 0; i < nch; ++i) slot_of[i] = -1;
+    for (int round = 0; round < nch; ++round) {
+      float best = -INFINITY;
+      int bi = -1, bs = -1;
+      for (int i = 0; i < nch; ++i) {
+        if (child_done[i]) continue;
+        for (int s = 0; s < 8; ++s) {
+          if (slot_used[s]) continue;
+          if (cost[i][s] > best) { best = cost[i][s]; bi = i; bs = s; }
+        }
+      }
+      child_done[bi] = true;
+      slot_used[bs] = true;
+      slot_of[bi] = bs;
+    }
+  }
+};
+
+}  // namespace
+
+int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
+  out.nodes.clear();
+  for (int t = 0; t < (int)PT_COUNT; ++t) { out.geom[t].clear(); out.info[t].clear(); }
+  out.max_depth = 0;
+  const size_t np = hs.prims.size();
+
+  // --- per-type binary trees ---------------------------------------------------------------------------------
+  std::vector<float> centroid(3 * np);
+  for (size_t i = 0; i < np; ++i)
+    for (int a = 0; a < 3; ++a) centroid[3 * i + a] = 0.5f * (hs.prims[i].lo[a] + hs.prims[i].hi[a]);
+
+  struct TypedTree { Builder* b; int root; uint32_t type; };
+  std::vector<Builder*> builders;
+  std::vector<TypedTree> trees;
+  for (uint32_t t = 0; t < PT_COUNT; ++t) {
+    Builder* b = new Builder{hs, {}, {}, {}};
+    builders.push_back(b);
+    for (size_t i = 0; i < np; ++i)
+      if (hs.prims[i].type == t) b->order.push_back((uint32_t)i);
+    if (b->order.empty()) continue;
+    b->centroid = centroid;  // shared copy (small relative to the build)
+    b->bin.reserve(b->order.size());
+    int root = b->build_range(0, (uint32_t)b->order.size());
+    trees.push_back(TypedTree{b, root, t});
+  }
+  auto cleanup = [&]() { for (Builder* b : builders) delete b; };
+
+  Assembler as{hs, out};
+  if (trees.empty()) {  // empty scene: a single node with no children (every ray misses)
+    Node8 n;
+    std::memset(&n, 0, sizeof(n));
+    n.ex = n.ey = n.ez = 1;
+    for (int s = 0; s < 8; ++s)
+      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = 255; n.qhi[a][s] = 0; }
+    out.nodes.push_back(n);
+    cleanup();
+    return RTB_OK;
+  }
+
+  // --- breadth-first collapse into wide nodes -------------------------------------------------------------------
+  struct Pending { uint32_t node; int tree; int bin_node; uint32_t depth; };
+  std::vector<Pending> queue;
+  size_t qhead = 0;
+  const bool joined = trees.size() > 1;
+  out.nodes.emplace_back();
+  if (joined) {
+    // root joins the typed subtree roots (each forced to be an internal node)
+    WideChild ch[8];
+    int nch = (int)trees.size();
+    uint32_t base = (uint32_t)out.nodes.size();
+    for (int i = 0; i < nch; ++i) {
+      ch[i].box = trees[i].b->bin[trees[i].root].box;
+      ch[i].leaf = false;
+      out.nodes.emplace_back();
+    }
+    int slot_of[8];
+    as.assign_slots(ch, nch, slot_of);
+    // internal children must be stored in ascending slot order
+    int idx[8];
+    std::iota(idx, idx + nch, 0);
+    std::sort(idx, idx + nch, [&](int a, int b) { return slot_of[a] < slot_of[b]; });
+    Node8 n;
+    std::memset(&n, 0, sizeof(n));
+    as.quantise(n, ch, slot_of, nch);
+    n.child_base = base;
+    n.prim_base = 0;
+    for (int k = 0; k < nch; ++k) {
+      int i = idx[k];
+      n.imask |= (uint8_t)(1u << slot_of[i]);
+      queue.push_back(Pending{base + (uint32_t)k, i, trees[i].root, 2});
+    }
+    out.nodes[0] = n;
+  } else {
+    queue.push_back(Pending{0, 0, trees[0].root, 1});
+  }
+
+  while (qhead < queue.size()) {
+    Pending pd = queue[qhead++];
+    Builder& b = *trees[pd.tree].b;
+    const uint32_t type = trees[pd.tree].type;
+    if (pd.depth > out.max_depth) out.max_depth = pd.depth;
+    // gather up to 8 children by opening the largest internal child
+    int cand[8];
+    int nc = 0;
+    const BinNode& rootbn = b.bin[pd.bin_node];
+    if (rootbn.left < 0) {
+      cand[nc++] = pd.bin_node;  // typed root that is itself a leaf: node with one leaf child
+    } else {
+      cand[nc++] = rootbn.left;
+      cand[nc++] = rootbn.right;
+      while (nc < 8) {
+        int best = -1;
+        float best_area = -1.f;
+        for (int i = 0; i < nc; ++i) {
+          const BinNode& c = b.bin[cand[i]];
+          if (c.left < 0) continue;
+          float a = c.box.area();
+          if (a > best_area) { best_area = a; best = i; }
+        }
+        if (best < 0) break;
+        int open = cand[best];
+        cand[best] = b.bin[open].left;
+        cand[nc++] = b.bin[open].right;
+      }
+    }
+    WideChild ch[8];
+    for (int i = 0; i < nc; ++i) {
+      ch[i].box = b.bin[cand[i]].box;
+      ch[i].bin_node = cand[i];
+      ch[i].leaf = b.bin[cand[i]].left < 0;
+    }
+    int slot_of[8];
+    as.assign_slots(ch, nc, slot_of);
+    int idx[8];
+    std::iota(idx, idx + nc, 0);
+    std::sort(idx, idx + nc, [&](int x, int y) { return slot_of[x] < slot_of[y]; });
+    Node8 n;
+    std::memset(&n, 0, sizeof(n));
+    as.quantise(n, ch, slot_of, nc);
+    const uint32_t gw = geom_words(type);
+    const uint32_t prim_base = (uint32_t)(out.info[type].size() / 2);
+    if (prim_base > REF_INDEX_MASK) { err = "too many primitives of one type"; cleanup(); return RTB_ERR_INVALID; }
+    n.prim_base = (type << REF_TYPE_SHIFT) | prim_base;
+    n.child_base = (uint32_t)out.nodes.size();
+    uint32_t off = 0;
+    for (int k = 0; k < nc; ++k) {
+      int i = idx[k];
+      int s = slot_of[i];
+      if (ch[i].leaf) {
+        const BinNode& lf = b.bin[ch[i].bin_node];
+        if (lf.count > 3 || off + lf.count > 24) { err = "internal: leaf too large"; cleanup(); return RTB_ERR_INVALID; }
+        n.meta[s] = (uint8_t)((lf.count << 5) | off);
+        for (uint32_t q = 0; q < lf.count; ++q) {
+          const HostPrim& p = hs.prims[b.order[lf.first + q]];
+          for (uint32_t w = 0; w < gw; ++w) out.geom[type].push_back(p.g[w]);
+          out.info[type].push_back(p.prim_id);
+          out.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
+        }
+        off += lf.count;
+      } else {
+        n.imask |= (uint8_t)(1u << s);
+        uint32_t child_node = (uint32_t)out.nodes.size();
+        out.nodes.emplace_back();
+        queue.push_back(Pending{child_node, pd.tree, ch[i].bin_node, pd.depth + 1});
+      }
+    }
+    out.nodes[pd.node] = n;
+  }
+  cleanup();
+  if (out.max_depth > 28) { err = "BVH too deep for the traversal stack"; return RTB_ERR_INVALID; }
+  return RTB_OK;
+}
+
+}  // namespace rtb

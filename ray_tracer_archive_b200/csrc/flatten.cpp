@@ -1,0 +1,362 @@
+// flatten.cpp — host side of the drop-in boundary: turns the reference's scene graph (one rtb_node per constructor
+// call) into world-space SoA primitives in primitive-id order.  What the reference evaluates lazily through
+// trait-object wrappers at every ray (hittable.rs:76-85 Translate, :147-176 RotateY, :195-201 FlipFace,
+// boxes.rs:19-68 Box, hittable_list.rs:43-49 list order) is resolved here once.
+#include <cmath>
+#include <cstring>
+
+#include "rtb_internal.hpp"
+
+namespace rtb {
+
+namespace {
+
+const double kPi = 3.14159265358979323846;
+
+struct Xform {           // world = Ry(angle) * p + t   (the reference only has Y rotations and translations)
+  double c = 1, s = 0;   // cos / sin of the accumulated angle
+  double t[3] = {0, 0, 0};
+  double angle_deg = 0;
+  bool identity_rot = true;
+  void point(const double p[3], double out[3]) const {  // hit -> world direction of hittable.rs:162-166
+    out[0] = c * p[0] + s * p[2] + t[0];
+    out[1] = p[1] + t[1];
+    out[2] = -s * p[0] + c * p[2] + t[2];
+  }
+  void vec(const double p[3], double out[3]) const {
+    out[0] = c * p[0] + s * p[2];
+    out[1] = p[1];
+    out[2] = -s * p[0] + c * p[2];
+  }
+};
+
+// front_face rewriting by wrappers, composed outer∘inner while walking down
+uint32_t compose_face(uint32_t outer, uint32_t inner_wrapper) {
+  // value of outer(inner(x)) where inner_wrapper ∈ {FLIPPED (FlipFace), TRUE (Translate/RotateY)}
+  if (inner_wrapper == FACE_TRUE) {
+    switch (outer) {
+      case FACE_NATURAL: return FACE_TRUE;
+      case FACE_FLIPPED: return FACE_FALSE;
+      default: return outer;
+    }
+  }
+  // inner is a flip
+  switch (outer) {
+    case FACE_NATURAL: return FACE_FLIPPED;
+    case FACE_FLIPPED: return FACE_NATURAL;
+    default: return outer;
+  }
+}
+
+void set_bounds(HostPrim& p, const double lo[3], const double hi[3]) {
+  for (int a = 0; a < 3; ++a) {
+    double m = std::fmax(std::fabs(lo[a]), std::fabs(hi[a]));
+    double pad = 1e-4 + 2e-6 * m;  // reference pads rect boxes by 1e-4 (aarect.rs:52-53); plus f32 slack
+    p.lo[a] = std::nextafterf((float)(lo[a] - pad), -INFINITY);
+    p.hi[a] = std::nextafterf((float)(hi[a] + pad), INFINITY);
+  }
+}
+
+struct Walker {
+  HostScene& hs;
+  const rtb_node* nodes;
+  uint32_t n_nodes;
+  const uint32_t* child_index;
+  uint32_t n_child_index;
+  std::string& err;
+  uint32_t depth = 0;
+
+  bool fail(const char* m) { err = m; return false; }
+
+  HostPrim& emit(uint32_t type, uint32_t material, uint32_t face_mode) {
+    hs.prims.emplace_back();
+    HostPrim& p = hs.prims.back();
+    std::memset(&p, 0, sizeof(p));
+    p.type = type;
+    p.prim_id = hs.n_prim_ids++;
+    p.material = material;
+    p.face_mode = face_mode;
+    return p;
+  }
+
+  bool check_mat(uint32_t m) {
+    if (m == RTB_NONE || m >= hs.materials.size()) return fail("primitive references a material that was not set");
+    return true;
+  }
+
+  void rect(int axis, double a0, double a1, double b0, double b1, double k, uint32_t mat, const Xform& x, uint32_t fm) {
+    // aarect.rs: XyRect axis 2 (a=x,b=y), XzRect axis 1 (a=x,b=z), YzRect axis 0 (a=y,b=z); outward normal = +axis
+    int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;
+    double Q[3], U[3] = {0, 0, 0}, V[3] = {0, 0, 0}, N[3] = {0, 0, 0};
+    Q[axis] = k; Q[ia] = a0; Q[ib] = b0;
+    U[ia] = a1 - a0;
+    V[ib] = b1 - b0;
+    N[axis] = 1.0;
+    double Qw[3], Uw[3], Vw[3], Nw[3];
+    x.point(Q, Qw); x.vec(U, Uw); x.vec(V, Vw); x.vec(N, Nw);
+    HostPrim& p = emit(PT_QUAD, mat, fm);
+    pack_quad(p, Qw, Uw, Vw, Nw);
+  }
+
+  bool walk(uint32_t ni, const Xform& x, uint32_t fm) {
+    if (ni >= n_nodes) return fail("node index out of range");
+    if (++depth > 256) return fail("scene graph too deep (cycle?)");
+    const rtb_node& n = nodes[ni];
+    const double* p = n.p;
+    bool ok = true;
+    auto child = [&](uint32_t k, uint32_t& out) -> bool {
+      if (k >= n.n_children || (uint64_t)n.first_child + k >= n_child_index) return fail("node is missing a child");
+      out = child_index[n.first_child + k];
+      return true;
+    };
+    switch (n.type) {
+      case RTB_NODE_SPHERE: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        if (!x.identity_rot && hs.materials[n.material].type != RTB_MAT_DIELECTRIC) {
+          // uv are object-space (sphere.rs:32-37); only an image texture reads them
+          uint32_t t = hs.materials[n.material].texture;
+          if (t < hs.textures.size() && hs.textures[t].type == RTB_TEX_IMAGE) {
+            ok = fail("image-textured sphere under RotateY is not supported"); break;
+          }
+        }
+        double c[3];
+        x.point(p, c);
+        HostPrim& pr = emit(PT_SPHERE, n.material, fm);
+        pack_sphere(pr, c, p[3]);
+        break;
+      }
+      case RTB_NODE_MOVING_SPHERE: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        double c0[3], c1[3];
+        x.point(p, c0); x.point(p + 3, c1);
+        HostPrim& pr = emit(PT_MOVING, n.material, fm);
+        pack_moving(pr, c0, c1, p[6], p[7], p[8]);
+        break;
+      }
+      case RTB_NODE_XY_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(2, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
+      case RTB_NODE_XZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(1, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
+      case RTB_NODE_YZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(0, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
+      case RTB_NODE_BOX: {  // boxes.rs:19-68: XY(z1) XY(z0) XZ(y1) XZ(y0) YZ(x1) YZ(x0)
+        if (!check_mat(n.material)) { ok = false; break; }
+        rect(2, p[0], p[3], p[1], p[4], p[5], n.material, x, fm);
+        rect(2, p[0], p[3], p[1], p[4], p[2], n.material, x, fm);
+        rect(1, p[0], p[3], p[2], p[5], p[4], n.material, x, fm);
+        rect(1, p[0], p[3], p[2], p[5], p[1], n.material, x, fm);
+        rect(0, p[1], p[4], p[2], p[5], p[3], n.material, x, fm);
+        rect(0, p[1], p[4], p[2], p[5], p[0], n.material, x, fm);
+        break;
+      }
+      case RTB_NODE_TRIANGLE: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        double a[3], b[3], c[3];
+        x.point(p, a); x.point(p + 3, b); x.point(p + 6, c);
+        HostPrim& pr = emit(PT_TRI, n.material, fm);
+        pack_tri(pr, a, b, c);
+        break;
+      }
+      case RTB_NODE_QUAD: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        double Q[3], U[3], V[3];
+        x.point(p, Q); x.vec(p + 3, U); x.vec(p + 6, V);
+        HostPrim& pr = emit(PT_QUAD, n.material, fm);
+        pack_quad(pr, Q, U, V, nullptr);
+        break;
+      }
+      case RTB_NODE_MESH: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        uint32_t mid = (uint32_t)p[0];
+        if (mid >= hs.meshes.size() || hs.meshes[mid].idx.empty()) { ok = fail("mesh id was not set"); break; }
+        const HostScene::Mesh& m = hs.meshes[mid];
+        hs.prims.reserve(hs.prims.size() + m.idx.size() / 3);
+        for (size_t k = 0; k + 2 < m.idx.size(); k += 3) {
+          double v[3][3];
+          for (int q = 0; q < 3; ++q) {
+            const float* f = &m.verts[3 * (size_t)m.idx[k + q]];
+            double d[3] = {f[0], f[1], f[2]};
+            x.point(d, v[q]);
+          }
+          HostPrim& pr = emit(PT_TRI, n.material, fm);
+          pack_tri(pr, v[0], v[1], v[2]);
+        }
+        break;
+      }
+      case RTB_NODE_TRANSLATE: {
+        uint32_t c;
+        if (!child(0, c)) { ok = false; break; }
+        Xform y = x;
+        double off[3];
+        x.vec(p, off);
+        for (int a = 0; a < 3; ++a) y.t[a] += off[a];
+        ok = walk(c, y, compose_face(fm, FACE_TRUE));
+        break;
+      }
+      case RTB_NODE_ROTATE_Y: {
+        uint32_t c;
+        if (!child(0, c)) { ok = false; break; }
+        Xform y = x;
+        y.angle_deg = x.angle_deg + p[0];
+        double rad = y.angle_deg * kPi / 180.0;  // hittable.rs:108
+        y.c = std::cos(rad); y.s = std::sin(rad);
+        y.identity_rot = false;
+        ok = walk(c, y, compose_face(fm, FACE_TRUE));
+        break;
+      }
+      case RTB_NODE_FLIP_FACE: {
+        uint32_t c;
+        if (!child(0, c)) { ok = false; break; }
+        ok = walk(c, x, compose_face(fm, FACE_FLIPPED));
+        break;
+      }
+      case RTB_NODE_CONSTANT_MEDIUM: {
+        if (!check_mat(n.material)) { ok = false; break; }
+        uint32_t c;
+        if (!child(0, c)) { ok = false; break; }
+        // resolve the boundary: Sphere or Box under Translate/RotateY wrappers (convex, as the reference requires)
+        Xform y = x;
+        uint32_t guard = 0;
+        while (ok) {
+          if (c >= n_nodes || ++guard > 64) { ok = fail("bad medium boundary"); break; }
+          const rtb_node& b = nodes[c];
+          if (b.type == RTB_NODE_TRANSLATE) {
+            double off[3];
+            y.vec(b.p, off);
+            for (int a = 0; a < 3; ++a) y.t[a] += off[a];
+          } else if (b.type == RTB_NODE_ROTATE_Y) {
+            y.angle_deg += b.p[0];
+            double rad = y.angle_deg * kPi / 180.0;
+            y.c = std::cos(rad); y.s = std::sin(rad);
+            y.identity_rot = false;
+          } else if (b.type == RTB_NODE_FLIP_FACE) {
+          } else {
+            break;
+          }
+          if (b.n_children < 1 || (uint64_t)b.first_child >= n_child_index) { ok = fail("bad medium boundary"); break; }
+          c = child_index[b.first_child];
+        }
+        if (!ok) break;
+        const rtb_node& b = nodes[c];
+        HostMedium m;
+        std::memset(&m, 0, sizeof(m));
+        m.material = n.material;
+        m.prim_id = hs.n_prim_ids++;
+        m.neg_inv_density = (float)(-1.0 / p[0]);  // constant_medium.rs:26
+        m.sin_t = (float)y.s; m.cos_t = (float)y.c;
+        for (int a = 0; a < 3; ++a) m.offset[a] = (float)y.t[a];
+        if (b.type == RTB_NODE_SPHERE) {
+          double cw[3];
+          y.point(b.p, cw);
+          m.boundary_type = RTB_BOUNDARY_SPHERE;
+          m.p[0] = (float)cw[0]; m.p[1] = (float)cw[1]; m.p[2] = (float)cw[2]; m.p[3] = (float)b.p[3];
+        } else if (b.type == RTB_NODE_BOX) {
+          m.boundary_type = RTB_BOUNDARY_BOX;
+          for (int a = 0; a < 6; ++a) m.p[a] = (float)b.p[a];
+        } else {
+          ok = fail("ConstantMedium boundary must be a Sphere or a Box (optionally under Translate/RotateY)");
+          break;
+        }
+        hs.media.push_back(m);
+        break;
+      }
+      case RTB_NODE_LIST:
+      case RTB_NODE_BVH: {
+        for (uint32_t k = 0; k < n.n_children && ok; ++k) {
+          uint32_t c;
+          if (!child(k, c)) { ok = false; break; }
+          ok = walk(c, x, fm);
+        }
+        break;
+      }
+      default: ok = fail("unknown node type");
+    }
+    --depth;
+    return ok;
+  }
+};
+
+}  // namespace
+
+void pack_sphere(HostPrim& p, const double c[3], double r) {
+  p.g[0] = (float)c[0]; p.g[1] = (float)c[1]; p.g[2] = (float)c[2]; p.g[3] = (float)r;
+  double ar = std::fabs(r);
+  double lo[3] = {c[0] - ar, c[1] - ar, c[2] - ar}, hi[3] = {c[0] + ar, c[1] + ar, c[2] + ar};
+  set_bounds(p, lo, hi);
+}
+
+void pack_moving(HostPrim& p, const double c0[3], const double c1[3], double t0, double t1, double r) {
+  // centre(time) = c0 + (time - t0)/(t1 - t0) * (c1 - c0) = A + time * B      moving_sphere.rs:36-39
+  double inv = 1.0 / (t1 - t0);
+  double lo[3], hi[3];
+  double ta = std::fmin(t0, 0.0), tb = std::fmax(t1, 1.0);  // bounds cover shutter times in [min(t0,0), max(t1,1)]
+  for (int a = 0; a < 3; ++a) {
+    double B = (c1[a] - c0[a]) * inv, A = c0[a] - t0 * B;
+    p.g[a] = (float)A;
+    p.g[4 + a] = (float)B;
+    double pa = A + ta * B, pb = A + tb * B;
+    lo[a] = std::fmin(pa, pb) - std::fabs(r);
+    hi[a] = std::fmax(pa, pb) + std::fabs(r);
+  }
+  p.g[3] = (float)r;
+  p.g[7] = 0.f;
+  set_bounds(p, lo, hi);
+}
+
+static void cross3(const double a[3], const double b[3], double o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+void pack_quad(HostPrim& p, const double Q[3], const double U[3], const double V[3], const double* outward) {
+  // plane form: word0 = (n, n.Q), word1 = (wa, wa.Q), word2 = (wb, wb.Q) with
+  //   t = (n.Q - n.o)/(n.d),  alpha = wa.P - wa.Q,  beta = wb.P - wb.Q,   wa = (V x n')/(n'.n'), wb = (n' x U)/(n'.n'), n' = U x V
+  double n[3], wa[3], wb[3];
+  cross3(U, V, n);
+  double nn = dot3(n, n);
+  cross3(V, n, wa);
+  cross3(n, U, wb);
+  double len = std::sqrt(nn);
+  double nh[3];
+  for (int a = 0; a < 3; ++a) { wa[a] /= nn; wb[a] /= nn; nh[a] = n[a] / len; }
+  if (outward) {  // axis-aligned rects have outward normal = +axis regardless of the (a,b) handedness (aarect.rs:43,93,162)
+    double ol = std::sqrt(dot3(outward, outward));
+    for (int a = 0; a < 3; ++a) nh[a] = outward[a] / ol;
+  }
+  for (int a = 0; a < 3; ++a) { p.g[a] = (float)nh[a]; p.g[4 + a] = (float)wa[a]; p.g[8 + a] = (float)wb[a]; }
+  p.g[3] = (float)dot3(nh, Q);
+  p.g[7] = (float)dot3(wa, Q);
+  p.g[11] = (float)dot3(wb, Q);
+  double lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    double c0 = Q[a], c1 = Q[a] + U[a], c2 = Q[a] + V[a], c3 = Q[a] + U[a] + V[a];
+    lo[a] = std::fmin(std::fmin(c0, c1), std::fmin(c2, c3));
+    hi[a] = std::fmax(std::fmax(c0, c1), std::fmax(c2, c3));
+  }
+  set_bounds(p, lo, hi);
+}
+
+void pack_tri(HostPrim& p, const double v0[3], const double v1[3], const double v2[3]) {
+  double lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    p.g[a] = (float)v0[a];
+    p.g[4 + a] = (float)(v1[a] - v0[a]);
+    p.g[8 + a] = (float)(v2[a] - v0[a]);
+    lo[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
+    hi[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
+  }
+  p.g[3] = p.g[7] = p.g[11] = 0.f;
+  set_bounds(p, lo, hi);
+}
+
+int flatten_graph(HostScene& hs, const rtb_node* nodes, uint32_t n_nodes, const uint32_t* child_index,
+                  uint32_t n_child_index, uint32_t root, std::string& err) {
+  hs.prims.clear();
+  hs.media.clear();
+  hs.n_prim_ids = 0;
+  Walker w{hs, nodes, n_nodes, child_index, n_child_index, err};
+  Xform id;
+  if (!w.walk(root, id, FACE_NATURAL)) return RTB_ERR_INVALID;
+  return RTB_OK;
+}
+
+}  // namespace rtb

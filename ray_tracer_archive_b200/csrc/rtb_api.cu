@@ -1,0 +1,708 @@
+// rtb_api.cu — the extern "C" boundary declared in include/rtb200.h.  Host orchestration only: scene tables,
+// flatten + BVH build (flatten.cpp, bvh_build.cpp), uploads, and the wavefront iteration loop that replaces the
+// reference's pixel/sample loop (main.rs:731-784).  There is no CPU path: without a CUDA device every entry fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rtb_device.cuh"
+#include "rtb_launch.hpp"
+
+using namespace rtb;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& m) { g_err = m; return code; }
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess)                                                                                    \
+      return set_err(RTB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  cudaError_t resize(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const T* src, size_t count, cudaStream_t st = 0) {
+    cudaError_t e = resize(count);
+    if (e != cudaSuccess || count == 0) return e;
+    return cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+};
+
+struct rtb_context {
+  int device = 0;
+  cudaDeviceProp prop;
+  // wavefront pool
+  uint32_t pool_n = 0;
+  DevBuf<float4> ray_o, ray_d, beta, rad;
+  DevBuf<float2> hit;
+  DevBuf<uint32_t> q_ext0, q_ext1, q_dead;
+  DevBuf<uint32_t> q_mat[Q_COUNT];
+  DevBuf<DevCounters> counters;
+  DevCounters* h_counters = nullptr;  // pinned
+  // image-sized buffers
+  DevBuf<float4> accum;
+  DevBuf<uint32_t> pix_order;
+  uint32_t pix_w = 0, pix_h = 0;
+  DevBuf<uint8_t> rgb8;
+  // probe scratch
+  DevBuf<float> p_org, p_dir, p_time, p_t;
+  DevBuf<uint32_t> p_id;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct rtb_scene {
+  rtb_context* ctx = nullptr;
+  HostScene hs;
+  HostBvh bvh;
+  bool built = false;      // host BVH is current
+  bool committed = false;  // device copies are current
+  uint32_t present_materials = 0;  // bit per rtb_material_type that some primitive/medium uses
+  // device copies
+  DevBuf<uint4> d_nodes;
+  DevBuf<float4> d_geom[PT_COUNT];
+  DevBuf<uint2> d_info[PT_COUNT];
+  DevBuf<float4> d_materials;
+  DevBuf<DevTexture> d_textures;
+  DevBuf<float4> d_perlin_vec[RTB_MAX_TABLES];
+  DevBuf<uint8_t> d_perlin_perm[RTB_MAX_TABLES];
+  DevBuf<uint8_t> d_images[RTB_MAX_TABLES];
+  DevScene dev;
+  LaunchCfg lc;
+};
+
+extern "C" {
+
+uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
+const char* rtb_last_error(void) { return g_err.c_str(); }
+
+int rtb_context_create(int device_id, rtb_context** out) {
+  if (!out) return set_err(RTB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_err(RTB_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                          " (librtb200 has no CPU fallback)");
+  if (device_id < 0 || device_id >= n) return set_err(RTB_ERR_INVALID, "device_id out of range");
+  CU(cudaSetDevice(device_id));
+  rtb_context* c = new rtb_context();
+  c->device = device_id;
+  CU(cudaGetDeviceProperties(&c->prop, device_id));
+  if (c->prop.major < 10) {
+    delete c;
+    return set_err(RTB_ERR_NO_DEVICE, "librtb200 is built for sm_100a only");
+  }
+  CU(cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters)));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  CU(c->counters.resize(1));
+  *out = c;
+  return RTB_OK;
+}
+
+void rtb_context_destroy(rtb_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+int rtb_context_device_info(rtb_context* c, int* sm_count, int* l2_bytes, int* clock_khz, char* name, size_t cap) {
+  if (!c) return set_err(RTB_ERR_INVALID, "ctx is NULL");
+  if (sm_count) *sm_count = c->prop.multiProcessorCount;
+  if (l2_bytes) *l2_bytes = c->prop.l2CacheSize;
+  if (clock_khz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    *clock_khz = khz;
+  }
+  if (name && cap) { std::strncpy(name, c->prop.name, cap - 1); name[cap - 1] = 0; }
+  return RTB_OK;
+}
+
+// ---- scene tables ---------------------------------------------------------------------------------------------
+int rtb_scene_create(rtb_context* ctx, rtb_scene** out) {
+  if (!out) return set_err(RTB_ERR_INVALID, "NULL argument");
+  rtb_scene* s = new rtb_scene();  // ctx == NULL: host-only scene (flatten / BVH build / export; cannot be committed)
+  s->ctx = ctx;
+  *out = s;
+  return RTB_OK;
+}
+void rtb_scene_destroy(rtb_scene* s) {
+  if (!s) return;
+  if (s->ctx) {
+    cudaSetDevice(s->ctx->device);
+    cudaDeviceSynchronize();
+  }
+  delete s;
+}
+
+int rtb_scene_set_materials(rtb_scene* s, const rtb_material* mats, uint32_t n) {
+  if (!s || (!mats && n)) return set_err(RTB_ERR_INVALID, "NULL argument");
+  for (uint32_t i = 0; i < n; ++i)
+    if (mats[i].type > RTB_MAT_ISOTROPIC) return set_err(RTB_ERR_INVALID, "unknown material type");
+  s->hs.materials.assign(mats, mats + n);
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_textures(rtb_scene* s, const rtb_texture* tex, uint32_t n) {
+  if (!s || (!tex && n)) return set_err(RTB_ERR_INVALID, "NULL argument");
+  for (uint32_t i = 0; i < n; ++i) {
+    if (tex[i].type > RTB_TEX_IMAGE) return set_err(RTB_ERR_INVALID, "unknown texture type");
+    if (tex[i].type == RTB_TEX_CHECKER && (tex[i].even >= n || tex[i].odd >= n))
+      return set_err(RTB_ERR_INVALID, "checker child out of range");
+    if (tex[i].type == RTB_TEX_NOISE && tex[i].table >= RTB_MAX_TABLES) return set_err(RTB_ERR_INVALID, "perlin table id too large");
+  }
+  s->hs.textures.assign(tex, tex + n);
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_image(rtb_scene* s, uint32_t id, const uint8_t* rgb, uint32_t w, uint32_t h) {
+  if (!s || id >= RTB_MAX_TABLES) return set_err(RTB_ERR_INVALID, "image id out of range");
+  if (s->hs.images.size() <= id) s->hs.images.resize(id + 1);
+  s->hs.images[id].rgb.assign(rgb, rgb + (size_t)w * h * 3);
+  s->hs.images[id].w = w;
+  s->hs.images[id].h = h;
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_perlin(rtb_scene* s, uint32_t id, const double* ranvec, const uint32_t* px, const uint32_t* py,
+                         const uint32_t* pz) {
+  if (!s || id >= RTB_MAX_TABLES || !ranvec || !px || !py || !pz) return set_err(RTB_ERR_INVALID, "bad perlin table");
+  if (s->hs.perlins.size() <= id) s->hs.perlins.resize(id + 1);
+  HostScene::Perlin& p = s->hs.perlins[id];
+  p.ranvec.resize(256 * 4);
+  p.perm.resize(768);
+  for (int i = 0; i < 256; ++i) {
+    p.ranvec[4 * i] = (float)ranvec[3 * i];
+    p.ranvec[4 * i + 1] = (float)ranvec[3 * i + 1];
+    p.ranvec[4 * i + 2] = (float)ranvec[3 * i + 2];
+    p.ranvec[4 * i + 3] = 0.f;
+    if (px[i] > 255 || py[i] > 255 || pz[i] > 255) return set_err(RTB_ERR_INVALID, "perm entry > 255");
+    p.perm[i] = (uint8_t)px[i];
+    p.perm[256 + i] = (uint8_t)py[i];
+    p.perm[512 + i] = (uint8_t)pz[i];
+  }
+  p.set = true;
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_mesh(rtb_scene* s, uint32_t id, const float* verts, uint32_t nv, const uint32_t* idx, uint32_t nt) {
+  if (!s || !verts || !idx) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (id >= 64) return set_err(RTB_ERR_INVALID, "mesh id out of range");
+  for (size_t i = 0; i < (size_t)nt * 3; ++i)
+    if (idx[i] >= nv) return set_err(RTB_ERR_INVALID, "mesh index out of range");
+  if (s->hs.meshes.size() <= id) s->hs.meshes.resize(id + 1);
+  s->hs.meshes[id].verts.assign(verts, verts + (size_t)nv * 3);
+  s->hs.meshes[id].idx.assign(idx, idx + (size_t)nt * 3);
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_lights(rtb_scene* s, const rtb_light* lights, uint32_t n) {
+  if (!s || (!lights && n)) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (n > RTB_MAX_LIGHTS) return set_err(RTB_ERR_UNSUPPORTED, "too many lights");
+  s->hs.lights.clear();
+  for (uint32_t i = 0; i < n; ++i) {
+    if (lights[i].type > RTB_LIGHT_SPHERE)
+      return set_err(RTB_ERR_UNSUPPORTED, "only XzRect and Sphere implement pdf_value/random (aarect.rs:107, sphere.rs:75)");
+    HostLight l;
+    l.type = lights[i].type;
+    for (int k = 0; k < 5; ++k) l.p[k] = (float)lights[i].p[k];
+    s->hs.lights.push_back(l);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+
+int rtb_scene_set_graph(rtb_scene* s, const rtb_node* nodes, uint32_t n_nodes, const uint32_t* child_index,
+                        uint32_t n_child_index, uint32_t root) {
+  if (!s || !nodes || (!child_index && n_child_index)) return set_err(RTB_ERR_INVALID, "NULL argument");
+  std::string err;
+  int rc = flatten_graph(s->hs, nodes, n_nodes, child_index, n_child_index, root, err);
+  s->built = s->committed = false;
+  if (rc != RTB_OK) return set_err(rc, err);
+  return RTB_OK;
+}
+
+// ---- flat SoA setters ------------------------------------------------------------------------------------------
+static void drop_type(HostScene& hs, uint32_t type) {
+  hs.prims.erase(std::remove_if(hs.prims.begin(), hs.prims.end(), [&](const HostPrim& p) { return p.type == type; }),
+                 hs.prims.end());
+}
+static uint32_t face_mode_of(uint32_t flags) {
+  if (flags & RTB_PRIM_FORCE_FRONT) return (flags & RTB_PRIM_FLIP_FACE) ? FACE_FALSE : FACE_TRUE;
+  return (flags & RTB_PRIM_FLIP_FACE) ? FACE_FLIPPED : FACE_NATURAL;
+}
+static HostPrim& add_flat(rtb_scene* s, uint32_t type, const uint32_t* mat, const uint32_t* flags, const uint32_t* id,
+                          uint32_t i) {
+  s->hs.prims.emplace_back();
+  HostPrim& p = s->hs.prims.back();
+  std::memset(&p, 0, sizeof(p));
+  p.type = type;
+  p.material = mat[i];
+  p.face_mode = flags ? face_mode_of(flags[i]) : FACE_NATURAL;
+  p.prim_id = id ? id[i] : s->hs.n_prim_ids;
+  s->hs.n_prim_ids = std::max(s->hs.n_prim_ids, p.prim_id + 1);
+  return p;
+}
+
+int rtb_scene_set_spheres(rtb_scene* s, const float* cr, const uint32_t* mat, const uint32_t* flags, const uint32_t* id,
+                          uint32_t n) {
+  if (!s || (n && (!cr || !mat))) return set_err(RTB_ERR_INVALID, "NULL argument");
+  drop_type(s->hs, PT_SPHERE);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostPrim& p = add_flat(s, PT_SPHERE, mat, flags, id, i);
+    double c[3] = {cr[4 * i], cr[4 * i + 1], cr[4 * i + 2]};
+    pack_sphere(p, c, cr[4 * i + 3]);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_moving_spheres(rtb_scene* s, const float* c0r, const float* c1, const float* t01, const uint32_t* mat,
+                                 const uint32_t* flags, const uint32_t* id, uint32_t n) {
+  if (!s || (n && (!c0r || !c1 || !t01 || !mat))) return set_err(RTB_ERR_INVALID, "NULL argument");
+  drop_type(s->hs, PT_MOVING);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostPrim& p = add_flat(s, PT_MOVING, mat, flags, id, i);
+    double a[3] = {c0r[4 * i], c0r[4 * i + 1], c0r[4 * i + 2]}, b[3] = {c1[3 * i], c1[3 * i + 1], c1[3 * i + 2]};
+    pack_moving(p, a, b, t01[2 * i], t01[2 * i + 1], c0r[4 * i + 3]);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_quads(rtb_scene* s, const float* q, const float* u, const float* v, const uint32_t* mat,
+                        const uint32_t* flags, const uint32_t* id, uint32_t n) {
+  if (!s || (n && (!q || !u || !v || !mat))) return set_err(RTB_ERR_INVALID, "NULL argument");
+  drop_type(s->hs, PT_QUAD);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostPrim& p = add_flat(s, PT_QUAD, mat, flags, id, i);
+    double Q[3] = {q[3 * i], q[3 * i + 1], q[3 * i + 2]}, U[3] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]},
+           V[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
+    pack_quad(p, Q, U, V, nullptr);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_triangles(rtb_scene* s, const float* v0, const float* v1, const float* v2, const uint32_t* mat,
+                            const uint32_t* flags, const uint32_t* id, uint32_t n) {
+  if (!s || (n && (!v0 || !v1 || !v2 || !mat))) return set_err(RTB_ERR_INVALID, "NULL argument");
+  drop_type(s->hs, PT_TRI);
+  s->hs.prims.reserve(s->hs.prims.size() + n);
+  for (uint32_t i = 0; i < n; ++i) {
+    HostPrim& p = add_flat(s, PT_TRI, mat, flags, id, i);
+    double a[3] = {v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]}, b[3] = {v1[3 * i], v1[3 * i + 1], v1[3 * i + 2]},
+           c[3] = {v2[3 * i], v2[3 * i + 1], v2[3 * i + 2]};
+    pack_tri(p, a, b, c);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+int rtb_scene_set_media(rtb_scene* s, const rtb_medium* media, uint32_t n) {
+  if (!s || (n && !media)) return set_err(RTB_ERR_INVALID, "NULL argument");
+  s->hs.media.clear();
+  for (uint32_t i = 0; i < n; ++i) {
+    const rtb_medium& m = media[i];
+    if (m.boundary_type > RTB_BOUNDARY_BOX) return set_err(RTB_ERR_UNSUPPORTED, "medium boundary must be sphere or box");
+    HostMedium h;
+    std::memset(&h, 0, sizeof(h));
+    h.boundary_type = m.boundary_type;
+    h.material = m.material;
+    h.prim_id = m.prim_id;
+    s->hs.n_prim_ids = std::max(s->hs.n_prim_ids, m.prim_id + 1);
+    h.neg_inv_density = (float)(-1.0 / m.density);
+    for (int k = 0; k < 6; ++k) h.p[k] = (float)m.p[k];
+    double rad = m.rot_y_deg * 3.14159265358979323846 / 180.0;
+    h.sin_t = (float)std::sin(rad);
+    h.cos_t = (float)std::cos(rad);
+    for (int k = 0; k < 3; ++k) h.offset[k] = (float)m.offset[k];
+    s->hs.media.push_back(h);
+  }
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+
+// ---- build (host) and commit (upload) ------------------------------------------------------------------------------
+int rtb_scene_build_bvh(rtb_scene* s) {
+  if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
+  HostScene& hs = s->hs;
+  if (hs.media.size() > RTB_MAX_MEDIA) return set_err(RTB_ERR_UNSUPPORTED, "too many media");
+  if (hs.materials.empty()) return set_err(RTB_ERR_STATE, "materials were not set");
+  s->present_materials = 0;
+  for (const HostPrim& p : hs.prims) {
+    if (p.material >= hs.materials.size()) return set_err(RTB_ERR_INVALID, "primitive material out of range");
+    s->present_materials |= 1u << hs.materials[p.material].type;
+  }
+  for (const HostMedium& m : hs.media) {
+    if (m.material >= hs.materials.size()) return set_err(RTB_ERR_INVALID, "medium material out of range");
+    s->present_materials |= 1u << hs.materials[m.material].type;
+  }
+  for (const rtb_material& m : hs.materials) {
+    if (m.type != RTB_MAT_DIELECTRIC && m.texture >= hs.textures.size())
+      return set_err(RTB_ERR_INVALID, "material texture out of range");
+  }
+  for (const rtb_texture& t : hs.textures) {
+    if (t.type == RTB_TEX_NOISE && (t.table >= hs.perlins.size() || !hs.perlins[t.table].set))
+      return set_err(RTB_ERR_STATE, "noise texture references a perlin table that was not set");
+  }
+  std::string err;
+  int rc = build_bvh8(hs, s->bvh, err);
+  if (rc != RTB_OK) return set_err(rc, err);
+  s->built = true;
+  return RTB_OK;
+}
+
+int rtb_scene_commit(rtb_scene* s) {
+  if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
+  if (!s->ctx) return set_err(RTB_ERR_STATE, "host-only scene (created without a context) cannot be committed");
+  if (!s->built) {
+    int rc = rtb_scene_build_bvh(s);
+    if (rc != RTB_OK) return rc;
+  }
+  HostScene& hs = s->hs;
+  CU(cudaSetDevice(s->ctx->device));
+
+  DevScene& d = s->dev;
+  std::memset(&d, 0, sizeof(d));
+  CU(s->d_nodes.upload(reinterpret_cast<const uint4*>(s->bvh.nodes.data()), s->bvh.nodes.size() * 5));
+  d.nodes = s->d_nodes.p;
+  d.n_nodes = (uint32_t)s->bvh.nodes.size();
+  for (uint32_t t = 0; t < PT_COUNT; ++t) {
+    CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
+    CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(s->bvh.info[t].data()), s->bvh.info[t].size() / 2));
+    d.geom[t] = s->d_geom[t].p;
+    d.info[t] = s->d_info[t].p;
+  }
+  std::vector<float4> mats(hs.materials.size());
+  for (size_t i = 0; i < mats.size(); ++i) {
+    uint32_t ty = hs.materials[i].type, tx = hs.materials[i].texture;
+    float a, b;
+    std::memcpy(&a, &ty, 4);
+    std::memcpy(&b, &tx, 4);
+    mats[i] = make_float4(a, b, (float)hs.materials[i].param, 0.f);
+  }
+  CU(s->d_materials.upload(mats.data(), mats.size()));
+  d.materials = s->d_materials.p;
+  d.n_materials = (uint32_t)mats.size();
+  std::vector<DevTexture> texs(hs.textures.size());
+  for (size_t i = 0; i < texs.size(); ++i) {
+    const rtb_texture& t = hs.textures[i];
+    texs[i] = DevTexture{t.type, t.even, t.odd, t.table, (float)t.rgb[0], (float)t.rgb[1], (float)t.rgb[2], (float)t.scale};
+  }
+  CU(s->d_textures.upload(texs.data(), texs.size()));
+  d.textures = s->d_textures.p;
+  for (size_t i = 0; i < hs.perlins.size() && i < RTB_MAX_TABLES; ++i) {
+    if (!hs.perlins[i].set) continue;
+    CU(s->d_perlin_vec[i].upload(reinterpret_cast<const float4*>(hs.perlins[i].ranvec.data()), 256));
+    CU(s->d_perlin_perm[i].upload(hs.perlins[i].perm.data(), 768));
+    d.perlin_vec[i] = s->d_perlin_vec[i].p;
+    d.perlin_perm[i] = s->d_perlin_perm[i].p;
+  }
+  for (size_t i = 0; i < hs.images.size() && i < RTB_MAX_TABLES; ++i) {
+    if (hs.images[i].rgb.empty()) continue;
+    CU(s->d_images[i].upload(hs.images[i].rgb.data(), hs.images[i].rgb.size()));
+    d.images[i].data = s->d_images[i].p;
+    d.images[i].w = hs.images[i].w;
+    d.images[i].h = hs.images[i].h;
+  }
+  d.n_lights = (uint32_t)hs.lights.size();
+  for (size_t i = 0; i < hs.lights.size(); ++i) {
+    d.lights[i].type = hs.lights[i].type;
+    for (int k = 0; k < 5; ++k) d.lights[i].p[k] = hs.lights[i].p[k];
+  }
+  d.n_media = (uint32_t)hs.media.size();
+  for (size_t i = 0; i < hs.media.size(); ++i) {
+    const HostMedium& m = hs.media[i];
+    DevMedium& o = d.media[i];
+    o.boundary_type = m.boundary_type; o.material = m.material; o.prim_id = m.prim_id;
+    o.neg_inv_density = m.neg_inv_density;
+    for (int k = 0; k < 6; ++k) o.p[k] = m.p[k];
+    o.sin_t = m.sin_t; o.cos_t = m.cos_t;
+    for (int k = 0; k < 3; ++k) o.off[k] = m.offset[k];
+  }
+  int e = configure_launch(s->lc, d.n_nodes, s->ctx->prop.multiProcessorCount);
+  if (e != 0) return set_err(RTB_ERR_CUDA, std::string("configure_launch: ") + cudaGetErrorString((cudaError_t)e));
+  CU(cudaStreamSynchronize(0));
+  s->committed = true;
+  return RTB_OK;
+}
+
+int rtb_scene_get_info(rtb_scene* s, rtb_scene_info* o) {
+  if (!s || !o) return set_err(RTB_ERR_INVALID, "NULL argument");
+  std::memset(o, 0, sizeof(*o));
+  for (const HostPrim& p : s->hs.prims) {
+    if (p.type == PT_SPHERE) o->n_spheres++;
+    else if (p.type == PT_MOVING) o->n_moving++;
+    else if (p.type == PT_QUAD) o->n_quads++;
+    else o->n_triangles++;
+  }
+  o->n_media = (uint32_t)s->hs.media.size();
+  o->n_lights = (uint32_t)s->hs.lights.size();
+  o->n_materials = (uint32_t)s->hs.materials.size();
+  o->n_textures = (uint32_t)s->hs.textures.size();
+  o->n_prims = s->hs.n_prim_ids;
+  o->n_bvh_nodes = (uint32_t)s->bvh.nodes.size();
+  o->bvh_width = 8;
+  o->bvh_max_depth = s->bvh.max_depth;
+  o->bvh_bytes = (uint64_t)s->bvh.nodes.size() * sizeof(Node8);
+  o->prim_bytes = 0;
+  for (uint32_t t = 0; t < PT_COUNT; ++t) o->prim_bytes += s->bvh.geom[t].size() * 4 + s->bvh.info[t].size() * 4;
+  return RTB_OK;
+}
+int rtb_scene_export_bvh(rtb_scene* s, void* nodes, size_t cap) {
+  if (!s || !nodes) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (!s->built) return set_err(RTB_ERR_STATE, "BVH not built (call rtb_scene_build_bvh or rtb_scene_commit)");
+  size_t bytes = s->bvh.nodes.size() * sizeof(Node8);
+  if (cap < bytes) return set_err(RTB_ERR_INVALID, "buffer too small");
+  std::memcpy(nodes, s->bvh.nodes.data(), bytes);
+  return RTB_OK;
+}
+int rtb_scene_export_prims(rtb_scene* s, uint32_t type, float* geom, size_t gcap, uint32_t* info, size_t icap) {
+  if (!s || type >= PT_COUNT) return set_err(RTB_ERR_INVALID, "bad argument");
+  if (!s->built) return set_err(RTB_ERR_STATE, "BVH not built (call rtb_scene_build_bvh or rtb_scene_commit)");
+  size_t gb = s->bvh.geom[type].size() * 4, ib = s->bvh.info[type].size() * 4;
+  if ((geom && gcap < gb) || (info && icap < ib)) return set_err(RTB_ERR_INVALID, "buffer too small");
+  if (geom && gb) std::memcpy(geom, s->bvh.geom[type].data(), gb);
+  if (info && ib) std::memcpy(info, s->bvh.info[type].data(), ib);
+  return RTB_OK;
+}
+
+// ---- camera ------------------------------------------------------------------------------------------------------
+static void camera_basis(const rtb_camera& c, DevCamera& f, DevCameraF64& g) {  // Camera::new, camera.rs:21-59
+  const double PI = 3.14159265358979323846;
+  double theta = c.vfov_deg * PI / 180.0;
+  double h = std::tan(theta / 2.0);
+  double vh = 2.0 * h, vw = c.aspect_ratio * vh;
+  double w[3], u[3], v[3];
+  double len = 0;
+  for (int a = 0; a < 3; ++a) { w[a] = c.lookfrom[a] - c.lookat[a]; len += w[a] * w[a]; }
+  len = std::sqrt(len);
+  for (int a = 0; a < 3; ++a) w[a] /= len;
+  u[0] = c.vup[1] * w[2] - c.vup[2] * w[1];
+  u[1] = c.vup[2] * w[0] - c.vup[0] * w[2];
+  u[2] = c.vup[0] * w[1] - c.vup[1] * w[0];
+  len = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  for (int a = 0; a < 3; ++a) u[a] /= len;
+  v[0] = w[1] * u[2] - w[2] * u[1];
+  v[1] = w[2] * u[0] - w[0] * u[2];
+  v[2] = w[0] * u[1] - w[1] * u[0];
+  for (int a = 0; a < 3; ++a) {
+    double hor = c.focus_dist * vw * u[a], ver = c.focus_dist * vh * v[a];
+    double llc = c.lookfrom[a] - hor / 2.0 - ver / 2.0 - c.focus_dist * w[a];
+    g.origin[a] = c.lookfrom[a]; g.llc[a] = llc; g.horizontal[a] = hor; g.vertical[a] = ver;
+    f.origin[a] = (float)c.lookfrom[a];
+    f.lmo[a] = (float)(llc - c.lookfrom[a]);
+    f.horizontal[a] = (float)hor; f.vertical[a] = (float)ver;
+    f.u[a] = (float)u[a]; f.v[a] = (float)v[a];
+  }
+  g.time0 = c.time0;
+  f.lens_radius = (float)(c.aperture / 2.0);
+  f.time0 = (float)c.time0; f.time1 = (float)c.time1;
+}
+
+// ---- render --------------------------------------------------------------------------------------------------------
+static int ensure_pool(rtb_context* c, uint32_t n) {
+  if (c->pool_n == n) return RTB_OK;
+  CU(c->ray_o.resize(n)); CU(c->ray_d.resize(n)); CU(c->beta.resize(n)); CU(c->rad.resize(n)); CU(c->hit.resize(n));
+  CU(c->q_ext0.resize(n)); CU(c->q_ext1.resize(n)); CU(c->q_dead.resize(n));
+  for (int k = 0; k < (int)Q_COUNT; ++k) CU(c->q_mat[k].resize(n));
+  c->pool_n = n;
+  return RTB_OK;
+}
+
+static int ensure_pix_order(rtb_context* c, uint32_t W, uint32_t H, cudaStream_t st) {
+  if (c->pix_w == W && c->pix_h == H && c->pix_order.p) return RTB_OK;
+  // 8x4-pixel tiles (one warp of neighbouring primary rays), tiles row-major
+  std::vector<uint32_t> order;
+  order.reserve((size_t)W * H);
+  for (uint32_t ty = 0; ty < H; ty += 4)
+    for (uint32_t tx = 0; tx < W; tx += 8)
+      for (uint32_t y = ty; y < std::min(ty + 4, H); ++y)
+        for (uint32_t x = tx; x < std::min(tx + 8, W); ++x) order.push_back(y * W + x);
+  CU(c->pix_order.upload(order.data(), order.size(), st));
+  CU(cudaStreamSynchronize(st));
+  c->pix_w = W; c->pix_h = H;
+  return RTB_OK;
+}
+
+int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rtb_params* p, void* d_accum,
+                      void* stream, rtb_stats* stats) {
+  if (!c || !s || !cam || !p || !d_accum) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (!s->committed) return set_err(RTB_ERR_STATE, "scene not committed (call rtb_scene_commit)");
+  if (p->width < 2 || p->height < 2) return set_err(RTB_ERR_INVALID, "image must be at least 2x2 (u = (i+xi)/(W-1), main.rs:752)");
+  if (p->max_depth < 1 || p->max_depth > 255) return set_err(RTB_ERR_INVALID, "max_depth must be in [1,255]");
+  if (p->spp == 0) return set_err(RTB_ERR_INVALID, "spp must be > 0");
+  if ((uint64_t)p->sample_offset + p->spp > (1u << 24)) return set_err(RTB_ERR_INVALID, "sample index exceeds 2^24");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t npix = (uint64_t)p->width * p->height;
+  const unsigned long long total = npix * p->spp;
+  uint32_t pool_n = p->pool_paths ? p->pool_paths : (1u << 21);
+  if (pool_n < 1024) pool_n = 1024;
+  if ((unsigned long long)pool_n > total) pool_n = (uint32_t)std::max<unsigned long long>(1024ull, total);
+  int rc = ensure_pool(c, pool_n);
+  if (rc) return rc;
+  rc = ensure_pix_order(c, p->width, p->height, st);
+  if (rc) return rc;
+
+  DevPool pool;
+  pool.n = pool_n;
+  pool.ray_o = c->ray_o.p; pool.ray_d = c->ray_d.p; pool.beta = c->beta.p; pool.rad = c->rad.p; pool.hit = c->hit.p;
+  pool.q_ext[0] = c->q_ext0.p; pool.q_ext[1] = c->q_ext1.p; pool.q_dead = c->q_dead.p;
+  for (int k = 0; k < (int)Q_COUNT; ++k) pool.q_mat[k] = c->q_mat[k].p;
+  pool.c = c->counters.p;
+  DevParams prm;
+  prm.width = p->width; prm.height = p->height; prm.spp = p->spp; prm.sample_offset = p->sample_offset;
+  prm.max_depth = p->max_depth; prm.rr_start = p->rr_start_depth; prm.seed = p->seed;
+  for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
+  prm.pix_order = c->pix_order.p;
+  prm.accum = (float4*)d_accum;
+  DevCamera dcam;
+  DevCameraF64 dcam64;
+  camera_basis(*cam, dcam, dcam64);
+
+  uint64_t launches = 0, extend_launches = 0;
+  CU(cudaEventRecord(c->ev0, st));
+  if (!(p->flags & RTB_RENDER_ACCUMULATE)) CU(cudaMemsetAsync(d_accum, 0, npix * sizeof(float4), st));
+  launch_init_pool(pool, total, st);
+  launch_generate(s->lc, pool, prm, dcam, st);
+  launch_advance(pool, st);
+  launches += 3;
+  const uint32_t present = s->present_materials;
+  const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
+  const uint32_t check_every = 8;
+  uint64_t iters = 0;
+  const uint64_t iter_cap = (uint64_t)(total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
+  for (;;) {
+    for (uint32_t k = 0; k < check_every; ++k) {
+      launch_extend(s->lc, s->dev, pool, prm, st);
+      launch_shade(s->lc, s->dev, pool, prm, present, st);
+      launch_generate(s->lc, pool, prm, dcam, st);
+      launch_advance(pool, st);
+      launches += 3 + n_shade;
+      extend_launches += 1;
+    }
+    iters += check_every;
+    CU(cudaMemcpyAsync(c->h_counters, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (c->h_counters->n_ext[c->h_counters->cur] == 0) break;
+    if (iters > iter_cap) return set_err(RTB_ERR_CUDA, "wavefront did not drain (internal error)");
+  }
+  CU(cudaEventRecord(c->ev1, st));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaGetLastError());
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    stats->paths = std::min<unsigned long long>(c->h_counters->next_path, total);
+    stats->segments = c->h_counters->segments;
+    stats->rejected = c->h_counters->rejected;
+    stats->iterations = c->h_counters->iter;
+    stats->launches = launches;
+    stats->extend_launches = extend_launches;
+    stats->ms_total = ms;
+  }
+  return RTB_OK;
+}
+
+int rtb_render(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rtb_params* p, float* accum_out,
+               rtb_stats* stats) {
+  if (!c || !p) return set_err(RTB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)p->width * p->height;
+  CU(c->accum.resize(npix));
+  int rc = rtb_render_device(c, s, cam, p, c->accum.p, nullptr, stats);
+  if (rc) return rc;
+  if (accum_out) CU(cudaMemcpy(accum_out, c->accum.p, npix * sizeof(float4), cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+int rtb_finalize_rgb8(rtb_context* c, const void* d_accum, uint32_t W, uint32_t H, uint32_t total_spp, uint8_t* out) {
+  if (!c || !out || !total_spp) return set_err(RTB_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const size_t npix = (size_t)W * H;
+  const float4* src = d_accum ? (const float4*)d_accum : c->accum.p;
+  if (!src) return set_err(RTB_ERR_STATE, "nothing rendered yet");
+  CU(c->rgb8.resize(npix * 3));
+  launch_finalize(src, c->rgb8.p, (uint32_t)npix, 1.0f / (float)total_spp, 0);
+  CU(cudaMemcpy(out, c->rgb8.p, npix * 3, cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+static int run_probe(rtb_context* c, rtb_scene* s, uint32_t n, uint32_t* id_out, float* t_out, rtb_stats* stats) {
+  CU(c->p_id.resize(n));
+  CU(c->p_t.resize(n));
+  CU(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), 0));
+  CU(cudaEventRecord(c->ev0, 0));
+  launch_probe(s->lc, s->dev, c->p_org.p, c->p_dir.p, c->p_time.p, n, c->p_id.p, c->p_t.p, c->counters.p, 0);
+  CU(cudaEventRecord(c->ev1, 0));
+  CU(cudaMemcpy(id_out, c->p_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(t_out, c->p_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(c->h_counters, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost));
+  CU(cudaGetLastError());
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    stats->paths = n;
+    stats->segments = n;
+    stats->launches = 1;
+    stats->extend_launches = 1;
+    stats->ms_total = ms;
+    stats->ms_extend = ms;
+    stats->nodes_visited = c->h_counters->nodes_visited;
+    stats->prims_tested = c->h_counters->prims_tested;
+  }
+  return RTB_OK;
+}
+
+int rtb_primary_hits(rtb_context* c, rtb_scene* s, const rtb_camera* cam, uint32_t W, uint32_t H, uint32_t* id_out,
+                     float* t_out, rtb_stats* stats) {
+  if (!c || !s || !cam || !id_out || !t_out) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (!s->committed) return set_err(RTB_ERR_STATE, "scene not committed (call rtb_scene_commit)");
+  if (W < 2 || H < 2) return set_err(RTB_ERR_INVALID, "image must be at least 2x2");
+  CU(cudaSetDevice(c->device));
+  const uint32_t n = W * H;
+  CU(c->p_org.resize((size_t)n * 3)); CU(c->p_dir.resize((size_t)n * 3)); CU(c->p_time.resize(n));
+  DevCamera f;
+  DevCameraF64 g;
+  camera_basis(*cam, f, g);
+  launch_primary_rays(g, W, H, c->p_org.p, c->p_dir.p, c->p_time.p, 0);
+  return run_probe(c, s, n, id_out, t_out, stats);
+}
+
+int rtb_trace_rays(rtb_context* c, rtb_scene* s, const float* org, const float* dir, const float* time, uint32_t n,
+                   uint32_t* id_out, float* t_out, rtb_stats* stats) {
+  if (!c || !s || !org || !dir || !id_out || !t_out) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (!s->committed) return set_err(RTB_ERR_STATE, "scene not committed (call rtb_scene_commit)");
+  if (n == 0) return RTB_OK;
+  CU(cudaSetDevice(c->device));
+  CU(c->p_org.upload(org, (size_t)n * 3));
+  CU(c->p_dir.upload(dir, (size_t)n * 3));
+  CU(c->p_time.resize(n));
+  if (time) CU(cudaMemcpyAsync(c->p_time.p, time, n * sizeof(float), cudaMemcpyHostToDevice, 0));
+  else CU(cudaMemsetAsync(c->p_time.p, 0, n * sizeof(float), 0));
+  return run_probe(c, s, n, id_out, t_out, stats);
+}
+
+}  // extern "C"

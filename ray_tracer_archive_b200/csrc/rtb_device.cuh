@@ -1,0 +1,360 @@
+// rtb_device.cuh — device-side data layout, Philox streams, wide-BVH traversal and primitive tests (sm_100a).
+// FP32 restatement of the reference's f64 arithmetic; every routine cites the reference lines it replaces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rtb_internal.hpp"
+
+namespace rtb {
+
+#define RTB_MAX_LIGHTS 8
+#define RTB_MAX_MEDIA 8
+#define RTB_MAX_TABLES 4
+#define RTB_STACK 32
+#define RTB_TMIN 0.001f  // main.rs:74
+#define RTB_PI 3.14159265358979323846f
+
+enum Queue : uint32_t { Q_TERMINAL = 0, Q_LAMBERT = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_ISOTROPIC = 4, Q_COUNT = 5 };
+
+struct DevTexture {  // 32 bytes
+  uint32_t type, even, odd, table;
+  float r, g, b, scale;
+};
+struct DevLight { uint32_t type; float p[5]; float _pad[2]; };
+struct DevMedium {
+  uint32_t boundary_type, material, prim_id;
+  float neg_inv_density;
+  float p[6];
+  float sin_t, cos_t;
+  float off[3];
+  float _pad;
+};
+struct DevImage { const uint8_t* data; uint32_t w, h; };
+
+struct DevScene {  // passed by value as a kernel parameter (constant bank)
+  const uint4* nodes;
+  uint32_t n_nodes;
+  uint32_t n_lights, n_media, n_materials;
+  const float4* geom[PT_COUNT];
+  const uint2* info[PT_COUNT];
+  const float4* materials;   // (type bits, texture bits, param, 0)
+  const DevTexture* textures;
+  const float4* perlin_vec[RTB_MAX_TABLES];
+  const uint8_t* perlin_perm[RTB_MAX_TABLES];
+  DevImage images[RTB_MAX_TABLES];
+  DevLight lights[RTB_MAX_LIGHTS];
+  DevMedium media[RTB_MAX_MEDIA];
+};
+
+struct DevCamera {  // camera.rs:6-17, basis computed on the host in f64
+  float origin[3], lmo[3] /* lower_left_corner - origin */, horizontal[3], vertical[3], u[3], v[3];
+  float lens_radius, time0, time1;
+};
+
+struct DevCounters {
+  uint32_t n_ext[2];
+  uint32_t n_mat[Q_COUNT];
+  uint32_t n_dead;
+  uint32_t cur;       // which n_ext/q_ext is being extended this iteration
+  uint32_t iter;
+  unsigned long long next_path, total_paths;
+  unsigned long long segments, rejected, paths_started;
+  unsigned long long nodes_visited, prims_tested;
+};
+
+struct DevPool {  // wavefront path state, SoA over `n` slots
+  uint32_t n;
+  float4* ray_o;   // origin xyz, time
+  float4* ray_d;   // direction xyz (un-normalised, ray.rs), w unused
+  float4* beta;    // throughput rgb, pixel index bits
+  float4* rad;     // radiance rgb, (sample << 8 | segments) bits
+  float2* hit;     // t, ref bits
+  uint32_t* q_ext[2];
+  uint32_t* q_mat[Q_COUNT];
+  uint32_t* q_dead;
+  DevCounters* c;
+};
+
+struct DevParams {
+  uint32_t width, height, spp, sample_offset;
+  int32_t max_depth;
+  uint32_t rr_start, seed;
+  float bg[3];
+  const uint32_t* pix_order;  // tile-ordered pixel indices
+  float4* accum;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {  // vec3.rs:68-76
+  return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) {
+  return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z));
+}
+__device__ __forceinline__ float3 unit(float3 a) { return rsqrtf(dot(a, a)) * a; }
+__device__ __forceinline__ float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }
+__device__ __forceinline__ float3 ld3(const float* p) { return f3(p[0], p[1], p[2]); }
+
+// ---- Philox4x32-10: key = (pixel, sample), counter = (block, bounce, seed, 'RTB2').  Replaces rand::random
+// (rt_weekend.rs:8-19); identical to oracle/rt_oracle.hpp so streams can be compared draw by draw.
+enum RngBlock : uint32_t { BLK_CAMERA0 = 0, BLK_CAMERA1 = 1, BLK_SCATTER = 2, BLK_AUX = 3, BLK_MEDIUM0 = 8 };
+
+__device__ __forceinline__ uint4 philox4(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t bounce, uint32_t seed) {
+  uint32_t c0 = block, c1 = bounce, c2 = seed, c3 = 0x52544232u;
+  uint32_t k0 = pixel, k1 = sample;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint32_t block, uint32_t bounce, uint32_t seed) {
+  uint4 r = philox4(pixel, sample, block, bounce, seed);
+  return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
+// ---- closest-hit record -----------------------------------------------------------------------------------------
+struct Closest {
+  float t;        // current t_max (closest_so_far, hittable_list.rs:42)
+  uint32_t ref;   // type << 29 | leaf index
+  uint32_t gid;   // primitive id, for the "later primitive wins equal t" rule (hittable_list.rs:44-47)
+};
+
+__device__ __forceinline__ void consider(Closest& best, float t, uint32_t ref, uint32_t gid) {
+  if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
+  if (t < best.t || (t == best.t && (best.ref == REF_MISS || gid > best.gid))) {
+    best.t = t; best.ref = ref; best.gid = gid;
+  }
+}
+
+// Sphere::hit, sphere.rs:41-65, in the cancellation-free form  disc' = r^2 - |oc - (oc.d/a) d|^2  (= det/a).
+// The reference's c = |oc|^2 - r^2 loses all bits in f32 for the r=1000 ground sphere.
+__device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+  float3 oc = o - c;
+  float a = dot(d, d);
+  float hb = dot(oc, d);
+  float inv_a = 1.0f / a;
+  float3 l = fma3(-hb * inv_a, d, oc);
+  float disc = fmaf(r, r, -dot(l, l));
+  if (disc < 0.0f) return false;
+  float sq = sqrtf(a * disc);
+  float root = (-hb - sq) * inv_a;
+  if (root < tmin || tmax < root) {
+    root = (-hb + sq) * inv_a;
+    if (root < tmin || tmax < root) return false;
+  }
+  t_out = root;
+  return true;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
+                                               float time, float tmin, Closest& best, uint32_t& n_tests) {
+  if (COUNT) ++n_tests;
+  float t;
+  if (type == PT_SPHERE) {
+    float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
+    if (!sphere_roots(o, d, xyz(s), s.w, tmin, best.t, t)) return;
+  } else if (type == PT_QUAD) {
+    // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square
+    float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
+    float denom = dot(xyz(w0), d);
+    t = (w0.w - dot(xyz(w0), o)) / denom;
+    if (!(t >= tmin && t <= best.t)) return;
+    float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
+    float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
+    float3 p = fma3(t, d, o);
+    float alpha = dot(xyz(w1), p) - w1.w;
+    float beta = dot(xyz(w2), p) - w2.w;
+    if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) return;
+  } else if (type == PT_TRI) {  // Moller-Trumbore, closed t-range like aarect.rs:33
+    float4 w0 = __ldg(sc.geom[PT_TRI] + 3 * idx);
+    float4 w1 = __ldg(sc.geom[PT_TRI] + 3 * idx + 1);
+    float4 w2 = __ldg(sc.geom[PT_TRI] + 3 * idx + 2);
+    float3 e1 = xyz(w1), e2 = xyz(w2);
+    float3 pv = cross(d, e2);
+    float det = dot(e1, pv);
+    if (det == 0.0f) return;
+    float inv = 1.0f / det;
+    float3 tv = o - xyz(w0);
+    float u = dot(tv, pv) * inv;
+    if (u < 0.0f || u > 1.0f) return;
+    float3 qv = cross(tv, e1);
+    float v = dot(d, qv) * inv;
+    if (v < 0.0f || u + v > 1.0f) return;
+    t = dot(e2, qv) * inv;
+    if (!(t >= tmin && t <= best.t)) return;
+  } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
+    float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
+    float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
+    float3 c = fma3(time, xyz(b), xyz(a));
+    if (!sphere_roots(o, d, c, a.w, tmin, best.t, t)) return;
+  }
+  uint32_t gid = __ldg(&sc.info[type][idx].x);
+  consider(best, t, (type << REF_TYPE_SHIFT) | idx, gid);
+}
+
+__device__ __forceinline__ float q2f(uint32_t word, uint32_t sel) {
+  // byte `sel&3` of `word` -> float, via 0x4B0000qq (= 2^23 + q) - 2^23 : one PRMT + one FADD, no I2F
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+// Wide-BVH closest-hit traversal.  `snodes` = first `n_snodes` nodes staged in shared memory (uint4 x5 each);
+// the rest are fetched with 128-bit read-only loads.  Semantics = HittableList::hit (hittable_list.rs:39-51)
+// over all surface primitives; media are handled by the caller.
+template <bool COUNT>
+__device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
+                                         float3 o, float3 d, float time, float tmin, Closest& best,
+                                         uint32_t& n_nodes_visited, uint32_t& n_tests) {
+  const float tiny = 1e-30f;
+  float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+  float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+  float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+  const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
+  const uint32_t octinv = 7u ^ ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+  uint2 stack[RTB_STACK];
+  int sp = 0;
+  uint2 grp = make_uint2(0u, (1u << (octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
+  for (;;) {
+    if (grp.y & 0xFF00u) {
+      uint32_t hits = grp.y >> 8;
+      const uint32_t prio = 31u - __clz(hits);
+      hits &= ~(1u << prio);
+      const uint32_t slot = prio ^ octinv;
+      const uint32_t gmask = grp.y & 0xFFu;
+      const uint32_t node = grp.x + __popc(gmask & ((1u << slot) - 1u));
+      if (hits) stack[sp++] = make_uint2(grp.x, (hits << 8) | gmask);
+      if (COUNT) ++n_nodes_visited;
+      uint4 w0, w1, w2, w3, w4;
+      if (node < n_snodes) {
+        const uint4* p = snodes + 5 * node;
+        w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3]; w4 = p[4];
+      } else {
+        const uint4* p = sc.nodes + 5 * (size_t)node;
+        w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3); w4 = __ldg(p + 4);
+      }
+      const uint32_t imask = w0.w >> 24;
+      // t = q * (step * idir) + (origin - o) * idir ; widened by the f32 rounding bound so that no true hit is culled
+      const float ax = __uint_as_float((w0.w & 0xFFu) << 23) * idx;
+      const float ay = __uint_as_float(((w0.w >> 8) & 0xFFu) << 23) * idy;
+      const float az = __uint_as_float(((w0.w >> 16) & 0xFFu) << 23) * idz;
+      const float bx = (__uint_as_float(w0.x) - o.x) * idx;
+      const float by = (__uint_as_float(w0.y) - o.y) * idy;
+      const float bz = (__uint_as_float(w0.z) - o.z) * idz;
+      const float eps = 4.0e-7f;
+      const float ex = eps * fmaf(256.0f, fabsf(ax), fabsf(bx));
+      const float ey = eps * fmaf(256.0f, fabsf(ay), fabsf(by));
+      const float ez = eps * fmaf(256.0f, fabsf(az), fabsf(bz));
+      const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
+      // near/far plane words per axis (children 0-3 | 4-7)
+      const uint32_t nx0 = nx ? w3.z : w2.x, nx1 = nx ? w3.w : w2.y, fx0 = nx ? w2.x : w3.z, fx1 = nx ? w2.y : w3.w;
+      const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
+      const uint32_t nz0 = nz ? w4.z : w3.x, nz1 = nz ? w4.w : w3.y, fz0 = nz ? w3.x : w4.z, fz1 = nz ? w3.y : w4.w;
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t sel = 0x7540u | (uint32_t)(i & 3);
+        const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, sel), ax, bnx);
+        const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, sel), ay, bny);
+        const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, sel), az, bnz);
+        const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, sel), ax, bfx);
+        const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, sel), ay, bfy);
+        const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, sel), az, bfz);
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
+        if (tn <= tf) hitmask |= 1u << i;
+      }
+      // leaf children: intersect now (all primitives of one node share a type)
+      uint32_t leaf = hitmask & ~imask;
+      const uint32_t ptype = w1.y >> REF_TYPE_SHIFT, pbase = w1.y & REF_INDEX_MASK;
+      while (leaf) {
+        const uint32_t s = __ffs(leaf) - 1;
+        leaf &= leaf - 1;
+        const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
+        const uint32_t cnt = m >> 5, first = pbase + (m & 31u);
+        for (uint32_t k = 0; k < cnt; ++k) intersect_prim<COUNT>(sc, ptype, first + k, o, d, time, tmin, best, n_tests);
+      }
+      // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
+      uint32_t ih = hitmask & imask;
+      if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
+      if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
+      if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
+      grp = make_uint2(w1.x, (ih << 8) | imask);
+    } else {
+      if (sp == 0) break;
+      grp = stack[--sp];
+    }
+  }
+}
+
+// ConstantMedium::hit, constant_medium.rs:31-71, for the (few) media of the scene; the boundary interval is found
+// analytically (sphere: both roots; box: slabs in the boundary's object space).  One uniform per (path, segment, medium).
+__device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, float3 d, float tmin, Closest& best,
+                                                uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t seed,
+                                                bool have_rng) {
+  for (uint32_t m = 0; m < sc.n_media; ++m) {
+    const DevMedium& md = sc.media[m];
+    float t1, t2;
+    if (md.boundary_type == RTB_BOUNDARY_SPHERE) {
+      float3 c = f3(md.p[0], md.p[1], md.p[2]);
+      float3 oc = o - c;
+      float a = dot(d, d), hb = dot(oc, d), inv_a = 1.0f / a;
+      float3 l = fma3(-hb * inv_a, d, oc);
+      float disc = fmaf(md.p[3], md.p[3], -dot(l, l));
+      if (disc < 0.0f) continue;
+      float sq = sqrtf(a * disc);
+      t1 = (-hb - sq) * inv_a;      // boundary.hit(r, -inf, inf): first root always in range
+      t2 = (-hb + sq) * inv_a;      // boundary.hit(r, t1 + 0.0001, inf)
+      if (t2 < t1 + 0.0001f) continue;
+    } else {
+      // object space of Translate(RotateY(Box)): hittable.rs:76,150-156
+      float3 oo = o - f3(md.off[0], md.off[1], md.off[2]);
+      float3 ro = f3(md.cos_t * oo.x - md.sin_t * oo.z, oo.y, md.sin_t * oo.x + md.cos_t * oo.z);
+      float3 rd = f3(md.cos_t * d.x - md.sin_t * d.z, d.y, md.sin_t * d.x + md.cos_t * d.z);
+      float lo = -INFINITY, hi = INFINITY;
+      const float ro_[3] = {ro.x, ro.y, ro.z}, rd_[3] = {rd.x, rd.y, rd.z};
+      bool miss = false;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (rd_[a] == 0.0f) {
+          if (ro_[a] < md.p[a] || ro_[a] > md.p[3 + a]) miss = true;
+          continue;
+        }
+        float inv = 1.0f / rd_[a];
+        float ta = (md.p[a] - ro_[a]) * inv, tb = (md.p[3 + a] - ro_[a]) * inv;
+        lo = fmaxf(lo, fminf(ta, tb));
+        hi = fminf(hi, fmaxf(ta, tb));
+      }
+      if (miss || !(hi >= lo + 0.0001f)) continue;
+      t1 = lo; t2 = hi;
+    }
+    if (t1 < tmin) t1 = tmin;
+    if (t2 > best.t) t2 = best.t;
+    if (t1 >= t2) continue;
+    if (t1 < 0.0f) t1 = 0.0f;
+    float len = sqrtf(dot(d, d));
+    float inside = (t2 - t1) * len;
+    float xi = have_rng ? u01(philox4(pixel, sample, BLK_MEDIUM0 + m, bounce, seed).x) : 0.5f;
+    float hd = md.neg_inv_density * logf(xi);
+    if (hd > inside) continue;
+    float t = t1 + hd / len;
+    consider(best, t, ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m, md.prim_id);
+  }
+}
+
+}  // namespace rtb

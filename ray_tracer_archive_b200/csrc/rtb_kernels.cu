@@ -1,0 +1,655 @@
+// rtb_kernels.cu — the wavefront path-tracing pipeline (sm_100a).  One iteration =
+//   extend (wide-BVH closest hit + media, classify into per-material queues)
+//   shade_terminal / shade_lambert / shade_metal / shade_dielectric / shade_isotropic (one kernel per material)
+//   generate (refill terminated slots with new camera paths)  ->  advance (swap queues)
+// replacing the reference's recursive ray_color (main.rs:63-139) and its per-pixel sample loop (main.rs:731-784).
+// Queues are compacted with warp ballots + one atomic per warp.  Tensor cores are not used: nothing here is a
+// dense contraction.
+#include <cuda_runtime.h>
+
+#include "rtb_device.cuh"
+#include "rtb_launch.hpp"
+
+namespace rtb {
+
+// ---- queue helpers ----------------------------------------------------------------------------------------------
+// must be executed by all 32 lanes of a converged warp
+__device__ __forceinline__ void warp_enqueue(uint32_t* __restrict__ q, uint32_t* counter, bool pred, uint32_t value) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+  if (mask == 0) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t leader = __ffs(mask) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// accumulate + write_color's NaN policy moved to per-sample rejection
+__device__ __forceinline__ void deposit(const DevParams& prm, DevCounters* c, uint32_t pixel, float3 L) {
+  if (!(isfinite(L.x) && isfinite(L.y) && isfinite(L.z))) {
+    atomicAdd(&c->rejected, 1ull);
+    return;
+  }
+  const float Y = 0.2126f * L.x + 0.7152f * L.y + 0.0722f * L.z;
+  red_add_v4(prm.accum + pixel, L.x, L.y, L.z, Y * Y);
+}
+
+// ---- stage the top of the BVH in shared memory -------------------------------------------------------------------
+__device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, uint32_t n_snodes) {
+  const uint32_t words = n_snodes * 5u;
+  for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) snodes[i] = __ldg(sc.nodes + i);  // coalesced 128-bit
+  __syncthreads();
+}
+
+// ---- extend ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
+k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
+  extern __shared__ uint4 snodes[];
+  DevCounters* c = pool.c;
+  const uint32_t cur = c->cur;
+  const uint32_t n = c->n_ext[cur];
+  if (n == 0) return;
+  stage_nodes(sc, snodes, n_snodes);
+  const uint32_t* __restrict__ q = pool.q_ext[cur];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t slot = 0, queue = Q_COUNT;
+    if (valid) {
+      slot = q[i];
+      const float4 ro = pool.ray_o[slot];
+      const float4 rd = pool.ray_d[slot];
+      const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
+      const uint32_t st = __float_as_uint(pool.rad[slot].w);
+      Closest best{INFINITY, REF_MISS, 0u};
+      uint32_t nv = 0, nt = 0;
+      traverse<false>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+      if (sc.n_media)
+        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+      pool.hit[slot] = make_float2(best.t, __uint_as_float(best.ref));
+      // classify by material (Material trait dispatch, material.rs:11-21)
+      queue = Q_TERMINAL;
+      if (best.ref != REF_MISS) {
+        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
+        const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
+        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
+        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
+              : mt == RTB_MAT_METAL      ? Q_METAL
+              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
+              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
+                                         : Q_TERMINAL;
+      }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
+  }
+}
+
+// ---- surface reconstruction in the shade kernels -------------------------------------------------------------------
+struct Surf {
+  float3 p, n, outward;  // n = normal against the ray (set_face_normal, hittable.rs:41-48)
+  bool front;
+  uint32_t mat, ref;
+};
+
+__device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, float3 o, float3 d, float time, float t) {
+  Surf s;
+  s.ref = ref;
+  s.p = fma3(t, d, o);
+  const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+  if (type == PT_MEDIUM) {  // constant_medium.rs:65-67: arbitrary normal, front_face = true
+    s.n = s.outward = f3(1.f, 0.f, 0.f);
+    s.front = true;
+    s.mat = sc.media[idx].material;
+    return s;
+  }
+  if (type == PT_SPHERE) {
+    const float4 g = __ldg(sc.geom[PT_SPHERE] + idx);
+    s.outward = (1.0f / g.w) * (s.p - xyz(g));  // sphere.rs:59
+  } else if (type == PT_MOVING) {
+    const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx), b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
+    s.outward = (1.0f / a.w) * (s.p - fma3(time, xyz(b), xyz(a)));  // moving_sphere.rs:57-58
+  } else if (type == PT_QUAD) {
+    s.outward = xyz(__ldg(sc.geom[PT_QUAD] + 3 * idx));
+  } else {
+    const float3 e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)), e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
+    s.outward = unit(cross(e1, e2));
+  }
+  const uint32_t info = __ldg(&sc.info[type][idx].y);
+  s.mat = info & 0xFFFFFFu;
+  bool ff = dot(d, s.outward) < 0.0f;
+  s.n = ff ? s.outward : -s.outward;
+  const uint32_t mode = info >> 24;  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
+  s.front = mode == FACE_NATURAL ? ff : mode == FACE_FLIPPED ? !ff : mode == FACE_TRUE;
+  return s;
+}
+
+__device__ __forceinline__ void surface_uv(const DevScene& sc, const Surf& s, float& u, float& v) {
+  const uint32_t type = s.ref >> REF_TYPE_SHIFT, idx = s.ref & REF_INDEX_MASK;
+  u = v = 0.f;  // MovingSphere / ConstantMedium leave u,v stale in the reference; defined 0
+  if (type == PT_SPHERE) {  // sphere.rs:32-37
+    const float theta = acosf(fminf(fmaxf(-s.outward.y, -1.f), 1.f));
+    const float phi = atan2f(-s.outward.z, s.outward.x) + RTB_PI;
+    u = phi / (2.0f * RTB_PI);
+    v = theta / RTB_PI;
+  } else if (type == PT_QUAD) {
+    const float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1), w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
+    u = dot(xyz(w1), s.p) - w1.w;
+    v = dot(xyz(w2), s.p) - w2.w;
+  } else if (type == PT_TRI) {
+    const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx)), e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)),
+                 e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
+    const float3 nn = cross(e1, e2), pl = s.p - v0;
+    const float inv = 1.0f / dot(nn, nn);
+    u = dot(nn, cross(pl, e2)) * inv;
+    v = dot(nn, cross(e1, pl)) * inv;
+  }
+}
+
+// Perlin::noise with the reference's double Hermite smoothing (perlin.rs:26-52,67-85) and turb (perlin.rs:86-98)
+__device__ float perlin_noise(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {
+  const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  u = u * u * (3.f - 2.f * u);
+  v = v * v * (3.f - 2.f * v);
+  w = w * w * (3.f - 2.f * w);
+  const int i = (int)fx, j = (int)fy, k = (int)fz;
+  const float uu = u * u * (3.f - 2.f * u), vv = v * v * (3.f - 2.f * v), ww = w * w * (3.f - 2.f * w);
+  float accum = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t h = perm[(i + a) & 255] ^ perm[256 + ((j + b) & 255)] ^ perm[512 + ((k + c) & 255)];
+        const float4 g = __ldg(vec + h);
+        const float wgt = (a ? uu : 1.f - uu) * (b ? vv : 1.f - vv) * (c ? ww : 1.f - ww);
+        accum += wgt * (g.x * (u - a) + g.y * (v - b) + g.z * (w - c));
+      }
+  return accum;
+}
+
+__device__ float3 tex_value(const DevScene& sc, uint32_t tex, const Surf& s) {
+  DevTexture t = sc.textures[tex];
+  if (t.type == RTB_TEX_CHECKER) {  // texture.rs:60-69, on the world-space point
+    const float sines = sinf(10.f * s.p.x) * sinf(10.f * s.p.y) * sinf(10.f * s.p.z);
+    t = sc.textures[sines < 0.f ? t.odd : t.even];
+  }
+  if (t.type == RTB_TEX_NOISE) {  // texture.rs:90-96
+    const float4* vec = sc.perlin_vec[t.table];
+    const uint8_t* perm = sc.perlin_perm[t.table];
+    float accum = 0.f, weight = 1.f;
+    float3 tp = s.p;
+    for (int i = 0; i < 7; ++i) {
+      accum += weight * perlin_noise(vec, perm, tp);
+      weight *= 0.5f;
+      tp = 2.0f * tp;
+    }
+    const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * fabsf(accum)));
+    return f3(g, g, g);
+  }
+  if (t.type == RTB_TEX_IMAGE) {  // texture.rs:118-140: nearest texel, v flipped
+    if (t.table >= RTB_MAX_TABLES || sc.images[t.table].data == nullptr) return f3(0.f, 1.f, 1.f);
+    const DevImage im = sc.images[t.table];
+    float u, v;
+    surface_uv(sc, s, u, v);
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    v = 1.0f - fminf(fmaxf(v, 0.f), 1.f);
+    uint32_t i = (uint32_t)(u * (float)im.w), j = (uint32_t)(v * (float)im.h);
+    if (i >= im.w) i = im.w - 1;
+    if (j >= im.h) j = im.h - 1;
+    const uint8_t* px = im.data + ((size_t)j * im.w + i) * 3;
+    const float k = 1.0f / 255.0f;
+    return f3(k * px[0], k * px[1], k * px[2]);
+  }
+  return f3(t.r, t.g, t.b);
+}
+
+struct Onb {  // onb.rs:19-42
+  float3 u, v, w;
+  __device__ __forceinline__ explicit Onb(float3 n) {
+    w = unit(n);
+    const float3 a = fabsf(w.x) > 0.9f ? f3(0.f, 1.f, 0.f) : f3(1.f, 0.f, 0.f);
+    v = unit(cross(w, a));
+    u = cross(w, v);
+  }
+  __device__ __forceinline__ float3 local(float3 a) const { return a.x * u + a.y * v + a.z * w; }
+};
+
+// HittableList::pdf_value over the light proxies (hittable_list.rs:73-80; aarect.rs:107-117; sphere.rs:75-84)
+__device__ float lights_pdf(const DevScene& sc, float3 o, float3 v) {
+  float sum = 0.f;
+  const float weight = 1.0f / (float)sc.n_lights;
+  for (uint32_t k = 0; k < sc.n_lights; ++k) {
+    const DevLight& L = sc.lights[k];
+    float pdf = 0.f;
+    if (L.type == RTB_LIGHT_XZ_RECT) {
+      const float t = (L.p[4] - o.y) / v.y;
+      if (t >= RTB_TMIN && t < INFINITY) {
+        const float x = fmaf(t, v.x, o.x), z = fmaf(t, v.z, o.z);
+        if (!(x < L.p[0] || x > L.p[1] || z < L.p[2] || z > L.p[3])) {
+          const float area = (L.p[1] - L.p[0]) * (L.p[3] - L.p[2]);
+          const float vv = dot(v, v);
+          const float cosine = fabsf(v.y) * rsqrtf(vv);
+          pdf = t * t * vv / (cosine * area);
+        }
+      }
+    } else {
+      const float3 c = f3(L.p[0], L.p[1], L.p[2]);
+      float t;
+      if (sphere_roots(o, v, c, L.p[3], RTB_TMIN, INFINITY, t)) {
+        const float3 oc = c - o;
+        const float q = L.p[3] * L.p[3] / dot(oc, oc);
+        const float cos_max = sqrtf(1.0f - q);
+        pdf = (1.0f + cos_max) / (2.0f * RTB_PI * q);  // 1/(2 pi (1-cos)) with 1-cos = q/(1+cos)
+      }
+    }
+    sum += weight * pdf;
+  }
+  return sum;
+}
+
+// HittableList::random (hittable_list.rs:81-84) -> XzRect::random (aarect.rs:118-125) | Sphere::random (sphere.rs:85-90)
+__device__ float3 lights_random(const DevScene& sc, float3 o, float pick, float r1, float r2) {
+  uint32_t k = (uint32_t)(pick * (float)sc.n_lights);
+  if (k >= sc.n_lights) k = sc.n_lights - 1;
+  const DevLight& L = sc.lights[k];
+  if (L.type == RTB_LIGHT_XZ_RECT)
+    return f3(fmaf(L.p[1] - L.p[0], r1, L.p[0]), L.p[4], fmaf(L.p[3] - L.p[2], r2, L.p[2])) - o;
+  const float3 dir = f3(L.p[0], L.p[1], L.p[2]) - o;
+  const float dist2 = dot(dir, dir);
+  const float q = L.p[3] * L.p[3] / dist2;
+  const float cos_max = sqrtf(1.0f - q);
+  const float z = 1.0f - r2 * (q / (1.0f + cos_max));  // pdf.rs:85: 1 + r2 (cos_max - 1)
+  const float phi = 2.0f * RTB_PI * r1;
+  const float s = sqrtf(fmaxf(0.f, 1.0f - z * z));
+  float sn, cs;
+  sincosf(phi, &sn, &cs);
+  return Onb(dir).local(f3(cs * s, sn * s, z));
+}
+
+// ---- common shade prologue/epilogue --------------------------------------------------------------------------------
+struct PathIO {
+  uint32_t slot, pixel, sample, segs;
+  float3 o, d, beta, L;
+  float time, t;
+  uint32_t ref;
+};
+
+__device__ __forceinline__ PathIO load_path(const DevPool& pool, uint32_t slot) {
+  PathIO io;
+  io.slot = slot;
+  const float4 ro = pool.ray_o[slot], rd = pool.ray_d[slot], b = pool.beta[slot], r = pool.rad[slot];
+  const float2 h = pool.hit[slot];
+  io.o = xyz(ro); io.time = ro.w; io.d = xyz(rd);
+  io.beta = xyz(b); io.pixel = __float_as_uint(b.w);
+  io.L = xyz(r);
+  const uint32_t st = __float_as_uint(r.w);
+  io.sample = st >> 8;
+  io.segs = (st & 0xFFu) + 1u;  // this hit closes segment number `segs`
+  io.t = h.x; io.ref = __float_as_uint(h.y);
+  return io;
+}
+
+// decide continuation (depth budget main.rs:71-73, Russian roulette), then write back or deposit.
+// returns true if the path continues.
+__device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevParams& prm, PathIO& io, bool scattered,
+                                              float3 no, float3 nd, float ntime, float rr_xi) {
+  bool alive = scattered && (int)io.segs < prm.max_depth;
+  if (alive && prm.rr_start > 0 && io.segs >= prm.rr_start) {
+    float qv = fmaxf(io.beta.x, fmaxf(io.beta.y, io.beta.z));
+    qv = qv < 0.05f ? 0.05f : (qv > 1.0f ? 1.0f : qv);
+    if (!(rr_xi < qv)) alive = false;
+    else io.beta = (1.0f / qv) * io.beta;
+  }
+  if (alive) {
+    pool.ray_o[io.slot] = make_float4(no.x, no.y, no.z, ntime);
+    pool.ray_d[io.slot] = make_float4(nd.x, nd.y, nd.z, 0.f);
+    pool.beta[io.slot] = make_float4(io.beta.x, io.beta.y, io.beta.z, __uint_as_float(io.pixel));
+    pool.rad[io.slot] = make_float4(io.L.x, io.L.y, io.L.z, __uint_as_float((io.sample << 8) | io.segs));
+  } else {
+    deposit(prm, pool.c, io.pixel, io.L);
+  }
+  return alive;
+}
+
+#define RTB_SHADE_LOOP_BEGIN(QID)                                                        \
+  DevCounters* c = pool.c;                                                               \
+  const uint32_t n = c->n_mat[QID];                                                      \
+  if (n == 0) return;                                                                    \
+  const uint32_t nxt = c->cur ^ 1u;                                                      \
+  const uint32_t* __restrict__ q = pool.q_mat[QID];                                      \
+  const uint32_t stride = gridDim.x * blockDim.x;                                        \
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {              \
+    const uint32_t i = base + threadIdx.x;                                               \
+    const bool valid = i < n;                                                            \
+    bool alive = false;                                                                  \
+    uint32_t slot = 0;                                                                   \
+    if (valid) {                                                                         \
+      slot = q[i];
+
+#define RTB_SHADE_LOOP_END                                                               \
+    }                                                                                    \
+    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);                          \
+    warp_enqueue(pool.q_dead, &c->n_dead, valid && !alive, slot);                        \
+  }
+
+// miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm) {
+  RTB_SHADE_LOOP_BEGIN(Q_TERMINAL)
+      PathIO io = load_path(pool, slot);
+      if (io.ref == REF_MISS) {
+        io.L = io.L + io.beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
+      } else {
+        const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
+        const float4 m = __ldg(&sc.materials[s.mat]);
+        if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front)
+          io.L = io.L + io.beta * tex_value(sc, __float_as_uint(m.y), s);
+      }
+      deposit(prm, c, io.pixel, io.L);
+  RTB_SHADE_LOOP_END
+}
+
+// Lambertian (material.rs:48-71) / Isotropic through the mixture pdf of main.rs:94-138
+template <bool ISO>
+__device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t slot) {
+  PathIO io = load_path(pool, slot);
+  const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
+  const float4 m = __ldg(&sc.materials[s.mat]);
+  const float3 atten = tex_value(sc, __float_as_uint(m.y), s);
+  const float4 us = philox_u(io.pixel, io.sample, BLK_SCATTER, io.segs, prm.seed);
+  const bool have_lights = sc.n_lights > 0;
+  float3 dir;
+  if (have_lights && us.x < 0.5f) {  // MixturePdf::generate, pdf.rs:73-79
+    dir = lights_random(sc, s.p, us.y, us.z, us.w);
+  } else if (ISO) {
+    const float z = 1.0f - 2.0f * us.z, phi = 2.0f * RTB_PI * us.w;
+    const float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    dir = f3(r * cs, r * sn, z);
+  } else {  // random_cosine_direction vec3.rs:253-262 (r1 = us.z, r2 = us.w) in the ONB of the normal, pdf.rs:32-34
+    const float phi = 2.0f * RTB_PI * us.z, sq = sqrtf(us.w);
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    dir = Onb(s.n).local(f3(cs * sq, sn * sq, sqrtf(1.0f - us.w)));
+  }
+  float mat_pdf, spdf;
+  if (ISO) {
+    mat_pdf = spdf = 1.0f / (4.0f * RTB_PI);
+  } else {
+    const float cosine = dot(unit(dir), unit(s.n));  // CosinePdf::value pdf.rs:24-31 ; scattering_pdf material.rs:64-71
+    mat_pdf = cosine <= 0.f ? 0.f : cosine / RTB_PI;
+    spdf = mat_pdf;
+  }
+  const float pdf_val = have_lights ? 0.5f * lights_pdf(sc, s.p, dir) + 0.5f * mat_pdf : mat_pdf;  // pdf.rs:70-72
+  const bool scattered = spdf > 0.f;  // zero-weight continuation culled
+  if (scattered) io.beta = io.beta * atten * (spdf / pdf_val);
+  float rr = 0.f;
+  if (prm.rr_start > 0 && io.segs >= prm.rr_start) rr = u01(philox4(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed).x);
+  return finish_bounce(pool, prm, io, scattered, s.p, dir, io.time, rr);
+}
+
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm) {
+  RTB_SHADE_LOOP_BEGIN(Q_LAMBERT)
+      alive = shade_diffuse<false>(sc, pool, prm, slot);
+  RTB_SHADE_LOOP_END
+}
+
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm) {
+  RTB_SHADE_LOOP_BEGIN(Q_ISOTROPIC)
+      alive = shade_diffuse<true>(sc, pool, prm, slot);
+  RTB_SHADE_LOOP_END
+}
+
+// Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_metal(DevScene sc, DevPool pool, DevParams prm) {
+  RTB_SHADE_LOOP_BEGIN(Q_METAL)
+      PathIO io = load_path(pool, slot);
+      const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
+      const float4 m = __ldg(&sc.materials[s.mat]);
+      const float fuzz = fminf(m.z, 1.0f);
+      const float3 ud = unit(io.d);
+      float3 dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);  // reflect, vec3.rs:115-117
+      const float4 ua = philox_u(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed);
+      if (fuzz > 0.f) {  // random_in_unit_sphere (vec3.rs:78-86) in closed form: uniform direction * cbrt(xi)
+        const float z = 1.0f - 2.0f * ua.y, phi = 2.0f * RTB_PI * ua.z, rad = cbrtf(ua.w);
+        const float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+        float sn, cs;
+        sincosf(phi, &sn, &cs);
+        dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
+      }
+      io.beta = io.beta * tex_value(sc, __float_as_uint(m.y), s);
+      alive = finish_bounce(pool, prm, io, true, s.p, dir, 0.0f, ua.x);
+  RTB_SHADE_LOOP_END
+}
+
+// Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm) {
+  RTB_SHADE_LOOP_BEGIN(Q_DIELECTRIC)
+      PathIO io = load_path(pool, slot);
+      const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
+      const float ir = __ldg(&sc.materials[s.mat]).z;
+      const float ratio = s.front ? 1.0f / ir : ir;
+      const float3 ud = unit(io.d);
+      const float cos_theta = fminf(-dot(ud, s.n), 1.0f);
+      const float sin_theta = sqrtf(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+      const bool cannot_refract = ratio * sin_theta > 1.0f;
+      float r0 = (1.0f - ratio) / (1.0f + ratio);
+      r0 *= r0;
+      const float om = 1.0f - cos_theta;
+      const float reflectance = r0 + (1.0f - r0) * (om * om) * (om * om) * om;
+      const float4 ua = philox_u(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed);
+      float3 dir;
+      if (cannot_refract || reflectance > ua.y) {
+        dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);
+      } else {
+        const float3 perp = ratio * fma3(cos_theta, s.n, ud);
+        const float par = -sqrtf(fabsf(1.0f - dot(perp, perp)));
+        dir = fma3(par, s.n, perp);
+      }
+      alive = finish_bounce(pool, prm, io, true, s.p, dir, io.time, ua.x);
+  RTB_SHADE_LOOP_END
+}
+
+// ---- generate: camera.rs:60-70 get_ray + the jitter of main.rs:752-753 ---------------------------------------------
+__device__ __forceinline__ void camera_ray(const DevCamera& cam, const DevParams& prm, uint32_t pixel, uint32_t sample,
+                                           float3& o, float3& d, float& time) {
+  const uint32_t row = pixel / prm.width, col = pixel - row * prm.width;
+  const uint32_t j = prm.height - 1 - row;  // scanline j is stored at image row H-1-j, main.rs:733
+  const float4 u0 = philox_u(pixel, sample, BLK_CAMERA0, 0, prm.seed);
+  const float4 u1 = philox_u(pixel, sample, BLK_CAMERA1, 0, prm.seed);
+  const float s = ((float)col + u0.x) / (float)(prm.width - 1);
+  const float t = ((float)j + u0.y) / (float)(prm.height - 1);
+  // random_in_unit_disk (vec3.rs:101-113) in closed form
+  const float rr = cam.lens_radius * sqrtf(u0.z);
+  float sn, cs;
+  sincosf(2.0f * RTB_PI * u0.w, &sn, &cs);
+  const float3 off = (rr * cs) * ld3(cam.u) + (rr * sn) * ld3(cam.v);
+  o = ld3(cam.origin) + off;
+  d = fma3(s, ld3(cam.horizontal), fma3(t, ld3(cam.vertical), ld3(cam.lmo))) - off;
+  time = fmaf(cam.time1 - cam.time0, u1.x, cam.time0);  // camera.rs:68
+}
+
+__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, DevParams prm, DevCamera cam) {
+  __shared__ unsigned long long s_first;
+  DevCounters* c = pool.c;
+  const uint32_t n = c->n_dead;
+  if (n == 0) return;
+  const unsigned long long total = c->total_paths;
+  if (c->next_path >= total) return;  // nothing left to start: terminated slots stay dead
+  const uint32_t nxt = c->cur ^ 1u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t npix = prm.width * prm.height;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
+    const uint32_t cnt = min(blockDim.x, n - base);
+    __syncthreads();
+    if (threadIdx.x == 0) s_first = atomicAdd(&c->next_path, (unsigned long long)cnt);
+    __syncthreads();
+    const unsigned long long path = s_first + threadIdx.x;
+    const bool alive = threadIdx.x < cnt && path < total;
+    uint32_t slot = 0;
+    if (alive) {
+      slot = pool.q_dead[base + threadIdx.x];
+      // sample-major order: all pixels (tile order) of sample k, then sample k+1: neighbouring lanes = neighbouring pixels
+      const uint32_t s_local = (uint32_t)(path / npix);
+      const uint32_t pixel = __ldg(prm.pix_order + (uint32_t)(path - (unsigned long long)s_local * npix));
+      const uint32_t sample = prm.sample_offset + s_local;
+      float3 o, d;
+      float time;
+      camera_ray(cam, prm, pixel, sample, o, d, time);
+      pool.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
+      pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+      pool.beta[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
+      pool.rad[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample << 8));
+    }
+    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);
+  }
+}
+
+__global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pool.n) pool.q_dead[i] = i;
+  if (i == 0) {
+    DevCounters* c = pool.c;
+    c->n_ext[0] = c->n_ext[1] = 0;
+    for (int k = 0; k < (int)Q_COUNT; ++k) c->n_mat[k] = 0;
+    c->n_dead = pool.n;
+    c->cur = 0;
+    c->iter = 0;
+    c->next_path = 0;
+    c->total_paths = total_paths;
+    c->segments = c->rejected = c->paths_started = 0;
+    c->nodes_visited = c->prims_tested = 0;
+  }
+}
+
+__global__ void k_advance(DevPool pool) {
+  DevCounters* c = pool.c;
+  const uint32_t cur = c->cur;
+  c->segments += c->n_ext[cur];
+  c->n_ext[cur] = 0;
+  for (int k = 0; k < (int)Q_COUNT; ++k) c->n_mat[k] = 0;
+  c->n_dead = 0;
+  c->cur = cur ^ 1u;
+  c->iter += 1;
+}
+
+// ---- write_color, main.rs:141-169 ----------------------------------------------------------------------------------
+__global__ void k_finalize(const float4* __restrict__ accum, uint8_t* __restrict__ rgb, uint32_t npix, float inv_spp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float4 a = accum[i];
+  float ch[3] = {a.x, a.y, a.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = ch[k];
+    if (v != v) v = 0.f;
+    v = sqrtf(inv_spp * v);
+    v = v < 0.f ? 0.f : (v > 0.999f ? 0.999f : v);
+    rgb[3 * (size_t)i + k] = (uint8_t)(256.0f * v);
+  }
+}
+
+// ---- parity probes: the same traverse<> the extend kernel runs --------------------------------------------------------
+__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
+k_probe(DevScene sc, const float* __restrict__ org, const float* __restrict__ dir, const float* __restrict__ time,
+        uint32_t n, uint32_t n_snodes, uint32_t* __restrict__ id_out, float* __restrict__ t_out, DevCounters* c) {
+  extern __shared__ uint4 snodes[];
+  stage_nodes(sc, snodes, n_snodes);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+  const float tm = time ? time[i] : 0.f;
+  Closest best{INFINITY, REF_MISS, 0u};
+  uint32_t nv = 0, nt = 0;
+  traverse<true>(sc, snodes, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
+  if (sc.n_media) intersect_media(sc, o, d, RTB_TMIN, best, 0, 0, 0, 0, false);
+  id_out[i] = best.ref == REF_MISS ? RTB_NONE : best.gid;
+  t_out[i] = best.t;
+  if (c) {
+    atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+    atomicAdd(&c->prims_tested, (unsigned long long)nt);
+  }
+}
+
+// pixel-centre primary rays, generated in f64 like the reference's camera (camera.rs:60-70) and rounded once
+__global__ void k_primary_rays(DevCameraF64 cam, uint32_t W, uint32_t H, float* __restrict__ org, float* __restrict__ dir,
+                               float* __restrict__ time) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * H) return;
+  const uint32_t row = i / W, col = i - row * W, j = H - 1 - row;
+  const double s = ((double)col + 0.5) / (double)(W - 1), t = ((double)j + 0.5) / (double)(H - 1);
+  for (int a = 0; a < 3; ++a) {
+    org[3 * i + a] = (float)cam.origin[a];
+    dir[3 * i + a] = (float)(cam.llc[a] + s * cam.horizontal[a] + t * cam.vertical[a] - cam.origin[a]);
+  }
+  time[i] = (float)cam.time0;
+}
+
+// ================================================= launchers ========================================================
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st) {
+  k_init_pool<<<cdiv(pool.n, 256), 256, 0, st>>>(pool, total_paths);
+}
+void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st) {
+  k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
+}
+void launch_advance(const DevPool& pool, cudaStream_t st) { k_advance<<<1, 1, 0, st>>>(pool); }
+void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st) {
+  k_extend<<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+}
+void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
+                  cudaStream_t st) {
+  k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+  if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+  if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+}
+void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
+  k_finalize<<<cdiv(npix, 256), 256, 0, st>>>(accum, rgb, npix, inv_spp);
+}
+void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
+                  uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st) {
+  k_probe<<<cdiv(n, RTB_EXTEND_THREADS), RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, org, dir, time, n, lc.n_snodes,
+                                                                                  id_out, t_out, c);
+}
+void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
+                         cudaStream_t st) {
+  k_primary_rays<<<cdiv(W * H, 256), 256, 0, st>>>(cam, W, H, org, dir, time);
+}
+
+int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
+  // stage as much of the (breadth-first ordered) node array as fits the shared-memory budget
+  const uint32_t budget = 64 * 1024;
+  uint32_t n_s = n_nodes;
+  if ((size_t)n_s * 80 > budget) n_s = budget / 80;
+  lc.n_snodes = n_s;
+  lc.extend_smem = n_s * 80;
+  cudaError_t e = cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, RTB_EXTEND_THREADS, lc.extend_smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) occ = 1;
+  lc.extend_grid = (uint32_t)(sm_count * occ);
+  int occ2 = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_shade_lambert, RTB_SHADE_THREADS, 0);
+  if (e != cudaSuccess) return (int)e;
+  if (occ2 < 1) occ2 = 1;
+  lc.shade_grid = (uint32_t)(sm_count * occ2);
+  return 0;
+}
+
+}  // namespace rtb

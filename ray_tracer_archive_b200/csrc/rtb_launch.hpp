@@ -1,0 +1,39 @@
+// rtb_launch.hpp — host-visible launch interface of rtb_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RTB_EXTEND_THREADS 256
+#define RTB_SHADE_THREADS 256
+
+namespace rtb {
+
+struct DevScene;
+struct DevPool;
+struct DevParams;
+struct DevCamera;
+struct DevCounters;
+
+struct DevCameraF64 {  // camera.rs:6-17 in f64, for the parity probe's primary rays
+  double origin[3], llc[3], horizontal[3], vertical[3];
+  double time0;
+};
+
+struct LaunchCfg {
+  uint32_t extend_grid = 0, shade_grid = 0, extend_smem = 0, n_snodes = 0;
+};
+
+int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
+void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
+void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);
+void launch_advance(const DevPool& pool, cudaStream_t st);
+void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st);
+void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
+                  cudaStream_t st);
+void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st);
+void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
+                  uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st);
+void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
+                         cudaStream_t st);
+
+}  // namespace rtb
