@@ -152,7 +152,9 @@ typedef struct rtb_params {
   uint32_t pool_paths;     /* wavefront pool size; 0 = default */
   uint32_t flags;          /* RTB_RENDER_* */
 } rtb_params;
-#define RTB_RENDER_ACCUMULATE 1u /* add into the accumulation buffer instead of clearing it first */
+#define RTB_RENDER_ACCUMULATE 1u  /* add into the accumulation buffer instead of clearing it first */
+#define RTB_RENDER_COUNT 2u       /* instrumented extend: fills stats->nodes_visited / prims_tested (slower) */
+#define RTB_RENDER_TIME_EXTEND 4u /* CUDA events around every extend launch: fills stats->ms_extend */
 
 typedef struct rtb_stats {
   uint64_t paths;          /* camera paths started */
@@ -162,8 +164,8 @@ typedef struct rtb_stats {
   uint64_t launches;       /* kernels launched by this call */
   uint64_t extend_launches;
   double ms_total;         /* device time of the whole call (CUDA events) */
-  double ms_extend;        /* device time inside the extend kernel (only if RTB_STATS_TIMING env/flag, else 0) */
-  uint64_t nodes_visited;  /* only in stats builds of the probe, else 0 */
+  double ms_extend;        /* summed device time of the extend launches (RTB_RENDER_TIME_EXTEND, else 0) */
+  uint64_t nodes_visited;  /* BVH nodes fetched / primitives tested by extend (RTB_RENDER_COUNT or the probes, else 0) */
   uint64_t prims_tested;
 } rtb_stats;
 

@@ -732,9 +732,14 @@ int orc_scene_set_mesh(orc_scene* o, uint32_t id, const float* verts, uint32_t n
 int orc_scene_build(orc_scene* o) { return o->s.build() ? 0 : -1; }
 uint32_t orc_scene_num_prims(orc_scene* o) { return o->s.build() ? o->s.n_prims : 0; }
 
-// pixel-centre primary rays (jitter 0.5, lens centre, time0); image row 0 = top = scanline j = H-1 (main.rs:733)
+// pixel-centre primary rays (jitter 0.5, lens centre, time0); image row 0 = top = scanline j = H-1 (main.rs:733).
+// stable_out / spread_out (optional): the device consumes f32 rays, so a pixel's answer is only well-defined if it
+// survives an f32-ulp perturbation of the ray.  stable_out = 1 where the same primitive is returned for the ray with
+// each direction component scaled by (1 +- eps); spread_out = max |t' - t| over those rays (the input-rounding
+// uncertainty of t).  Rays through an exact edge (e.g. the Cornell box's x = y = 0 corner line seen from its
+// symmetric camera) are knife-edge even in the reference's f64 and are reported as unstable rather than compared.
 int orc_primary_hits(orc_scene* o, const rtb_camera* cam, uint32_t W, uint32_t H, uint32_t* ids, double* ts,
-                     int threads) {
+                     uint8_t* stable_out, double* spread_out, double eps, int threads) {
   if (!o->s.build()) return -1;
   Camera c(*cam);
   const Scene& sc = o->s;
@@ -745,8 +750,23 @@ int orc_primary_hits(orc_scene* o, const rtb_camera* cam, uint32_t W, uint32_t H
       Ray r = c.get_ray(u, v, 0.0, 0.0, c.time0);
       HitRecord rec;
       bool h = sc.world->hit(r, 0.001, INF, rec, HitCtx());
-      ids[(size_t)row * W + i] = h ? rec.prim : RTB_NONE;
-      ts[(size_t)row * W + i] = h ? rec.t : INF;
+      const size_t k = (size_t)row * W + i;
+      ids[k] = h ? rec.prim : RTB_NONE;
+      ts[k] = h ? rec.t : INF;
+      if (stable_out) {
+        bool stable = true;
+        double spread = 0.0;
+        for (int q = 0; q < 6 && stable; ++q) {
+          Ray rp = r;
+          rp.d.at(q >> 1) *= (q & 1) ? (1.0 + eps) : (1.0 - eps);
+          HitRecord r2;
+          bool h2 = sc.world->hit(rp, 0.001, INF, r2, HitCtx());
+          if (h2 != h || (h && r2.prim != rec.prim)) stable = false;
+          else if (h) spread = std::fmax(spread, std::fabs(r2.t - rec.t));
+        }
+        stable_out[k] = stable ? 1 : 0;
+        if (spread_out) spread_out[k] = spread;
+      }
     }
   });
   return 0;

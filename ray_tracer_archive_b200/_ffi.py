@@ -19,7 +19,7 @@ NODE_LIST, NODE_BVH = 32, 33
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = 0, 1, 2, 3, 4
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = 0, 1, 2, 3
 LIGHT_XZ_RECT, LIGHT_SPHERE = 0, 1
-RENDER_ACCUMULATE = 1
+RENDER_ACCUMULATE, RENDER_COUNT, RENDER_TIME_EXTEND = 1, 2, 4
 
 NODE_DTYPE = np.dtype([("type", "<u4"), ("material", "<u4"), ("first_child", "<u4"), ("n_children", "<u4"),
                        ("p", "<f8", (12,))])

@@ -65,6 +65,7 @@ struct rtb_context {
   DevBuf<float> p_org, p_dir, p_time, p_t;
   DevBuf<uint32_t> p_id;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ext_events;  // pairs around every extend launch when RTB_RENDER_TIME_EXTEND is set
 };
 
 struct rtb_scene {
@@ -124,6 +125,7 @@ void rtb_context_destroy(rtb_context* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->ext_events) cudaEventDestroy(e);
   delete c;
 }
 
@@ -590,11 +592,27 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
   const uint32_t check_every = 8;
+  const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
+  size_t ev_used = 0;
   uint64_t iters = 0;
   const uint64_t iter_cap = (uint64_t)(total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
   for (;;) {
     for (uint32_t k = 0; k < check_every; ++k) {
-      launch_extend(s->lc, s->dev, pool, prm, st);
+      if (time_ext) {
+        if (c->ext_events.size() < ev_used + 2) {
+          cudaEvent_t a, b;
+          CU(cudaEventCreate(&a));
+          CU(cudaEventCreate(&b));
+          c->ext_events.push_back(a);
+          c->ext_events.push_back(b);
+        }
+        CU(cudaEventRecord(c->ext_events[ev_used], st));
+      }
+      launch_extend(s->lc, s->dev, pool, prm, count, st);
+      if (time_ext) {
+        CU(cudaEventRecord(c->ext_events[ev_used + 1], st));
+        ev_used += 2;
+      }
       launch_shade(s->lc, s->dev, pool, prm, present, st);
       launch_generate(s->lc, pool, prm, dcam, st);
       launch_advance(pool, st);
@@ -621,6 +639,15 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     stats->launches = launches;
     stats->extend_launches = extend_launches;
     stats->ms_total = ms;
+    stats->nodes_visited = c->h_counters->nodes_visited;
+    stats->prims_tested = c->h_counters->prims_tested;
+    double ms_ext = 0;
+    for (size_t k = 0; k + 1 < ev_used; k += 2) {
+      float e = 0;
+      cudaEventElapsedTime(&e, c->ext_events[k], c->ext_events[k + 1]);
+      ms_ext += e;
+    }
+    stats->ms_extend = ms_ext;
   }
   return RTB_OK;
 }

@@ -142,24 +142,55 @@ __device__ __forceinline__ void consider(Closest& best, float t, uint32_t ref, u
   }
 }
 
-// Sphere::hit, sphere.rs:41-65, in the cancellation-free form  disc' = r^2 - |oc - (oc.d/a) d|^2  (= det/a).
-// The reference's c = |oc|^2 - r^2 loses all bits in f32 for the r=1000 ground sphere.
-__device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
-  float3 oc = o - c;
-  float a = dot(d, d);
-  float hb = dot(oc, d);
-  float inv_a = 1.0f / a;
-  float3 l = fma3(-hb * inv_a, d, oc);
-  float disc = fmaf(r, r, -dot(l, l));
-  if (disc < 0.0f) return false;
-  float sq = sqrtf(a * disc);
-  float root = (-hb - sq) * inv_a;
-  if (root < tmin || tmax < root) {
-    root = (-hb + sq) * inv_a;
-    if (root < tmin || tmax < root) return false;
+// Sphere::hit, sphere.rs:41-65, literally, in f64: used only where the f32 form below is ill-conditioned
+// (grazing rays, or an origin much farther from the centre than from the hit — the r=1000 ground sphere).
+static __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+  const double ox = (double)o.x - (double)c.x, oy = (double)o.y - (double)c.y, oz = (double)o.z - (double)c.z;
+  const double dx = d.x, dy = d.y, dz = d.z;
+  const double a = dx * dx + dy * dy + dz * dz;
+  const double hb = ox * dx + oy * dy + oz * dz;
+  const double cc = ox * ox + oy * oy + oz * oz - (double)r * (double)r;
+  const double det = hb * hb - a * cc;
+  if (det < 0.0) return false;
+  const double sq = sqrt(det);
+  double root = (-hb - sq) / a;
+  if (root < (double)tmin || (double)tmax < root) {
+    root = (-hb + sq) / a;
+    if (root < (double)tmin || (double)tmax < root) return false;
   }
-  t_out = root;
+  t_out = (float)root;
   return true;
+}
+
+// Sphere::hit in f32, in the cancellation-free form  disc' = r^2 - |oc - (oc.d/a) d|^2  (= det/a): the reference's
+// c = |oc|^2 - r^2 loses all bits in f32 for large spheres.  Falls back to f64 when the sign of disc' or the root
+// cannot be trusted to ~1e-6.
+__device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+  const float3 oc = o - c;
+  const float a = dot(d, d);
+  const float hb = dot(oc, d);
+  const float oo = dot(oc, oc);
+  const float inv_a = 1.0f / a;
+  const float3 l = fma3(-hb * inv_a, d, oc);
+  const float disc = fmaf(r, r, -dot(l, l));
+  bool need64 = disc * disc < 1e-9f * r * r * oo;  // |disc| within ~3e-5 r|oc| of zero: grazing
+  if (!need64) {
+    if (disc < 0.0f) return false;
+    const float sq = sqrtf(a * disc);
+    float root = (-hb - sq) * inv_a;
+    if (root < tmin || tmax < root) {
+      root = (-hb + sq) * inv_a;
+      if (root < tmin || tmax < root) return false;
+    }
+    // f32 is accurate to ~1e-6 relative when the origin-to-centre distance is <= 16 hit distances and the rounding of
+    // disc' (~4e-7 r|oc|) moves the root by < 1e-6 t:  dt = d(disc')/(2 sqrt(a disc'))
+    const float tta = root * root * a;
+    if (oo <= 256.0f * tta && r * r * oo <= 25.0f * tta * disc) {
+      t_out = root;
+      return true;
+    }
+  }
+  return sphere_roots_f64(o, d, c, r, tmin, tmax, t_out);
 }
 
 template <bool COUNT>

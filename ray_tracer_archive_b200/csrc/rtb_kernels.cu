@@ -47,6 +47,9 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 }
 
 // ---- extend ------------------------------------------------------------------------------------------------------
+// COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
+// segment); the timed path runs COUNT = false.
+template <bool COUNT>
 __global__ void __launch_bounds__(RTB_EXTEND_THREADS)
 k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
@@ -61,6 +64,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t i = base + threadIdx.x;
     const bool valid = i < n;
     uint32_t slot = 0, queue = Q_COUNT;
+    uint32_t nv = 0, nt = 0;
     if (valid) {
       slot = q[i];
       const float4 ro = pool.ray_o[slot];
@@ -68,8 +72,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
       const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
       const uint32_t st = __float_as_uint(pool.rad[slot].w);
       Closest best{INFINITY, REF_MISS, 0u};
-      uint32_t nv = 0, nt = 0;
-      traverse<false>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+      traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
       if (sc.n_media)
         intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
       pool.hit[slot] = make_float2(best.t, __uint_as_float(best.ref));
@@ -88,6 +91,14 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
 #pragma unroll
     for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
+    if (COUNT) {
+      nv = __reduce_add_sync(0xffffffffu, nv);
+      nt = __reduce_add_sync(0xffffffffu, nt);
+      if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+        atomicAdd(&c->prims_tested, (unsigned long long)nt);
+      }
+    }
   }
 }
 
@@ -604,8 +615,10 @@ void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& 
   k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
 }
 void launch_advance(const DevPool& pool, cudaStream_t st) { k_advance<<<1, 1, 0, st>>>(pool); }
-void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st) {
-  k_extend<<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
+                   cudaStream_t st) {
+  if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+  else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
 }
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
                   cudaStream_t st) {
@@ -635,12 +648,14 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;
   lc.extend_smem = n_s * 80;
-  cudaError_t e = cudaFuncSetAttribute(k_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend, RTB_EXTEND_THREADS, lc.extend_smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
   lc.extend_grid = (uint32_t)(sm_count * occ);

@@ -27,7 +27,8 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);
 void launch_advance(const DevPool& pool, cudaStream_t st);
-void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st);
+void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
+                   cudaStream_t st);
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
                   cudaStream_t st);
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st);

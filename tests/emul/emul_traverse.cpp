@@ -1,0 +1,55 @@
+// emul_traverse.cpp — TEST INFRASTRUCTURE.  Compiles the UNMODIFIED device header csrc/rtb_device.cuh with g++ by
+// supplying host stand-ins for the handful of CUDA intrinsics it uses, so the exact traversal / intersection source
+// the GPU runs can be checked against the oracle on a machine without a GPU.  Not linked into librtb200.so.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>  // float3/float4/uint4 + make_* ; __device__ etc. degrade to ignored attributes
+
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+  uint8_t b[8];
+  for (int i = 0; i < 4; ++i) { b[i] = (x >> (8 * i)) & 0xFF; b[4 + i] = (y >> (8 * i)) & 0xFF; }
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= (uint32_t)b[(s >> (4 * i)) & 7] << (8 * i);
+  return r;
+}
+template <class T> static inline T __ldg(const T* p) { return *p; }
+#define __forceinline__ inline
+
+#include "../../ray_tracer_archive_b200/csrc/rtb_device.cuh"
+
+using namespace rtb;
+
+extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
+                          const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
+                          const float* geom3, const uint32_t* info3, uint32_t n_snodes, const float* org,
+                          const float* dir, const float* time, uint32_t n, uint32_t* ids, float* ts,
+                          uint64_t* nodes_visited, uint64_t* prims_tested) {
+  static DevScene sc;
+  std::memset(&sc, 0, sizeof(sc));
+  sc.nodes = (const uint4*)nodes;
+  sc.n_nodes = n_nodes;
+  const float* g[4] = {geom0, geom1, geom2, geom3};
+  const uint32_t* inf[4] = {info0, info1, info2, info3};
+  for (int t = 0; t < 4; ++t) { sc.geom[t] = (const float4*)g[t]; sc.info[t] = (const uint2*)inf[t]; }
+  uint64_t nv_total = 0, nt_total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    Closest best{INFINITY, REF_MISS, 0u};
+    uint32_t nv = 0, nt = 0;
+    traverse<true>(sc, (const uint4*)nodes, n_snodes < n_nodes ? n_snodes : n_nodes, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
+                   f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
+    ids[i] = best.ref == REF_MISS ? RTB_NONE : best.gid;
+    ts[i] = best.t;
+    nv_total += nv; nt_total += nt;
+  }
+  if (nodes_visited) *nodes_visited = nv_total;
+  if (prims_tested) *prims_tested = nt_total;
+  return 0;
+}

@@ -1,0 +1,95 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/rtb200.h declares, and its host-side error
+behaviour.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rtb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(rtb):
+    lib = rtb._ffi.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in rtb200.h but not exported by librtb200.so"
+        assert n in rtb._ffi.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.rtb_abi_version() == 1
+
+
+def test_struct_layouts_match_header(rtb):
+    F = rtb._ffi
+    assert C.sizeof(F.Camera) == 15 * 8
+    assert C.sizeof(F.Params) == 13 * 4
+    assert C.sizeof(F.Stats) == 10 * 8
+    assert F.NODE_DTYPE.itemsize == 112 and F.LIGHT_DTYPE.itemsize == 48
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device error path")
+def test_no_cpu_fallback(rtb):
+    with pytest.raises(rtb.RtbError) as e:
+        rtb.Context(0)
+    assert e.value.code == -2  # RTB_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_host_only_scene_errors(rtb):
+    from ray_tracer_archive_b200 import scene as S
+    lib = rtb._ffi.load()
+    m = S.Lambertian.construct((0.5, 0.5, 0.5))
+    cs = rtb.compile_scene(S.HittableList([S.Sphere((0, 0, 0), 1.0, m)]))
+    s = rtb.Scene(None)
+    # build before materials are set
+    with pytest.raises(rtb.RtbError) as e:
+        s.build_bvh()
+    assert e.value.code == -4
+    s.set_compiled(cs)
+    s.build_bvh()
+    assert s.info()["n_prims"] == 1 and s.info()["n_bvh_nodes"] == 1
+    with pytest.raises(rtb.RtbError) as e:  # host-only scenes cannot be committed
+        s.commit()
+    assert e.value.code == -4
+    # malformed graph: child index out of range
+    bad = cs.nodes.copy()
+    bad[-1]["first_child"] = 99
+    rc = lib.rtb_scene_set_graph(s.h, rtb._ffi.ptr(bad), len(bad), rtb._ffi.ptr(cs.child_index), len(cs.child_index), cs.root)
+    assert rc == -1 and b"child" in lib.rtb_last_error()
+    # unsupported light type
+    lights = np.zeros(1, dtype=rtb._ffi.LIGHT_DTYPE)
+    lights[0]["type"] = 7
+    assert lib.rtb_scene_set_lights(s.h, rtb._ffi.ptr(lights), 1) == -5
+
+
+def test_flatten_ids_and_face_modes(rtb):
+    """Primitive ids follow list order with Box -> 6 sides (boxes.rs:19-68); the Cornell scene has ids 0..12."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    s = rtb.Scene(None, rtb.compile_scene(cfg.world, cfg.lights))
+    info = s.info()
+    assert (info["n_quads"], info["n_spheres"], info["n_prims"], info["n_lights"]) == (12, 1, 13, 2)
+    _, prims = s.export_bvh()
+    quad_info = prims[2][1].reshape(-1, 2)
+    ids = sorted(quad_info[:, 0].tolist())
+    assert ids == list(range(12))
+    mode = {int(i): int(m >> 24) for i, m in quad_info}
+    assert mode[2] == 1                       # FlipFace(light): front_face toggled (hittable.rs:195-201)
+    assert all(mode[i] == 2 for i in range(6, 12))  # Translate(RotateY(Box)): front_face forced true (hittable.rs:82-83)
+    assert all(mode[i] == 0 for i in (0, 1, 3, 4, 5))
+    assert int(prims[0][1][0]) == 12          # the glass sphere is the last object

@@ -1,0 +1,299 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI (ctypes), against the f64 oracle on identical scenes.
+
+P1  primary-ray closest hit: primitive ids bit-exact, t within 1e-5 relative          
+P2  converged images at 4096 spp: mean relative luminance error <= 1 %, no pixel beyond 5 sigma of its MC error
+P3  white furnace (closed form)      D1  sample split across calls == one call      plus ABI error behaviour.
+The oracle finishes in seconds only at reduced sizes; full-size configs are covered by P1 where the linear-scan
+oracle is affordable (C1, C2) and by size-independent properties (height-field closest-hit, C4 at 1M triangles).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_pair(rtb, orc, ctx, cfg):
+    cs = rtb.compile_scene(cfg.world, cfg.lights)
+    return rtb.Scene(ctx, cs), orc.OracleScene(cs), cs
+
+
+# ------------------------------------------------------------------------------------------------------------- P1
+def _p1(rtb, orc, ctx, cfg, W, Hh, max_unstable=0.005):
+    dev, osc, _ = _scene_pair(rtb, orc, ctx, cfg)
+    ids, ts, st = dev.primary_hits(cfg.camera, W, Hh)
+    oid, ot, stable, spread = osc.primary_hits(cfg.camera, W, Hh, stability_eps=2.5e-7)
+    unstable, worst = H.check_primary_parity(ids, ts, oid, ot, stable, spread, max_unstable)
+    print(f"{cfg.name}: {W}x{Hh} ids exact on {oid.size - unstable} stable px ({unstable} knife-edge), max t err {worst:.2e},"
+          f" {st['nodes_visited'] / oid.size:.2f} nodes/ray {st['prims_tested'] / oid.size:.2f} prims/ray")
+    return ids, oid
+
+
+def test_p1_random_spheres_full_size(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_random_spheres()
+    _p1(rtb, orc, ctx, cfg, cfg.width, cfg.height)
+
+
+def test_p1_cornell_full_size(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    ids, oid = _p1(rtb, orc, ctx, cfg, cfg.width, cfg.height)
+    assert set(np.unique(oid).tolist()) >= {0, 1, 2, 3, 4, 5, 12}
+
+
+def test_p1_final_scene(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_final_scene()
+    _p1(rtb, orc, ctx, cfg, 400, 400)
+
+
+def test_p1_mesh_small(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_mesh(nx=100, nz=50)
+    _p1(rtb, orc, ctx, cfg, 320, 180)
+
+
+def test_p1_other_scenes(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    base = scenes.config_cornell()
+    for name, world, cam in [
+        ("two_spheres", scenes.two_spheres(), rtb.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0)),
+        ("simple_light", scenes.simple_light(), rtb.Camera.new((26, 3, 6), (0, 2, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0)),
+        ("cornell_smoke", scenes.cornell_smoke(), base.camera),
+    ]:
+        base.world, base.lights, base.camera, base.name = world, None, cam, name
+        _p1(rtb, orc, ctx, base, 240, 160)
+
+
+def test_tie_break_and_flat_api(rtb, orc, ctx):
+    """Equal t: the later primitive wins (hittable_list.rs:44-47), also through the flat SoA entry points."""
+    from ray_tracer_archive_b200 import scene as S
+    m = S.Lambertian.construct((0.5, 0.5, 0.5))
+    world = S.HittableList([S.XzRect.construct(0, 1, 0, 1, 0.0, m), S.XzRect.construct(0, 1, 0, 1, 0.0, m),
+                            S.XzRect.construct(-1, 2, -1, 2, 0.0, m), S.Sphere.construct((5, 0, 5), 1.0, m)])
+    cs = rtb.compile_scene(world)
+    dev, osc = rtb.Scene(ctx, cs), orc.OracleScene(cs)
+    o = [[0.5, 1, 0.5], [1.5, 1, 0.5], [5, 5, 5], [9, 9, 9]]
+    d = [[0, -1, 0], [0, -2, 0], [0, -1, 0], [0, 1, 0]]
+    ids, ts, _ = dev.trace_rays(o, d)
+    oid, ot = osc.trace_rays(o, d)
+    assert ids.tolist() == oid.tolist() == [2, 2, 3, H.NONE]
+    np.testing.assert_allclose(ts[:3], ot[:3], rtol=1e-6)
+    # the same scene through rtb_scene_set_quads / rtb_scene_set_spheres
+    lib = rtb._ffi.load()
+    flat = rtb.Scene(ctx)
+    flat.set_tables(cs)
+    q = np.array([[0, 0, 0], [0, 0, 0], [-1, 0, -1]], np.float32)
+    u = np.array([[1, 0, 0], [1, 0, 0], [3, 0, 0]], np.float32)
+    v = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 3]], np.float32)
+    mat = np.zeros(3, np.uint32)
+    pid = np.array([0, 1, 2], np.uint32)
+    rtb._ffi.check(lib.rtb_scene_set_quads(flat.h, rtb._ffi.ptr(q), rtb._ffi.ptr(u), rtb._ffi.ptr(v), rtb._ffi.ptr(mat), None,
+                                           rtb._ffi.ptr(pid), 3))
+    sp = np.array([[5, 0, 5, 1]], np.float32)
+    rtb._ffi.check(lib.rtb_scene_set_spheres(flat.h, rtb._ffi.ptr(sp), rtb._ffi.ptr(np.zeros(1, np.uint32)), None,
+                                             rtb._ffi.ptr(np.array([3], np.uint32)), 1))
+    flat.commit()
+    ids2, ts2, _ = flat.trace_rays(o, d)
+    assert ids2.tolist() == [2, 2, 3, H.NONE]
+    np.testing.assert_allclose(ts2[:3], ts[:3], rtol=1e-6)
+
+
+def test_heightfield_closest_hit_full_1M_triangles(rtb, ctx):
+    """C4 at full size (1 000 000 triangles): size-independent properties of a height field.
+    (a) vertical rays hit exactly the triangle whose xz-projection contains them, at the interpolated height;
+    (b) for slanted rays the reported (id, t) is a true intersection of that triangle and the ray stays above the
+        surface before it (so it is the closest hit)."""
+    from ray_tracer_archive_b200 import scenes, scene as S
+    nx, nz = 1000, 500
+    verts, tris = scenes.heightfield_mesh(nx, nz, seed=1)
+    m = S.Lambertian.construct((0.73, 0.73, 0.73))
+    dev = rtb.Scene(ctx, rtb.compile_scene(S.HittableList([S.TriangleMesh(verts, tris, m)])))
+    assert dev.info()["n_triangles"] == 2 * nx * nz
+    rng = np.random.default_rng(5)
+    n = 200000
+    x = rng.uniform(66, 489, n)
+    z = rng.uniform(66, 489, n)
+    o = np.stack([x, np.full(n, 500.0), z], 1).astype(np.float32)
+    d = np.tile(np.array([[0, -1, 0]], np.float32), (n, 1))
+    ids, ts, _ = dev.trace_rays(o, d)
+    assert (ids != H.NONE).all()
+    v = verts.astype(np.float64)
+    tri = tris[ids]
+    a, b, c = v[tri[:, 0]], v[tri[:, 1]], v[tri[:, 2]]
+
+    def bary_xz(p, a, b, c):
+        d00 = (b[:, 0] - a[:, 0]) * (c[:, 2] - a[:, 2]) - (c[:, 0] - a[:, 0]) * (b[:, 2] - a[:, 2])
+        w1 = ((p[:, 0] - a[:, 0]) * (c[:, 2] - a[:, 2]) - (c[:, 0] - a[:, 0]) * (p[:, 2] - a[:, 2])) / d00
+        w2 = ((b[:, 0] - a[:, 0]) * (p[:, 2] - a[:, 2]) - (p[:, 0] - a[:, 0]) * (b[:, 2] - a[:, 2])) / d00
+        return w1, w2
+    w1, w2 = bary_xz(o.astype(np.float64), a, b, c)
+    eps = 1e-4
+    assert ((w1 > -eps) & (w2 > -eps) & (w1 + w2 < 1 + eps)).all()
+    y = a[:, 1] + w1 * (b[:, 1] - a[:, 1]) + w2 * (c[:, 1] - a[:, 1])
+    np.testing.assert_allclose(500.0 - ts, y, atol=2e-3)
+    # (b) slanted rays from above
+    o2 = np.stack([rng.uniform(100, 450, n), np.full(n, 420.0), rng.uniform(100, 450, n)], 1).astype(np.float32)
+    tgt = np.stack([rng.uniform(70, 485, n), np.full(n, 150.0), rng.uniform(70, 485, n)], 1)
+    d2 = (tgt - o2).astype(np.float32)
+    ids2, ts2, _ = dev.trace_rays(o2, d2)
+    hit = ids2 != H.NONE
+    assert hit.mean() > 0.99
+    tri = tris[ids2[hit]]
+    a, b, c = v[tri[:, 0]], v[tri[:, 1]], v[tri[:, 2]]
+    p = o2[hit].astype(np.float64) + ts2[hit, None].astype(np.float64) * d2[hit].astype(np.float64)
+    nrm = np.cross(b - a, c - a)
+    dist = np.abs(np.einsum("ij,ij->i", p - a, nrm)) / np.linalg.norm(nrm, axis=1)
+    assert dist.max() < 5e-3
+    w1, w2 = bary_xz(p, a, b, c)
+    assert ((w1 > -1e-3) & (w2 > -1e-3) & (w1 + w2 < 1 + 1e-3)).all()
+    # the ray is above the height field at 16 points before the hit: sample heights with vertical probe rays
+    fr = rng.uniform(0.05, 0.95, (hit.sum(), 1))
+    q = o2[hit].astype(np.float64) + fr * ts2[hit, None] * d2[hit].astype(np.float64)
+    inside = (q[:, 0] > 66) & (q[:, 0] < 489) & (q[:, 2] > 66) & (q[:, 2] < 489)
+    po = np.stack([q[:, 0], np.full(len(q), 500.0), q[:, 2]], 1).astype(np.float32)
+    _, tq, _ = dev.trace_rays(po, np.tile(np.array([[0, -1, 0]], np.float32), (len(q), 1)))
+    surf_y = 500.0 - tq
+    assert (q[inside, 1] > surf_y[inside] - 5e-3).all()
+
+
+# ------------------------------------------------------------------------------------------------------------- P2
+def _p2(rtb, orc, ctx, cfg, W, Hh, spp=4096, rr=0, max_z=5.0, pool=0):
+    dev, osc, _ = _scene_pair(rtb, orc, ctx, cfg)
+    prm = rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=3, rr_start_depth=rr, pool_paths=pool)
+    acc, st = dev.render(cfg.camera, prm)
+    prm_o = rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=1234)  # independent sample set
+    oacc, oseg, orej = osc.render(cfg.camera, prm_o)
+    mean_rel, z = H.compare_images(acc, oacc, spp - 0, spp - 0)
+    seg_ratio = st["segments"] / oseg
+    print(f"{cfg.name}: {W}x{Hh}x{spp} mean-lum err {100 * mean_rel:.3f}%  max z {z.max():.2f}  99.9% z {np.quantile(z, 0.999):.2f}"
+          f"  segments gpu/oracle {seg_ratio:.4f}  rejected {st['rejected']}/{orej}")
+    assert st["paths"] == W * Hh * spp
+    assert mean_rel <= 0.01
+    assert z.max() <= max_z
+    if rr == 0:
+        assert abs(seg_ratio - 1) < 0.01  # same expected path length
+    assert st["rejected"] <= 1e-5 * st["paths"] + orej * 2 + 8
+    return acc, oacc, st
+
+
+def test_p2_cornell_mixture_pdf(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    _p2(rtb, orc, ctx, scenes.config_cornell(), 48, 48)
+
+
+def test_p2_random_spheres(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    _p2(rtb, orc, ctx, scenes.config_random_spheres(), 64, 36)
+
+
+def test_p2_final_scene_media_textures_motion(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    _p2(rtb, orc, ctx, scenes.config_final_scene(boxes_per_side=8, n_small=120), 40, 40)
+
+
+def test_p2_mesh_cornell(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    _p2(rtb, orc, ctx, scenes.config_mesh(nx=24, nz=12), 40, 24)
+
+
+def test_p2_cornell_smoke_box_media(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    cfg.world, cfg.lights, cfg.name = scenes.cornell_smoke(), scenes.cornell_smoke_lights(), "cornell_smoke"
+    _p2(rtb, orc, ctx, cfg, 40, 40)
+
+
+def test_p2_checker_perlin_light(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    cfg.world, cfg.lights, cfg.name = scenes.simple_light(), None, "simple_light"
+    cfg.camera = rtb.Camera.new((26, 3, 6), (0, 2, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0)
+    _p2(rtb, orc, ctx, cfg, 48, 32)
+    cfg.world, cfg.name, cfg.background = scenes.two_spheres(), "two_spheres", (0.7, 0.8, 1.0)
+    cfg.camera = rtb.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.0, 10.0)
+    _p2(rtb, orc, ctx, cfg, 48, 32)
+    cfg.world, cfg.name = scenes.earth(), "earth"
+    _p2(rtb, orc, ctx, cfg, 48, 32, spp=1024)
+
+
+def test_p2_russian_roulette_is_unbiased(rtb, orc, ctx):
+    """RR is not in the reference; with it on (GPU) the image must still match the RR-free oracle."""
+    from ray_tracer_archive_b200 import scenes
+    _, _, st = _p2(rtb, orc, ctx, scenes.config_cornell(), 48, 48, rr=3)
+    assert st["segments"] < 48 * 48 * 4096 * 12
+
+
+# ------------------------------------------------------------------------------------------------------ P3 / D1 / misc
+def test_white_furnace_exact(rtb, ctx):
+    from ray_tracer_archive_b200 import scene as S
+    world = S.HittableList([S.Sphere((0, 0, 0), 1.0, S.Lambertian.construct((0.6, 0.6, 0.6)))])
+    dev = rtb.Scene(ctx, rtb.compile_scene(world))
+    cam = rtb.Camera.new((0, 0, 4), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 4.0)
+    acc, st = dev.render(cam, rtb.make_params(64, 64, 16, background=(1, 1, 1)))
+    mean = acc[..., :3] / 16
+    assert abs(mean[32, 32, 0] - 0.6) < 1e-5 and abs(mean[0, 0, 0] - 1.0) < 1e-6
+    assert np.all((mean > 0.6 - 1e-5) & (mean < 1.0 + 1e-5))
+    assert st["rejected"] == 0 and st["segments"] >= 64 * 64 * 16
+
+
+def test_d1_sample_split_matches_single_call(rtb, ctx):
+    """The multi-GPU partition on one GPU: samples [0,n/2) and [n/2,n) accumulated by two calls == one call of n
+    samples (same global sample indices -> same sample set; only the f32 summation order differs)."""
+    from ray_tracer_archive_b200 import scenes, parallel
+    cfg = scenes.config_cornell()
+    dev = rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights))
+    W = Hh = 64
+    spp = 64
+    one, st1 = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, seed=9))
+    f0, c0 = parallel.rank_sample_range(spp, 0, 2)
+    f1, c1 = parallel.rank_sample_range(spp, 1, 2)
+    assert (f0, c0, f1, c1) == (0, 32, 32, 32)
+    dev.render(cfg.camera, rtb.make_params(W, Hh, c0, seed=9, sample_offset=f0, total_spp=spp), readback=False)
+    two, st2 = dev.render(cfg.camera, rtb.make_params(W, Hh, c1, seed=9, sample_offset=f1, total_spp=spp,
+                                                      flags=rtb._ffi.RENDER_ACCUMULATE))
+    np.testing.assert_allclose(two, one, rtol=2e-4, atol=1e-4)
+    # scheduling independence: a different pool size gives the same sample set
+    three, _ = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, seed=9, pool_paths=5000))
+    np.testing.assert_allclose(three, one, rtol=2e-4, atol=1e-4)
+    assert st1["segments"] > 0
+
+
+def test_finalize_rgb8_matches_write_color(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    dev = rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights))
+    acc, _ = dev.render(cfg.camera, rtb.make_params(32, 32, 64))
+    rgb = dev.finalize_rgb8(32, 32, 64)
+    lib = orc.load()
+    out = np.zeros(3, np.uint8)
+    worst = 0
+    for yx in [(0, 0), (5, 7), (16, 16), (31, 31), (2, 16)]:
+        s = np.ascontiguousarray(acc[yx][:3], dtype=np.float64)
+        lib.orc_write_color(s.ctypes.data_as(C.c_void_p), 64, out.ctypes.data_as(C.c_void_p))
+        worst = max(worst, int(np.abs(out.astype(int) - rgb[yx].astype(int)).max()))
+    assert worst <= 1  # f32 sqrt vs f64 sqrt may straddle an integer boundary
+
+
+def test_abi_state_errors(rtb, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    s = rtb.Scene(ctx)
+    with pytest.raises(rtb.RtbError) as e:
+        s.render(cfg.camera, rtb.make_params(8, 8, 1))
+    assert e.value.code == -4
+    s.set_compiled(rtb.compile_scene(cfg.world, cfg.lights))
+    s.commit()
+    with pytest.raises(rtb.RtbError):
+        s.render(cfg.camera, rtb.make_params(1, 8, 1))     # W-1 == 0 (main.rs:752)
+    with pytest.raises(rtb.RtbError):
+        s.render(cfg.camera, rtb.make_params(8, 8, 1, max_depth=0))
+    acc, st = s.render(cfg.camera, rtb.make_params(8, 8, 2))
+    assert st["paths"] == 128 and np.isfinite(acc).all()
+    info = ctx.device_info()
+    assert info["sm_count"] > 0
