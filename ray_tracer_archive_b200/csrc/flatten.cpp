@@ -338,9 +338,9 @@ void pack_quad(HostPrim& p, const double Q[3], const double U[3], const double V
 void pack_tri(HostPrim& p, const double v0[3], const double v1[3], const double v2[3]) {
   double lo[3], hi[3];
   for (int a = 0; a < 3; ++a) {
-    p.g[a] = (float)v0[a];
-    p.g[4 + a] = (float)(v1[a] - v0[a]);
-    p.g[8 + a] = (float)(v2[a] - v0[a]);
+    p.g[a] = (float)v0[a];      // vertices, not edges: the watertight test needs the shared vertices bit-identical
+    p.g[4 + a] = (float)v1[a];
+    p.g[8 + a] = (float)v2[a];
     lo[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
     hi[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
   }

@@ -213,22 +213,45 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     float alpha = dot(xyz(w1), p) - w1.w;
     float beta = dot(xyz(w2), p) - w2.w;
     if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) return;
-  } else if (type == PT_TRI) {  // Moller-Trumbore, closed t-range like aarect.rs:33
-    float4 w0 = __ldg(sc.geom[PT_TRI] + 3 * idx);
-    float4 w1 = __ldg(sc.geom[PT_TRI] + 3 * idx + 1);
-    float4 w2 = __ldg(sc.geom[PT_TRI] + 3 * idx + 2);
-    float3 e1 = xyz(w1), e2 = xyz(w2);
-    float3 pv = cross(d, e2);
-    float det = dot(e1, pv);
+  } else if (type == PT_TRI) {
+    // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
+    // Watertight edge functions (Woop, Benthin, Wald 2013): vertices are translated to the ray origin and sheared so
+    // the ray runs along +z; the edge function of a shared edge is computed from the SAME two translated vertices by
+    // both triangles (exact negatives, no FMA contraction), so f32 rounding can never open a crack in a mesh.
+    const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx));
+    const float3 v1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1));
+    const float3 v2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const int kz = ax > ay ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    // (kx, ky, kz) cyclic; swapped when d[kz] < 0 to keep the winding
+    float3 dp = kz == 0 ? f3(d.y, d.z, d.x) : (kz == 1 ? f3(d.z, d.x, d.y) : d);
+    float3 A = v0 - o, B = v1 - o, C = v2 - o;
+    A = kz == 0 ? f3(A.y, A.z, A.x) : (kz == 1 ? f3(A.z, A.x, A.y) : A);
+    B = kz == 0 ? f3(B.y, B.z, B.x) : (kz == 1 ? f3(B.z, B.x, B.y) : B);
+    C = kz == 0 ? f3(C.y, C.z, C.x) : (kz == 1 ? f3(C.z, C.x, C.y) : C);
+    if (dp.z < 0.0f) {
+      float s;
+      s = dp.x; dp.x = dp.y; dp.y = s;
+      s = A.x; A.x = A.y; A.y = s;
+      s = B.x; B.x = B.y; B.y = s;
+      s = C.x; C.x = C.y; C.y = s;
+    }
+    const float Sz = 1.0f / dp.z, Sx = dp.x * Sz, Sy = dp.y * Sz;
+    const float Ax = __fsub_rn(A.x, __fmul_rn(Sx, A.z)), Ay = __fsub_rn(A.y, __fmul_rn(Sy, A.z));
+    const float Bx = __fsub_rn(B.x, __fmul_rn(Sx, B.z)), By = __fsub_rn(B.y, __fmul_rn(Sy, B.z));
+    const float Cx = __fsub_rn(C.x, __fmul_rn(Sx, C.z)), Cy = __fsub_rn(C.y, __fmul_rn(Sy, C.z));
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // exactly on an edge in f32: decide in f64 (products are exact there)
+      U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+      V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+      W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
+    const float det = U + V + W;
     if (det == 0.0f) return;
-    float inv = 1.0f / det;
-    float3 tv = o - xyz(w0);
-    float u = dot(tv, pv) * inv;
-    if (u < 0.0f || u > 1.0f) return;
-    float3 qv = cross(tv, e1);
-    float v = dot(d, qv) * inv;
-    if (v < 0.0f || u + v > 1.0f) return;
-    t = dot(e2, qv) * inv;
+    t = (U * (Sz * A.z) + V * (Sz * B.z) + W * (Sz * C.z)) / det;
     if (!(t >= tmin && t <= best.t)) return;
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);

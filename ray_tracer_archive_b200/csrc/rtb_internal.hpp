@@ -25,7 +25,7 @@ struct HostPrim {      // one flattened primitive, any type
   uint32_t prim_id;    // list-order id (hittable_list.rs:43-49)
   uint32_t material;
   uint32_t face_mode;  // FaceMode
-  float g[12];         // device geometry words (see pack_* in flatten.cpp)
+  float g[12];         // device geometry words: sphere (c,r); moving (A,r)(B,0); quad plane form; triangle v0,v1,v2
   float lo[3], hi[3];  // bounds (padded)
 };
 

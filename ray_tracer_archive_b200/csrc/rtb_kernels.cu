@@ -129,7 +129,8 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, flo
   } else if (type == PT_QUAD) {
     s.outward = xyz(__ldg(sc.geom[PT_QUAD] + 3 * idx));
   } else {
-    const float3 e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)), e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
+    const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx));
+    const float3 e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)) - v0, e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2)) - v0;
     s.outward = unit(cross(e1, e2));
   }
   const uint32_t info = __ldg(&sc.info[type][idx].y);
@@ -154,8 +155,8 @@ __device__ __forceinline__ void surface_uv(const DevScene& sc, const Surf& s, fl
     u = dot(xyz(w1), s.p) - w1.w;
     v = dot(xyz(w2), s.p) - w2.w;
   } else if (type == PT_TRI) {
-    const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx)), e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)),
-                 e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
+    const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx)), e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)) - v0,
+                 e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2)) - v0;
     const float3 nn = cross(e1, e2), pl = s.p - v0;
     const float inv = 1.0f / dot(nn, nn);
     u = dot(nn, cross(pl, e2)) * inv;

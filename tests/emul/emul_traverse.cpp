@@ -12,6 +12,8 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   uint8_t b[8];
@@ -21,6 +23,7 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   return r;
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+#undef __forceinline__
 #define __forceinline__ inline
 
 #include "../../ray_tracer_archive_b200/csrc/rtb_device.cuh"
