@@ -73,6 +73,26 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def measure_l2_bandwidth(torch):
+    """L2-resident copy (read + write bytes) of 48 MB -> 48 MB (96 MB < 126 MB L2), best of 5 runs of 50 copies.
+    MEASURED_PEAKS.json has no L2 figure (SURVEY §8d asks the builder to measure one)."""
+    n = 48 << 20
+    a = torch.empty(n, dtype=torch.uint8, device="cuda")
+    b = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        b.copy_(a)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 50 * 2 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -265,17 +285,25 @@ def main():
         ach_gbs = bytes_seg * seg_per_launch / (avg_launch_ms * 1e-3) / 1e9
         scene_bytes = info["bvh_bytes"] + info["prim_bytes"]
         in_l2 = scene_bytes <= dev["l2_bytes"]
-        t_flops, t_bytes = flops_seg / (fp32_peak * 1e12), bytes_seg / (peaks["hbm_gbs"] * 1e9)
+        # BASELINE.json: roofline = slower of FP32 intersection math at peak and BVH/primitive bytes at L2 bandwidth
+        # (scene <= L2) or HBM bandwidth (scene > L2).  L2 bandwidth: measured here by an L2-resident copy.
+        l2_gbs = measure_l2_bandwidth(torch)
+        mem_gbs, mem_name = (l2_gbs, "l2") if in_l2 else (peaks["hbm_gbs"], "hbm")
+        t_flops, t_bytes = flops_seg / (fp32_peak * 1e12), bytes_seg / (mem_gbs * 1e9)
+        fp_bound = t_flops >= t_bytes
         roofline = {
-            "kernel": "k_extend", "bound": "fp32" if t_flops >= t_bytes else "hbm",
-            "achieved": ach_tflops if t_flops >= t_bytes else ach_gbs,
-            "peak": fp32_peak if t_flops >= t_bytes else peaks["hbm_gbs"],
-            "unit": "TFLOP/s" if t_flops >= t_bytes else "GB/s",
-            "frac": (ach_tflops / fp32_peak) if t_flops >= t_bytes else (ach_gbs / peaks["hbm_gbs"]),
+            "kernel": "k_extend", "bound": "fp32" if fp_bound else mem_name,
+            "achieved": ach_tflops if fp_bound else ach_gbs,
+            "peak": fp32_peak if fp_bound else mem_gbs,
+            "unit": "TFLOP/s" if fp_bound else "GB/s",
+            "frac": (ach_tflops / fp32_peak) if fp_bound else (ach_gbs / mem_gbs),
             "traffic": None,
-            "peak_source": f"FP32 = SMs*128*2*f_SM at the median SM clock seen in this run ({sm_mhz:.0f} MHz); HBM {which} {peaks['hbm_gbs']} GB/s",
+            "peak_source": f"FP32 = SMs*128*2*f_SM at the median SM clock seen in this run ({sm_mhz:.0f} MHz) = {fp32_peak:.1f} TFLOP/s; "
+                           f"L2 = {l2_gbs:.0f} GB/s measured in this run (L2-resident 2x48 MB copy); HBM {which} {peaks['hbm_gbs']} GB/s",
+            "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_peak, "frac": ach_tflops / fp32_peak},
             "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": ach_gbs / peaks["hbm_gbs"],
                     "scene_bytes": scene_bytes, "scene_fits_l2": bool(in_l2)},
+            "l2": {"achieved_gbs": ach_gbs, "peak_gbs": l2_gbs, "frac": ach_gbs / l2_gbs},
             "algorithmic": {"nodes_per_segment": nodes_per_seg, "prims_per_segment": prims_per_seg,
                             "flops_per_segment": flops_seg, "bytes_per_segment": bytes_seg,
                             "segments_per_launch": seg_per_launch},

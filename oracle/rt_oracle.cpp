@@ -650,7 +650,7 @@ static SampleOut ray_color(const Scene& sc, Ray r, V3 background, int max_depth,
     }
     if (rr_start > 0 && segments >= rr_start) {  // Russian roulette (not in the reference; unbiased)
       double q = std::fmax(beta.x, std::fmax(beta.y, beta.z));
-      q = q < 0.05 ? 0.05 : (q > 1.0 ? 1.0 : q);
+      q = q < 0.2 ? 0.2 : (q > 1.0 ? 1.0 : q);
       if (!(ua[0] < q)) break;
       beta = beta / q;
     }

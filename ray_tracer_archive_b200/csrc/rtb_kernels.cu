@@ -317,7 +317,7 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
   bool alive = scattered && (int)io.segs < prm.max_depth;
   if (alive && prm.rr_start > 0 && io.segs >= prm.rr_start) {
     float qv = fmaxf(io.beta.x, fmaxf(io.beta.y, io.beta.z));
-    qv = qv < 0.05f ? 0.05f : (qv > 1.0f ? 1.0f : qv);
+    qv = qv < 0.2f ? 0.2f : (qv > 1.0f ? 1.0f : qv);  // survival probability in [0.2, 1]: weights grow by <= 5x
     if (!(rr_xi < qv)) alive = false;
     else io.beta = (1.0f / qv) * io.beta;
   }

@@ -118,8 +118,11 @@ def synthetic_earth(width=1024, height=512, seed=7) -> np.ndarray:
     return img
 
 
-def final_scene(seed=1, boxes_per_side=20, n_small=1000, earth: Optional[np.ndarray] = None) -> HittableList:
-    """main.rs:521-649 (commented in the reference)."""
+def final_scene(seed=1, boxes_per_side=20, n_small=1000, earth: Optional[np.ndarray] = None,
+                flip_light=True) -> HittableList:
+    """main.rs:521-649 (commented in the reference).  flip_light: the commented scene predates the front_face test in
+    DiffuseLight::emitted (material.rs:184-190); with the live emitted() its un-flipped ceiling light would shine
+    upward only, so it is wrapped in FlipFace exactly like the live cornell_box does (main.rs:360-362)."""
     rng = np.random.default_rng(seed)
     boxes1 = HittableList.new()
     ground = Lambertian.construct((0.48, 0.83, 0.53))
@@ -132,7 +135,8 @@ def final_scene(seed=1, boxes_per_side=20, n_small=1000, earth: Optional[np.ndar
     objects = HittableList.new()
     objects.add(BVHNode.construct2(boxes1, 0.0, 1.0))
     light = DiffuseLight.construct_color((7.0, 7.0, 7.0))
-    objects.add(XzRect.construct(123.0, 423.0, 147.0, 412.0, 554.0, light))
+    lrect = XzRect.construct(123.0, 423.0, 147.0, 412.0, 554.0, light)
+    objects.add(FlipFace.construct(lrect) if flip_light else lrect)
     center1 = (400.0, 400.0, 200.0)
     center2 = (430.0, 400.0, 200.0)
     objects.add(MovingSphere.construct(center1, center2, 0.0, 1.0, 50.0, Lambertian.construct((0.7, 0.3, 0.1))))
@@ -269,7 +273,7 @@ def simple_light(seed=1) -> HittableList:  # main.rs:300-335
     return objects
 
 
-def cornell_smoke() -> HittableList:  # main.rs:435-519
+def cornell_smoke(flip_light=True) -> HittableList:  # main.rs:435-519 (flip_light: see final_scene)
     objects = HittableList.new()
     red = Lambertian.construct((0.65, 0.05, 0.05))
     white = Lambertian.construct((0.73, 0.73, 0.73))
@@ -277,7 +281,8 @@ def cornell_smoke() -> HittableList:  # main.rs:435-519
     light = DiffuseLight.construct_color((7.0, 7.0, 7.0))
     objects.add(YzRect.construct(0.0, 555.0, 0.0, 555.0, 555.0, green))
     objects.add(YzRect.construct(0.0, 555.0, 0.0, 555.0, 0.0, red))
-    objects.add(XzRect.construct(113.0, 443.0, 127.0, 432.0, 554.0, light))
+    lrect = XzRect.construct(113.0, 443.0, 127.0, 432.0, 554.0, light)
+    objects.add(FlipFace.construct(lrect) if flip_light else lrect)
     objects.add(XzRect.construct(0.0, 555.0, 0.0, 555.0, 555.0, white))
     objects.add(XzRect.construct(0.0, 555.0, 0.0, 555.0, 0.0, white))
     objects.add(XyRect.construct(0.0, 555.0, 0.0, 555.0, 555.0, white))

