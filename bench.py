@@ -93,6 +93,32 @@ def measure_l2_bandwidth(torch):
     return best
 
 
+def bounded_cpu_sample(osc, rtb, cfg, cores, budget_s=12.0):
+    """Times the oracle (the reference's CPU algorithm) on a bounded sample of the workload: a probe render at 1/16
+    resolution calibrates the rate, then full resolution with as many spp as fit the budget, or a reduced resolution at
+    1 spp when even that does not fit (the 1M-triangle linear scan).  Rate in segments/s is spp- and
+    resolution-independent to first order; the sample is stated in the JSON."""
+    pw, ph = max(cfg.width // 16, 8), max(cfg.height // 16, 8)
+    prm = rtb.make_params(pw, ph, 1, cfg.max_depth, cfg.background, seed=1)
+    t0 = time.perf_counter()
+    osc.render(cfg.camera, prm, threads=cores)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    paths_budget = pw * ph / dt * budget_s
+    npix = cfg.width * cfg.height
+    if paths_budget >= npix:
+        w, h, spp = cfg.width, cfg.height, int(min(max(paths_budget // npix, 1), 64))
+    else:
+        k = (paths_budget / npix) ** 0.5
+        w, h, spp = max(int(cfg.width * k), 8), max(int(cfg.height * k), 8), 1
+    prm = rtb.make_params(w, h, spp, cfg.max_depth, cfg.background, seed=1)
+    t0 = time.perf_counter()
+    _, segs, _ = osc.render(cfg.camera, prm, threads=cores)
+    dt = time.perf_counter() - t0
+    sample = (f"{spp} spp at {w}x{h} (full size {cfg.width}x{cfg.height}); {segs} segments in {dt:.1f} s; f64 oracle, "
+              "linear HittableList scan as the reference executes")
+    return segs, dt, sample
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -113,19 +139,13 @@ def run_reference(args, rank):
     cs = rtb.compile_scene(cfg.world, cfg.lights)
     osc = orc.OracleScene(cs)
     cores = os.cpu_count() or 1
-    sample_spp = 1
-    prm = rtb.make_params(cfg.width, cfg.height, sample_spp, cfg.max_depth, cfg.background, seed=1)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        osc.render(cfg.camera, prm, threads=cores)
-    t0 = time.perf_counter()
-    segs = 0
+    segs, dt, sample = 0, 0.0, ""
+    budget = 12.0 if args.steps <= 3 else max(40.0 / args.steps, 3.0)
     for k in range(args.steps):
-        prm.sample_offset = k
-        _, s, _ = osc.render(cfg.camera, prm, threads=cores)
-        segs += s
-    dt = time.perf_counter() - t0
+        s_, d_, sample = bounded_cpu_sample(osc, rtb, cfg, cores, budget_s=budget)
+        segs += s_
+        dt += d_
     val = segs / dt / 1e6
-    sample = f"{sample_spp} spp at full {cfg.width}x{cfg.height} per step (linear HittableList scan, f64, as the reference executes)"
     print(json.dumps({
         "impl": "reference", "metric": "path segments/sec", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -317,14 +337,8 @@ def main():
             orc.build()
             osc = orc.OracleScene(cs)
             cores = os.cpu_count() or 1
-            cspp = 2
-            cprm = rtb.make_params(cfg.width, cfg.height, cspp, cfg.max_depth, cfg.background, seed=1)
-            t0 = time.perf_counter()
-            _, csegs, _ = osc.render(cfg.camera, cprm, threads=cores)
-            cdt = time.perf_counter() - t0
-            cpu_baseline = {"value": csegs / cdt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                            "sample": f"{cspp} spp at full {cfg.width}x{cfg.height} ({csegs} segments in {cdt:.1f} s), "
-                                      "f64 oracle, linear HittableList scan as the reference executes"}
+            csegs, cdt, csample = bounded_cpu_sample(osc, rtb, cfg, cores)
+            cpu_baseline = {"value": csegs / cdt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": csample}
         line = {
             "metric": "path segments/sec", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
