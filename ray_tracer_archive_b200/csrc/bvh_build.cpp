@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
 
 #include "rtb_internal.hpp"
@@ -43,6 +44,7 @@ struct Builder {
   std::vector<uint32_t> order;      // indices into hs.prims for the current type
   std::vector<float> centroid;      // 3 per prim (indexed by prim index)
   std::vector<BinNode> bin;
+  uint32_t max_leaf = 1;            // primitives per leaf slot (1..3)
 
   int build_range(uint32_t first, uint32_t count) {
     int me = (int)bin.size();
@@ -56,7 +58,7 @@ struct Builder {
     bin[me].box = box;
     bin[me].first = first;
     bin[me].count = count;
-    if (count <= 3) return me;
+    if (count <= max_leaf) return me;
     // binned SAH over the widest centroid axis first, all three axes evaluated
     const int NB = 16;
     float best_cost = INFINITY;
@@ -231,6 +233,10 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   std::vector<TypedTree> trees;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     Builder* b = new Builder{hs, {}, {}, {}};
+    // one primitive per leaf slot: a sphere/quad test costs more than a (quantised) box test and single-primitive
+    // leaves fill the 8 slots of a node; triangles keep up to 2 per slot to bound the node count of large meshes
+    b->max_leaf = (t == PT_TRI) ? 2u : 1u;
+    if (const char* e = getenv("RTB_MAX_LEAF")) b->max_leaf = (uint32_t)std::max(1, std::min(3, atoi(e)));
     builders.push_back(b);
     for (size_t i = 0; i < np; ++i)
       if (hs.prims[i].type == t) b->order.push_back((uint32_t)i);

@@ -58,6 +58,8 @@ struct DevCounters {
   uint32_t n_dead;
   uint32_t cur;       // which n_ext/q_ext is being extended this iteration
   uint32_t iter;
+  uint32_t ext_cursor;  // next unclaimed entry of the extend queue (dynamic ray fetch)
+  uint32_t _pad;
   unsigned long long next_path, total_paths;
   unsigned long long segments, rejected, paths_started;
   unsigned long long nodes_visited, prims_tested;
@@ -271,89 +273,118 @@ __device__ __forceinline__ float q2f(uint32_t word, uint32_t sel) {
 // Wide-BVH closest-hit traversal.  `snodes` = first `n_snodes` nodes staged in shared memory (uint4 x5 each);
 // the rest are fetched with 128-bit read-only loads.  Semantics = HittableList::hit (hittable_list.rs:39-51)
 // over all surface primitives; media are handled by the caller.
+// The traversal is split into trav_init / trav_step (ONE node visit or one stack pop per call) so that the extend
+// kernel can keep all 32 lanes of a warp busy by swapping finished rays for new ones between steps.
+struct Trav {
+  float3 o, d;
+  float idx, idy, idz, time;
+  uint32_t octinv;  // 7 ^ (sign bits of d): children are visited in descending (slot ^ octinv)
+  uint2 grp;        // current node group: x = first child node, y = hit-priority mask << 8 | internal mask
+  int sp;
+  Closest best;
+};
+
+__device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float time) {
+  const float tiny = 1e-30f;
+  tv.o = o; tv.d = d; tv.time = time;
+  tv.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
+  tv.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+  tv.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+  tv.octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+  tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
+  tv.sp = 0;
+  tv.best = Closest{INFINITY, REF_MISS, 0u};
+}
+
+// returns false when the traversal is complete
+template <bool COUNT>
+__device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
+                                          Trav& tv, uint2* __restrict__ stack, float tmin,
+                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
+  if (!(tv.grp.y & 0xFF00u)) {
+    if (tv.sp == 0) return false;
+    tv.grp = stack[--tv.sp];
+    return true;
+  }
+  const uint32_t octinv = tv.octinv;
+  uint32_t hits = tv.grp.y >> 8;
+  const uint32_t prio = 31u - __clz(hits);
+  hits &= ~(1u << prio);
+  const uint32_t slot = prio ^ octinv;
+  const uint32_t gmask = tv.grp.y & 0xFFu;
+  const uint32_t node = tv.grp.x + __popc(gmask & ((1u << slot) - 1u));
+  if (hits) stack[tv.sp++] = make_uint2(tv.grp.x, (hits << 8) | gmask);
+  if (COUNT) ++n_nodes_visited;
+  uint4 w0, w1, w2, w3, w4;
+  if (node < n_snodes) {
+    const uint4* p = snodes + 5 * node;
+    w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3]; w4 = p[4];
+  } else {
+    const uint4* p = sc.nodes + 5 * (size_t)node;
+    w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3); w4 = __ldg(p + 4);
+  }
+  const uint32_t imask = w0.w >> 24;
+  const bool nx = !(octinv & 1u), ny = !(octinv & 2u), nz = !(octinv & 4u);  // direction component negative
+  // t = q * (step * idir) + (origin - o) * idir ; widened by the f32 rounding bound so that no true hit is culled
+  const float ax = __uint_as_float((w0.w & 0xFFu) << 23) * tv.idx;
+  const float ay = __uint_as_float(((w0.w >> 8) & 0xFFu) << 23) * tv.idy;
+  const float az = __uint_as_float(((w0.w >> 16) & 0xFFu) << 23) * tv.idz;
+  const float bx = (__uint_as_float(w0.x) - tv.o.x) * tv.idx;
+  const float by = (__uint_as_float(w0.y) - tv.o.y) * tv.idy;
+  const float bz = (__uint_as_float(w0.z) - tv.o.z) * tv.idz;
+  const float eps = 4.0e-7f;
+  const float ex = eps * fmaf(256.0f, fabsf(ax), fabsf(bx));
+  const float ey = eps * fmaf(256.0f, fabsf(ay), fabsf(by));
+  const float ez = eps * fmaf(256.0f, fabsf(az), fabsf(bz));
+  const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
+  // near/far plane words per axis (children 0-3 | 4-7)
+  const uint32_t nx0 = nx ? w3.z : w2.x, nx1 = nx ? w3.w : w2.y, fx0 = nx ? w2.x : w3.z, fx1 = nx ? w2.y : w3.w;
+  const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
+  const uint32_t nz0 = nz ? w4.z : w3.x, nz1 = nz ? w4.w : w3.y, fz0 = nz ? w3.x : w4.z, fz1 = nz ? w3.y : w4.w;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t sel = 0x7540u | (uint32_t)(i & 3);
+    const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, sel), ax, bnx);
+    const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, sel), ay, bny);
+    const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, sel), az, bnz);
+    const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, sel), ax, bfx);
+    const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, sel), ay, bfy);
+    const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, sel), az, bfz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tv.best.t));
+    if (tn <= tf) hitmask |= 1u << i;
+  }
+  // leaf children: intersect now (all primitives of one node share a type)
+  uint32_t leaf = hitmask & ~imask;
+  const uint32_t ptype = w1.y >> REF_TYPE_SHIFT, pbase = w1.y & REF_INDEX_MASK;
+  while (leaf) {
+    const uint32_t s = __ffs(leaf) - 1;
+    leaf &= leaf - 1;
+    const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
+    const uint32_t cnt = m >> 5, first = pbase + (m & 31u);
+    for (uint32_t k = 0; k < cnt; ++k)
+      intersect_prim<COUNT>(sc, ptype, first + k, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+  }
+  // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
+  uint32_t ih = hitmask & imask;
+  if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
+  if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
+  if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
+  tv.grp = make_uint2(w1.x, (ih << 8) | imask);
+  return true;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
-  const float tiny = 1e-30f;
-  float idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-  float idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-  float idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
-  const bool nx = d.x < 0.0f, ny = d.y < 0.0f, nz = d.z < 0.0f;
-  const uint32_t octinv = 7u ^ ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+  Trav tv;
   uint2 stack[RTB_STACK];
-  int sp = 0;
-  uint2 grp = make_uint2(0u, (1u << (octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
-  for (;;) {
-    if (grp.y & 0xFF00u) {
-      uint32_t hits = grp.y >> 8;
-      const uint32_t prio = 31u - __clz(hits);
-      hits &= ~(1u << prio);
-      const uint32_t slot = prio ^ octinv;
-      const uint32_t gmask = grp.y & 0xFFu;
-      const uint32_t node = grp.x + __popc(gmask & ((1u << slot) - 1u));
-      if (hits) stack[sp++] = make_uint2(grp.x, (hits << 8) | gmask);
-      if (COUNT) ++n_nodes_visited;
-      uint4 w0, w1, w2, w3, w4;
-      if (node < n_snodes) {
-        const uint4* p = snodes + 5 * node;
-        w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3]; w4 = p[4];
-      } else {
-        const uint4* p = sc.nodes + 5 * (size_t)node;
-        w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3); w4 = __ldg(p + 4);
-      }
-      const uint32_t imask = w0.w >> 24;
-      // t = q * (step * idir) + (origin - o) * idir ; widened by the f32 rounding bound so that no true hit is culled
-      const float ax = __uint_as_float((w0.w & 0xFFu) << 23) * idx;
-      const float ay = __uint_as_float(((w0.w >> 8) & 0xFFu) << 23) * idy;
-      const float az = __uint_as_float(((w0.w >> 16) & 0xFFu) << 23) * idz;
-      const float bx = (__uint_as_float(w0.x) - o.x) * idx;
-      const float by = (__uint_as_float(w0.y) - o.y) * idy;
-      const float bz = (__uint_as_float(w0.z) - o.z) * idz;
-      const float eps = 4.0e-7f;
-      const float ex = eps * fmaf(256.0f, fabsf(ax), fabsf(bx));
-      const float ey = eps * fmaf(256.0f, fabsf(ay), fabsf(by));
-      const float ez = eps * fmaf(256.0f, fabsf(az), fabsf(bz));
-      const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
-      // near/far plane words per axis (children 0-3 | 4-7)
-      const uint32_t nx0 = nx ? w3.z : w2.x, nx1 = nx ? w3.w : w2.y, fx0 = nx ? w2.x : w3.z, fx1 = nx ? w2.y : w3.w;
-      const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
-      const uint32_t nz0 = nz ? w4.z : w3.x, nz1 = nz ? w4.w : w3.y, fz0 = nz ? w3.x : w4.z, fz1 = nz ? w3.y : w4.w;
-      uint32_t hitmask = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t sel = 0x7540u | (uint32_t)(i & 3);
-        const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, sel), ax, bnx);
-        const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, sel), ay, bny);
-        const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, sel), az, bnz);
-        const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, sel), ax, bfx);
-        const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, sel), ay, bfy);
-        const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, sel), az, bfz);
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, best.t));
-        if (tn <= tf) hitmask |= 1u << i;
-      }
-      // leaf children: intersect now (all primitives of one node share a type)
-      uint32_t leaf = hitmask & ~imask;
-      const uint32_t ptype = w1.y >> REF_TYPE_SHIFT, pbase = w1.y & REF_INDEX_MASK;
-      while (leaf) {
-        const uint32_t s = __ffs(leaf) - 1;
-        leaf &= leaf - 1;
-        const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
-        const uint32_t cnt = m >> 5, first = pbase + (m & 31u);
-        for (uint32_t k = 0; k < cnt; ++k) intersect_prim<COUNT>(sc, ptype, first + k, o, d, time, tmin, best, n_tests);
-      }
-      // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
-      uint32_t ih = hitmask & imask;
-      if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
-      if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
-      if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
-      grp = make_uint2(w1.x, (ih << 8) | imask);
-    } else {
-      if (sp == 0) break;
-      grp = stack[--sp];
-    }
-  }
+  trav_init(tv, o, d, time);
+  tv.best = best;
+  while (trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
+  best = tv.best;
 }
 
 // ConstantMedium::hit, constant_medium.rs:31-71, for the (few) media of the scene; the boundary interval is found

@@ -47,8 +47,14 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 }
 
 // ---- extend ------------------------------------------------------------------------------------------------------
+// Persistent warps with dynamic ray fetch: every lane owns one in-flight ray and advances it by ONE node visit (or
+// stack pop) per loop iteration, so the 32 lanes execute the node-decode code together.  Rays finish after different
+// numbers of visits; instead of idling until the slowest lane is done (17 of 32 lanes active in the first version,
+// profiles/r1_c1_ncu_summary.md), finished lanes are written out and refilled from the queue as soon as
+// RTB_REFILL_LANES of them are waiting.  Work is claimed from a device-side cursor, one atomic per refill per warp.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
+#define RTB_REFILL_LANES 8
 template <bool COUNT>
 __global__ void __launch_bounds__(RTB_EXTEND_THREADS)
 k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
@@ -59,45 +65,79 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   if (n == 0) return;
   stage_nodes(sc, snodes, n_snodes);
   const uint32_t* __restrict__ q = pool.q_ext[cur];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
-    const uint32_t i = base + threadIdx.x;
-    const bool valid = i < n;
-    uint32_t slot = 0, queue = Q_COUNT;
-    uint32_t nv = 0, nt = 0;
-    if (valid) {
-      slot = q[i];
-      const float4 ro = pool.ray_o[slot];
-      const float4 rd = pool.ray_d[slot];
-      const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
-      const uint32_t st = __float_as_uint(pool.rad[slot].w);
-      Closest best{INFINITY, REF_MISS, 0u};
-      traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
-      if (sc.n_media)
-        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
-      pool.hit[slot] = make_float2(best.t, __uint_as_float(best.ref));
-      // classify by material (Material trait dispatch, material.rs:11-21)
-      queue = Q_TERMINAL;
-      if (best.ref != REF_MISS) {
-        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
-        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
-        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
-              : mt == RTB_MAT_METAL      ? Q_METAL
-              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
-              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
-                                         : Q_TERMINAL;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
+  uint32_t state = EMPTY, slot = 0;
+  bool exhausted = false;  // warp-uniform: the queue has no more rays
+  Trav tv;
+  uint2 stack[RTB_STACK];
+  uint32_t nv = 0, nt = 0;
+  for (;;) {
+    const uint32_t running = __ballot_sync(0xffffffffu, state == RUNNING);
+    const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
+    const uint32_t waiting = exhausted ? __popc(done) : 32u - __popc(running);
+    if (running == 0u || waiting >= RTB_REFILL_LANES) {
+      // ---- write out finished rays: media, hit record, per-material queues -------------------------------------
+      uint32_t queue = Q_COUNT;
+      if (state == DONE) {
+        if (sc.n_media) {
+          const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
+          const uint32_t st = __float_as_uint(pool.rad[slot].w);
+          intersect_media(sc, tv.o, tv.d, RTB_TMIN, tv.best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+        }
+        pool.hit[slot] = make_float2(tv.best.t, __uint_as_float(tv.best.ref));
+        // classify by material (Material trait dispatch, material.rs:11-21)
+        queue = Q_TERMINAL;
+        if (tv.best.ref != REF_MISS) {
+          const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT, idx = tv.best.ref & REF_INDEX_MASK;
+          const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
+          const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
+          queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
+                : mt == RTB_MAT_METAL      ? Q_METAL
+                : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
+                : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
+                                           : Q_TERMINAL;
+        }
+        state = EMPTY;
+      }
+      if (done) {
+#pragma unroll
+        for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
+      }
+      // ---- refill empty lanes from the extend queue ------------------------------------------------------------
+      if (!exhausted) {
+        const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&c->ext_cursor, (uint32_t)__popc(empty));
+        first = __shfl_sync(0xffffffffu, first, 0);
+        exhausted = first + __popc(empty) >= n;
+        if (state == EMPTY) {
+          const uint32_t i = first + __popc(empty & lt_mask);
+          if (i < n) {
+            slot = q[i];
+            const float4 ro = pool.ray_o[slot];
+            const float4 rd = pool.ray_d[slot];
+            trav_init(tv, xyz(ro), xyz(rd), ro.w);
+            state = RUNNING;
+          }
+        }
+      }
+      if (__ballot_sync(0xffffffffu, state == RUNNING) == 0u) {
+        if (exhausted) break;
+        continue;
       }
     }
-#pragma unroll
-    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
-    if (COUNT) {
-      nv = __reduce_add_sync(0xffffffffu, nv);
-      nt = __reduce_add_sync(0xffffffffu, nt);
-      if ((threadIdx.x & 31u) == 0) {
-        atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-        atomicAdd(&c->prims_tested, (unsigned long long)nt);
-      }
+    if (state == RUNNING) {
+      if (!trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, RTB_TMIN, nv, nt)) state = DONE;
+    }
+  }
+  if (COUNT) {
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if (lane == 0) {
+      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+      atomicAdd(&c->prims_tested, (unsigned long long)nt);
     }
   }
 }
@@ -537,6 +577,7 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
     c->cur = 0;
     c->iter = 0;
     c->next_path = 0;
+    c->ext_cursor = 0;
     c->total_paths = total_paths;
     c->segments = c->rejected = c->paths_started = 0;
     c->nodes_visited = c->prims_tested = 0;
@@ -550,6 +591,7 @@ __global__ void k_advance(DevPool pool) {
   c->n_ext[cur] = 0;
   for (int k = 0; k < (int)Q_COUNT; ++k) c->n_mat[k] = 0;
   c->n_dead = 0;
+  c->ext_cursor = 0;
   c->cur = cur ^ 1u;
   c->iter += 1;
 }
