@@ -7,6 +7,9 @@
 // dense contraction.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "rtb_device.cuh"
 #include "rtb_launch.hpp"
 
@@ -57,7 +60,7 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 #define RTB_REFILL_LANES 8
 template <bool COUNT>
 __global__ void __launch_bounds__(RTB_EXTEND_THREADS)
-k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
+k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes, uint32_t refill_lanes) {
   extern __shared__ uint4 snodes[];
   DevCounters* c = pool.c;
   const uint32_t cur = c->cur;
@@ -77,7 +80,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t running = __ballot_sync(0xffffffffu, state == RUNNING);
     const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
     const uint32_t waiting = exhausted ? __popc(done) : 32u - __popc(running);
-    if (running == 0u || waiting >= RTB_REFILL_LANES) {
+    if (running == 0u || waiting >= refill_lanes) {
       // ---- write out finished rays: media, hit record, per-material queues -------------------------------------
       uint32_t queue = Q_COUNT;
       if (state == DONE) {
@@ -138,6 +141,60 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     if (lane == 0) {
       atomicAdd(&c->nodes_visited, (unsigned long long)nv);
       atomicAdd(&c->prims_tested, (unsigned long long)nt);
+    }
+  }
+}
+
+// The first version: one ray per thread to completion, grid-stride (kept for A/B measurements, RTB_EXTEND_MODE=static).
+template <bool COUNT>
+__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
+k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
+  extern __shared__ uint4 snodes[];
+  DevCounters* c = pool.c;
+  const uint32_t cur = c->cur;
+  const uint32_t n = c->n_ext[cur];
+  if (n == 0) return;
+  stage_nodes(sc, snodes, n_snodes);
+  const uint32_t* __restrict__ q = pool.q_ext[cur];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
+    const uint32_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t slot = 0, queue = Q_COUNT;
+    uint32_t nv = 0, nt = 0;
+    if (valid) {
+      slot = q[i];
+      const float4 ro = pool.ray_o[slot];
+      const float4 rd = pool.ray_d[slot];
+      const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
+      const uint32_t st = __float_as_uint(pool.rad[slot].w);
+      Closest best{INFINITY, REF_MISS, 0u};
+      traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+      if (sc.n_media)
+        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+      pool.hit[slot] = make_float2(best.t, __uint_as_float(best.ref));
+      // classify by material (Material trait dispatch, material.rs:11-21)
+      queue = Q_TERMINAL;
+      if (best.ref != REF_MISS) {
+        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
+        const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
+        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
+        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
+              : mt == RTB_MAT_METAL      ? Q_METAL
+              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
+              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
+                                         : Q_TERMINAL;
+      }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
+    if (COUNT) {
+      nv = __reduce_add_sync(0xffffffffu, nv);
+      nt = __reduce_add_sync(0xffffffffu, nt);
+      if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+        atomicAdd(&c->prims_tested, (unsigned long long)nt);
+      }
     }
   }
 }
@@ -658,10 +715,21 @@ void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& 
   k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
 }
 void launch_advance(const DevPool& pool, cudaStream_t st) { k_advance<<<1, 1, 0, st>>>(pool); }
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
-  if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
-  else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+  static const bool use_static = getenv("RTB_EXTEND_MODE") && !strcmp(getenv("RTB_EXTEND_MODE"), "static");
+  static const uint32_t refill = (uint32_t)env_int("RTB_REFILL_LANES", RTB_REFILL_LANES);
+  if (use_static) {
+    if (count) k_extend_static<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    else k_extend_static<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    return;
+  }
+  if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
+  else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
 }
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
                   cudaStream_t st) {
@@ -694,6 +762,10 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_extend_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_extend_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
