@@ -50,8 +50,7 @@ struct rtb_context {
   cudaDeviceProp prop;
   // wavefront pool
   uint32_t pool_n = 0;
-  DevBuf<float4> ray_o, ray_d, beta, rad;
-  DevBuf<float2> hit;
+  DevBuf<float4> ray, st, hit;
   DevBuf<uint32_t> q_ext0, q_ext1, q_dead;
   DevBuf<uint32_t> q_mat[Q_COUNT];
   DevBuf<DevCounters> counters;
@@ -394,17 +393,24 @@ int rtb_scene_commit(rtb_scene* s) {
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
   }
-  std::vector<float4> mats(hs.materials.size());
-  for (size_t i = 0; i < mats.size(); ++i) {
-    uint32_t ty = hs.materials[i].type, tx = hs.materials[i].texture;
-    float a, b;
+  std::vector<float4> mats(hs.materials.size() * 2);
+  for (size_t i = 0; i < hs.materials.size(); ++i) {
+    uint32_t ty = hs.materials[i].type, tx = hs.materials[i].texture, tt = 0xFFu;
+    float4 rgb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tx < hs.textures.size()) {
+      tt = hs.textures[tx].type;
+      if (tt == RTB_TEX_SOLID) rgb = make_float4((float)hs.textures[tx].rgb[0], (float)hs.textures[tx].rgb[1], (float)hs.textures[tx].rgb[2], 0.f);
+    }
+    float a, b, d;
     std::memcpy(&a, &ty, 4);
     std::memcpy(&b, &tx, 4);
-    mats[i] = make_float4(a, b, (float)hs.materials[i].param, 0.f);
+    std::memcpy(&d, &tt, 4);
+    mats[2 * i] = make_float4(a, b, (float)hs.materials[i].param, d);
+    mats[2 * i + 1] = rgb;
   }
   CU(s->d_materials.upload(mats.data(), mats.size()));
   d.materials = s->d_materials.p;
-  d.n_materials = (uint32_t)mats.size();
+  d.n_materials = (uint32_t)hs.materials.size();
   std::vector<DevTexture> texs(hs.textures.size());
   for (size_t i = 0; i < texs.size(); ++i) {
     const rtb_texture& t = hs.textures[i];
@@ -524,7 +530,7 @@ static void camera_basis(const rtb_camera& c, DevCamera& f, DevCameraF64& g) {  
 // ---- render --------------------------------------------------------------------------------------------------------
 static int ensure_pool(rtb_context* c, uint32_t n) {
   if (c->pool_n == n) return RTB_OK;
-  CU(c->ray_o.resize(n)); CU(c->ray_d.resize(n)); CU(c->beta.resize(n)); CU(c->rad.resize(n)); CU(c->hit.resize(n));
+  CU(c->ray.resize((size_t)n * 2)); CU(c->st.resize((size_t)n * 2)); CU(c->hit.resize(n));
   CU(c->q_ext0.resize(n)); CU(c->q_ext1.resize(n)); CU(c->q_dead.resize(n));
   for (int k = 0; k < (int)Q_COUNT; ++k) CU(c->q_mat[k].resize(n));
   c->pool_n = n;
@@ -568,7 +574,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
 
   DevPool pool;
   pool.n = pool_n;
-  pool.ray_o = c->ray_o.p; pool.ray_d = c->ray_d.p; pool.beta = c->beta.p; pool.rad = c->rad.p; pool.hit = c->hit.p;
+  pool.ray = c->ray.p; pool.st = c->st.p; pool.hit = c->hit.p;
   pool.q_ext[0] = c->q_ext0.p; pool.q_ext[1] = c->q_ext1.p; pool.q_dead = c->q_dead.p;
   for (int k = 0; k < (int)Q_COUNT; ++k) pool.q_mat[k] = c->q_mat[k].p;
   pool.c = c->counters.p;
@@ -613,10 +619,9 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
         CU(cudaEventRecord(c->ext_events[ev_used + 1], st));
         ev_used += 2;
       }
-      launch_shade(s->lc, s->dev, pool, prm, present, st);
-      launch_generate(s->lc, pool, prm, dcam, st);
+      launch_shade(s->lc, s->dev, pool, prm, dcam, present, st);
       launch_advance(pool, st);
-      launches += 3 + n_shade;
+      launches += 2 + n_shade;
       extend_launches += 1;
     }
     iters += check_every;

@@ -38,7 +38,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t n_lights, n_media, n_materials;
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
-  const float4* materials;   // (type bits, texture bits, param, 0)
+  const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
   const DevTexture* textures;
   const float4* perlin_vec[RTB_MAX_TABLES];
   const uint8_t* perlin_perm[RTB_MAX_TABLES];
@@ -67,11 +67,9 @@ struct DevCounters {
 
 struct DevPool {  // wavefront path state, SoA over `n` slots
   uint32_t n;
-  float4* ray_o;   // origin xyz, time
-  float4* ray_d;   // direction xyz (un-normalised, ray.rs), w unused
-  float4* beta;    // throughput rgb, pixel index bits
-  float4* rad;     // radiance rgb, (sample << 8 | segments) bits
-  float2* hit;     // t, ref bits
+  float4* ray;     // [2s] origin xyz, time ; [2s+1] direction xyz (un-normalised, ray.rs), 0   — one 32-byte sector
+  float4* st;      // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
+  float4* hit;     // t, ref bits, (material | face mode << 24) bits, 0
   uint32_t* q_ext[2];
   uint32_t* q_mat[Q_COUNT];
   uint32_t* q_dead;

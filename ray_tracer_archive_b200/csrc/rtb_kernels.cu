@@ -85,23 +85,24 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes, uint32_t r
       uint32_t queue = Q_COUNT;
       if (state == DONE) {
         if (sc.n_media) {
-          const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
-          const uint32_t st = __float_as_uint(pool.rad[slot].w);
+          const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
+          const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
           intersect_media(sc, tv.o, tv.d, RTB_TMIN, tv.best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
         }
-        pool.hit[slot] = make_float2(tv.best.t, __uint_as_float(tv.best.ref));
-        // classify by material (Material trait dispatch, material.rs:11-21)
+        // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
         queue = Q_TERMINAL;
+        uint32_t minfo = 0;
         if (tv.best.ref != REF_MISS) {
           const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT, idx = tv.best.ref & REF_INDEX_MASK;
-          const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
-          const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
+          minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
+          const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
           queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
                 : mt == RTB_MAT_METAL      ? Q_METAL
                 : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
                 : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
                                            : Q_TERMINAL;
         }
+        pool.hit[slot] = make_float4(tv.best.t, __uint_as_float(tv.best.ref), __uint_as_float(minfo), 0.f);
         state = EMPTY;
       }
       if (done) {
@@ -119,8 +120,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes, uint32_t r
           const uint32_t i = first + __popc(empty & lt_mask);
           if (i < n) {
             slot = q[i];
-            const float4 ro = pool.ray_o[slot];
-            const float4 rd = pool.ray_d[slot];
+            const float4 ro = pool.ray[2 * slot];
+            const float4 rd = pool.ray[2 * slot + 1];
             trav_init(tv, xyz(ro), xyz(rd), ro.w);
             state = RUNNING;
           }
@@ -164,27 +165,29 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     uint32_t nv = 0, nt = 0;
     if (valid) {
       slot = q[i];
-      const float4 ro = pool.ray_o[slot];
-      const float4 rd = pool.ray_d[slot];
-      const uint32_t pixel = __float_as_uint(pool.beta[slot].w);
-      const uint32_t st = __float_as_uint(pool.rad[slot].w);
+      const float4 ro = pool.ray[2 * slot];
+      const float4 rd = pool.ray[2 * slot + 1];
       Closest best{INFINITY, REF_MISS, 0u};
       traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
-      if (sc.n_media)
+      if (sc.n_media) {
+        const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
+        const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
         intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
-      pool.hit[slot] = make_float2(best.t, __uint_as_float(best.ref));
-      // classify by material (Material trait dispatch, material.rs:11-21)
+      }
+      // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
       queue = Q_TERMINAL;
+      uint32_t minfo = 0;
       if (best.ref != REF_MISS) {
         const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        const uint32_t mat = type == PT_MEDIUM ? sc.media[idx].material : (__ldg(&sc.info[type][idx].y) & 0xFFFFFFu);
-        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[mat].x));
+        minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
+        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
         queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
               : mt == RTB_MAT_METAL      ? Q_METAL
               : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
               : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
                                          : Q_TERMINAL;
       }
+      pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
     }
 #pragma unroll
     for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
@@ -206,7 +209,7 @@ struct Surf {
   uint32_t mat, ref;
 };
 
-__device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, float3 o, float3 d, float time, float t) {
+__device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uint32_t minfo, float3 o, float3 d, float time, float t) {
   Surf s;
   s.ref = ref;
   s.p = fma3(t, d, o);
@@ -214,7 +217,7 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, flo
   if (type == PT_MEDIUM) {  // constant_medium.rs:65-67: arbitrary normal, front_face = true
     s.n = s.outward = f3(1.f, 0.f, 0.f);
     s.front = true;
-    s.mat = sc.media[idx].material;
+    s.mat = minfo & 0xFFFFFFu;
     return s;
   }
   if (type == PT_SPHERE) {
@@ -230,11 +233,10 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, flo
     const float3 e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)) - v0, e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2)) - v0;
     s.outward = unit(cross(e1, e2));
   }
-  const uint32_t info = __ldg(&sc.info[type][idx].y);
-  s.mat = info & 0xFFFFFFu;
+  s.mat = minfo & 0xFFFFFFu;
   bool ff = dot(d, s.outward) < 0.0f;
   s.n = ff ? s.outward : -s.outward;
-  const uint32_t mode = info >> 24;  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
+  const uint32_t mode = minfo >> 24;  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
   s.front = mode == FACE_NATURAL ? ff : mode == FACE_FLIPPED ? !ff : mode == FACE_TRUE;
   return s;
 }
@@ -285,7 +287,7 @@ __device__ float perlin_noise(const float4* __restrict__ vec, const uint8_t* __r
   return accum;
 }
 
-__device__ float3 tex_value(const DevScene& sc, uint32_t tex, const Surf& s) {
+__device__ float3 tex_value_slow(const DevScene& sc, uint32_t tex, const Surf& s) {
   DevTexture t = sc.textures[tex];
   if (t.type == RTB_TEX_CHECKER) {  // texture.rs:60-69, on the world-space point
     const float sines = sinf(10.f * s.p.x) * sinf(10.f * s.p.y) * sinf(10.f * s.p.z);
@@ -319,6 +321,12 @@ __device__ float3 tex_value(const DevScene& sc, uint32_t tex, const Surf& s) {
     return f3(k * px[0], k * px[1], k * px[2]);
   }
   return f3(t.r, t.g, t.b);
+}
+
+// material word 0 = (type, texture, param, texture type); word 1 = solid albedo (saves the texture fetch)
+__device__ __forceinline__ float3 tex_value(const DevScene& sc, const float4 m0, uint32_t mat, const Surf& s) {
+  if (__float_as_uint(m0.w) == RTB_TEX_SOLID) return xyz(__ldg(&sc.materials[2 * mat + 1]));
+  return tex_value_slow(sc, __float_as_uint(m0.y), s);
 }
 
 struct Onb {  // onb.rs:19-42
@@ -389,21 +397,21 @@ struct PathIO {
   uint32_t slot, pixel, sample, segs;
   float3 o, d, beta, L;
   float time, t;
-  uint32_t ref;
+  uint32_t ref, minfo;
 };
 
 __device__ __forceinline__ PathIO load_path(const DevPool& pool, uint32_t slot) {
   PathIO io;
   io.slot = slot;
-  const float4 ro = pool.ray_o[slot], rd = pool.ray_d[slot], b = pool.beta[slot], r = pool.rad[slot];
-  const float2 h = pool.hit[slot];
+  const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1], b = pool.st[2 * slot], r = pool.st[2 * slot + 1];
+  const float4 h = pool.hit[slot];
   io.o = xyz(ro); io.time = ro.w; io.d = xyz(rd);
   io.beta = xyz(b); io.pixel = __float_as_uint(b.w);
   io.L = xyz(r);
   const uint32_t st = __float_as_uint(r.w);
   io.sample = st >> 8;
   io.segs = (st & 0xFFu) + 1u;  // this hit closes segment number `segs`
-  io.t = h.x; io.ref = __float_as_uint(h.y);
+  io.t = h.x; io.ref = __float_as_uint(h.y); io.minfo = __float_as_uint(h.z);
   return io;
 }
 
@@ -419,14 +427,50 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
     else io.beta = (1.0f / qv) * io.beta;
   }
   if (alive) {
-    pool.ray_o[io.slot] = make_float4(no.x, no.y, no.z, ntime);
-    pool.ray_d[io.slot] = make_float4(nd.x, nd.y, nd.z, 0.f);
-    pool.beta[io.slot] = make_float4(io.beta.x, io.beta.y, io.beta.z, __uint_as_float(io.pixel));
-    pool.rad[io.slot] = make_float4(io.L.x, io.L.y, io.L.z, __uint_as_float((io.sample << 8) | io.segs));
+    pool.ray[2 * io.slot] = make_float4(no.x, no.y, no.z, ntime);
+    pool.ray[2 * io.slot + 1] = make_float4(nd.x, nd.y, nd.z, 0.f);
+    pool.st[2 * io.slot] = make_float4(io.beta.x, io.beta.y, io.beta.z, __uint_as_float(io.pixel));
+    pool.st[2 * io.slot + 1] = make_float4(io.L.x, io.L.y, io.L.z, __uint_as_float((io.sample << 8) | io.segs));
   } else {
     deposit(prm, pool.c, io.pixel, io.L);
   }
   return alive;
+}
+
+// ---- generate: camera.rs:60-70 get_ray + the jitter of main.rs:752-753 ---------------------------------------------
+__device__ __forceinline__ void camera_ray(const DevCamera& cam, const DevParams& prm, uint32_t pixel, uint32_t sample,
+                                           float3& o, float3& d, float& time) {
+  const uint32_t row = pixel / prm.width, col = pixel - row * prm.width;
+  const uint32_t j = prm.height - 1 - row;  // scanline j is stored at image row H-1-j, main.rs:733
+  const float4 u0 = philox_u(pixel, sample, BLK_CAMERA0, 0, prm.seed);
+  const float4 u1 = philox_u(pixel, sample, BLK_CAMERA1, 0, prm.seed);
+  const float s = ((float)col + u0.x) / (float)(prm.width - 1);
+  const float t = ((float)j + u0.y) / (float)(prm.height - 1);
+  // random_in_unit_disk (vec3.rs:101-113) in closed form
+  const float rr = cam.lens_radius * sqrtf(u0.z);
+  float sn, cs;
+  sincosf(2.0f * RTB_PI * u0.w, &sn, &cs);
+  const float3 off = (rr * cs) * ld3(cam.u) + (rr * sn) * ld3(cam.v);
+  o = ld3(cam.origin) + off;
+  d = fma3(s, ld3(cam.horizontal), fma3(t, ld3(cam.vertical), ld3(cam.lmo))) - off;
+  time = fmaf(cam.time1 - cam.time0, u1.x, cam.time0);  // camera.rs:68
+}
+
+// start camera path number `path` in `slot`.  Sample-major order: all pixels (8x4 tiles) of sample k, then k+1, so
+// consecutive path numbers are neighbouring pixels.
+__device__ __forceinline__ void start_path(const DevPool& pool, const DevParams& prm, const DevCamera& cam, uint32_t slot,
+                                           unsigned long long path) {
+  const uint32_t npix = prm.width * prm.height;
+  const uint32_t s_local = (uint32_t)(path / npix);
+  const uint32_t pixel = __ldg(prm.pix_order + (uint32_t)(path - (unsigned long long)s_local * npix));
+  const uint32_t sample = prm.sample_offset + s_local;
+  float3 o, d;
+  float time;
+  camera_ray(cam, prm, pixel, sample, o, d, time);
+  pool.ray[2 * slot] = make_float4(o.x, o.y, o.z, time);
+  pool.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, 0.f);
+  pool.st[2 * slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
+  pool.st[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample << 8));
 }
 
 #define RTB_SHADE_LOOP_BEGIN(QID)                                                        \
@@ -434,6 +478,7 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
   const uint32_t n = c->n_mat[QID];                                                      \
   if (n == 0) return;                                                                    \
   const uint32_t nxt = c->cur ^ 1u;                                                      \
+  const unsigned long long total_paths = c->total_paths;                                 \
   const uint32_t* __restrict__ q = pool.q_mat[QID];                                      \
   const uint32_t stride = gridDim.x * blockDim.x;                                        \
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {              \
@@ -444,23 +489,40 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
     if (valid) {                                                                         \
       slot = q[i];
 
+/* terminated paths are restarted in place (fused regeneration): one 64-bit atomic per warp claims path numbers */  \
 #define RTB_SHADE_LOOP_END                                                               \
     }                                                                                    \
+    {                                                                                    \
+      const bool dead = valid && !alive;                                                 \
+      const uint32_t dmask = __ballot_sync(0xffffffffu, dead);                           \
+      if (dmask) {                                                                       \
+        const uint32_t lane = threadIdx.x & 31u, leader = __ffs(dmask) - 1;              \
+        unsigned long long first = 0;                                                    \
+        if (lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(dmask)); \
+        first = __shfl_sync(0xffffffffu, first, leader);                                 \
+        if (dead) {                                                                      \
+          const unsigned long long path = first + __popc(dmask & ((1u << lane) - 1u));   \
+          if (path < total_paths) {                                                      \
+            start_path(pool, prm, cam, slot, path);                                      \
+            alive = true;                                                                \
+          }                                                                              \
+        }                                                                                \
+      }                                                                                  \
+    }                                                                                    \
     warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);                          \
-    warp_enqueue(pool.q_dead, &c->n_dead, valid && !alive, slot);                        \
   }
 
 // miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
-__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_TERMINAL)
       PathIO io = load_path(pool, slot);
       if (io.ref == REF_MISS) {
         io.L = io.L + io.beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
       } else {
-        const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
-        const float4 m = __ldg(&sc.materials[s.mat]);
+        const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
+        const float4 m = __ldg(&sc.materials[2 * s.mat]);
         if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front)
-          io.L = io.L + io.beta * tex_value(sc, __float_as_uint(m.y), s);
+          io.L = io.L + io.beta * tex_value(sc, m, s.mat, s);
       }
       deposit(prm, c, io.pixel, io.L);
   RTB_SHADE_LOOP_END
@@ -470,9 +532,9 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_terminal(DevScene s
 template <bool ISO>
 __device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t slot) {
   PathIO io = load_path(pool, slot);
-  const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
-  const float4 m = __ldg(&sc.materials[s.mat]);
-  const float3 atten = tex_value(sc, __float_as_uint(m.y), s);
+  const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
+  const float4 m = __ldg(&sc.materials[2 * s.mat]);
+  const float3 atten = tex_value(sc, m, s.mat, s);
   const float4 us = philox_u(io.pixel, io.sample, BLK_SCATTER, io.segs, prm.seed);
   const bool have_lights = sc.n_lights > 0;
   float3 dir;
@@ -506,24 +568,24 @@ __device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool&
   return finish_bounce(pool, prm, io, scattered, s.p, dir, io.time, rr);
 }
 
-__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_LAMBERT)
       alive = shade_diffuse<false>(sc, pool, prm, slot);
   RTB_SHADE_LOOP_END
 }
 
-__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_ISOTROPIC)
       alive = shade_diffuse<true>(sc, pool, prm, slot);
   RTB_SHADE_LOOP_END
 }
 
 // Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
-__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_metal(DevScene sc, DevPool pool, DevParams prm) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_metal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_METAL)
       PathIO io = load_path(pool, slot);
-      const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
-      const float4 m = __ldg(&sc.materials[s.mat]);
+      const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
+      const float4 m = __ldg(&sc.materials[2 * s.mat]);
       const float fuzz = fminf(m.z, 1.0f);
       const float3 ud = unit(io.d);
       float3 dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);  // reflect, vec3.rs:115-117
@@ -535,17 +597,17 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_metal(DevScene sc, 
         sincosf(phi, &sn, &cs);
         dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
       }
-      io.beta = io.beta * tex_value(sc, __float_as_uint(m.y), s);
+      io.beta = io.beta * tex_value(sc, m, s.mat, s);
       alive = finish_bounce(pool, prm, io, true, s.p, dir, 0.0f, ua.x);
   RTB_SHADE_LOOP_END
 }
 
 // Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
-__global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_DIELECTRIC)
       PathIO io = load_path(pool, slot);
-      const Surf s = surface_at(sc, io.ref, io.o, io.d, io.time, io.t);
-      const float ir = __ldg(&sc.materials[s.mat]).z;
+      const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
+      const float ir = __ldg(&sc.materials[2 * s.mat]).z;
       const float ratio = s.front ? 1.0f / ir : ir;
       const float3 ud = unit(io.d);
       const float cos_theta = fminf(-dot(ud, s.n), 1.0f);
@@ -568,25 +630,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_shade_dielectric(DevScene
   RTB_SHADE_LOOP_END
 }
 
-// ---- generate: camera.rs:60-70 get_ray + the jitter of main.rs:752-753 ---------------------------------------------
-__device__ __forceinline__ void camera_ray(const DevCamera& cam, const DevParams& prm, uint32_t pixel, uint32_t sample,
-                                           float3& o, float3& d, float& time) {
-  const uint32_t row = pixel / prm.width, col = pixel - row * prm.width;
-  const uint32_t j = prm.height - 1 - row;  // scanline j is stored at image row H-1-j, main.rs:733
-  const float4 u0 = philox_u(pixel, sample, BLK_CAMERA0, 0, prm.seed);
-  const float4 u1 = philox_u(pixel, sample, BLK_CAMERA1, 0, prm.seed);
-  const float s = ((float)col + u0.x) / (float)(prm.width - 1);
-  const float t = ((float)j + u0.y) / (float)(prm.height - 1);
-  // random_in_unit_disk (vec3.rs:101-113) in closed form
-  const float rr = cam.lens_radius * sqrtf(u0.z);
-  float sn, cs;
-  sincosf(2.0f * RTB_PI * u0.w, &sn, &cs);
-  const float3 off = (rr * cs) * ld3(cam.u) + (rr * sn) * ld3(cam.v);
-  o = ld3(cam.origin) + off;
-  d = fma3(s, ld3(cam.horizontal), fma3(t, ld3(cam.vertical), ld3(cam.lmo))) - off;
-  time = fmaf(cam.time1 - cam.time0, u1.x, cam.time0);  // camera.rs:68
-}
-
+// ---- generate (initial fill of the pool; afterwards terminated slots are restarted inside the shade kernels) ----
 __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, DevParams prm, DevCamera cam) {
   __shared__ unsigned long long s_first;
   DevCounters* c = pool.c;
@@ -596,7 +640,6 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, De
   if (c->next_path >= total) return;  // nothing left to start: terminated slots stay dead
   const uint32_t nxt = c->cur ^ 1u;
   const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t npix = prm.width * prm.height;
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
     const uint32_t cnt = min(blockDim.x, n - base);
     __syncthreads();
@@ -607,17 +650,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, De
     uint32_t slot = 0;
     if (alive) {
       slot = pool.q_dead[base + threadIdx.x];
-      // sample-major order: all pixels (tile order) of sample k, then sample k+1: neighbouring lanes = neighbouring pixels
-      const uint32_t s_local = (uint32_t)(path / npix);
-      const uint32_t pixel = __ldg(prm.pix_order + (uint32_t)(path - (unsigned long long)s_local * npix));
-      const uint32_t sample = prm.sample_offset + s_local;
-      float3 o, d;
-      float time;
-      camera_ray(cam, prm, pixel, sample, o, d, time);
-      pool.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
-      pool.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
-      pool.beta[slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
-      pool.rad[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample << 8));
+      start_path(pool, prm, cam, slot, path);
     }
     warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);
   }
@@ -731,13 +764,13 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
   if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
   else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
 }
-void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
-                  cudaStream_t st) {
-  k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
-  if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
-  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
-  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
-  if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm);
+void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
+                  const DevCamera& cam, uint32_t present, cudaStream_t st) {
+  k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
 }
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
   k_finalize<<<cdiv(npix, 256), 256, 0, st>>>(accum, rgb, npix, inv_spp);

@@ -29,8 +29,8 @@ void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& 
 void launch_advance(const DevPool& pool, cudaStream_t st);
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st);
-void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t present,
-                  cudaStream_t st);
+void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
+                  const DevCamera& cam, uint32_t present, cudaStream_t st);
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st);
 void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
                   uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st);
