@@ -50,90 +50,138 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 }
 
 // ---- extend ------------------------------------------------------------------------------------------------------
-// Persistent warps with dynamic ray fetch: every lane owns one in-flight ray and advances it by ONE node visit (or
+// Persistent warps with dynamic ray fetch.  Every lane owns one in-flight ray and advances it by ONE node visit (or
 // stack pop) per loop iteration, so the 32 lanes execute the node-decode code together.  Rays finish after different
-// numbers of visits; instead of idling until the slowest lane is done (17 of 32 lanes active in the first version,
-// profiles/r1_c1_ncu_summary.md), finished lanes are written out and refilled from the queue as soon as
-// RTB_REFILL_LANES of them are waiting.  Work is claimed from a device-side cursor, one atomic per refill per warp.
+// numbers of visits; instead of idling until the slowest lane of the warp is done (17 of 32 lanes active in the
+// one-ray-per-thread version, profiles/r1_c1_ncu_summary.md) a finished lane immediately swaps its ray:
+//   * rays are PREFETCHED 32 at a time by the whole warp (coalesced queue read, ray fetch, 1/d) into a per-warp
+//     shared-memory buffer; an idle lane takes the next prepared ray with three LDS.128;
+//   * results are pushed to a per-warp shared-memory buffer and WRITTEN OUT 32 at a time by the whole warp
+//     (media, material classification, hit record, per-material queues).
+// So the expensive set-up / tear-down code always runs with full warps and only the swap itself is divergent.
+// Work is claimed from a device-side cursor, one atomic per 32 rays.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
-#define RTB_REFILL_LANES 8
+struct ExtIn { float4 o_time, d_slot, idir_oct; };
+struct ExtOut { float t; uint32_t ref, gid, slot; };
+#define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
+
 template <bool COUNT>
-__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
-k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes, uint32_t refill_lanes) {
+__global__ void __launch_bounds__(RTB_EXTEND_THREADS, 3)
+k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
+  __shared__ ExtIn s_in[RTB_EXTEND_WARPS][32];
+  __shared__ ExtOut s_out[RTB_EXTEND_WARPS][32];
   DevCounters* c = pool.c;
   const uint32_t cur = c->cur;
   const uint32_t n = c->n_ext[cur];
   if (n == 0) return;
   stage_nodes(sc, snodes, n_snodes);
   const uint32_t* __restrict__ q = pool.q_ext[cur];
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  ExtIn* in = s_in[warp];
+  ExtOut* out = s_out[warp];
   enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
   uint32_t state = EMPTY, slot = 0;
-  bool exhausted = false;  // warp-uniform: the queue has no more rays
+  uint32_t in_head = 0, in_count = 0, out_count = 0;  // warp-uniform
+  bool exhausted = false;                              // warp-uniform: the queue has no more rays
   Trav tv;
   uint2 stack[RTB_STACK];
   uint32_t nv = 0, nt = 0;
-  for (;;) {
-    const uint32_t running = __ballot_sync(0xffffffffu, state == RUNNING);
-    const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
-    const uint32_t waiting = exhausted ? __popc(done) : 32u - __popc(running);
-    if (running == 0u || waiting >= refill_lanes) {
-      // ---- write out finished rays: media, hit record, per-material queues -------------------------------------
-      uint32_t queue = Q_COUNT;
-      if (state == DONE) {
-        if (sc.n_media) {
-          const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
-          const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
-          intersect_media(sc, tv.o, tv.d, RTB_TMIN, tv.best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
-        }
-        // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
-        queue = Q_TERMINAL;
-        uint32_t minfo = 0;
-        if (tv.best.ref != REF_MISS) {
-          const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT, idx = tv.best.ref & REF_INDEX_MASK;
-          minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
-          const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
-          queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
-                : mt == RTB_MAT_METAL      ? Q_METAL
-                : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
-                : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
-                                           : Q_TERMINAL;
-        }
-        pool.hit[slot] = make_float4(tv.best.t, __uint_as_float(tv.best.ref), __uint_as_float(minfo), 0.f);
-        state = EMPTY;
+
+  auto flush = [&]() {  // executed by the whole warp
+    __syncwarp();
+    uint32_t queue = Q_COUNT, oslot = 0;
+    if (lane < out_count) {
+      const ExtOut h = out[lane];
+      oslot = h.slot;
+      Closest best{h.t, h.ref, h.gid};
+      if (sc.n_media) {
+        const float4 ro = pool.ray[2 * oslot], rd = pool.ray[2 * oslot + 1];
+        const uint32_t pixel = __float_as_uint(pool.st[2 * oslot].w);
+        const uint32_t st = __float_as_uint(pool.st[2 * oslot + 1].w);
+        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
       }
-      if (done) {
+      // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
+      queue = Q_TERMINAL;
+      uint32_t minfo = 0;
+      if (best.ref != REF_MISS) {
+        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
+        minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
+        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
+        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
+              : mt == RTB_MAT_METAL      ? Q_METAL
+              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
+              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
+                                         : Q_TERMINAL;
+      }
+      pool.hit[oslot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
+    }
 #pragma unroll
-        for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
-      }
-      // ---- refill empty lanes from the extend queue ------------------------------------------------------------
-      if (!exhausted) {
-        const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
+    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, oslot);
+    out_count = 0;
+    __syncwarp();
+  };
+
+  for (;;) {
+    // ---- idle lanes take prepared rays ----------------------------------------------------------------------------
+    const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
+    if (empty) {
+      if (in_head == in_count && !exhausted) {  // prefetch the next 32 rays with the whole warp
         uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&c->ext_cursor, (uint32_t)__popc(empty));
+        if (lane == 0) first = atomicAdd(&c->ext_cursor, 32u);
         first = __shfl_sync(0xffffffffu, first, 0);
-        exhausted = first + __popc(empty) >= n;
-        if (state == EMPTY) {
-          const uint32_t i = first + __popc(empty & lt_mask);
-          if (i < n) {
-            slot = q[i];
-            const float4 ro = pool.ray[2 * slot];
-            const float4 rd = pool.ray[2 * slot + 1];
-            trav_init(tv, xyz(ro), xyz(rd), ro.w);
-            state = RUNNING;
-          }
+        exhausted = first + 32u >= n;
+        in_head = 0;
+        in_count = first < n ? min(32u, n - first) : 0u;
+        __syncwarp();
+        if (lane < in_count) {
+          const uint32_t sl = q[first + lane];
+          const float4 ro = pool.ray[2 * sl], rd = pool.ray[2 * sl + 1];
+          Trav t0;
+          trav_init(t0, xyz(ro), xyz(rd), ro.w);
+          in[lane].o_time = ro;
+          in[lane].d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
+          in[lane].idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
         }
+        __syncwarp();
       }
-      if (__ballot_sync(0xffffffffu, state == RUNNING) == 0u) {
-        if (exhausted) break;
-        continue;
+      const uint32_t avail = in_count - in_head;
+      if (avail) {
+        const uint32_t rank = __popc(empty & lt_mask);
+        if (state == EMPTY && rank < avail) {
+          const ExtIn r = in[in_head + rank];
+          tv.o = xyz(r.o_time); tv.time = r.o_time.w;
+          tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
+          tv.idx = r.idir_oct.x; tv.idy = r.idir_oct.y; tv.idz = r.idir_oct.z;
+          tv.octinv = __float_as_uint(r.idir_oct.w);
+          tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);
+          tv.sp = 0;
+          tv.best = Closest{INFINITY, REF_MISS, 0u};
+          state = RUNNING;
+        }
+        in_head += min((uint32_t)__popc(empty), avail);
       }
     }
+    if (__ballot_sync(0xffffffffu, state == RUNNING) == 0u) {
+      if (out_count) flush();
+      if (exhausted && in_head == in_count) break;
+      continue;
+    }
+    // ---- one node visit (or pop) per lane ---------------------------------------------------------------------------
     if (state == RUNNING) {
       if (!trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, RTB_TMIN, nv, nt)) state = DONE;
+    }
+    // ---- finished lanes push their result -------------------------------------------------------------------------
+    const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
+    if (done) {
+      if (out_count + __popc(done) > 32u) flush();
+      if (state == DONE) {
+        out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, tv.best.gid, slot};
+        state = EMPTY;
+      }
+      out_count += __popc(done);
     }
   }
   if (COUNT) {
@@ -755,14 +803,13 @@ static int env_int(const char* name, int dflt) {
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
   static const bool use_static = getenv("RTB_EXTEND_MODE") && !strcmp(getenv("RTB_EXTEND_MODE"), "static");
-  static const uint32_t refill = (uint32_t)env_int("RTB_REFILL_LANES", RTB_REFILL_LANES);
   if (use_static) {
     if (count) k_extend_static<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
     else k_extend_static<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
     return;
   }
-  if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
-  else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes, refill);
+  if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+  else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
 }
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
                   const DevCamera& cam, uint32_t present, cudaStream_t st) {
@@ -787,7 +834,7 @@ void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float*
 
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   // stage as much of the (breadth-first ordered) node array as fits the shared-memory budget
-  const uint32_t budget = 64 * 1024;
+  const uint32_t budget = 56 * 1024;  // + 16 KB of per-warp ray buffers: three CTAs per SM fit the 228 KB
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;
