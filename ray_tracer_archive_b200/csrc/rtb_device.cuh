@@ -273,6 +273,7 @@ __device__ __forceinline__ float q2f(uint32_t word, uint32_t sel) {
 // over all surface primitives; media are handled by the caller.
 // The traversal is split into trav_init / trav_step (ONE node visit or one stack pop per call) so that the extend
 // kernel can keep all 32 lanes of a warp busy by swapping finished rays for new ones between steps.
+// Every step is exactly one node visit: lanes never spend an iteration on bookkeeping while others decode a node.
 struct Trav {
   float3 o, d;
   float idx, idy, idz, time;
@@ -299,10 +300,9 @@ template <bool COUNT>
 __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
                                           Trav& tv, uint2* __restrict__ stack, float tmin,
                                           uint32_t& n_nodes_visited, uint32_t& n_tests) {
-  if (!(tv.grp.y & 0xFF00u)) {
+  if (!(tv.grp.y & 0xFF00u)) {  // group exhausted: pop (stack entries always have hits left) and visit in the same step
     if (tv.sp == 0) return false;
     tv.grp = stack[--tv.sp];
-    return true;
   }
   const uint32_t octinv = tv.octinv;
   uint32_t hits = tv.grp.y >> 8;
