@@ -64,6 +64,8 @@ struct rtb_context {
   DevBuf<float> p_org, p_dir, p_time, p_t;
   DevBuf<uint32_t> p_id;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ShadeStreams ss;
+  bool ss_ok = false;
   std::vector<cudaEvent_t> ext_events;  // pairs around every extend launch when RTB_RENDER_TIME_EXTEND is set
 };
 
@@ -112,6 +114,12 @@ int rtb_context_create(int device_id, rtb_context** out) {
   CU(cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters)));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  for (int k = 0; k < 4; ++k) {
+    CU(cudaStreamCreateWithFlags(&c->ss.side[k], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ss.join[k], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->ss.fork, cudaEventDisableTiming));
+  c->ss_ok = true;
   CU(c->counters.resize(1));
   *out = c;
   return RTB_OK;
@@ -124,6 +132,10 @@ void rtb_context_destroy(rtb_context* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ss_ok) {
+    for (int k = 0; k < 4; ++k) { cudaStreamDestroy(c->ss.side[k]); cudaEventDestroy(c->ss.join[k]); }
+    cudaEventDestroy(c->ss.fork);
+  }
   for (cudaEvent_t e : c->ext_events) cudaEventDestroy(e);
   delete c;
 }
@@ -598,6 +610,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
   const uint32_t check_every = 8;
+  static const bool serial_shade = getenv("RTB_SERIAL_SHADE") != nullptr;
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   size_t ev_used = 0;
   uint64_t iters = 0;
@@ -619,7 +632,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
         CU(cudaEventRecord(c->ext_events[ev_used + 1], st));
         ev_used += 2;
       }
-      launch_shade(s->lc, s->dev, pool, prm, dcam, present, st);
+      launch_shade(s->lc, s->dev, pool, prm, dcam, present, st, serial_shade ? nullptr : &c->ss);
       launch_advance(pool, st);
       launches += 2 + n_shade;
       extend_launches += 1;

@@ -802,7 +802,10 @@ static int env_int(const char* name, int dflt) {
 }
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
-  static const bool use_static = getenv("RTB_EXTEND_MODE") && !strcmp(getenv("RTB_EXTEND_MODE"), "static");
+  // one-ray-per-thread wins on small trees (all lanes start at the root together); dynamic fetch wins on deep trees
+  // where the number of node visits per ray varies widely (measured: profiles/r1_ab_extend.md)
+  static const char* mode = getenv("RTB_EXTEND_MODE");
+  const bool use_static = mode ? !strcmp(mode, "static") : !lc.dynamic_fetch;
   if (use_static) {
     if (count) k_extend_static<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
     else k_extend_static<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
@@ -811,13 +814,39 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
   if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
   else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
 }
+// The per-material kernels of one iteration are independent (they only append to the next extend queue), so they are
+// forked onto side streams after `extend` and joined before `advance`: the small queues (terminal, metal, dielectric)
+// overlap the large one instead of each paying its own ramp-up and tail.
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
-                  const DevCamera& cam, uint32_t present, cudaStream_t st) {
-  k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+                  const DevCamera& cam, uint32_t present, cudaStream_t st, const ShadeStreams* ss) {
+  const bool fork = ss != nullptr;
+  int k = 0;
+  if (fork) cudaEventRecord(ss->fork, st);
+  auto side = [&](void (*kern)(DevScene, DevPool, DevParams, DevCamera)) {
+    if (!fork) {
+      kern<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+      return;
+    }
+    cudaStream_t s2 = ss->side[k];
+    cudaStreamWaitEvent(s2, ss->fork, 0);
+    kern<<<lc.shade_grid, RTB_SHADE_THREADS, 0, s2>>>(sc, pool, prm, cam);
+    cudaEventRecord(ss->join[k], s2);
+    ++k;
+  };
+  // the (usually) largest queue stays on the main stream
+  if (present & (1u << RTB_MAT_LAMBERTIAN)) {
+    side(k_shade_terminal);
+    if (present & (1u << RTB_MAT_METAL)) side(k_shade_metal);
+    if (present & (1u << RTB_MAT_DIELECTRIC)) side(k_shade_dielectric);
+    if (present & (1u << RTB_MAT_ISOTROPIC)) side(k_shade_isotropic);
+    k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  } else {
+    if (present & (1u << RTB_MAT_METAL)) side(k_shade_metal);
+    if (present & (1u << RTB_MAT_DIELECTRIC)) side(k_shade_dielectric);
+    if (present & (1u << RTB_MAT_ISOTROPIC)) side(k_shade_isotropic);
+    k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  }
+  for (int j = 0; j < k; ++j) cudaStreamWaitEvent(st, ss->join[j], 0);
 }
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
   k_finalize<<<cdiv(npix, 256), 256, 0, st>>>(accum, rgb, npix, inv_spp);
@@ -838,6 +867,7 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;
+  lc.dynamic_fetch = n_nodes > 4096;
   lc.extend_smem = n_s * 80;
   cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
