@@ -610,7 +610,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
   const uint32_t check_every = 8;
-  static const bool serial_shade = getenv("RTB_SERIAL_SHADE") != nullptr;
+  static const bool serial_shade = getenv("RTB_CONCURRENT_SHADE") == nullptr;  // fork/join measured: no gain (profiles/)
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   size_t ev_used = 0;
   uint64_t iters = 0;
