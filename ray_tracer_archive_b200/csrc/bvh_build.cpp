@@ -126,11 +126,15 @@ struct WideChild {
   bool leaf;
 };
 
+// child planes are quantised to 7 bits: the device turns a byte into the float 128+q with ONE byte-permute
+// (0x43000000 | q << 16) and no int->float conversion; 8 bits would need an extra FADD per plane (48 per node visit)
+const int QMAX = 127;
+
 uint8_t exp_byte_for(float extent) {
-  // smallest power-of-two step s = 2^(e-127) with 255*s >= extent
+  // smallest power-of-two step s = 2^(e-127) with QMAX*s >= extent
   if (!(extent > 0.f)) return 1;
   int e;
-  std::frexp(extent / 255.0f, &e);  // extent/255 = m * 2^e, m in [0.5,1)  ->  2^e >= extent/255
+  std::frexp(extent / (float)QMAX, &e);  // extent/QMAX = m * 2^e, m in [0.5,1)  ->  2^e >= extent/QMAX
   int biased = e + 127;
   if (biased < 1) biased = 1;
   if (biased > 254) biased = 254;
@@ -159,24 +163,24 @@ struct Assembler {
       eb[a] = exp_byte_for(nb.hi[a] - nb.lo[a]);
       for (;;) {  // make sure 255 steps really cover the extent in float arithmetic
         step[a] = step_from_byte(eb[a]);
-        if (nb.lo[a] + 255.f * step[a] >= nb.hi[a] || eb[a] >= 254) break;
+        if (nb.lo[a] + (float)QMAX * step[a] >= nb.hi[a] || eb[a] >= 254) break;
         ++eb[a];
       }
     }
     n.ex = eb[0]; n.ey = eb[1]; n.ez = eb[2];
     for (int s = 0; s < 8; ++s)
-      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = 255; n.qhi[a][s] = 0; }  // empty: inverted box, never hit
+      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = QMAX; n.qhi[a][s] = 0; }  // empty: inverted box, never hit
     for (int i = 0; i < nch; ++i) {
       int s = slot_of[i];
       for (int a = 0; a < 3; ++a) {
         double o = nb.lo[a], st = step[a];
         int ql = (int)std::floor(((double)ch[i].box.lo[a] - o) / st);
         int qh = (int)std::ceil(((double)ch[i].box.hi[a] - o) / st);
-        ql = ql < 0 ? 0 : (ql > 255 ? 255 : ql);
-        qh = qh < 0 ? 0 : (qh > 255 ? 255 : qh);
+        ql = ql < 0 ? 0 : (ql > QMAX ? QMAX : ql);
+        qh = qh < 0 ? 0 : (qh > QMAX ? QMAX : qh);
         // verify in float, the arithmetic the device uses (o + q*step is exact or rounded; widen if needed)
         while (ql > 0 && nb.lo[a] + (float)ql * step[a] > ch[i].box.lo[a]) --ql;
-        while (qh < 255 && nb.lo[a] + (float)qh * step[a] < ch[i].box.hi[a]) ++qh;
+        while (qh < QMAX && nb.lo[a] + (float)qh * step[a] < ch[i].box.hi[a]) ++qh;
         n.qlo[a][s] = (uint8_t)ql;
         n.qhi[a][s] = (uint8_t)qh;
       }
@@ -254,7 +258,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     std::memset(&n, 0, sizeof(n));
     n.ex = n.ey = n.ez = 1;
     for (int s = 0; s < 8; ++s)
-      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = 255; n.qhi[a][s] = 0; }
+      for (int a = 0; a < 3; ++a) { n.qlo[a][s] = QMAX; n.qhi[a][s] = 0; }
     out.nodes.push_back(n);
     cleanup();
     return RTB_OK;

@@ -264,8 +264,9 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t sel) {
-  // byte `sel&3` of `word` -> float, via 0x4B0000qq (= 2^23 + q) - 2^23 : one PRMT + one FADD, no I2F
-  return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+  // 7-bit plane byte `sel&3` of `word` -> the float 128 + q, with ONE byte permute and no conversion:
+  // bits = 0x43000000 | q << 16  (exponent 2^7, q in the top mantissa bits).  The 128 is folded into the node bias.
+  return __uint_as_float(__byte_perm(word, 0x43000000u, sel));
 }
 
 // Wide-BVH closest-hit traversal.  `snodes` = first `n_snodes` nodes staged in shared memory (uint4 x5 each);
@@ -330,11 +331,13 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const float bx = (__uint_as_float(w0.x) - tv.o.x) * tv.idx;
   const float by = (__uint_as_float(w0.y) - tv.o.y) * tv.idy;
   const float bz = (__uint_as_float(w0.z) - tv.o.z) * tv.idz;
-  const float eps = 4.0e-7f;
+  const float eps = 4.0e-7f;  // bound on the f32 rounding of q a + b (|q a| <= 255 |a| incl. the folded 128)
   const float ex = eps * fmaf(256.0f, fabsf(ax), fabsf(bx));
   const float ey = eps * fmaf(256.0f, fabsf(ay), fabsf(by));
   const float ez = eps * fmaf(256.0f, fabsf(az), fabsf(bz));
-  const float bnx = bx - ex, bfx = bx + ex, bny = by - ey, bfy = by + ey, bnz = bz - ez, bfz = bz + ez;
+  // planes decode as (128 + q): fold -128 a into the bias (error 128 ulp(a) << the quantisation step a)
+  const float cx = fmaf(-128.0f, ax, bx), cy = fmaf(-128.0f, ay, by), cz = fmaf(-128.0f, az, bz);
+  const float bnx = cx - ex, bfx = cx + ex, bny = cy - ey, bfy = cy + ey, bnz = cz - ez, bfz = cz + ez;
   // near/far plane words per axis (children 0-3 | 4-7)
   const uint32_t nx0 = nx ? w3.z : w2.x, nx1 = nx ? w3.w : w2.y, fx0 = nx ? w2.x : w3.z, fx1 = nx ? w2.y : w3.w;
   const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
@@ -342,7 +345,7 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   uint32_t hitmask = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint32_t sel = 0x7540u | (uint32_t)(i & 3);
+    const uint32_t sel = 0x7044u | ((uint32_t)(i & 3) << 8);
     const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, sel), ax, bnx);
     const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, sel), ay, bny);
     const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, sel), az, bnz);
