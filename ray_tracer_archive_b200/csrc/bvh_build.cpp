@@ -10,6 +10,7 @@
 // The per-type trees hang under one root, so every node's leaf children share one primitive type.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cstdlib>
 #include <numeric>
@@ -301,6 +302,8 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     queue.push_back(Pending{0, 0, trees[0].root, 1});
   }
 
+  float open_min_rel = 1.0f / 8.0f;
+  if (const char* e = getenv("RTB_OPEN_MIN_REL")) open_min_rel = (float)atof(e);
   while (qhead < queue.size()) {
     Pending pd = queue[qhead++];
     Builder& b = *trees[pd.tree].b;
@@ -321,6 +324,14 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
         for (int i = 0; i < nc; ++i) {
           const BinNode& c = b.bin[cand[i]];
           if (c.left < 0) continue;
+          // child planes are quantised relative to THIS node's extent: do not pull the children of a subtree that is
+          // tiny next to the node (the 22-unit sphere field beside the r=1000 ground sphere) up into its coarse grid
+          float rel = 0.f;
+          for (int a = 0; a < 3; ++a) {
+            const float E = rootbn.box.hi[a] - rootbn.box.lo[a];
+            if (E > 0.f) rel = std::fmax(rel, (c.box.hi[a] - c.box.lo[a]) / E);
+          }
+          if (rel < open_min_rel) continue;
           float a = c.box.area();
           if (a > best_area) { best_area = a; best = i; }
         }
