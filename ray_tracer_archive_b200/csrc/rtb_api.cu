@@ -595,6 +595,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   prm.max_depth = p->max_depth; prm.rr_start = p->rr_start_depth; prm.seed = p->seed;
   for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
   prm.pix_order = c->pix_order.p;
+  prm.inv_npix = 1.0 / (double)npix;
   prm.accum = (float4*)d_accum;
   DevCamera dcam;
   DevCameraF64 dcam64;

@@ -82,6 +82,7 @@ struct DevParams {
   uint32_t rr_start, seed;
   float bg[3];
   const uint32_t* pix_order;  // tile-ordered pixel indices
+  double inv_npix;
   float4* accum;
 };
 

@@ -509,7 +509,10 @@ __device__ __forceinline__ void camera_ray(const DevCamera& cam, const DevParams
 __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams& prm, const DevCamera& cam, uint32_t slot,
                                            unsigned long long path) {
   const uint32_t npix = prm.width * prm.height;
-  const uint32_t s_local = (uint32_t)(path / npix);
+  // path / npix without a 64-bit integer division: double reciprocal + one correction step (exact below 2^52)
+  uint32_t s_local = (uint32_t)((double)path * prm.inv_npix);
+  if ((unsigned long long)s_local * npix > path) --s_local;
+  else if ((unsigned long long)(s_local + 1u) * npix <= path) ++s_local;
   const uint32_t pixel = __ldg(prm.pix_order + (uint32_t)(path - (unsigned long long)s_local * npix));
   const uint32_t sample = prm.sample_offset + s_local;
   float3 o, d;
