@@ -211,10 +211,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    reduce_events = []
+
     def step(flags=0):
         flush.zero_()  # flush L2 between steps
         st = scene.render_device(cfg.camera, params(flags), accum.data_ptr(), stream.cuda_stream)
-        parallel.reduce_accum(accum, dst=0)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        parallel.reduce_accum(accum, dst=0)  # NCCL reduce of the float4 accumulation buffer onto rank 0
+        r1.record(stream)
+        reduce_events.append((r0, r1))
         return st
 
     for _ in range(W):
@@ -224,6 +230,7 @@ def main():
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reduce_events.clear()
     e0.record(stream)
     segs = launches = 0
     for _ in range(args.steps):
@@ -234,6 +241,7 @@ def main():
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
+    reduce_ms = sum(a.elapsed_time(b) for a, b in reduce_events) / max(len(reduce_events), 1)
     tot = torch.tensor([ms, float(segs), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = tot.clone()
@@ -357,6 +365,8 @@ def main():
                        "l2": "L2 flushed (256 MB write) between steps; path-state pool exceeds the 126 MB L2; the scene is cache-resident by design"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(all_launches),
+            "reduce": {"collective": "ncclReduce(sum) of W*H float4 onto rank 0" if world > 1 else "none (1 GPU)",
+                       "bytes": npix * 16, "ms_per_step_rank0": reduce_ms, "frac_of_step": reduce_ms / (ms / args.steps)},
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
