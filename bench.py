@@ -176,6 +176,10 @@ def main():
         run_reference(args, rank)
         return
 
+    # exactly ONE line may reach stdout (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -373,7 +377,7 @@ def main():
             "segments_per_step": all_segs / args.steps,
             "paths_per_step": npix * spp * world,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
