@@ -18,7 +18,7 @@ _VP, _U32 = C.c_void_p, C.c_uint32
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("rt_oracle.cpp", "rt_oracle_flat.cpp", "rt_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("rt_oracle.cpp", "rt_oracle.hpp")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE])
 
@@ -38,6 +38,8 @@ def load():
         lib.orc_scene_set_perlin.argtypes = [_VP, _U32, _VP, _VP, _VP, _VP]
         lib.orc_scene_set_mesh.argtypes = [_VP, _U32, _VP, _U32, _VP, _U32]
         lib.orc_scene_build.argtypes = [_VP]
+        lib.orc_scene_attach_bvh.argtypes = [_VP, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32]
+        lib.orc_scene_use_bvh.argtypes = [_VP, C.c_int]
         lib.orc_scene_num_prims.restype = _U32
         lib.orc_scene_num_prims.argtypes = [_VP]
         lib.orc_primary_hits.argtypes = [_VP, _VP, _U32, _U32, _VP, _VP, _VP, _VP, C.c_double, C.c_int]
@@ -99,6 +101,20 @@ class OracleScene:
         if getattr(self, "h", None):
             self.lib.orc_scene_destroy(self.h)
             self.h = None
+
+    def attach_bvh(self, host_or_device_scene):
+        """Use the product's exported BVH to cull candidates (the per-primitive tests stay the reference's own)."""
+        nodes, prims = host_or_device_scene.export_bvh()
+        self._bvh_keep = (nodes, prims)
+        args = [_p(nodes), len(nodes) // 80]
+        for g, inf in prims:
+            args += [_p(inf) if len(inf) else None, len(inf) // 2]
+        rc = self.lib.orc_scene_attach_bvh(self.h, *args)
+        if rc != 0:
+            raise RuntimeError("attach_bvh: " + self.lib.orc_scene_error(self.h).decode())
+
+    def use_bvh(self, on=True):
+        self.lib.orc_scene_use_bvh(self.h, 1 if on else 0)
 
     def num_prims(self):
         return self.lib.orc_scene_num_prims(self.h)

@@ -5,6 +5,7 @@
 #include "rt_oracle.hpp"
 
 #include <atomic>
+#include <functional>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -369,6 +370,27 @@ struct Scene {
   uint32_t n_prims = 0, n_media = 0;
   bool built = false;
   std::string err;
+  // ---- accelerated closest hit (optional): the SAME per-primitive reference tests, with the product's exported BVH used
+  // only to cull candidates.  prim_obj[id] = primitive `id` re-wrapped in copies of its ancestor Translate / RotateY /
+  // FlipFace wrappers, so prim_obj[id]->hit() is exactly what the nested list scan would evaluate for it.
+  std::vector<HP> prim_obj;
+  std::vector<HP> media_obj;
+  std::vector<std::function<HP(HP)>> wrap_stack;
+  struct Accel {
+    std::vector<uint8_t> nodes;       // 80-byte nodes as exported by rtb_scene_export_bvh
+    std::vector<uint32_t> info[4];    // (prim id, material|mode) pairs, leaf order, per type
+    bool on = false;
+  } accel;
+
+  HP wrapped(HP leaf) const {
+    for (size_t k = wrap_stack.size(); k-- > 0;) leaf = wrap_stack[k](leaf);
+    return leaf;
+  }
+  void register_prim(uint32_t id, HP leaf) {
+    if (id == RTB_NONE) return;
+    if (prim_obj.size() <= id) prim_obj.resize(id + 1);
+    prim_obj[id] = wrapped(leaf);
+  }
 
   V3 tex_value(uint32_t t, double u, double v, V3 p) const {
     const rtb_texture& tx = texs[t];
@@ -416,18 +438,21 @@ struct Scene {
       r->a0 = a0; r->a1 = a1; r->b0 = b0; r->b1 = b1; r->k = k;
       r->mat = (int)n.material;
       r->id = new_id();
+      register_prim(r->id, r);
       return r;
     };
     switch (n.type) {
       case RTB_NODE_SPHERE: {
         auto s = std::make_shared<Sphere>();
         s->c = V3(p[0], p[1], p[2]); s->r = p[3]; s->mat = (int)n.material; s->id = new_id();
+        register_prim(s->id, s);
         return s;
       }
       case RTB_NODE_MOVING_SPHERE: {
         auto s = std::make_shared<MovingSphere>();
         s->c0 = V3(p[0], p[1], p[2]); s->c1 = V3(p[3], p[4], p[5]);
         s->t0 = p[6]; s->t1 = p[7]; s->r = p[8]; s->mat = (int)n.material; s->id = new_id();
+        register_prim(s->id, s);
         return s;
       }
       case RTB_NODE_XY_RECT: return rect(2, p[0], p[1], p[2], p[3], p[4]);
@@ -449,12 +474,14 @@ struct Scene {
         t->e1 = V3(p[3], p[4], p[5]) - t->v0;
         t->e2 = V3(p[6], p[7], p[8]) - t->v0;
         t->mat = (int)n.material; t->id = new_id();
+        register_prim(t->id, t);
         return t;
       }
       case RTB_NODE_QUAD: {
         auto q = std::make_shared<Quad>();
         q->Q = V3(p[0], p[1], p[2]); q->u = V3(p[3], p[4], p[5]); q->v = V3(p[6], p[7], p[8]);
         q->mat = (int)n.material; q->id = new_id();
+        register_prim(q->id, q);
         return q;
       }
       case RTB_NODE_MESH: {
@@ -471,25 +498,35 @@ struct Scene {
           t->e1 = V3(b[0], b[1], b[2]) - t->v0;
           t->e2 = V3(c[0], c[1], c[2]) - t->v0;
           t->mat = (int)n.material; t->id = new_id();
+          register_prim(t->id, t);
           l->objects.push_back(t);
         }
         return l;
       }
       case RTB_NODE_TRANSLATE: {
         auto t = std::make_shared<Translate>();
-        t->ptr = child(0); t->offset = V3(p[0], p[1], p[2]);
+        t->offset = V3(p[0], p[1], p[2]);
+        const V3 off = t->offset;
+        wrap_stack.push_back([off](HP c) -> HP { auto w = std::make_shared<Translate>(); w->ptr = c; w->offset = off; return w; });
+        t->ptr = child(0);
+        wrap_stack.pop_back();
         return t->ptr ? t : nullptr;
       }
       case RTB_NODE_ROTATE_Y: {  // hittable.rs:107-111
         auto r = std::make_shared<RotateY>();
-        r->ptr = child(0);
         double radians = p[0] * PI / 180.0;
         r->sin_theta = std::sin(radians); r->cos_theta = std::cos(radians);
+        const double sn = r->sin_theta, cs = r->cos_theta;
+        wrap_stack.push_back([sn, cs](HP c) -> HP { auto w = std::make_shared<RotateY>(); w->ptr = c; w->sin_theta = sn; w->cos_theta = cs; return w; });
+        r->ptr = child(0);
+        wrap_stack.pop_back();
         return r->ptr ? r : nullptr;
       }
       case RTB_NODE_FLIP_FACE: {
         auto f = std::make_shared<FlipFace>();
+        wrap_stack.push_back([](HP c) -> HP { auto w = std::make_shared<FlipFace>(); w->ptr = c; return w; });
         f->ptr = child(0);
+        wrap_stack.pop_back();
         return f->ptr ? f : nullptr;
       }
       case RTB_NODE_CONSTANT_MEDIUM: {  // constant_medium.rs:23-29
@@ -500,6 +537,7 @@ struct Scene {
         m->boundary = build_node(child_index[n.first_child], true);
         m->neg_inv_density = -1.0 / p[0];
         m->mat = (int)n.material;
+        if (m->boundary && !in_boundary) media_obj.push_back(wrapped(m));
         return m->boundary ? m : nullptr;
       }
       case RTB_NODE_LIST:
@@ -520,6 +558,7 @@ struct Scene {
   bool build() {
     if (built) return true;
     n_prims = 0; n_media = 0;
+    prim_obj.clear(); media_obj.clear(); wrap_stack.clear();
     world = build_node(root, false);
     if (!world) return false;
     lights = std::make_shared<HittableList>();
@@ -540,6 +579,91 @@ struct Scene {
     return true;
   }
 };
+
+
+// Closest hit through the exported BVH: candidates from a plain f64 slab traversal of the (conservative, 7-bit
+// quantised) child boxes, each candidate evaluated by the reference's own per-primitive test; the tie rule "equal t ->
+// later primitive" (hittable_list.rs:44-47) is applied explicitly because candidates arrive in BVH order.
+static bool hit_accel(const Scene& sc, const Ray& r, double t_min, double t_max, HitRecord& rec, const HitCtx& cx,
+                      uint64_t* n_nodes, uint64_t* n_prims) {
+  const uint8_t* base = sc.accel.nodes.data();
+  const size_t n_nodes_total = sc.accel.nodes.size() / 80;
+  if (n_nodes_total == 0) return false;
+  double closest = t_max;
+  bool found = false;
+  uint32_t best_id = 0;
+  HitRecord tmp;
+  uint32_t stack[256];
+  int sp = 0;
+  stack[sp++] = 0;
+  const double inv[3] = {1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z};
+  while (sp) {
+    const uint32_t ni = stack[--sp];
+    if (ni >= n_nodes_total) continue;
+    const uint8_t* nd = base + (size_t)ni * 80;
+    if (n_nodes) ++*n_nodes;
+    float of[3];
+    std::memcpy(of, nd, 12);
+    const uint8_t* e = nd + 12;
+    const uint32_t imask = nd[15];
+    uint32_t child_base, prim_base;
+    std::memcpy(&child_base, nd + 16, 4);
+    std::memcpy(&prim_base, nd + 20, 4);
+    const uint8_t* meta = nd + 24;
+    const uint8_t* qlo = nd + 32;  // [3][8]
+    const uint8_t* qhi = nd + 56;  // [3][8]
+    uint32_t rank = 0;
+    for (int s = 0; s < 8; ++s) {
+      const bool internal = (imask >> s) & 1u;
+      const uint32_t my_rank = rank;
+      if (internal) ++rank;
+      double tn = t_min, tf = closest;
+      bool miss = false;
+      for (int a = 0; a < 3 && !miss; ++a) {
+        if (qlo[a * 8 + s] > qhi[a * 8 + s]) { miss = true; break; }  // empty slot
+        const double step = std::ldexp(1.0, (int)e[a] - 127);
+        const double ext = 127.0 * step;
+        const double lo = (double)of[a] + qlo[a * 8 + s] * step - 1e-6 * ext;
+        const double hi = (double)of[a] + qhi[a * 8 + s] * step + 1e-6 * ext;
+        const double o = r.o[a], d = r.d[a];
+        if (d == 0.0) {
+          if (o < lo || o > hi) miss = true;
+          continue;
+        }
+        double t0 = (lo - o) * inv[a], t1 = (hi - o) * inv[a];
+        if (t0 > t1) std::swap(t0, t1);
+        tn = std::fmax(tn, t0 - 1e-9 * std::fabs(t0));
+        tf = std::fmin(tf, t1 + 1e-9 * std::fabs(t1));
+        if (tn > tf) miss = true;
+      }
+      if (miss) continue;
+      if (internal) {
+        if (sp < 255) stack[sp++] = child_base + my_rank;
+      } else {
+        const uint32_t cnt = meta[s] >> 5, off = meta[s] & 31u;
+        const uint32_t type = prim_base >> 29, first = (prim_base & ((1u << 29) - 1u)) + off;
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const uint32_t gid = sc.accel.info[type][2 * (size_t)(first + k)];
+          if (n_prims) ++*n_prims;
+          if (sc.prim_obj[gid]->hit(r, t_min, closest, tmp, cx)) {
+            if (!found || tmp.t < closest || gid > best_id) {
+              found = true; closest = tmp.t; best_id = gid; rec = tmp;
+            }
+          }
+        }
+      }
+    }
+  }
+  for (const HP& m : sc.media_obj) {  // ConstantMedium is order-independent: accepted iff its sampled t <= closest so far
+    if (m->hit(r, t_min, closest, tmp, cx)) { found = true; closest = tmp.t; rec = tmp; }
+  }
+  return found;
+}
+
+static inline bool world_hit(const Scene& sc, const Ray& r, double t_min, double t_max, HitRecord& rec, const HitCtx& cx) {
+  if (sc.accel.on) return hit_accel(sc, r, t_min, t_max, rec, cx, nullptr, nullptr);
+  return sc.world->hit(r, t_min, t_max, rec, cx);
+}
 
 // ---- camera, camera.rs:21-70 -------------------------------------------------------------------------------
 struct Camera {
@@ -582,7 +706,7 @@ static SampleOut ray_color(const Scene& sc, Ray r, V3 background, int max_depth,
     const uint32_t bounce = segments;
     HitRecord rec;
     HitCtx cx; cx.rng = &rng; cx.bounce = bounce;
-    if (!sc.world->hit(r, 0.001, INF, rec, cx)) {  // main.rs:74-76
+    if (!world_hit(sc, r, 0.001, INF, rec, cx)) {  // main.rs:74-76
       L = L + beta * background;
       break;
     }
@@ -730,6 +854,25 @@ int orc_scene_set_mesh(orc_scene* o, uint32_t id, const float* verts, uint32_t n
   return 0;
 }
 int orc_scene_build(orc_scene* o) { return o->s.build() ? 0 : -1; }
+// attach the product's exported BVH (rtb_scene_export_bvh / rtb_scene_export_prims) as a candidate culler
+int orc_scene_attach_bvh(orc_scene* o, const void* nodes80, uint32_t n_nodes, const uint32_t* info0, uint32_t n0,
+                         const uint32_t* info1, uint32_t n1, const uint32_t* info2, uint32_t n2, const uint32_t* info3,
+                         uint32_t n3) {
+  if (!o->s.build()) return -1;
+  Scene::Accel& a = o->s.accel;
+  a.nodes.assign((const uint8_t*)nodes80, (const uint8_t*)nodes80 + (size_t)n_nodes * 80);
+  const uint32_t* inf[4] = {info0, info1, info2, info3};
+  const uint32_t cnt[4] = {n0, n1, n2, n3};
+  for (int t = 0; t < 4; ++t) {
+    a.info[t].clear();
+    if (cnt[t]) a.info[t].assign(inf[t], inf[t] + (size_t)cnt[t] * 2);
+    for (size_t k = 0; k < cnt[t]; ++k)
+      if (a.info[t][2 * k] >= o->s.prim_obj.size() || !o->s.prim_obj[a.info[t][2 * k]]) { o->s.err = "BVH references an unknown primitive id"; return -2; }
+  }
+  a.on = true;
+  return 0;
+}
+void orc_scene_use_bvh(orc_scene* o, int on) { o->s.accel.on = on && !o->s.accel.nodes.empty(); }
 uint32_t orc_scene_num_prims(orc_scene* o) { return o->s.build() ? o->s.n_prims : 0; }
 
 // pixel-centre primary rays (jitter 0.5, lens centre, time0); image row 0 = top = scanline j = H-1 (main.rs:733).
@@ -749,7 +892,7 @@ int orc_primary_hits(orc_scene* o, const rtb_camera* cam, uint32_t W, uint32_t H
       double u = ((double)i + 0.5) / (double)(W - 1), v = ((double)j + 0.5) / (double)(H - 1);  // main.rs:752-753
       Ray r = c.get_ray(u, v, 0.0, 0.0, c.time0);
       HitRecord rec;
-      bool h = sc.world->hit(r, 0.001, INF, rec, HitCtx());
+      bool h = world_hit(sc, r, 0.001, INF, rec, HitCtx());
       const size_t k = (size_t)row * W + i;
       ids[k] = h ? rec.prim : RTB_NONE;
       ts[k] = h ? rec.t : INF;
@@ -760,7 +903,7 @@ int orc_primary_hits(orc_scene* o, const rtb_camera* cam, uint32_t W, uint32_t H
           Ray rp = r;
           rp.d.at(q >> 1) *= (q & 1) ? (1.0 + eps) : (1.0 - eps);
           HitRecord r2;
-          bool h2 = sc.world->hit(rp, 0.001, INF, r2, HitCtx());
+          bool h2 = world_hit(sc, rp, 0.001, INF, r2, HitCtx());
           if (h2 != h || (h && r2.prim != rec.prim)) stable = false;
           else if (h) spread = std::fmax(spread, std::fabs(r2.t - rec.t));
         }
@@ -779,7 +922,7 @@ int orc_trace_rays(orc_scene* o, const double* org, const double* dir, const dou
     Ray r{V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
           time ? time[i] : 0.0};
     HitRecord rec;
-    bool h = o->s.world->hit(r, 0.001, INF, rec, HitCtx());
+    bool h = world_hit(o->s, r, 0.001, INF, rec, HitCtx());
     ids[i] = h ? rec.prim : RTB_NONE;
     ts[i] = h ? rec.t : INF;
   }

@@ -23,8 +23,10 @@ def _scene_pair(rtb, orc, ctx, cfg):
 
 
 # ------------------------------------------------------------------------------------------------------------- P1
-def _p1(rtb, orc, ctx, cfg, W, Hh, max_unstable=0.005):
+def _p1(rtb, orc, ctx, cfg, W, Hh, max_unstable=0.005, oracle_bvh=False):
     dev, osc, _ = _scene_pair(rtb, orc, ctx, cfg)
+    if oracle_bvh:  # candidate culling only; bit-identical to the linear scan (tests/test_host_bvh.py)
+        osc.attach_bvh(dev)
     ids, ts, st = dev.primary_hits(cfg.camera, W, Hh)
     oid, ot, stable, spread = osc.primary_hits(cfg.camera, W, Hh, stability_eps=2.5e-7)
     unstable, worst = H.check_primary_parity(ids, ts, oid, ot, stable, spread, max_unstable)
@@ -50,6 +52,19 @@ def test_p1_final_scene(rtb, orc, ctx):
     from ray_tracer_archive_b200 import scenes
     cfg = scenes.config_final_scene()
     _p1(rtb, orc, ctx, cfg, 400, 400)
+
+
+def test_p1_final_scene_full_size(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_final_scene()
+    _p1(rtb, orc, ctx, cfg, cfg.width, cfg.height, oracle_bvh=True)
+
+
+def test_p1_mesh_full_size_1M_triangles(rtb, orc, ctx):
+    """C4 at BASELINE.json's full size: 1920x1080 primary rays against 1 000 000 triangles + the Cornell walls."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_mesh()
+    _p1(rtb, orc, ctx, cfg, cfg.width, cfg.height, oracle_bvh=True)
 
 
 def test_p1_mesh_small(rtb, orc, ctx):

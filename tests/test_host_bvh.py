@@ -136,3 +136,24 @@ def test_quantised_boxes_are_conservative(rtb):
                 assert np.all(lo <= c - r) and np.all(hi >= c + r)
                 checked += 1
     assert checked == len(spheres)
+
+
+def test_oracle_bvh_mode_is_bit_identical_to_linear_scan(rtb, orc):
+    """The oracle may use the product's exported BVH to CULL candidates (needed for the 1M-triangle config); the
+    per-primitive tests and the tie rule stay the reference's.  Closest hits and whole renders must not change by a bit."""
+    from ray_tracer_archive_b200 import scenes
+    cfgs = [scenes.config_cornell(), scenes.config_random_spheres(), scenes.config_final_scene(n_small=300, boxes_per_side=10),
+            scenes.config_mesh(nx=40, nz=20)]
+    smoke = scenes.config_cornell()
+    smoke.world, smoke.lights = scenes.cornell_smoke(), scenes.cornell_smoke_lights()
+    for cfg in cfgs + [smoke]:
+        cs = rtb.compile_scene(cfg.world, cfg.lights)
+        hs, osc = rtb.Scene(None, cs), orc.OracleScene(cs)
+        a_ids, a_t = osc.primary_hits(cfg.camera, 96, 64)
+        prm = rtb.make_params(24, 24, 8, cfg.max_depth, cfg.background, seed=4)
+        acc1, seg1, _ = osc.render(cfg.camera, prm)
+        osc.attach_bvh(hs)
+        b_ids, b_t = osc.primary_hits(cfg.camera, 96, 64)
+        acc2, seg2, _ = osc.render(cfg.camera, prm)
+        assert np.array_equal(a_ids, b_ids) and np.array_equal(a_t, b_t), cfg.name
+        assert np.array_equal(acc1, acc2) and seg1 == seg2, cfg.name
