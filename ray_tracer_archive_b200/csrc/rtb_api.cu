@@ -45,16 +45,28 @@ struct DevBuf {
   }
 };
 
-struct rtb_context {
-  int device = 0;
-  cudaDeviceProp prop;
-  // wavefront pool
+// One wavefront instance: its own path pool, queues, counters and stream.  A render runs RTB_LANES of them
+// concurrently on disjoint sample ranges: while one lane is in its ALU-bound extend kernel another is in its
+// DRAM-latency-bound shade kernels, so the two kinds of work overlap on the SMs.
+struct Lane {
   uint32_t pool_n = 0;
   DevBuf<float4> ray, st, hit;
   DevBuf<uint32_t> q_ext0, q_ext1, q_dead;
   DevBuf<uint32_t> q_mat[Q_COUNT];
   DevBuf<DevCounters> counters;
   DevCounters* h_counters = nullptr;  // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+#define RTB_MAX_LANES 4
+
+struct rtb_context {
+  int device = 0;
+  cudaDeviceProp prop;
+  Lane lanes[RTB_MAX_LANES];
+  cudaEvent_t ev_fork = nullptr;
+  DevBuf<DevCounters> counters;        // probes
+  DevCounters* h_counters = nullptr;   // pinned
   // image-sized buffers
   DevBuf<float4> accum;
   DevBuf<uint32_t> pix_order;
@@ -112,6 +124,14 @@ int rtb_context_create(int device_id, rtb_context** out) {
     return set_err(RTB_ERR_NO_DEVICE, "librtb200 is built for sm_100a only");
   }
   CU(cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters)));
+  for (int k = 0; k < RTB_MAX_LANES; ++k) {
+    Lane& L = c->lanes[k];
+    CU(cudaMallocHost((void**)&L.h_counters, sizeof(DevCounters)));
+    CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    CU(L.counters.resize(1));
+  }
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
   for (int k = 0; k < 4; ++k) {
@@ -130,6 +150,13 @@ void rtb_context_destroy(rtb_context* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (int k = 0; k < RTB_MAX_LANES; ++k) {
+    Lane& L = c->lanes[k];
+    if (L.h_counters) cudaFreeHost(L.h_counters);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    if (L.done) cudaEventDestroy(L.done);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ss_ok) {
@@ -540,12 +567,12 @@ static void camera_basis(const rtb_camera& c, DevCamera& f, DevCameraF64& g) {  
 }
 
 // ---- render --------------------------------------------------------------------------------------------------------
-static int ensure_pool(rtb_context* c, uint32_t n) {
-  if (c->pool_n == n) return RTB_OK;
-  CU(c->ray.resize((size_t)n * 2)); CU(c->st.resize((size_t)n * 2)); CU(c->hit.resize(n));
-  CU(c->q_ext0.resize(n)); CU(c->q_ext1.resize(n)); CU(c->q_dead.resize(n));
-  for (int k = 0; k < (int)Q_COUNT; ++k) CU(c->q_mat[k].resize(n));
-  c->pool_n = n;
+static int ensure_pool(Lane& c, uint32_t n) {
+  if (c.pool_n >= n) return RTB_OK;
+  CU(c.ray.resize((size_t)n * 2)); CU(c.st.resize((size_t)n * 2)); CU(c.hit.resize(n));
+  CU(c.q_ext0.resize(n)); CU(c.q_ext1.resize(n)); CU(c.q_dead.resize(n));
+  for (int k = 0; k < (int)Q_COUNT; ++k) CU(c.q_mat[k].resize(n));
+  c.pool_n = n;
   return RTB_OK;
 }
 
@@ -576,73 +603,113 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t npix = (uint64_t)p->width * p->height;
   const unsigned long long total = npix * p->spp;
-  uint32_t pool_n = p->pool_paths ? p->pool_paths : (1u << 21);
-  if (pool_n < 1024) pool_n = 1024;
-  if ((unsigned long long)pool_n > total) pool_n = (uint32_t)std::max<unsigned long long>(1024ull, total);
-  int rc = ensure_pool(c, pool_n);
+  const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
+  // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
+  // per-launch timings / counters describe the kernel alone)
+  static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 2;
+  int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(env_lanes, RTB_MAX_LANES));
+  if ((uint32_t)n_lanes > p->spp) n_lanes = (int)p->spp;
+  uint32_t pool_total = p->pool_paths ? p->pool_paths : (1u << 21);
+  int rc = ensure_pix_order(c, p->width, p->height, st);
   if (rc) return rc;
-  rc = ensure_pix_order(c, p->width, p->height, st);
-  if (rc) return rc;
-
-  DevPool pool;
-  pool.n = pool_n;
-  pool.ray = c->ray.p; pool.st = c->st.p; pool.hit = c->hit.p;
-  pool.q_ext[0] = c->q_ext0.p; pool.q_ext[1] = c->q_ext1.p; pool.q_dead = c->q_dead.p;
-  for (int k = 0; k < (int)Q_COUNT; ++k) pool.q_mat[k] = c->q_mat[k].p;
-  pool.c = c->counters.p;
-  DevParams prm;
-  prm.width = p->width; prm.height = p->height; prm.spp = p->spp; prm.sample_offset = p->sample_offset;
-  prm.max_depth = p->max_depth; prm.rr_start = p->rr_start_depth; prm.seed = p->seed;
-  for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
-  prm.pix_order = c->pix_order.p;
-  prm.inv_npix = 1.0 / (double)npix;
-  prm.accum = (float4*)d_accum;
   DevCamera dcam;
   DevCameraF64 dcam64;
   camera_basis(*cam, dcam, dcam64);
 
+  struct LaneRun { DevPool pool; DevParams prm; unsigned long long total; bool active; uint64_t iters, iter_cap; };
+  LaneRun run[RTB_MAX_LANES];
+  uint32_t first_sample = 0;
+  for (int k = 0; k < n_lanes; ++k) {
+    Lane& L = c->lanes[k];
+    const uint32_t cnt = p->spp / n_lanes + ((uint32_t)k < p->spp % n_lanes ? 1u : 0u);
+    LaneRun& R = run[k];
+    R.total = npix * cnt;
+    uint32_t pool_n = std::max(1024u, pool_total / (uint32_t)n_lanes);
+    if ((unsigned long long)pool_n > R.total) pool_n = (uint32_t)std::max<unsigned long long>(1024ull, R.total);
+    rc = ensure_pool(L, pool_n);
+    if (rc) return rc;
+    R.pool.n = pool_n;
+    R.pool.ray = L.ray.p; R.pool.st = L.st.p; R.pool.hit = L.hit.p;
+    R.pool.q_ext[0] = L.q_ext0.p; R.pool.q_ext[1] = L.q_ext1.p; R.pool.q_dead = L.q_dead.p;
+    for (int q = 0; q < (int)Q_COUNT; ++q) R.pool.q_mat[q] = L.q_mat[q].p;
+    R.pool.c = L.counters.p;
+    DevParams& prm = R.prm;
+    prm.width = p->width; prm.height = p->height; prm.spp = cnt; prm.sample_offset = p->sample_offset + first_sample;
+    prm.max_depth = p->max_depth; prm.rr_start = p->rr_start_depth; prm.seed = p->seed;
+    for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
+    prm.pix_order = c->pix_order.p;
+    prm.inv_npix = 1.0 / (double)npix;
+    prm.accum = (float4*)d_accum;
+    first_sample += cnt;
+    R.active = true;
+    R.iters = 0;
+    R.iter_cap = (uint64_t)(R.total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
+  }
+
   uint64_t launches = 0, extend_launches = 0;
   CU(cudaEventRecord(c->ev0, st));
   if (!(p->flags & RTB_RENDER_ACCUMULATE)) CU(cudaMemsetAsync(d_accum, 0, npix * sizeof(float4), st));
-  launch_init_pool(pool, total, st);
-  launch_generate(s->lc, pool, prm, dcam, st);
-  launch_advance(pool, st);
-  launches += 3;
+  CU(cudaEventRecord(c->ev_fork, st));
+  for (int k = 0; k < n_lanes; ++k) {
+    cudaStream_t ls = c->lanes[k].stream;
+    CU(cudaStreamWaitEvent(ls, c->ev_fork, 0));
+    launch_init_pool(run[k].pool, run[k].total, ls);
+    launch_generate(s->lc, run[k].pool, run[k].prm, dcam, ls);
+    launch_advance(run[k].pool, ls);
+    launches += 3;
+  }
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
   const uint32_t check_every = 8;
   static const bool serial_shade = getenv("RTB_CONCURRENT_SHADE") == nullptr;  // fork/join measured: no gain (profiles/)
-  const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   size_t ev_used = 0;
-  uint64_t iters = 0;
-  const uint64_t iter_cap = (uint64_t)(total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
-  for (;;) {
-    for (uint32_t k = 0; k < check_every; ++k) {
-      if (time_ext) {
-        if (c->ext_events.size() < ev_used + 2) {
-          cudaEvent_t a, b;
-          CU(cudaEventCreate(&a));
-          CU(cudaEventCreate(&b));
-          c->ext_events.push_back(a);
-          c->ext_events.push_back(b);
+  int n_active = n_lanes;
+  while (n_active > 0) {
+    for (uint32_t it = 0; it < check_every; ++it) {
+      for (int k = 0; k < n_lanes; ++k) {  // interleave the lanes' launches so that their phases stay staggered
+        if (!run[k].active) continue;
+        cudaStream_t ls = c->lanes[k].stream;
+        if (time_ext) {
+          if (c->ext_events.size() < ev_used + 2) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            c->ext_events.push_back(a);
+            c->ext_events.push_back(b);
+          }
+          CU(cudaEventRecord(c->ext_events[ev_used], ls));
         }
-        CU(cudaEventRecord(c->ext_events[ev_used], st));
+        launch_extend(s->lc, s->dev, run[k].pool, run[k].prm, count, ls);
+        if (time_ext) {
+          CU(cudaEventRecord(c->ext_events[ev_used + 1], ls));
+          ev_used += 2;
+        }
+        launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls, serial_shade ? nullptr : &c->ss);
+        launch_advance(run[k].pool, ls);
+        launches += 2 + n_shade;
+        extend_launches += 1;
       }
-      launch_extend(s->lc, s->dev, pool, prm, count, st);
-      if (time_ext) {
-        CU(cudaEventRecord(c->ext_events[ev_used + 1], st));
-        ev_used += 2;
-      }
-      launch_shade(s->lc, s->dev, pool, prm, dcam, present, st, serial_shade ? nullptr : &c->ss);
-      launch_advance(pool, st);
-      launches += 2 + n_shade;
-      extend_launches += 1;
     }
-    iters += check_every;
-    CU(cudaMemcpyAsync(c->h_counters, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (c->h_counters->n_ext[c->h_counters->cur] == 0) break;
-    if (iters > iter_cap) return set_err(RTB_ERR_CUDA, "wavefront did not drain (internal error)");
+    for (int k = 0; k < n_lanes; ++k)
+      if (run[k].active)
+        CU(cudaMemcpyAsync(c->lanes[k].h_counters, c->lanes[k].counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost,
+                           c->lanes[k].stream));
+    for (int k = 0; k < n_lanes; ++k) {
+      if (!run[k].active) continue;
+      CU(cudaStreamSynchronize(c->lanes[k].stream));
+      run[k].iters += check_every;
+      const DevCounters* h = c->lanes[k].h_counters;
+      if (h->n_ext[h->cur] == 0) {
+        run[k].active = false;
+        --n_active;
+      } else if (run[k].iters > run[k].iter_cap) {
+        return set_err(RTB_ERR_CUDA, "wavefront did not drain (internal error)");
+      }
+    }
+  }
+  for (int k = 0; k < n_lanes; ++k) {
+    CU(cudaEventRecord(c->lanes[k].done, c->lanes[k].stream));
+    CU(cudaStreamWaitEvent(st, c->lanes[k].done, 0));
   }
   CU(cudaEventRecord(c->ev1, st));
   CU(cudaEventSynchronize(c->ev1));
@@ -651,15 +718,18 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     std::memset(stats, 0, sizeof(*stats));
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    stats->paths = std::min<unsigned long long>(c->h_counters->next_path, total);
-    stats->segments = c->h_counters->segments;
-    stats->rejected = c->h_counters->rejected;
-    stats->iterations = c->h_counters->iter;
+    for (int k = 0; k < n_lanes; ++k) {
+      const DevCounters* h = c->lanes[k].h_counters;
+      stats->paths += std::min<unsigned long long>(h->next_path, run[k].total);
+      stats->segments += h->segments;
+      stats->rejected += h->rejected;
+      stats->iterations = std::max<uint64_t>(stats->iterations, h->iter);
+      stats->nodes_visited += h->nodes_visited;
+      stats->prims_tested += h->prims_tested;
+    }
     stats->launches = launches;
     stats->extend_launches = extend_launches;
     stats->ms_total = ms;
-    stats->nodes_visited = c->h_counters->nodes_visited;
-    stats->prims_tested = c->h_counters->prims_tested;
     double ms_ext = 0;
     for (size_t k = 0; k + 1 < ev_used; k += 2) {
       float e = 0;
