@@ -11,7 +11,7 @@ for arg in sys.argv[1:]:
     name, spp = arg.split(":")
     cfg = get_config(name, int(spp))
     sc = rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights))
-    prm = lambda fl=0: rtb.make_params(cfg.width, cfg.height, cfg.spp, cfg.max_depth, cfg.background, seed=1, flags=fl)
+    prm = lambda fl=0: rtb.make_params(cfg.width, cfg.height, cfg.spp, cfg.max_depth, cfg.background, seed=1, flags=fl, pool_paths=int(os.environ.get('RTB_POOL', '0')))
     sc.render(cfg.camera, prm(), readback=False)
     best = None
     for _ in range(2):
