@@ -606,10 +606,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
   // per-launch timings / counters describe the kernel alone)
-  static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 2;
+  static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 3;
   int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(env_lanes, RTB_MAX_LANES));
   if ((uint32_t)n_lanes > p->spp) n_lanes = (int)p->spp;
-  uint32_t pool_total = p->pool_paths ? p->pool_paths : (1u << 21);
+  uint32_t pool_total = p->pool_paths ? p->pool_paths : (1u << 22);  // all lanes together; 112 B per slot
   int rc = ensure_pix_order(c, p->width, p->height, st);
   if (rc) return rc;
   DevCamera dcam;

@@ -7,6 +7,7 @@
 // dense contraction.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -886,11 +887,13 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
+  if (getenv("RTB_EXTEND_OCC")) occ = std::max(1, std::min(occ, atoi(getenv("RTB_EXTEND_OCC"))));
   lc.extend_grid = (uint32_t)(sm_count * occ);
   int occ2 = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_shade_lambert, RTB_SHADE_THREADS, 0);
   if (e != cudaSuccess) return (int)e;
   if (occ2 < 1) occ2 = 1;
+  if (getenv("RTB_SHADE_OCC")) occ2 = std::max(1, std::min(occ2, atoi(getenv("RTB_SHADE_OCC"))));
   lc.shade_grid = (uint32_t)(sm_count * occ2);
   return 0;
 }
