@@ -887,7 +887,9 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
-  if (getenv("RTB_EXTEND_OCC")) occ = std::max(1, std::min(occ, atoi(getenv("RTB_EXTEND_OCC"))));
+  // two extend CTAs per SM (of the three that fit): leaves a third of the register file to the shade kernels of the
+  // other wavefront lanes, which then really run beside extend (measured +8 % on C1, profiles/r1_ab_extend.md)
+  occ = std::min(occ, getenv("RTB_EXTEND_OCC") ? std::max(1, atoi(getenv("RTB_EXTEND_OCC"))) : 2);
   lc.extend_grid = (uint32_t)(sm_count * occ);
   int occ2 = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_shade_lambert, RTB_SHADE_THREADS, 0);
