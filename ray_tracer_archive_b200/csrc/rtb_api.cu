@@ -426,6 +426,7 @@ int rtb_scene_commit(rtb_scene* s) {
   CU(s->d_nodes.upload(reinterpret_cast<const uint4*>(s->bvh.nodes.data()), s->bvh.nodes.size() * 5));
   d.nodes = s->d_nodes.p;
   d.n_nodes = (uint32_t)s->bvh.nodes.size();
+  d.prmt_magic = 0x43000000u;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
     CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(s->bvh.info[t].data()), s->bvh.info[t].size() / 2));

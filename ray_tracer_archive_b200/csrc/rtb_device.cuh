@@ -36,6 +36,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   const uint4* nodes;
   uint32_t n_nodes;
   uint32_t n_lights, n_media, n_materials;
+  uint32_t prmt_magic;  // = 0x43000000, see q2f()
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
@@ -264,10 +265,12 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
   consider(best, t, (type << REF_TYPE_SHIFT) | idx, gid);
 }
 
-__device__ __forceinline__ float q2f(uint32_t word, uint32_t sel) {
-  // 7-bit plane byte `sel&3` of `word` -> the float 128 + q, with ONE byte permute and no conversion:
+__device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
+  // 7-bit plane byte `sel>>8 & 3` of `word` -> the float 128 + q, with ONE byte permute and no conversion:
   // bits = 0x43000000 | q << 16  (exponent 2^7, q in the top mantissa bits).  The 128 is folded into the node bias.
-  return __uint_as_float(__byte_perm(word, 0x43000000u, sel));
+  // `magic` = 0x43000000 is kept in a REGISTER so that the selector can be the instruction's immediate operand
+  // (otherwise ptxas materialises a selector register with an extra MOV before each of the 48 PRMTs of a node).
+  return __uint_as_float(__byte_perm(word, magic, sel));
 }
 
 // Wide-BVH closest-hit traversal.  `snodes` = first `n_snodes` nodes staged in shared memory (uint4 x5 each);
@@ -344,15 +347,16 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
   const uint32_t nz0 = nz ? w4.z : w3.x, nz1 = nz ? w4.w : w3.y, fz0 = nz ? w3.x : w4.z, fz1 = nz ? w3.y : w4.w;
   uint32_t hitmask = 0;
+  const uint32_t magic = sc.prmt_magic;  // 0x43000000, read from the constant bank (ptxas cannot fold it into the PRMT)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const uint32_t sel = 0x7044u | ((uint32_t)(i & 3) << 8);
-    const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, sel), ax, bnx);
-    const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, sel), ay, bny);
-    const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, sel), az, bnz);
-    const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, sel), ax, bfx);
-    const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, sel), ay, bfy);
-    const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, sel), az, bfz);
+    const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, magic, sel), ax, bnx);
+    const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, magic, sel), ay, bny);
+    const float tnz = fmaf(q2f(i < 4 ? nz0 : nz1, magic, sel), az, bnz);
+    const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, magic, sel), ax, bfx);
+    const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, magic, sel), ay, bfy);
+    const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, magic, sel), az, bfz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tv.best.t));
     if (tn <= tf) hitmask |= 1u << i;

@@ -39,6 +39,7 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   std::memset(&sc, 0, sizeof(sc));
   sc.nodes = (const uint4*)nodes;
   sc.n_nodes = n_nodes;
+  sc.prmt_magic = 0x43000000u;
   const float* g[4] = {geom0, geom1, geom2, geom3};
   const uint32_t* inf[4] = {info0, info1, info2, info3};
   for (int t = 0; t < 4; ++t) { sc.geom[t] = (const float4*)g[t]; sc.info[t] = (const uint2*)inf[t]; }
