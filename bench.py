@@ -119,6 +119,17 @@ def bounded_cpu_sample(osc, rtb, cfg, cores, budget_s=12.0):
     return segs, dt, sample
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(workload)
+        return t["dram_bytes_per_launch"] if t else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -338,7 +349,7 @@ def main():
             "peak": fp32_peak if fp_bound else mem_gbs,
             "unit": "TFLOP/s" if fp_bound else "GB/s",
             "frac": (ach_tflops / fp32_peak) if fp_bound else (ach_gbs / mem_gbs),
-            "traffic": None,
+            "traffic": ncu_traffic(args.workload),
             "peak_source": f"FP32 = SMs*128*2*f_SM at the median SM clock seen in this run ({sm_mhz:.0f} MHz) = {fp32_peak:.1f} TFLOP/s; "
                            f"L2 = {l2_gbs:.0f} GB/s measured in this run (L2-resident 2x48 MB copy); HBM {which} {peaks['hbm_gbs']} GB/s",
             "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_peak, "frac": ach_tflops / fp32_peak},
