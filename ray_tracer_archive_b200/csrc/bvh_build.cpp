@@ -3,9 +3,9 @@
 // of the [start,end) range and so drops objects (bvh.rs:86,108) — it is not replicated.  Closest-hit semantics stay
 // those of the linear HittableList scan (hittable_list.rs:39-51); the BVH only culls.
 //
-// Pipeline: per primitive type a binned-SAH binary tree (leaves <= 3 primitives)  ->  collapse to 8-wide nodes by
+// Pipeline: per primitive type a binned-SAH binary tree (1 primitive per leaf, 2 for triangles)  ->  collapse to 8-wide nodes by
 // repeatedly opening the child with the largest surface area  ->  children assigned to octant-ordered slots (so the
-// traversal visits near children first by XOR-ing the slot with the ray octant)  ->  child boxes quantised to 8 bits
+// traversal visits near children first by XOR-ing the slot with the ray octant)  ->  child boxes quantised to 7 bits
 // per plane relative to the node origin with a power-of-two step, rounded outward (conservative).
 // The per-type trees hang under one root, so every node's leaf children share one primitive type.
 #include <algorithm>
