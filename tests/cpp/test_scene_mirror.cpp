@@ -1,0 +1,73 @@
+// C++ host-side test: the reference's cornell_box() (raytracer/src/main.rs:337-433) and light list (:669-686) written
+// with the C++ mirror of its constructors, handed to librtb200 through the C ABI (host-only scene: no GPU needed here).
+// Prints the flattened scene summary and the serialized records so the pytest wrapper can compare them with the Python
+// mirror's.  With a GPU (argv[1] == "render") it also renders 16 spp and prints the segment count.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rtb200_scene.hpp"
+
+using namespace rtb200;
+
+static std::shared_ptr<HittableList> cornell_box() {
+  auto objects = HittableList::new_();
+  auto red = Lambertian::construct({0.65, 0.05, 0.05});
+  auto white = Lambertian::construct({0.73, 0.73, 0.73});
+  auto green = Lambertian::construct({0.12, 0.45, 0.15});
+  auto light = DiffuseLight::construct_color({15.0, 15.0, 15.0});
+  objects->add(YzRect::construct(0.0, 555.0, 0.0, 555.0, 555.0, green));
+  objects->add(YzRect::construct(0.0, 555.0, 0.0, 555.0, 0.0, red));
+  objects->add(FlipFace::construct(XzRect::construct(213.0, 343.0, 227.0, 332.0, 554.0, light)));
+  objects->add(XzRect::construct(0.0, 555.0, 0.0, 555.0, 0.0, white));
+  objects->add(XzRect::construct(0.0, 555.0, 0.0, 555.0, 555.0, white));
+  objects->add(XyRect::construct(0.0, 555.0, 0.0, 555.0, 555.0, white));
+  HittablePtr box1 = Box::construct({0.0, 0.0, 0.0}, {165.0, 330.0, 165.0}, white);
+  box1 = RotateY::construct(box1, 15.0);
+  box1 = Translate::construct(box1, {265.0, 0.0, 295.0});
+  objects->add(box1);
+  objects->add(Sphere::construct({190.0, 90.0, 190.0}, 90.0, Dielectric::construct(1.5)));
+  return objects;
+}
+
+int main(int argc, char** argv) {
+  auto world = cornell_box();
+  auto lights = HittableList::new_();
+  lights->add(XzRect::construct(213.0, 343.0, 227.0, 332.0, 554.0, DiffuseLight::construct_color({15.0, 15.0, 15.0})));
+  lights->add(Sphere::construct({190.0, 90.0, 190.0}, 90.0, Dielectric::construct(1.5)));
+  SceneRecords rec;
+  rec.set_world(world, lights);
+
+  const bool render = argc > 1 && !std::strcmp(argv[1], "render");
+  rtb_context* ctx = nullptr;
+  if (render && rtb_context_create(0, &ctx) != 0) { std::printf("context: %s\n", rtb_last_error()); return 2; }
+  rtb_scene* scene = nullptr;
+  if (rtb_scene_create(ctx, &scene) != 0) return 3;
+  rec.upload(scene);
+  if (rtb_scene_build_bvh(scene) != 0) { std::printf("build: %s\n", rtb_last_error()); return 4; }
+  rtb_scene_info info;
+  rtb_scene_get_info(scene, &info);
+  std::printf("quads %u spheres %u prims %u lights %u materials %u textures %u nodes %u\n", info.n_quads, info.n_spheres,
+              info.n_prims, info.n_lights, info.n_materials, info.n_textures, info.n_bvh_nodes);
+  std::printf("records %zu children %zu root %u\n", rec.nodes.size(), rec.child_index.size(), rec.root);
+  for (const rtb_node& n : rec.nodes) {
+    std::printf("node %u %u %u %u", n.type, n.material, n.first_child, n.n_children);
+    for (double v : n.p) std::printf(" %.17g", v);
+    std::printf("\n");
+  }
+  // error behaviour: a host-only scene cannot be committed
+  if (!ctx) {
+    int rc = rtb_scene_commit(scene);
+    std::printf("commit_without_context %d\n", rc);
+  } else {
+    if (rtb_scene_commit(scene) != 0) { std::printf("commit: %s\n", rtb_last_error()); return 5; }
+    rtb_camera cam{{278, 278, -800}, {278, 278, 0}, {0, 1, 0}, 40.0, 1.0, 0.0, 10.0, 0.0, 1.0};
+    rtb_params prm{};
+    prm.width = 64; prm.height = 64; prm.spp = 16; prm.total_spp = 16; prm.max_depth = 50; prm.seed = 1;
+    rtb_stats st;
+    if (rtb_render(ctx, scene, &cam, &prm, nullptr, &st) != 0) { std::printf("render: %s\n", rtb_last_error()); return 6; }
+    std::printf("rendered paths %llu segments %llu\n", (unsigned long long)st.paths, (unsigned long long)st.segments);
+  }
+  rtb_scene_destroy(scene);
+  if (ctx) rtb_context_destroy(ctx);
+  return 0;
+}
