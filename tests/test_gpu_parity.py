@@ -119,6 +119,54 @@ def test_tie_break_and_flat_api(rtb, orc, ctx):
     np.testing.assert_allclose(ts2[:3], ts[:3], rtol=1e-6)
 
 
+def test_flat_api_triangles_moving_spheres_media(rtb, orc, ctx):
+    """rtb_scene_set_triangles / _moving_spheres / _media (callers that flatten themselves) give the same closest hits
+    and the same image as the graph entry point and the oracle."""
+    from ray_tracer_archive_b200 import scene as S
+    F = rtb._ffi
+    lam = S.Lambertian.construct((0.6, 0.5, 0.4))
+    boundary = S.Sphere.construct((0.0, 1.0, 0.0), 1.5, S.Dielectric.construct(1.5))
+    world = S.HittableList([
+        S.Triangle((-3, 0, -3), (3, 0, -3), (0, 0, 3), lam), S.Triangle((-3, 3, -3), (0, 3, 3), (3, 3, -3), lam),
+        S.MovingSphere.construct((-1.5, 1, 0), (-1.5, 1.6, 0), 0.0, 1.0, 0.4, lam),
+        S.ConstantMedium.construct_color(boundary, 0.8, (0.9, 0.9, 0.9))])
+    cs = rtb.compile_scene(world)
+    graph, osc = rtb.Scene(ctx, cs), orc.OracleScene(cs)
+    lib = rtb._ffi.load()
+    flat = rtb.Scene(ctx)
+    flat.set_tables(cs)
+    v0 = np.array([[-3, 0, -3], [-3, 3, -3]], np.float32)
+    v1 = np.array([[3, 0, -3], [0, 3, 3]], np.float32)
+    v2 = np.array([[0, 0, 3], [3, 3, -3]], np.float32)
+    z2 = np.zeros(2, np.uint32)
+    F.check(lib.rtb_scene_set_triangles(flat.h, F.ptr(v0), F.ptr(v1), F.ptr(v2), F.ptr(z2), None, F.ptr(np.array([0, 1], np.uint32)), 2))
+    F.check(lib.rtb_scene_set_moving_spheres(flat.h, F.ptr(np.array([[-1.5, 1, 0, 0.4]], np.float32)),
+                                             F.ptr(np.array([[-1.5, 1.6, 0]], np.float32)), F.ptr(np.array([[0, 1]], np.float32)),
+                                             F.ptr(np.zeros(1, np.uint32)), None, F.ptr(np.array([2], np.uint32)), 1))
+    med = np.zeros(1, dtype=np.dtype([("boundary_type", "<u4"), ("material", "<u4"), ("prim_id", "<u4"), ("_pad", "<u4"),
+                                      ("density", "<f8"), ("p", "<f8", (6,)), ("rot_y_deg", "<f8"), ("offset", "<f8", (3,))]))
+    iso = [i for i in range(len(cs.materials)) if int(cs.materials[i]["type"]) == F.MAT_ISOTROPIC][0]
+    med[0] = (0, iso, 3, 0, 0.8, [0.0, 1.0, 0.0, 1.5, 0, 0], 0.0, [0, 0, 0])
+    assert med.dtype.itemsize == 104
+    F.check(lib.rtb_scene_set_media(flat.h, F.ptr(med), 1))
+    flat.commit()
+    assert flat.info()["n_prims"] == graph.info()["n_prims"] == 4
+    rng = np.random.default_rng(2)
+    o = rng.uniform((-3, 0.2, -3), (3, 2.8, 3), (4000, 3)).astype(np.float32)
+    d = rng.normal(0, 1, (4000, 3)).astype(np.float32)
+    tm = rng.random(4000).astype(np.float32)
+    a = graph.trace_rays(o, d, tm)
+    b = flat.trace_rays(o, d, tm)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    oid, ot = osc.trace_rays(o.astype(np.float64), d.astype(np.float64), tm.astype(np.float64))
+    assert (a[0] != oid).sum() <= 2
+    cam = rtb.Camera.new((0, 1.5, 9), (0, 1.2, 0), (0, 1, 0), 40.0, 1.0, 0.0, 9.0)
+    prm = rtb.make_params(32, 32, 256, background=(0.7, 0.8, 1.0), seed=5)
+    acc_g, _ = graph.render(cam, prm)
+    acc_f, _ = flat.render(cam, prm)
+    np.testing.assert_allclose(acc_f, acc_g, rtol=2e-4, atol=2e-3)
+
+
 def test_heightfield_closest_hit_full_1M_triangles(rtb, ctx):
     """C4 at full size (1 000 000 triangles): size-independent properties of a height field.
     (a) vertical rays hit exactly the triangle whose xz-projection contains them, at the interpolated height;
