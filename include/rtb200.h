@@ -224,6 +224,8 @@ typedef struct rtb_scene_info {
 int rtb_scene_get_info(rtb_scene* s, rtb_scene_info* out);
 /* copies out the leaf-ordered device layout: geometry as float4 words + (prim_id, material|flags<<24) pairs */
 int rtb_scene_export_bvh(rtb_scene* s, void* nodes_80B, size_t cap_bytes);
+/* primitives kept out of the tree and tested first for every ray: refs = type << 29 | index into that type's arrays */
+int rtb_scene_export_globals(rtb_scene* s, uint32_t* refs, uint32_t cap, uint32_t* n_out);
 int rtb_scene_export_prims(rtb_scene* s, uint32_t type /*0 sphere 1 moving 2 quad 3 triangle*/, float* geom,
                            size_t geom_cap_bytes, uint32_t* info_pairs, size_t info_cap_bytes);
 

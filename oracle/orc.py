@@ -38,7 +38,7 @@ def load():
         lib.orc_scene_set_perlin.argtypes = [_VP, _U32, _VP, _VP, _VP, _VP]
         lib.orc_scene_set_mesh.argtypes = [_VP, _U32, _VP, _U32, _VP, _U32]
         lib.orc_scene_build.argtypes = [_VP]
-        lib.orc_scene_attach_bvh.argtypes = [_VP, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32]
+        lib.orc_scene_attach_bvh.argtypes = [_VP, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32, _VP, _U32]
         lib.orc_scene_use_bvh.argtypes = [_VP, C.c_int]
         lib.orc_scene_num_prims.restype = _U32
         lib.orc_scene_num_prims.argtypes = [_VP]
@@ -109,6 +109,10 @@ class OracleScene:
         args = [_p(nodes), len(nodes) // 80]
         for g, inf in prims:
             args += [_p(inf) if len(inf) else None, len(inf) // 2]
+        # primitives the product keeps out of the tree ("globals"): always candidates
+        refs = host_or_device_scene.export_globals()
+        gids = np.array([prims[int(r) >> 29][1][2 * (int(r) & ((1 << 29) - 1))] for r in refs], dtype=np.uint32)
+        args += [_p(gids) if len(gids) else None, len(gids)]
         rc = self.lib.orc_scene_attach_bvh(self.h, *args)
         if rc != 0:
             raise RuntimeError("attach_bvh: " + self.lib.orc_scene_error(self.h).decode())

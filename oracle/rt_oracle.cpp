@@ -379,6 +379,7 @@ struct Scene {
   struct Accel {
     std::vector<uint8_t> nodes;       // 80-byte nodes as exported by rtb_scene_export_bvh
     std::vector<uint32_t> info[4];    // (prim id, material|mode) pairs, leaf order, per type
+    std::vector<uint32_t> globals;    // prim ids that are always candidates (kept out of the product's tree)
     bool on = false;
   } accel;
 
@@ -593,6 +594,12 @@ static bool hit_accel(const Scene& sc, const Ray& r, double t_min, double t_max,
   bool found = false;
   uint32_t best_id = 0;
   HitRecord tmp;
+  for (uint32_t gid : sc.accel.globals) {
+    if (n_prims) ++*n_prims;
+    if (sc.prim_obj[gid]->hit(r, t_min, closest, tmp, cx)) {
+      if (!found || tmp.t < closest || gid > best_id) { found = true; closest = tmp.t; best_id = gid; rec = tmp; }
+    }
+  }
   uint32_t stack[256];
   int sp = 0;
   stack[sp++] = 0;
@@ -857,7 +864,7 @@ int orc_scene_build(orc_scene* o) { return o->s.build() ? 0 : -1; }
 // attach the product's exported BVH (rtb_scene_export_bvh / rtb_scene_export_prims) as a candidate culler
 int orc_scene_attach_bvh(orc_scene* o, const void* nodes80, uint32_t n_nodes, const uint32_t* info0, uint32_t n0,
                          const uint32_t* info1, uint32_t n1, const uint32_t* info2, uint32_t n2, const uint32_t* info3,
-                         uint32_t n3) {
+                         uint32_t n3, const uint32_t* global_ids, uint32_t n_globals) {
   if (!o->s.build()) return -1;
   Scene::Accel& a = o->s.accel;
   a.nodes.assign((const uint8_t*)nodes80, (const uint8_t*)nodes80 + (size_t)n_nodes * 80);
@@ -869,6 +876,9 @@ int orc_scene_attach_bvh(orc_scene* o, const void* nodes80, uint32_t n_nodes, co
     for (size_t k = 0; k < cnt[t]; ++k)
       if (a.info[t][2 * k] >= o->s.prim_obj.size() || !o->s.prim_obj[a.info[t][2 * k]]) { o->s.err = "BVH references an unknown primitive id"; return -2; }
   }
+  a.globals.assign(global_ids, global_ids + n_globals);
+  for (uint32_t g : a.globals)
+    if (g >= o->s.prim_obj.size() || !o->s.prim_obj[g]) { o->s.err = "unknown global primitive id"; return -2; }
   a.on = true;
   return 0;
 }

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB", os.path.join(_HERE, "librtb200.so"))  # RTB200_LIB: A/B builds only
 
 RTB_NONE = 0xFFFFFFFF
 
@@ -102,6 +102,7 @@ SIGNATURES = {
     "rtb_scene_commit": (_I, [_VP]),
     "rtb_scene_get_info": (_I, [_VP, C.POINTER(SceneInfo)]),
     "rtb_scene_export_bvh": (_I, [_VP, _VP, _SZ]),
+    "rtb_scene_export_globals": (_I, [_VP, _VP, _U32, C.POINTER(C.c_uint32)]),
     "rtb_scene_export_prims": (_I, [_VP, _U32, _VP, _SZ, _VP, _SZ]),
     "rtb_render": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _VP, C.POINTER(Stats)]),
     "rtb_render_device": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _VP, _VP, C.POINTER(Stats)]),

@@ -226,7 +226,31 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   out.nodes.clear();
   for (int t = 0; t < (int)PT_COUNT; ++t) { out.geom[t].clear(); out.info[t].clear(); }
   out.max_depth = 0;
+  out.global_refs.clear();
   const size_t np = hs.prims.size();
+
+  // --- "global" primitives: a primitive whose box is (nearly) the whole scene box (the r=1000 ground sphere of
+  // book 1) cannot be culled by any node and only coarsens the quantisation grid of the node that holds
+  // it.  Up to RTB_MAX_GLOBALS of them are kept out of the tree and tested first for every ray (which also gives an
+  // early t_max that culls nodes behind them).
+  std::vector<char> is_global(np, 0);
+  {
+    Box3 scene;
+    for (size_t i = 0; i < np; ++i) scene.grow(hs.prims[i].lo, hs.prims[i].hi);
+    const float scene_area = scene.area();
+    const bool enabled = !(getenv("RTB_GLOBALS") && atoi(getenv("RTB_GLOBALS")) == 0);
+    if (enabled && np > 4 && scene_area > 0.f) {
+      std::vector<std::pair<float, uint32_t>> big;
+      for (size_t i = 0; i < np; ++i) {
+        Box3 b;
+        b.grow(hs.prims[i].lo, hs.prims[i].hi);
+        const float a = b.area();
+        if (a >= 0.8f * scene_area) big.emplace_back(-a, (uint32_t)i);  // dominates the scene box (walls at 1/3 do not pay)
+      }
+      std::sort(big.begin(), big.end());
+      for (size_t k = 0; k < big.size() && k < RTB_MAX_GLOBALS; ++k) is_global[big[k].second] = 1;
+    }
+  }
 
   // --- per-type binary trees ---------------------------------------------------------------------------------
   std::vector<float> centroid(3 * np);
@@ -244,14 +268,26 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     if (const char* e = getenv("RTB_MAX_LEAF")) b->max_leaf = (uint32_t)std::max(1, std::min(3, atoi(e)));
     builders.push_back(b);
     for (size_t i = 0; i < np; ++i)
-      if (hs.prims[i].type == t) b->order.push_back((uint32_t)i);
+      if (hs.prims[i].type == t && !is_global[i]) b->order.push_back((uint32_t)i);
     if (b->order.empty()) continue;
     b->centroid = centroid;  // shared copy (small relative to the build)
     b->bin.reserve(b->order.size());
     int root = b->build_range(0, (uint32_t)b->order.size());
     trees.push_back(TypedTree{b, root, t});
   }
-  auto cleanup = [&]() { for (Builder* b : builders) delete b; };
+  auto cleanup = [&]() {
+    for (Builder* b : builders) delete b;
+    // global primitives live at the end of their type's leaf-ordered arrays; no node references them
+    for (size_t i = 0; i < np; ++i) {
+      if (!is_global[i]) continue;
+      const HostPrim& p = hs.prims[i];
+      const uint32_t idx = (uint32_t)(out.info[p.type].size() / 2);
+      for (uint32_t w = 0; w < geom_words(p.type); ++w) out.geom[p.type].push_back(p.g[w]);
+      out.info[p.type].push_back(p.prim_id);
+      out.info[p.type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
+      out.global_refs.push_back((p.type << REF_TYPE_SHIFT) | idx);
+    }
+  };
 
   Assembler as{hs, out};
   if (trees.empty()) {  // empty scene: a single node with no children (every ray misses)

@@ -427,6 +427,8 @@ int rtb_scene_commit(rtb_scene* s) {
   d.nodes = s->d_nodes.p;
   d.n_nodes = (uint32_t)s->bvh.nodes.size();
   d.prmt_magic = 0x43000000u;
+  d.n_global = (uint32_t)s->bvh.global_refs.size();
+  for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
     CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(s->bvh.info[t].data()), s->bvh.info[t].size() / 2));
@@ -522,6 +524,16 @@ int rtb_scene_export_bvh(rtb_scene* s, void* nodes, size_t cap) {
   size_t bytes = s->bvh.nodes.size() * sizeof(Node8);
   if (cap < bytes) return set_err(RTB_ERR_INVALID, "buffer too small");
   std::memcpy(nodes, s->bvh.nodes.data(), bytes);
+  return RTB_OK;
+}
+int rtb_scene_export_globals(rtb_scene* s, uint32_t* refs, uint32_t cap, uint32_t* n_out) {
+  if (!s || !n_out) return set_err(RTB_ERR_INVALID, "bad argument");
+  if (!s->built) return set_err(RTB_ERR_STATE, "BVH not built (call rtb_scene_build_bvh or rtb_scene_commit)");
+  *n_out = (uint32_t)s->bvh.global_refs.size();
+  if (refs) {
+    if (cap < *n_out) return set_err(RTB_ERR_INVALID, "buffer too small");
+    for (uint32_t k = 0; k < *n_out; ++k) refs[k] = s->bvh.global_refs[k];
+  }
   return RTB_OK;
 }
 int rtb_scene_export_prims(rtb_scene* s, uint32_t type, float* geom, size_t gcap, uint32_t* info, size_t icap) {

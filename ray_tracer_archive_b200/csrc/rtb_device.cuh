@@ -37,6 +37,8 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t n_nodes;
   uint32_t n_lights, n_media, n_materials;
   uint32_t prmt_magic;  // = 0x43000000, see q2f()
+  uint32_t n_global;    // primitives tested for every ray before the traversal (kept out of the tree)
+  uint32_t global_ref[RTB_MAX_GLOBALS];
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
@@ -381,6 +383,16 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   return true;
 }
 
+// the scene's "global" primitives (huge relative to the scene, kept out of the tree): tested first, which also
+// establishes an early t_max for the traversal
+template <bool COUNT>
+__device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float tmin, uint32_t& n_tests) {
+  for (uint32_t k = 0; k < sc.n_global; ++k) {
+    const uint32_t ref = sc.global_ref[k];
+    intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+  }
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
@@ -389,6 +401,7 @@ __device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __rest
   uint2 stack[RTB_STACK];
   trav_init(tv, o, d, time);
   tv.best = best;
+  trav_globals<COUNT>(sc, tv, tmin, n_tests);
   while (trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
 }

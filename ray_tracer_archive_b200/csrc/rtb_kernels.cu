@@ -160,6 +160,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);
           tv.sp = 0;
           tv.best = Closest{INFINITY, REF_MISS, 0u};
+          trav_globals<COUNT>(sc, tv, RTB_TMIN, nt);
           state = RUNNING;
         }
         in_head += min((uint32_t)__popc(empty), avail);
@@ -565,7 +566,7 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
   }
 
 // miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_TERMINAL)
       PathIO io = load_path(pool, slot);
       if (io.ref == REF_MISS) {
@@ -620,20 +621,20 @@ __device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool&
   return finish_bounce(pool, prm, io, scattered, s.p, dir, io.time, rr);
 }
 
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_LAMBERT)
       alive = shade_diffuse<false>(sc, pool, prm, slot);
   RTB_SHADE_LOOP_END
 }
 
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_ISOTROPIC)
       alive = shade_diffuse<true>(sc, pool, prm, slot);
   RTB_SHADE_LOOP_END
 }
 
 // Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_metal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_metal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_METAL)
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_metal(DevScene s
 }
 
 // Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, 3) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_DIELECTRIC)
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);

@@ -5,6 +5,9 @@
 
 #define RTB_EXTEND_THREADS 256
 #define RTB_SHADE_THREADS 256
+#ifndef RTB_SHADE_MIN_BLOCKS
+#define RTB_SHADE_MIN_BLOCKS 3
+#endif
 
 namespace rtb {
 

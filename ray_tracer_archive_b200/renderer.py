@@ -111,6 +111,13 @@ class Scene:
             prims.append((g, inf))
         return nodes, prims
 
+    def export_globals(self):
+        """refs (type << 29 | index) of the primitives that are tested for every ray instead of living in the tree"""
+        refs = np.zeros(8, dtype=np.uint32)
+        n = C.c_uint32()
+        F.check(self.lib.rtb_scene_export_globals(self.h, F.ptr(refs), 8, C.byref(n)))
+        return refs[:n.value].copy()
+
     # ---- hot path -------------------------------------------------------------------------------------------
     def render(self, cam: F.Camera, params: F.Params, readback: bool = True):
         """rtb_render: returns (accum (H,W,4) float32 or None, stats dict)."""

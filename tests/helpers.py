@@ -45,7 +45,7 @@ def build_emul():
                                "-I/usr/local/cuda/include", "-o", out, src])
     lib = C.CDLL(out)
     VP = C.c_void_p
-    lib.emul_trace.argtypes = [VP, C.c_uint32] + [VP] * 8 + [C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP]
+    lib.emul_trace.argtypes = [VP, C.c_uint32] + [VP] * 8 + [VP, C.c_uint32, C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP]
     return lib
 
 
@@ -66,6 +66,8 @@ def emul_trace(lib, host_scene, origin, direction, time=None, n_snodes=10 ** 6):
     args = [_p(nodes), info["n_bvh_nodes"]]
     for g, inf in prims:
         args += [_p(g), _p(inf)]
+    glob = host_scene.export_globals()
+    args += [_p(glob), len(glob)]
     lib.emul_trace(*args, n_snodes, _p(o), _p(d), _p(tm), n, _p(ids), _p(ts), C.byref(nv), C.byref(nt))
     return ids, ts, nv.value, nt.value
 
