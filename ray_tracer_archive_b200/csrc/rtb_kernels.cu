@@ -63,12 +63,15 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 // Work is claimed from a device-side cursor, one atomic per 32 rays.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
+// extend runs 2 CTAs/SM (configure_launch) with at most 88 registers: 2 x 256 x 88 = 45 K of the 64 K registers, so one
+// 256-thread shade CTA (72 registers) of another lane fits beside them
+#define RTB_EXTEND_MAXREG 88
 struct ExtIn { float4 o_time, d_slot, idir_oct; };
 struct ExtOut { float t; uint32_t ref, gid, slot; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RTB_EXTEND_THREADS, 3)
+__global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ ExtIn s_in[RTB_EXTEND_WARPS][32];
@@ -198,7 +201,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
 
 // The first version: one ray per thread to completion, grid-stride (kept for A/B measurements, RTB_EXTEND_MODE=static).
 template <bool COUNT>
-__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
+__global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   DevCounters* c = pool.c;
