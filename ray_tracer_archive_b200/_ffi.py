@@ -130,6 +130,8 @@ def load():
                            "(the CUDA library is the only implementation; there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if "RTB200_LIB" in os.environ and not hasattr(lib, name):
+            continue  # A/B build of an older ABI (tools only)
         fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args

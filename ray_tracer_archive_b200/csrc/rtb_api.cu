@@ -615,7 +615,6 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const uint64_t npix = (uint64_t)p->width * p->height;
-  const unsigned long long total = npix * p->spp;
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
   // per-launch timings / counters describe the kernel alone)

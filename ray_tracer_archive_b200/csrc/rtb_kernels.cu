@@ -63,9 +63,10 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 // Work is claimed from a device-side cursor, one atomic per 32 rays.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
-// extend runs 2 CTAs/SM (configure_launch) with at most 88 registers: 2 x 256 x 88 = 45 K of the 64 K registers, so one
-// 256-thread shade CTA (72 registers) of another lane fits beside them
-#define RTB_EXTEND_MAXREG 88
+// extend runs 2 CTAs/SM (configure_launch) with at most 80 registers: 2 x 256 x 80 = 41 K of the 64 K registers, so a
+// 256-thread shade CTA (72 registers) of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476,
+// 80: 4497, 88: 4326, 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
+#define RTB_EXTEND_MAXREG 80
 struct ExtIn { float4 o_time, d_slot, idir_oct; };
 struct ExtOut { float t; uint32_t ref, gid, slot; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
@@ -804,10 +805,6 @@ void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& 
   k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
 }
 void launch_advance(const DevPool& pool, cudaStream_t st) { k_advance<<<1, 1, 0, st>>>(pool); }
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
   // one-ray-per-thread wins on small trees (all lanes start at the root together); dynamic fetch wins on deep trees
