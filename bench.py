@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "window": "warm-up + timed + e2e steps"}
 
 
 def measure_l2_bandwidth(torch):
@@ -238,12 +238,13 @@ def main():
         reduce_events.append((r0, r1))
         return st
 
+    # clocks / throttle reasons are sampled from the first warm-up step to the last e2e step (everything under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         step()
     # ---- timed region: exactly K steps, device time, max over ranks ---------------------------------------------
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reduce_events.clear()
     e0.record(stream)
@@ -254,7 +255,6 @@ def main():
         launches += st["launches"]
     e1.record(stream)
     barrier()
-    sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     reduce_ms = sum(a.elapsed_time(b) for a, b in reduce_events) / max(len(reduce_events), 1)
     tot = torch.tensor([ms, float(segs), float(launches)], dtype=torch.float64, device="cuda")
@@ -306,6 +306,7 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.SUM)
         dt = emx[0].item()
     e2e_value = et[1].item() / dt / 1e6
+    sampler.stop_flag = True
 
     # ---- roofline of the dominant kernel (extend), measured live on rank 0 ------------------------------------------
     roofline = None
