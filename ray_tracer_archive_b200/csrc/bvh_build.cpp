@@ -239,7 +239,12 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     for (size_t i = 0; i < np; ++i) scene.grow(hs.prims[i].lo, hs.prims[i].hi);
     const float scene_area = scene.area();
     const bool enabled = !(getenv("RTB_GLOBALS") && atoi(getenv("RTB_GLOBALS")) == 0);
-    if (enabled && np > 4 && scene_area > 0.f) {
+    const size_t tiny = getenv("RTB_TINY_SCENE") ? (size_t)atoi(getenv("RTB_TINY_SCENE")) : 16;
+    if (enabled && np <= tiny && np <= RTB_MAX_GLOBALS) {
+      // a scene this small (the 13-primitive Cornell box) is cheaper to scan than to traverse: one node visit decodes
+      // 48 planes, about as much work as ten quad tests
+      for (size_t i = 0; i < np; ++i) is_global[i] = 1;
+    } else if (enabled && scene_area > 0.f) {
       std::vector<std::pair<float, uint32_t>> big;
       for (size_t i = 0; i < np; ++i) {
         Box3 b;
@@ -248,7 +253,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
         if (a >= 0.8f * scene_area) big.emplace_back(-a, (uint32_t)i);  // dominates the scene box (walls at 1/3 do not pay)
       }
       std::sort(big.begin(), big.end());
-      for (size_t k = 0; k < big.size() && k < RTB_MAX_GLOBALS; ++k) is_global[big[k].second] = 1;
+      for (size_t k = 0; k < big.size() && k < 4; ++k) is_global[big[k].second] = 1;
     }
   }
 

@@ -428,6 +428,7 @@ int rtb_scene_commit(rtb_scene* s) {
   d.n_nodes = (uint32_t)s->bvh.nodes.size();
   d.prmt_magic = 0x43000000u;
   d.n_global = (uint32_t)s->bvh.global_refs.size();
+  d.tree_empty = (d.n_global == (uint32_t)s->hs.prims.size()) ? 1u : 0u;
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));

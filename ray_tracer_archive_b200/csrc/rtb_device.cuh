@@ -38,6 +38,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t n_lights, n_media, n_materials;
   uint32_t prmt_magic;  // = 0x43000000, see q2f()
   uint32_t n_global;    // primitives tested for every ray before the traversal (kept out of the tree)
+  uint32_t tree_empty;  // all primitives are global (tiny scene): skip the traversal
   uint32_t global_ref[RTB_MAX_GLOBALS];
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
@@ -391,6 +392,7 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
     const uint32_t ref = sc.global_ref[k];
     intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
   }
+  if (sc.tree_empty) tv.grp.y = 0u;  // nothing left to traverse: the first trav_step returns false
 }
 
 template <bool COUNT>

@@ -14,7 +14,7 @@ enum PrimType : uint32_t { PT_SPHERE = 0, PT_MOVING = 1, PT_QUAD = 2, PT_TRI = 3
 static const uint32_t REF_TYPE_SHIFT = 29u;
 static const uint32_t REF_INDEX_MASK = (1u << REF_TYPE_SHIFT) - 1u;
 static const uint32_t REF_MISS = 0xFFFFFFFFu;
-#define RTB_MAX_GLOBALS 4
+#define RTB_MAX_GLOBALS 16
 
 // face-orientation modes: how Translate/RotateY/FlipFace wrappers rewrite front_face (hittable.rs:82-83,173,199)
 enum FaceMode : uint32_t { FACE_NATURAL = 0, FACE_FLIPPED = 1, FACE_TRUE = 2, FACE_FALSE = 3 };

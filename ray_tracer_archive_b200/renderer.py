@@ -113,9 +113,9 @@ class Scene:
 
     def export_globals(self):
         """refs (type << 29 | index) of the primitives that are tested for every ray instead of living in the tree"""
-        refs = np.zeros(8, dtype=np.uint32)
+        refs = np.zeros(64, dtype=np.uint32)
         n = C.c_uint32()
-        F.check(self.lib.rtb_scene_export_globals(self.h, F.ptr(refs), 8, C.byref(n)))
+        F.check(self.lib.rtb_scene_export_globals(self.h, F.ptr(refs), 64, C.byref(n)))
         return refs[:n.value].copy()
 
     # ---- hot path -------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ using namespace rtb;
 extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
                           const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
                           const float* geom3, const uint32_t* info3, const uint32_t* globals, uint32_t n_globals,
-                          uint32_t n_snodes, const float* org,
+                          uint32_t tree_empty, uint32_t n_snodes, const float* org,
                           const float* dir, const float* time, uint32_t n, uint32_t* ids, float* ts,
                           uint64_t* nodes_visited, uint64_t* prims_tested) {
   static DevScene sc;
@@ -42,6 +42,7 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   sc.n_nodes = n_nodes;
   sc.prmt_magic = 0x43000000u;
   sc.n_global = n_globals;
+  sc.tree_empty = tree_empty;
   for (uint32_t k = 0; k < n_globals && k < RTB_MAX_GLOBALS; ++k) sc.global_ref[k] = globals[k];
   const float* g[4] = {geom0, geom1, geom2, geom3};
   const uint32_t* inf[4] = {info0, info1, info2, info3};

@@ -39,13 +39,14 @@ def build_emul():
     """tests/emul/libemul.so: the device header compiled for the host (see emul_traverse.cpp)."""
     src = os.path.join(HERE, "emul", "emul_traverse.cpp")
     out = os.path.join(HERE, "emul", "libemul.so")
-    dev = os.path.join(ROOT, "ray_tracer_archive_b200", "csrc", "rtb_device.cuh")
-    if not os.path.exists(out) or max(os.path.getmtime(src), os.path.getmtime(dev)) > os.path.getmtime(out):
+    csrc = os.path.join(ROOT, "ray_tracer_archive_b200", "csrc")
+    deps = [src, os.path.join(ROOT, "include", "rtb200.h")] + [os.path.join(csrc, f) for f in ("rtb_device.cuh", "rtb_internal.hpp")]
+    if not os.path.exists(out) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(out):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-attributes", "-D__noinline__=",
                                "-I/usr/local/cuda/include", "-o", out, src])
     lib = C.CDLL(out)
     VP = C.c_void_p
-    lib.emul_trace.argtypes = [VP, C.c_uint32] + [VP] * 8 + [VP, C.c_uint32, C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP]
+    lib.emul_trace.argtypes = [VP, C.c_uint32] + [VP] * 8 + [VP, C.c_uint32, C.c_uint32, C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP]
     return lib
 
 
@@ -67,7 +68,7 @@ def emul_trace(lib, host_scene, origin, direction, time=None, n_snodes=10 ** 6):
     for g, inf in prims:
         args += [_p(g), _p(inf)]
     glob = host_scene.export_globals()
-    args += [_p(glob), len(glob)]
+    args += [_p(glob), len(glob), 1 if len(glob) == info["n_spheres"] + info["n_moving"] + info["n_quads"] + info["n_triangles"] else 0]
     lib.emul_trace(*args, n_snodes, _p(o), _p(d), _p(tm), n, _p(ids), _p(ts), C.byref(nv), C.byref(nt))
     return ids, ts, nv.value, nt.value
 
