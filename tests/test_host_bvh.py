@@ -47,7 +47,7 @@ def test_emulated_device_traversal_matches_oracle(rtb, orc, emul, name, cfg, W, 
     ok = surf & ~mism & (oid != H.NONE)
     rel = np.abs(ts[ok] - ot[ok]) / ot[ok]
     assert np.quantile(rel, 0.999) < 1e-5 and rel.max() < 2e-4
-    assert nv > 0 and nt > 0
+    assert nt > 0 and (nv > 0 or hs.info()["n_prims"] <= 16)  # scenes of <= 16 primitives are scanned, not traversed
 
 
 def _media_ids(cs):
