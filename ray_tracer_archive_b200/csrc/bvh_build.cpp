@@ -12,6 +12,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <future>
 #include <cstdlib>
 #include <numeric>
 
@@ -23,7 +26,10 @@ namespace {
 struct Box3 {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   void grow(const float l[3], const float h[3]) {
-    for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], l[a]); hi[a] = std::fmax(hi[a], h[a]); }
+    for (int a = 0; a < 3; ++a) {  // plain compares: std::fmin/fmax carry NaN semantics and do not inline to min/max
+      lo[a] = l[a] < lo[a] ? l[a] : lo[a];
+      hi[a] = h[a] > hi[a] ? h[a] : hi[a];
+    }
   }
   void grow(const Box3& b) { grow(b.lo, b.hi); }
   void grow_pt(const float p[3]) { grow(p, p); }
@@ -38,86 +44,134 @@ struct BinNode {  // binary tree node
   Box3 box;
   int left = -1, right = -1;  // children, or -1 for a leaf
   uint32_t first = 0, count = 0;
+  uint32_t nleaves = 1;       // leaf nodes in this subtree
+};
+
+struct Rec {  // one primitive's padded bounds; the records themselves are partitioned, so every range the builder
+  float lo[3], hi[3];  // touches is contiguous in memory (index-only partitioning made the build DRAM-latency-bound)
+  uint32_t prim;
+  float centroid(int a) const { return 0.5f * (lo[a] + hi[a]); }
 };
 
 struct Builder {
   const HostScene& hs;
-  std::vector<uint32_t> order;      // indices into hs.prims for the current type
-  std::vector<float> centroid;      // 3 per prim (indexed by prim index)
+  std::vector<Rec> recs;            // the current type's primitives, partitioned in place
   std::vector<BinNode> bin;
   uint32_t max_leaf = 1;            // primitives per leaf slot (1..3)
+  int par_depth = 5;                // levels of the tree whose halves are built concurrently
 
-  int build_range(uint32_t first, uint32_t count) {
-    int me = (int)bin.size();
-    bin.emplace_back();
+  // binned SAH split of order[first, first+count): fills the node's bounds; returns false for a leaf
+  bool split(uint32_t first, uint32_t count, BinNode& node, uint32_t& mid) {
     Box3 box, cbox;
     for (uint32_t i = first; i < first + count; ++i) {
-      const HostPrim& p = hs.prims[order[i]];
+      const Rec& p = recs[i];
       box.grow(p.lo, p.hi);
-      cbox.grow_pt(&centroid[3 * (size_t)order[i]]);
+      const float c[3] = {p.centroid(0), p.centroid(1), p.centroid(2)};
+      cbox.grow_pt(c);
     }
-    bin[me].box = box;
-    bin[me].first = first;
-    bin[me].count = count;
-    if (count <= max_leaf) return me;
-    // binned SAH over the widest centroid axis first, all three axes evaluated
+    node.box = box;
+    node.first = first;
+    node.count = count;
+    node.left = node.right = -1;
+    node.nleaves = 1;
+    if (count <= max_leaf) return false;
+    // 16 bins per axis, all three axes binned in one pass over the primitives
     const int NB = 16;
+    Box3 bb[3][NB];
+    uint32_t bc[3][NB] = {{0}};
+    float k[3], lo[3];
+    bool valid[3];
+    for (int a = 0; a < 3; ++a) {
+      const float ext = cbox.hi[a] - cbox.lo[a];
+      valid[a] = ext > 0.f;
+      k[a] = valid[a] ? NB / ext : 0.f;
+      lo[a] = cbox.lo[a];
+    }
+    for (uint32_t i = first; i < first + count; ++i) {
+      const Rec& p = recs[i];
+      for (int a = 0; a < 3; ++a) {
+        if (!valid[a]) continue;
+        int b = (int)((p.centroid(a) - lo[a]) * k[a]);
+        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+        bb[a][b].grow(p.lo, p.hi);
+        bc[a][b]++;
+      }
+    }
     float best_cost = INFINITY;
     int best_axis = -1, best_bin = -1;
     for (int a = 0; a < 3; ++a) {
-      float ext = cbox.hi[a] - cbox.lo[a];
-      if (!(ext > 0.f)) continue;
-      Box3 bb[NB];
-      uint32_t bc[NB] = {0};
-      float k = NB / ext;
-      for (uint32_t i = first; i < first + count; ++i) {
-        const HostPrim& p = hs.prims[order[i]];
-        int b = (int)((centroid[3 * (size_t)order[i] + a] - cbox.lo[a]) * k);
-        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-        bb[b].grow(p.lo, p.hi);
-        bc[b]++;
-      }
+      if (!valid[a]) continue;
       float right_area[NB];
       uint32_t right_cnt[NB];
       Box3 acc;
       uint32_t cnt = 0;
       for (int b = NB - 1; b > 0; --b) {
-        acc.grow(bb[b]);
-        cnt += bc[b];
+        acc.grow(bb[a][b]);
+        cnt += bc[a][b];
         right_area[b] = acc.area();
         right_cnt[b] = cnt;
       }
       Box3 accl;
       uint32_t cl = 0;
       for (int b = 0; b < NB - 1; ++b) {
-        accl.grow(bb[b]);
-        cl += bc[b];
+        accl.grow(bb[a][b]);
+        cl += bc[a][b];
         if (cl == 0 || right_cnt[b + 1] == 0) continue;
-        float cost = accl.area() * (float)cl + right_area[b + 1] * (float)right_cnt[b + 1];
+        const float cost = accl.area() * (float)cl + right_area[b + 1] * (float)right_cnt[b + 1];
         if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
       }
     }
-    uint32_t mid;
     if (best_axis < 0) {
       mid = first + count / 2;  // all centroids coincide: split the range
     } else {
-      float ext = cbox.hi[best_axis] - cbox.lo[best_axis];
-      float k = NB / ext;
-      float lo = cbox.lo[best_axis];
-      auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t pi) {
-        int b = (int)((centroid[3 * (size_t)pi + best_axis] - lo) * k);
+      const float kk = k[best_axis], l0 = lo[best_axis];
+      const int ba = best_axis;
+      auto it = std::partition(recs.begin() + first, recs.begin() + first + count, [&](const Rec& p) {
+        int b = (int)((p.centroid(ba) - l0) * kk);
         b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
         return b <= best_bin;
       });
-      mid = (uint32_t)(it - order.begin());
+      mid = (uint32_t)(it - recs.begin());
       if (mid == first || mid == first + count) mid = first + count / 2;
     }
-    int l = build_range(first, mid - first);
-    int r = build_range(mid, first + count - mid);
-    bin[me].left = l;
-    bin[me].right = r;
+    return true;
+  }
+
+  // builds the subtree of order[first, first+count) into `v` and returns its root index in `v`.  Large subtrees near
+  // the top are built concurrently: the two halves touch disjoint ranges of `order`, the left half goes to its own
+  // node vector and is spliced in afterwards.
+  int build_into(std::vector<BinNode>& v, uint32_t first, uint32_t count, int depth) {
+    const int me = (int)v.size();
+    v.emplace_back();
+    BinNode nd;
+    uint32_t mid = 0;
+    const bool inner = split(first, count, nd, mid);
+    v[me] = nd;
+    if (!inner) return me;
+    int l, r;
+    if (count >= 32768 && depth < par_depth) {
+      std::vector<BinNode> lv;
+      lv.reserve(2 * (size_t)(mid - first) / max_leaf + 16);
+      auto fut = std::async(std::launch::async, [&]() { build_into(lv, first, mid - first, depth + 1); });
+      r = build_into(v, mid, first + count - mid, depth + 1);
+      fut.get();
+      const int off = (int)v.size();
+      for (BinNode n : lv) {
+        if (n.left >= 0) { n.left += off; n.right += off; }
+        v.push_back(n);
+      }
+      l = off;  // the left subtree's root was lv[0]
+    } else {
+      l = build_into(v, first, mid - first, depth + 1);
+      r = build_into(v, mid, first + count - mid, depth + 1);
+    }
+    v[me].left = l;
+    v[me].right = r;
+    v[me].nleaves = v[l].nleaves + v[r].nleaves;
     return me;
   }
+
+  int build_range(uint32_t first, uint32_t count) { return build_into(bin, first, count, 0); }
 };
 
 struct WideChild {
@@ -257,27 +311,31 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     }
   }
 
+  const bool timing = getenv("RTB_BVH_TIMING") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto t_start = now();
   // --- per-type binary trees ---------------------------------------------------------------------------------
-  std::vector<float> centroid(3 * np);
-  for (size_t i = 0; i < np; ++i)
-    for (int a = 0; a < 3; ++a) centroid[3 * i + a] = 0.5f * (hs.prims[i].lo[a] + hs.prims[i].hi[a]);
-
   struct TypedTree { Builder* b; int root; uint32_t type; };
   std::vector<Builder*> builders;
   std::vector<TypedTree> trees;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
-    Builder* b = new Builder{hs, {}, {}, {}};
+    Builder* b = new Builder{hs};
     // one primitive per leaf slot: a sphere/quad test costs more than a (quantised) box test and single-primitive
     // leaves fill the 8 slots of a node; triangles keep up to 2 per slot to bound the node count of large meshes
     b->max_leaf = (t == PT_TRI) ? 2u : 1u;
     if (const char* e = getenv("RTB_MAX_LEAF")) b->max_leaf = (uint32_t)std::max(1, std::min(3, atoi(e)));
     builders.push_back(b);
     for (size_t i = 0; i < np; ++i)
-      if (hs.prims[i].type == t && !is_global[i]) b->order.push_back((uint32_t)i);
-    if (b->order.empty()) continue;
-    b->centroid = centroid;  // shared copy (small relative to the build)
-    b->bin.reserve(b->order.size());
-    int root = b->build_range(0, (uint32_t)b->order.size());
+      if (hs.prims[i].type == t && !is_global[i]) {
+        Rec r;
+        for (int a = 0; a < 3; ++a) { r.lo[a] = hs.prims[i].lo[a]; r.hi[a] = hs.prims[i].hi[a]; }
+        r.prim = (uint32_t)i;
+        b->recs.push_back(r);
+      }
+    if (b->recs.empty()) continue;
+    if (const char* e = getenv("RTB_BVH_PAR")) b->par_depth = atoi(e);
+    b->bin.reserve(2 * b->recs.size());
+    int root = b->build_range(0, (uint32_t)b->recs.size());
     trees.push_back(TypedTree{b, root, t});
   }
   auto cleanup = [&]() {
@@ -294,6 +352,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     }
   };
 
+  auto t_binary = now();
   Assembler as{hs, out};
   if (trees.empty()) {  // empty scene: a single node with no children (every ray misses)
     Node8 n;
@@ -410,7 +469,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
         if (lf.count > 3 || off + lf.count > 24) { err = "internal: leaf too large"; cleanup(); return RTB_ERR_INVALID; }
         n.meta[s] = (uint8_t)((lf.count << 5) | off);
         for (uint32_t q = 0; q < lf.count; ++q) {
-          const HostPrim& p = hs.prims[b.order[lf.first + q]];
+          const HostPrim& p = hs.prims[b.recs[lf.first + q].prim];
           for (uint32_t w = 0; w < gw; ++w) out.geom[type].push_back(p.g[w]);
           out.info[type].push_back(p.prim_id);
           out.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
@@ -426,6 +485,12 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     out.nodes[pd.node] = n;
   }
   cleanup();
+  if (timing) {
+    auto t_end = now();
+    std::fprintf(stderr, "[rtb200] BVH build: binary SAH %.3f s, collapse + quantise %.3f s, %zu nodes\n",
+                 std::chrono::duration<double>(t_binary - t_start).count(),
+                 std::chrono::duration<double>(t_end - t_binary).count(), out.nodes.size());
+  }
   if (out.max_depth > 28) { err = "BVH too deep for the traversal stack"; return RTB_ERR_INVALID; }
   return RTB_OK;
 }

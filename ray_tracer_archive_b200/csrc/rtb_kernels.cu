@@ -572,16 +572,20 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
 // miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
   RTB_SHADE_LOOP_BEGIN(Q_TERMINAL)
-      PathIO io = load_path(pool, slot);
-      if (io.ref == REF_MISS) {
-        io.L = io.L + io.beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
+      // a miss needs only the throughput/radiance sector; the ray is fetched for emitters alone
+      const float4 h = pool.hit[slot], b = pool.st[2 * slot], r = pool.st[2 * slot + 1];
+      float3 L = xyz(r);
+      const float3 beta = xyz(b);
+      const uint32_t ref = __float_as_uint(h.y);
+      if (ref == REF_MISS) {
+        L = L + beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
       } else {
-        const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
+        const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
+        const Surf s = surface_at(sc, ref, __float_as_uint(h.z), xyz(ro), xyz(rd), ro.w, h.x);
         const float4 m = __ldg(&sc.materials[2 * s.mat]);
-        if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front)
-          io.L = io.L + io.beta * tex_value(sc, m, s.mat, s);
+        if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front) L = L + beta * tex_value(sc, m, s.mat, s);
       }
-      deposit(prm, c, io.pixel, io.L);
+      deposit(prm, c, __float_as_uint(b.w), L);
   RTB_SHADE_LOOP_END
 }
 
