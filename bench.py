@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--rr", type=int, default=0, help="Russian-roulette start depth (0 = reference behaviour, off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's spp is SPLIT across the ranks (BASELINE config C5) instead of "
+                         "rendered by every rank (weak, default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -212,13 +215,17 @@ def main():
     info = scene.info()
     npix = cfg.width * cfg.height
     spp = cfg.spp
+    if args.strong:  # rank r renders its share of the workload's samples
+        spp = parallel.rank_sample_range(cfg.spp, rank, world)[1]
+    first_sample = parallel.rank_sample_range(cfg.spp, rank, world)[0] if args.strong else rank * spp
+    total_spp = cfg.spp if args.strong else world * spp
     accum = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     stream = torch.cuda.current_stream()
 
     def params(flags=0):
         return rtb.make_params(cfg.width, cfg.height, spp, cfg.max_depth, cfg.background, seed=1,
-                               sample_offset=rank * spp, total_spp=world * spp, rr_start_depth=args.rr,
+                               sample_offset=first_sample, total_spp=total_spp, rr_start_depth=args.rr,
                                pool_paths=args.pool, flags=flags)
 
     def barrier():
@@ -380,10 +387,10 @@ def main():
                                                   "reference per-primitive tests, candidates culled by the shipped BVH8")}
         line = {
             "metric": "path segments/sec", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg.name, "width": cfg.width, "height": cfg.height, "spp_per_gpu": spp,
-                       "total_spp": world * spp, "max_depth": cfg.max_depth, "rr_start_depth": args.rr,
+                       "total_spp": total_spp, "max_depth": cfg.max_depth, "rr_start_depth": args.rr,
                        "prims": info["n_prims"], "bvh_nodes": info["n_bvh_nodes"], "parallelism": f"spp-split x{world} + NCCL reduce",
                        "l2": "L2 flushed (256 MB write) between steps; path-state pool exceeds the 126 MB L2; the scene is cache-resident by design"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -395,7 +402,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "cpu_baseline_fair": cpu_fair,
             "segments_per_step": all_segs / args.steps,
-            "paths_per_step": npix * spp * world,
+            "paths_per_step": npix * total_spp,
         }
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:

@@ -93,3 +93,21 @@ def test_flatten_ids_and_face_modes(rtb):
     assert all(mode[i] == 2 for i in range(6, 12))  # Translate(RotateY(Box)): front_face forced true (hittable.rs:82-83)
     assert all(mode[i] == 0 for i in (0, 1, 3, 4, 5))
     assert int(prims[0][1][0]) == 12          # the glass sphere is the last object
+
+
+def test_obj_loader_and_ppm_writer(rtb, tmp_path):
+    """OBJ-style mesh -> TriangleMesh -> host flatten."""
+    from ray_tracer_archive_b200 import io, scene as S
+    obj = ["# unit quad + a triangle", "v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "v 0.5 2 0", "f 1 2 3 4", "f 4/1/1 3/2/2 -1"]
+    mesh = io.load_obj(obj, S.Lambertian.construct((0.5, 0.5, 0.5)), scale=2.0, offset=(1, 0, 0))
+    assert mesh.indices.tolist() == [[0, 1, 2], [0, 2, 3], [3, 2, 4]]
+    np.testing.assert_allclose(mesh.vertices[2], [3, 2, 0])
+    s = rtb.Scene(None, rtb.compile_scene(S.HittableList([mesh])))
+    assert s.info()["n_triangles"] == 3 and s.info()["n_prims"] == 3
+    img = (np.arange(4 * 5 * 3) % 256).astype(np.uint8).reshape(4, 5, 3)
+    out = tmp_path / "x.ppm"
+    io.save_image(str(out), img)
+    raw = out.read_bytes()
+    assert raw.startswith(b"P6\n5 4\n255\n") and raw[-60:] == img.tobytes()
+    with pytest.raises(ValueError):
+        io.load_obj(["v 0 0 0", "f 1 2 3"], mesh.mat)
