@@ -54,6 +54,7 @@ struct Rec {  // one primitive's padded bounds; the records themselves are parti
 };
 
 struct Builder {
+  explicit Builder(const HostScene& h) : hs(h) {}
   const HostScene& hs;
   std::vector<Rec> recs;            // the current type's primitives, partitioned in place
   std::vector<BinNode> bin;
@@ -319,7 +320,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   std::vector<Builder*> builders;
   std::vector<TypedTree> trees;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
-    Builder* b = new Builder{hs};
+    Builder* b = new Builder(hs);
     // one primitive per leaf slot: a sphere/quad test costs more than a (quantised) box test and single-primitive
     // leaves fill the 8 slots of a node; triangles keep up to 2 per slot to bound the node count of large meshes
     b->max_leaf = (t == PT_TRI) ? 2u : 1u;
