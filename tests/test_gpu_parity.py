@@ -286,6 +286,44 @@ def test_p2_checker_perlin_light(rtb, orc, ctx):
     _p2(rtb, orc, ctx, cfg, 48, 32, spp=1024)
 
 
+def _block_stats(acc, spp, bs):
+    """Mean luminance and its standard error over bs x bs pixel blocks (accum = sum R,G,B,Y^2 per pixel)."""
+    a = np.asarray(acc, dtype=np.float64)
+    Hh, W = a.shape[0] // bs * bs, a.shape[1] // bs * bs
+    a = a[:Hh, :W].reshape(Hh // bs, bs, W // bs, bs, 4)
+    n = bs * bs * spp
+    sum_y = H.luminance(a[..., :3]).sum(axis=(1, 3))
+    sum_y2 = a[..., 3].sum(axis=(1, 3))
+    mean = sum_y / n
+    var = np.maximum(sum_y2 / n - mean * mean, 0.0)
+    return mean, var / n
+
+
+@pytest.mark.parametrize("which", ["C1", "C2"])
+def test_p2_full_resolution_low_spp(rtb, orc, ctx, which):
+    """Full config resolution (1200x675 is not a multiple of the 8x4 pixel tiles; every pixel must receive exactly its
+    samples): 16 spp on both sides, compared on 15x15-pixel blocks (3600 samples per block)."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_random_spheres() if which == "C1" else scenes.config_cornell()
+    dev, osc, _ = _scene_pair(rtb, orc, ctx, cfg)
+    osc.attach_bvh(dev)
+    spp = 16
+    acc, st = dev.render(cfg.camera, rtb.make_params(cfg.width, cfg.height, spp, cfg.max_depth, cfg.background, seed=11))
+    oacc, oseg, _ = osc.render(cfg.camera, rtb.make_params(cfg.width, cfg.height, spp, cfg.max_depth, cfg.background, seed=12))
+    assert st["paths"] == cfg.width * cfg.height * spp
+    # every pixel got all its samples: background-only pixels (C1's sky) sum to exactly spp * background
+    if which == "C1":
+        top = acc[0, :, :3] / spp
+        np.testing.assert_allclose(top, np.broadcast_to(np.float32(cfg.background), top.shape), rtol=2e-6)
+    mg, vg = _block_stats(acc, spp, 15)
+    mr, vr = _block_stats(oacc, spp, 15)
+    z = np.abs(mg - mr) / np.sqrt(vg + vr + (3e-4 * mr + 1e-6) ** 2)
+    mean_rel = abs(mg.mean() - mr.mean()) / mr.mean()
+    print(f"{cfg.name}: {cfg.width}x{cfg.height}x{spp} block z max {z.max():.2f}, mean-lum err {100 * mean_rel:.3f}%, "
+          f"segments gpu/oracle {st['segments'] / oseg:.4f}")
+    assert mean_rel <= 0.01 and z.max() <= 5.0 and abs(st["segments"] / oseg - 1) < 0.01
+
+
 def test_p2_russian_roulette_is_unbiased(rtb, orc, ctx):
     """RR is not in the reference; with it on (GPU) the image must still match the RR-free oracle."""
     from ray_tracer_archive_b200 import scenes
