@@ -9,3 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 --csv --l
 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 4 -c 2 -f -o gpurun_out/${TAG}_extend $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_shade_lambert -s 4 -c 1 -f -o gpurun_out/${TAG}_lambert $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 ls -la gpurun_out/ | grep ${TAG}
+ncu --set full --clock-control none --import-source on -k regex:k_shade_terminal -s 4 -c 1 -f -o gpurun_out/${TAG}_terminal $CMD > gpurun_out/${TAG}_ncu4.log 2>&1
+ls -la gpurun_out/ | grep ${TAG}

@@ -411,6 +411,18 @@ int rtb_scene_build_bvh(rtb_scene* s) {
   return RTB_OK;
 }
 
+// Material trait dispatch (material.rs:11-21) resolved on the host: which per-material shade kernel handles a hit
+static uint32_t queue_of_material(const HostScene& hs, uint32_t m) {
+  if (m >= hs.materials.size()) return Q_TERMINAL;
+  switch (hs.materials[m].type) {
+    case RTB_MAT_LAMBERTIAN: return Q_LAMBERT;
+    case RTB_MAT_METAL: return Q_METAL;
+    case RTB_MAT_DIELECTRIC: return Q_DIELECTRIC;
+    case RTB_MAT_ISOTROPIC: return Q_ISOTROPIC;
+    default: return Q_TERMINAL;  // DiffuseLight: emitted, no scatter (material.rs:184-190)
+  }
+}
+
 int rtb_scene_commit(rtb_scene* s) {
   if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
   if (!s->ctx) return set_err(RTB_ERR_STATE, "host-only scene (created without a context) cannot be committed");
@@ -432,7 +444,11 @@ int rtb_scene_commit(rtb_scene* s) {
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
-    CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(s->bvh.info[t].data()), s->bvh.info[t].size() / 2));
+    // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
+    std::vector<uint32_t> info = s->bvh.info[t];
+    for (size_t i = 1; i < info.size(); i += 2) info[i] |= queue_of_material(hs, info[i] & 0xFFFFFFu) << 26;
+    CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(info.data()), info.size() / 2));
+    CU(cudaStreamSynchronize(0));  // `info` is a temporary
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
   }
@@ -485,6 +501,7 @@ int rtb_scene_commit(rtb_scene* s) {
     const HostMedium& m = hs.media[i];
     DevMedium& o = d.media[i];
     o.boundary_type = m.boundary_type; o.material = m.material; o.prim_id = m.prim_id;
+    o.minfo = (m.material & 0xFFFFFFu) | (FACE_TRUE << 24) | (queue_of_material(hs, m.material) << 26);
     o.neg_inv_density = m.neg_inv_density;
     for (int k = 0; k < 6; ++k) o.p[k] = m.p[k];
     o.sin_t = m.sin_t; o.cos_t = m.cos_t;
@@ -652,6 +669,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
     prm.pix_order = c->pix_order.p;
     prm.inv_npix = 1.0 / (double)npix;
+    static const uint32_t env_opt = getenv("RTB_OPT") ? (uint32_t)atoi(getenv("RTB_OPT")) : 0u;
+    prm.opt = env_opt;
+    prm.inv_wm1 = (float)(1.0 / (double)(p->width - 1));
+    prm.inv_hm1 = (float)(1.0 / (double)(p->height - 1));
     prm.accum = (float4*)d_accum;
     first_sample += cnt;
     R.active = true;

@@ -16,6 +16,12 @@ namespace rtb {
 #define RTB_PI 3.14159265358979323846f
 
 enum Queue : uint32_t { Q_TERMINAL = 0, Q_LAMBERT = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_ISOTROPIC = 4, Q_COUNT = 5 };
+// per-primitive info word y (device copy): material (24 bits) | face mode << 24 (2 bits) | shade queue << 26 (3 bits).
+// The queue is resolved from the material type on the host at commit, so `extend` classifies a hit without touching
+// the material table (one dependent load less on its tail).
+#define RTB_MINFO_MAT(m) ((m) & 0xFFFFFFu)
+#define RTB_MINFO_FACE(m) (((m) >> 24) & 3u)
+#define RTB_MINFO_QUEUE(m) (((m) >> 26) & 7u)
 
 struct DevTexture {  // 32 bytes
   uint32_t type, even, odd, table;
@@ -28,7 +34,7 @@ struct DevMedium {
   float p[6];
   float sin_t, cos_t;
   float off[3];
-  float _pad;
+  uint32_t minfo;  // hit-record word of this medium: material | FACE_TRUE << 24 | queue << 26
 };
 struct DevImage { const uint8_t* data; uint32_t w, h; };
 
@@ -73,7 +79,7 @@ struct DevPool {  // wavefront path state, SoA over `n` slots
   uint32_t n;
   float4* ray;     // [2s] origin xyz, time ; [2s+1] direction xyz (un-normalised, ray.rs), 0   — one 32-byte sector
   float4* st;      // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
-  float4* hit;     // t, ref bits, (material | face mode << 24) bits, 0
+  float4* hit;     // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
   uint32_t* q_ext[2];
   uint32_t* q_mat[Q_COUNT];
   uint32_t* q_dead;
@@ -87,6 +93,8 @@ struct DevParams {
   float bg[3];
   const uint32_t* pix_order;  // tile-ordered pixel indices
   double inv_npix;
+  float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1)
+  uint32_t opt;               // A/B switches (env RTB_OPT; 0 in production): 1 no shade prefetch, 2 no ray prefetch, 4 late claim
   float4* accum;
 };
 
@@ -108,6 +116,36 @@ __device__ __forceinline__ float3 fma3(float s, float3 a, float3 b) {
 __device__ __forceinline__ float3 unit(float3 a) { return rsqrtf(dot(a, a)) * a; }
 __device__ __forceinline__ float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }
 __device__ __forceinline__ float3 ld3(const float* p) { return f3(p[0], p[1], p[2]); }
+
+// One-instruction MUFU reciprocal / square root (<= 1-2 ulp) instead of the IEEE sequences `1.0f / x` and sqrtf()
+// compile to (MUFU + Newton step + range check + slow-path call, ~10 instructions each).  Every use is covered by an
+// explicit error bound: the slab test is widened (trav_step), the sphere test falls back to f64 when ill-conditioned.
+// The host build (tests/emul) uses the exact operations.
+__device__ __forceinline__ float rcp_fast(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+__device__ __forceinline__ float log_fast(float x) {
+#ifdef __CUDA_ARCH__
+  return __logf(x);
+#else
+  return logf(x);
+#endif
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
 
 // ---- Philox4x32-10: key = (pixel, sample), counter = (block, bounce, seed, 'RTB2').  Replaces rand::random
 // (rt_weekend.rs:8-19); identical to oracle/rt_oracle.hpp so streams can be compared draw by draw.
@@ -157,10 +195,23 @@ static __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float3 
   const double cc = ox * ox + oy * oy + oz * oz - (double)r * (double)r;
   const double det = hb * hb - a * cc;
   if (det < 0.0) return false;
+#ifdef __CUDA_ARCH__
+  // sqrt(det) and 1/a to ~1e-14 relative: f32 MUFU seed + one Newton step in f64 (the result is rounded to f32)
+  double sq = 0.0;
+  if (det > 0.0) {
+    const double y = (double)rsqrtf((float)det);
+    sq = det * y;
+    sq = fma(0.5 * y, fma(-sq, sq, det), sq);
+  }
+  double inv_a = (double)rcp_fast((float)a);
+  inv_a = inv_a * fma(-a, inv_a, 2.0);
+#else
   const double sq = sqrt(det);
-  double root = (-hb - sq) / a;
+  const double inv_a = 1.0 / a;
+#endif
+  double root = (-hb - sq) * inv_a;
   if (root < (double)tmin || (double)tmax < root) {
-    root = (-hb + sq) / a;
+    root = (-hb + sq) * inv_a;
     if (root < (double)tmin || (double)tmax < root) return false;
   }
   t_out = (float)root;
@@ -175,13 +226,13 @@ __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float
   const float a = dot(d, d);
   const float hb = dot(oc, d);
   const float oo = dot(oc, oc);
-  const float inv_a = 1.0f / a;
+  const float inv_a = rcp_fast(a);
   const float3 l = fma3(-hb * inv_a, d, oc);
   const float disc = fmaf(r, r, -dot(l, l));
   bool need64 = disc * disc < 1e-9f * r * r * oo;  // |disc| within ~3e-5 r|oc| of zero: grazing
   if (!need64) {
     if (disc < 0.0f) return false;
-    const float sq = sqrtf(a * disc);
+    const float sq = sqrt_fast(a * disc);
     float root = (-hb - sq) * inv_a;
     if (root < tmin || tmax < root) {
       root = (-hb + sq) * inv_a;
@@ -210,7 +261,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square
     float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
     float denom = dot(xyz(w0), d);
-    t = (w0.w - dot(xyz(w0), o)) / denom;
+    t = (w0.w - dot(xyz(w0), o)) * rcp_fast(denom);
     if (!(t >= tmin && t <= best.t)) return;
     float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
     float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
@@ -241,7 +292,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
       s = B.x; B.x = B.y; B.y = s;
       s = C.x; C.x = C.y; C.y = s;
     }
-    const float Sz = 1.0f / dp.z, Sx = dp.x * Sz, Sy = dp.y * Sz;
+    const float Sz = rcp_fast(dp.z), Sx = dp.x * Sz, Sy = dp.y * Sz;
     const float Ax = __fsub_rn(A.x, __fmul_rn(Sx, A.z)), Ay = __fsub_rn(A.y, __fmul_rn(Sy, A.z));
     const float Bx = __fsub_rn(B.x, __fmul_rn(Sx, B.z)), By = __fsub_rn(B.y, __fmul_rn(Sy, B.z));
     const float Cx = __fsub_rn(C.x, __fmul_rn(Sx, C.z)), Cy = __fsub_rn(C.y, __fmul_rn(Sy, C.z));
@@ -256,7 +307,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
     const float det = U + V + W;
     if (det == 0.0f) return;
-    t = (U * (Sz * A.z) + V * (Sz * B.z) + W * (Sz * C.z)) / det;
+    t = (U * (Sz * A.z) + V * (Sz * B.z) + W * (Sz * C.z)) * rcp_fast(det);
     if (!(t >= tmin && t <= best.t)) return;
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
@@ -294,9 +345,9 @@ struct Trav {
 __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float time) {
   const float tiny = 1e-30f;
   tv.o = o; tv.d = d; tv.time = time;
-  tv.idx = 1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));
-  tv.idy = 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
-  tv.idz = 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
+  tv.idx = rcp_fast(fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x));  // <= 1 ulp: covered by the slab widening below
+  tv.idy = rcp_fast(fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y));
+  tv.idz = rcp_fast(fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z));
   tv.octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
   tv.sp = 0;
@@ -338,7 +389,7 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const float bx = (__uint_as_float(w0.x) - tv.o.x) * tv.idx;
   const float by = (__uint_as_float(w0.y) - tv.o.y) * tv.idy;
   const float bz = (__uint_as_float(w0.z) - tv.o.z) * tv.idz;
-  const float eps = 4.0e-7f;  // bound on the f32 rounding of q a + b (|q a| <= 255 |a| incl. the folded 128)
+  const float eps = 5.0e-7f;  // bound on the f32 rounding of q a + b (|q a| <= 255 |a| incl. the folded 128) + 1 ulp of idir
   const float ex = eps * fmaf(256.0f, fabsf(ax), fabsf(bx));
   const float ey = eps * fmaf(256.0f, fabsf(ay), fabsf(by));
   const float ez = eps * fmaf(256.0f, fabsf(az), fabsf(bz));
@@ -349,10 +400,15 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const uint32_t nx0 = nx ? w3.z : w2.x, nx1 = nx ? w3.w : w2.y, fx0 = nx ? w2.x : w3.z, fx1 = nx ? w2.y : w3.w;
   const uint32_t ny0 = ny ? w4.x : w2.z, ny1 = ny ? w4.y : w2.w, fy0 = ny ? w2.z : w4.x, fy1 = ny ? w2.w : w4.y;
   const uint32_t nz0 = nz ? w4.z : w3.x, nz1 = nz ? w4.w : w3.y, fz0 = nz ? w3.x : w4.z, fz1 = nz ? w3.y : w4.w;
-  uint32_t hitmask = 0;
+  // child i is hit iff max(tn_xyz, tmin) <= min(tf_xyz, t_max)  <=>  tn3 <= tf3  and  tn3 <= t_max  and  tmin <= tf3
+  // (tmin <= t_max always).  The three differences are FADDs (FMA pipe); their sign bits are OR-ed with one LOP3 and
+  // shifted into the mask with one funnel shift: 4 ALU-pipe instructions per child (2 FMNMX3, LOP3, SHF) instead of
+  // 6.4 (2 FMNMX, 2 FMNMX3, FSETP, SEL, IADD3/3) — the node test is ALU-pipe bound (profiles/r1d_c1_ncu_summary.md).
+  uint32_t missmask = 0;
   const uint32_t magic = sc.prmt_magic;  // 0x43000000, read from the constant bank (ptxas cannot fold it into the PRMT)
+  const float tmax = tv.best.t;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 7; i >= 0; --i) {
     const uint32_t sel = 0x7044u | ((uint32_t)(i & 3) << 8);
     const float tnx = fmaf(q2f(i < 4 ? nx0 : nx1, magic, sel), ax, bnx);
     const float tny = fmaf(q2f(i < 4 ? ny0 : ny1, magic, sel), ay, bny);
@@ -360,10 +416,12 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     const float tfx = fmaf(q2f(i < 4 ? fx0 : fx1, magic, sel), ax, bfx);
     const float tfy = fmaf(q2f(i < 4 ? fy0 : fy1, magic, sel), ay, bfy);
     const float tfz = fmaf(q2f(i < 4 ? fz0 : fz1, magic, sel), az, bfz);
-    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tv.best.t));
-    if (tn <= tf) hitmask |= 1u << i;
+    const float tn = fmaxf(fmaxf(tnx, tny), tnz);
+    const float tf = fminf(fminf(tfx, tfy), tfz);
+    const uint32_t neg = __float_as_uint(tf - tn) | __float_as_uint(tmax - tn) | __float_as_uint(tf - tmin);
+    missmask = __funnelshift_l(neg, missmask, 1);  // (missmask << 1) | sign bit; child 0 ends in bit 0
   }
+  const uint32_t hitmask = ~missmask & 0xFFu;
   // leaf children: intersect now (all primitives of one node share a type)
   uint32_t leaf = hitmask & ~imask;
   const uint32_t ptype = w1.y >> REF_TYPE_SHIFT, pbase = w1.y & REF_INDEX_MASK;
@@ -419,11 +477,11 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
     if (md.boundary_type == RTB_BOUNDARY_SPHERE) {
       float3 c = f3(md.p[0], md.p[1], md.p[2]);
       float3 oc = o - c;
-      float a = dot(d, d), hb = dot(oc, d), inv_a = 1.0f / a;
+      float a = dot(d, d), hb = dot(oc, d), inv_a = rcp_fast(a);
       float3 l = fma3(-hb * inv_a, d, oc);
       float disc = fmaf(md.p[3], md.p[3], -dot(l, l));
       if (disc < 0.0f) continue;
-      float sq = sqrtf(a * disc);
+      float sq = sqrt_fast(a * disc);
       t1 = (-hb - sq) * inv_a;      // boundary.hit(r, -inf, inf): first root always in range
       t2 = (-hb + sq) * inv_a;      // boundary.hit(r, t1 + 0.0001, inf)
       if (t2 < t1 + 0.0001f) continue;
@@ -441,7 +499,7 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
           if (ro_[a] < md.p[a] || ro_[a] > md.p[3 + a]) miss = true;
           continue;
         }
-        float inv = 1.0f / rd_[a];
+        float inv = rcp_fast(rd_[a]);
         float ta = (md.p[a] - ro_[a]) * inv, tb = (md.p[3 + a] - ro_[a]) * inv;
         lo = fmaxf(lo, fminf(ta, tb));
         hi = fminf(hi, fmaxf(ta, tb));
@@ -453,12 +511,12 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
     if (t2 > best.t) t2 = best.t;
     if (t1 >= t2) continue;
     if (t1 < 0.0f) t1 = 0.0f;
-    float len = sqrtf(dot(d, d));
+    float len = sqrt_fast(dot(d, d));
     float inside = (t2 - t1) * len;
     float xi = have_rng ? u01(philox4(pixel, sample, BLK_MEDIUM0 + m, bounce, seed).x) : 0.5f;
-    float hd = md.neg_inv_density * logf(xi);
+    float hd = md.neg_inv_density * log_fast(xi);
     if (hd > inside) continue;
-    float t = t1 + hd / len;
+    float t = t1 + hd * rcp_fast(len);
     consider(best, t, ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m, md.prim_id);
   }
 }

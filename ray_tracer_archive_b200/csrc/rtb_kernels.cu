@@ -29,6 +29,24 @@ __device__ __forceinline__ void warp_enqueue(uint32_t* __restrict__ q, uint32_t*
   if (pred) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// Append `value` to per-material queue `queue` (Q_COUNT = none).  Lanes are grouped by queue with one MATCH.ANY; the
+// leader of every group issues its atomicAdd in the SAME instruction, so a warp whose rays go to 3-4 different queues
+// pays one atomic round trip instead of one per queue (the five serial ballot+atomic+shuffle rounds were 17 % of the
+// extend kernel's stall samples, profiles/r1d_c1_ncu_summary.md).  Must be executed by all 32 lanes.
+__device__ __forceinline__ void warp_enqueue_mat(const DevPool& pool, DevCounters* c, uint32_t queue, uint32_t value) {
+  const uint32_t peers = __match_any_sync(0xffffffffu, queue);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t leader = __ffs(peers) - 1;
+  const bool live = queue < Q_COUNT;
+  uint32_t base = 0;
+  if (live && lane == leader) base = atomicAdd(&c->n_mat[queue], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (live) pool.q_mat[queue][base + __popc(peers & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -67,7 +85,7 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
 // 256-thread shade CTA (72 registers) of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476,
 // 80: 4497, 88: 4326, 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
-struct ExtIn { float4 o_time, d_slot, idir_oct; };
+struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, gid, group word) after the global primitives
 struct ExtOut { float t; uint32_t ref, gid, slot; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
@@ -108,23 +126,18 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const uint32_t st = __float_as_uint(pool.st[2 * oslot + 1].w);
         intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
       }
-      // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
+      // classify by material (Material trait dispatch, material.rs:11-21): the info word carries material | face mode |
+      // shade queue, resolved on the host
       queue = Q_TERMINAL;
       uint32_t minfo = 0;
       if (best.ref != REF_MISS) {
         const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
-        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
-        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
-              : mt == RTB_MAT_METAL      ? Q_METAL
-              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
-              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
-                                         : Q_TERMINAL;
+        minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
+        queue = RTB_MINFO_QUEUE(minfo);
       }
       pool.hit[oslot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
     }
-#pragma unroll
-    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, oslot);
+    warp_enqueue_mat(pool, c, queue, oslot);
     out_count = 0;
     __syncwarp();
   };
@@ -144,11 +157,15 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         if (lane < in_count) {
           const uint32_t sl = q[first + lane];
           const float4 ro = pool.ray[2 * sl], rd = pool.ray[2 * sl + 1];
+          // set-up runs here with the whole warp: 1/d, and the scene's global primitives (tested before the tree)
           Trav t0;
           trav_init(t0, xyz(ro), xyz(rd), ro.w);
+          trav_globals<COUNT>(sc, t0, RTB_TMIN, nt);
           in[lane].o_time = ro;
           in[lane].d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
           in[lane].idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
+          in[lane].best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.best.gid),
+                                      __uint_as_float(t0.grp.y));
         }
         __syncwarp();
       }
@@ -161,10 +178,9 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
           tv.idx = r.idir_oct.x; tv.idy = r.idir_oct.y; tv.idz = r.idir_oct.z;
           tv.octinv = __float_as_uint(r.idir_oct.w);
-          tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);
+          tv.grp = make_uint2(0u, __float_as_uint(r.best.w));
           tv.sp = 0;
-          tv.best = Closest{INFINITY, REF_MISS, 0u};
-          trav_globals<COUNT>(sc, tv, RTB_TMIN, nt);
+          tv.best = Closest{r.best.x, __float_as_uint(r.best.y), __float_as_uint(r.best.z)};
           state = RUNNING;
         }
         in_head += min((uint32_t)__popc(empty), avail);
@@ -212,13 +228,22 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   stage_nodes(sc, snodes, n_snodes);
   const uint32_t* __restrict__ q = pool.q_ext[cur];
   const uint32_t stride = gridDim.x * blockDim.x;
+  // Software pipeline over the grid-stride loop: the queue entry is read two rays ahead and the ray's 32-byte sector
+  // is prefetched into L1 one ray ahead, so the dependent q[i] -> ray[slot] DRAM gather (11.5 % of the kernel's stall
+  // samples when issued at the point of use) is in flight during the previous ray's traversal.
+  const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t slot_cur = i0 < n ? q[i0] : 0u;
+  uint32_t slot_nxt = i0 + stride < n ? q[i0 + stride] : 0u;
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
     const uint32_t i = base + threadIdx.x;
     const bool valid = i < n;
-    uint32_t slot = 0, queue = Q_COUNT;
+    const uint32_t slot = slot_cur;
+    uint32_t queue = Q_COUNT;
     uint32_t nv = 0, nt = 0;
+    slot_cur = slot_nxt;
+    if (i + stride < n && !(prm.opt & 2u)) prefetch_l1(pool.ray + 2 * (size_t)slot_cur);
+    slot_nxt = i + 2 * stride < n ? q[i + 2 * stride] : 0u;
     if (valid) {
-      slot = q[i];
       const float4 ro = pool.ray[2 * slot];
       const float4 rd = pool.ray[2 * slot + 1];
       Closest best{INFINITY, REF_MISS, 0u};
@@ -228,23 +253,18 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
         intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
       }
-      // classify by material (Material trait dispatch, material.rs:11-21); the hit record carries material | face mode
+      // classify by material (Material trait dispatch, material.rs:11-21): the info word carries material | face mode |
+      // shade queue, resolved on the host
       queue = Q_TERMINAL;
       uint32_t minfo = 0;
       if (best.ref != REF_MISS) {
         const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        minfo = type == PT_MEDIUM ? (sc.media[idx].material | (FACE_TRUE << 24)) : __ldg(&sc.info[type][idx].y);
-        const uint32_t mt = __float_as_uint(__ldg(&sc.materials[2 * (minfo & 0xFFFFFFu)].x));
-        queue = mt == RTB_MAT_LAMBERTIAN ? Q_LAMBERT
-              : mt == RTB_MAT_METAL      ? Q_METAL
-              : mt == RTB_MAT_DIELECTRIC ? Q_DIELECTRIC
-              : mt == RTB_MAT_ISOTROPIC  ? Q_ISOTROPIC
-                                         : Q_TERMINAL;
+        minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
+        queue = RTB_MINFO_QUEUE(minfo);
       }
       pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
     }
-#pragma unroll
-    for (uint32_t k = 0; k < Q_COUNT; ++k) warp_enqueue(pool.q_mat[k], &c->n_mat[k], queue == k, slot);
+    warp_enqueue_mat(pool, c, queue, slot);
     if (COUNT) {
       nv = __reduce_add_sync(0xffffffffu, nv);
       nt = __reduce_add_sync(0xffffffffu, nt);
@@ -271,15 +291,15 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uin
   if (type == PT_MEDIUM) {  // constant_medium.rs:65-67: arbitrary normal, front_face = true
     s.n = s.outward = f3(1.f, 0.f, 0.f);
     s.front = true;
-    s.mat = minfo & 0xFFFFFFu;
+    s.mat = RTB_MINFO_MAT(minfo);
     return s;
   }
   if (type == PT_SPHERE) {
     const float4 g = __ldg(sc.geom[PT_SPHERE] + idx);
-    s.outward = (1.0f / g.w) * (s.p - xyz(g));  // sphere.rs:59
+    s.outward = rcp_fast(g.w) * (s.p - xyz(g));  // sphere.rs:59
   } else if (type == PT_MOVING) {
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx), b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
-    s.outward = (1.0f / a.w) * (s.p - fma3(time, xyz(b), xyz(a)));  // moving_sphere.rs:57-58
+    s.outward = rcp_fast(a.w) * (s.p - fma3(time, xyz(b), xyz(a)));  // moving_sphere.rs:57-58
   } else if (type == PT_QUAD) {
     s.outward = xyz(__ldg(sc.geom[PT_QUAD] + 3 * idx));
   } else {
@@ -287,10 +307,10 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uin
     const float3 e1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)) - v0, e2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2)) - v0;
     s.outward = unit(cross(e1, e2));
   }
-  s.mat = minfo & 0xFFFFFFu;
+  s.mat = RTB_MINFO_MAT(minfo);
   bool ff = dot(d, s.outward) < 0.0f;
   s.n = ff ? s.outward : -s.outward;
-  const uint32_t mode = minfo >> 24;  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
+  const uint32_t mode = RTB_MINFO_FACE(minfo);  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
   s.front = mode == FACE_NATURAL ? ff : mode == FACE_FLIPPED ? !ff : mode == FACE_TRUE;
   return s;
 }
@@ -402,14 +422,14 @@ __device__ float lights_pdf(const DevScene& sc, float3 o, float3 v) {
     const DevLight& L = sc.lights[k];
     float pdf = 0.f;
     if (L.type == RTB_LIGHT_XZ_RECT) {
-      const float t = (L.p[4] - o.y) / v.y;
+      const float t = (L.p[4] - o.y) * rcp_fast(v.y);
       if (t >= RTB_TMIN && t < INFINITY) {
         const float x = fmaf(t, v.x, o.x), z = fmaf(t, v.z, o.z);
         if (!(x < L.p[0] || x > L.p[1] || z < L.p[2] || z > L.p[3])) {
           const float area = (L.p[1] - L.p[0]) * (L.p[3] - L.p[2]);
           const float vv = dot(v, v);
           const float cosine = fabsf(v.y) * rsqrtf(vv);
-          pdf = t * t * vv / (cosine * area);
+          pdf = t * t * vv * rcp_fast(cosine * area);
         }
       }
     } else {
@@ -417,9 +437,9 @@ __device__ float lights_pdf(const DevScene& sc, float3 o, float3 v) {
       float t;
       if (sphere_roots(o, v, c, L.p[3], RTB_TMIN, INFINITY, t)) {
         const float3 oc = c - o;
-        const float q = L.p[3] * L.p[3] / dot(oc, oc);
-        const float cos_max = sqrtf(1.0f - q);
-        pdf = (1.0f + cos_max) / (2.0f * RTB_PI * q);  // 1/(2 pi (1-cos)) with 1-cos = q/(1+cos)
+        const float q = L.p[3] * L.p[3] * rcp_fast(dot(oc, oc));
+        const float cos_max = sqrt_fast(1.0f - q);
+        pdf = (1.0f + cos_max) * rcp_fast(2.0f * RTB_PI * q);  // 1/(2 pi (1-cos)) with 1-cos = q/(1+cos)
       }
     }
     sum += weight * pdf;
@@ -436,13 +456,13 @@ __device__ float3 lights_random(const DevScene& sc, float3 o, float pick, float 
     return f3(fmaf(L.p[1] - L.p[0], r1, L.p[0]), L.p[4], fmaf(L.p[3] - L.p[2], r2, L.p[2])) - o;
   const float3 dir = f3(L.p[0], L.p[1], L.p[2]) - o;
   const float dist2 = dot(dir, dir);
-  const float q = L.p[3] * L.p[3] / dist2;
-  const float cos_max = sqrtf(1.0f - q);
-  const float z = 1.0f - r2 * (q / (1.0f + cos_max));  // pdf.rs:85: 1 + r2 (cos_max - 1)
+  const float q = L.p[3] * L.p[3] * rcp_fast(dist2);
+  const float cos_max = sqrt_fast(1.0f - q);
+  const float z = 1.0f - r2 * (q * rcp_fast(1.0f + cos_max));  // pdf.rs:85: 1 + r2 (cos_max - 1)
   const float phi = 2.0f * RTB_PI * r1;
-  const float s = sqrtf(fmaxf(0.f, 1.0f - z * z));
+  const float s = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
   float sn, cs;
-  sincosf(phi, &sn, &cs);
+  __sincosf(phi, &sn, &cs);
   return Onb(dir).local(f3(cs * s, sn * s, z));
 }
 
@@ -478,7 +498,7 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
     float qv = fmaxf(io.beta.x, fmaxf(io.beta.y, io.beta.z));
     qv = qv < 0.2f ? 0.2f : (qv > 1.0f ? 1.0f : qv);  // survival probability in [0.2, 1]: weights grow by <= 5x
     if (!(rr_xi < qv)) alive = false;
-    else io.beta = (1.0f / qv) * io.beta;
+    else io.beta = rcp_fast(qv) * io.beta;
   }
   if (alive) {
     pool.ray[2 * io.slot] = make_float4(no.x, no.y, no.z, ntime);
@@ -497,17 +517,21 @@ __device__ __forceinline__ void camera_ray(const DevCamera& cam, const DevParams
   const uint32_t row = pixel / prm.width, col = pixel - row * prm.width;
   const uint32_t j = prm.height - 1 - row;  // scanline j is stored at image row H-1-j, main.rs:733
   const float4 u0 = philox_u(pixel, sample, BLK_CAMERA0, 0, prm.seed);
-  const float4 u1 = philox_u(pixel, sample, BLK_CAMERA1, 0, prm.seed);
-  const float s = ((float)col + u0.x) / (float)(prm.width - 1);
-  const float t = ((float)j + u0.y) / (float)(prm.height - 1);
-  // random_in_unit_disk (vec3.rs:101-113) in closed form
-  const float rr = cam.lens_radius * sqrtf(u0.z);
-  float sn, cs;
-  sincosf(2.0f * RTB_PI * u0.w, &sn, &cs);
-  const float3 off = (rr * cs) * ld3(cam.u) + (rr * sn) * ld3(cam.v);
-  o = ld3(cam.origin) + off;
-  d = fma3(s, ld3(cam.horizontal), fma3(t, ld3(cam.vertical), ld3(cam.lmo))) - off;
-  time = fmaf(cam.time1 - cam.time0, u1.x, cam.time0);  // camera.rs:68
+  const float s = ((float)col + u0.x) * prm.inv_wm1;  // main.rs:752-753: (i + xi) / (W - 1), (j + xi) / (H - 1)
+  const float t = ((float)j + u0.y) * prm.inv_hm1;
+  o = ld3(cam.origin);
+  d = fma3(s, ld3(cam.horizontal), fma3(t, ld3(cam.vertical), ld3(cam.lmo)));
+  if (cam.lens_radius > 0.0f) {  // random_in_unit_disk (vec3.rs:101-113) in closed form; a pinhole's offset is exactly 0
+    const float rr = cam.lens_radius * sqrt_fast(u0.z);
+    float sn, cs;
+    __sincosf(2.0f * RTB_PI * u0.w, &sn, &cs);
+    const float3 off = (rr * cs) * ld3(cam.u) + (rr * sn) * ld3(cam.v);
+    o = o + off;
+    d = d - off;
+  }
+  time = cam.time0;
+  if (cam.time1 != cam.time0)  // camera.rs:68; the second Philox block is only drawn when the shutter is open
+    time = fmaf(cam.time1 - cam.time0, philox_u(pixel, sample, BLK_CAMERA1, 0, prm.seed).x, cam.time0);
 }
 
 // start camera path number `path` in `slot`.  Sample-major order: all pixels (8x4 tiles) of sample k, then k+1, so
@@ -530,7 +554,9 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
   pool.st[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample << 8));
 }
 
-#define RTB_SHADE_LOOP_BEGIN(QID)                                                        \
+// (An L2 prefetch of the next path's state sectors one iteration ahead was measured and removed: it doubled the
+// request count of a request-bound kernel, C1 57.9 -> 62.3 ms single-lane, profiles/r2_ab.md.)
+#define RTB_SHADE_LOOP_HEAD(QID)                                                         \
   DevCounters* c = pool.c;                                                               \
   const uint32_t n = c->n_mat[QID];                                                      \
   if (n == 0) return;                                                                    \
@@ -542,9 +568,8 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
     const uint32_t i = base + threadIdx.x;                                               \
     const bool valid = i < n;                                                            \
     bool alive = false;                                                                  \
-    uint32_t slot = 0;                                                                   \
-    if (valid) {                                                                         \
-      slot = q[i];
+    const uint32_t slot = valid ? q[i] : 0u;
+#define RTB_SHADE_LOOP_BEGIN(QID) RTB_SHADE_LOOP_HEAD(QID) if (valid) {
 
 /* terminated paths are restarted in place (fused regeneration): one 64-bit atomic per warp claims path numbers */  \
 #define RTB_SHADE_LOOP_END                                                               \
@@ -571,7 +596,15 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
 
 // miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_BEGIN(Q_TERMINAL)
+  RTB_SHADE_LOOP_HEAD(Q_TERMINAL)
+    // Every path of this queue ends here, so the replacement path numbers are claimed FIRST: the atomic's round trip
+    // overlaps the state loads below instead of following them.
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    const uint32_t lane = threadIdx.x & 31u, leader = (__ffs(vmask) - 1) & 31u;
+    unsigned long long first = 0;
+    const bool late = (prm.opt & 4u) != 0;
+    if (!late && vmask && lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(vmask));
+    if (valid) {
       // a miss needs only the throughput/radiance sector; the ray is fetched for emitters alone
       const float4 h = pool.hit[slot], b = pool.st[2 * slot], r = pool.st[2 * slot + 1];
       float3 L = xyz(r);
@@ -586,7 +619,18 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
         if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front) L = L + beta * tex_value(sc, m, s.mat, s);
       }
       deposit(prm, c, __float_as_uint(b.w), L);
-  RTB_SHADE_LOOP_END
+    }
+    if (late && vmask && lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(vmask));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (valid) {  // fused regeneration: restart the slot with the next camera path
+      const unsigned long long path = first + __popc(vmask & ((1u << lane) - 1u));
+      if (path < total_paths) {
+        start_path(pool, prm, cam, slot, path);
+        alive = true;
+      }
+    }
+    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);
+  }
 }
 
 // Lambertian (material.rs:48-71) / Isotropic through the mixture pdf of main.rs:94-138
@@ -603,27 +647,28 @@ __device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool&
     dir = lights_random(sc, s.p, us.y, us.z, us.w);
   } else if (ISO) {
     const float z = 1.0f - 2.0f * us.z, phi = 2.0f * RTB_PI * us.w;
-    const float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+    const float r = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
     float sn, cs;
-    sincosf(phi, &sn, &cs);
+    __sincosf(phi, &sn, &cs);
     dir = f3(r * cs, r * sn, z);
   } else {  // random_cosine_direction vec3.rs:253-262 (r1 = us.z, r2 = us.w) in the ONB of the normal, pdf.rs:32-34
-    const float phi = 2.0f * RTB_PI * us.z, sq = sqrtf(us.w);
+    const float phi = 2.0f * RTB_PI * us.z, sq = sqrt_fast(us.w);
     float sn, cs;
-    sincosf(phi, &sn, &cs);
-    dir = Onb(s.n).local(f3(cs * sq, sn * sq, sqrtf(1.0f - us.w)));
+    __sincosf(phi, &sn, &cs);
+    dir = Onb(s.n).local(f3(cs * sq, sn * sq, sqrt_fast(1.0f - us.w)));
   }
   float mat_pdf, spdf;
   if (ISO) {
     mat_pdf = spdf = 1.0f / (4.0f * RTB_PI);
   } else {
     const float cosine = dot(unit(dir), unit(s.n));  // CosinePdf::value pdf.rs:24-31 ; scattering_pdf material.rs:64-71
-    mat_pdf = cosine <= 0.f ? 0.f : cosine / RTB_PI;
+    mat_pdf = cosine <= 0.f ? 0.f : cosine * (1.0f / RTB_PI);
     spdf = mat_pdf;
   }
   const float pdf_val = have_lights ? 0.5f * lights_pdf(sc, s.p, dir) + 0.5f * mat_pdf : mat_pdf;  // pdf.rs:70-72
   const bool scattered = spdf > 0.f;  // zero-weight continuation culled
-  if (scattered) io.beta = io.beta * atten * (spdf / pdf_val);
+  // without lights the mixture is the material pdf itself: the weight is exactly 1 (white-furnace test relies on it)
+  if (scattered) io.beta = have_lights ? io.beta * atten * (spdf * rcp_fast(pdf_val)) : io.beta * atten;
   float rr = 0.f;
   if (prm.rr_start > 0 && io.segs >= prm.rr_start) rr = u01(philox4(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed).x);
   return finish_bounce(pool, prm, io, scattered, s.p, dir, io.time, rr);
@@ -653,9 +698,9 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
       const float4 ua = philox_u(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed);
       if (fuzz > 0.f) {  // random_in_unit_sphere (vec3.rs:78-86) in closed form: uniform direction * cbrt(xi)
         const float z = 1.0f - 2.0f * ua.y, phi = 2.0f * RTB_PI * ua.z, rad = cbrtf(ua.w);
-        const float r = sqrtf(fmaxf(0.f, 1.0f - z * z));
+        const float r = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
         float sn, cs;
-        sincosf(phi, &sn, &cs);
+        __sincosf(phi, &sn, &cs);
         dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
       }
       io.beta = io.beta * tex_value(sc, m, s.mat, s);
@@ -669,12 +714,12 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
       const float ir = __ldg(&sc.materials[2 * s.mat]).z;
-      const float ratio = s.front ? 1.0f / ir : ir;
+      const float ratio = s.front ? rcp_fast(ir) : ir;
       const float3 ud = unit(io.d);
       const float cos_theta = fminf(-dot(ud, s.n), 1.0f);
-      const float sin_theta = sqrtf(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+      const float sin_theta = sqrt_fast(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
       const bool cannot_refract = ratio * sin_theta > 1.0f;
-      float r0 = (1.0f - ratio) / (1.0f + ratio);
+      float r0 = (1.0f - ratio) * rcp_fast(1.0f + ratio);
       r0 *= r0;
       const float om = 1.0f - cos_theta;
       const float reflectance = r0 + (1.0f - r0) * (om * om) * (om * om) * om;
@@ -684,7 +729,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
         dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);
       } else {
         const float3 perp = ratio * fma3(cos_theta, s.n, ud);
-        const float par = -sqrtf(fabsf(1.0f - dot(perp, perp)));
+        const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
         dir = fma3(par, s.n, perp);
       }
       alive = finish_bounce(pool, prm, io, true, s.p, dir, io.time, ua.x);
@@ -872,7 +917,7 @@ void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float*
 
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   // stage as much of the (breadth-first ordered) node array as fits the shared-memory budget
-  const uint32_t budget = 56 * 1024;  // + 16 KB of per-warp ray buffers: three CTAs per SM fit the 228 KB
+  const uint32_t budget = 56 * 1024;  // + 20 KB of per-warp ray/result buffers (dynamic fetch); extend runs 2 CTAs per SM
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;

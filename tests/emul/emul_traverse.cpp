@@ -15,6 +15,10 @@ static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+  sh &= 31u;
+  return sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
+}
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   uint8_t b[8];
   for (int i = 0; i < 4; ++i) { b[i] = (x >> (8 * i)) & 0xFF; b[4 + i] = (y >> (8 * i)) & 0xFF; }
