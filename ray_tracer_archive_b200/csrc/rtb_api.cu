@@ -51,8 +51,8 @@ struct DevBuf {
 struct Lane {
   uint32_t pool_n = 0;
   DevBuf<float4> ray, st, hit;
-  DevBuf<uint32_t> q_ext0, q_ext1, q_dead;
-  DevBuf<uint32_t> q_mat[Q_COUNT];
+  DevBuf<uint8_t> cls;                    // per-slot shade class
+  DevBuf<unsigned long long> cursor;      // per-chunk path cursor
   DevBuf<DevCounters> counters;
   DevCounters* h_counters = nullptr;  // pinned
   cudaStream_t stream = nullptr;
@@ -76,8 +76,6 @@ struct rtb_context {
   DevBuf<float> p_org, p_dir, p_time, p_t;
   DevBuf<uint32_t> p_id;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  ShadeStreams ss;
-  bool ss_ok = false;
   std::vector<cudaEvent_t> ext_events;  // pairs around every extend launch when RTB_RENDER_TIME_EXTEND is set
 };
 
@@ -134,12 +132,6 @@ int rtb_context_create(int device_id, rtb_context** out) {
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
-  for (int k = 0; k < 4; ++k) {
-    CU(cudaStreamCreateWithFlags(&c->ss.side[k], cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ss.join[k], cudaEventDisableTiming));
-  }
-  CU(cudaEventCreateWithFlags(&c->ss.fork, cudaEventDisableTiming));
-  c->ss_ok = true;
   CU(c->counters.resize(1));
   *out = c;
   return RTB_OK;
@@ -159,10 +151,6 @@ void rtb_context_destroy(rtb_context* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->ss_ok) {
-    for (int k = 0; k < 4; ++k) { cudaStreamDestroy(c->ss.side[k]); cudaEventDestroy(c->ss.join[k]); }
-    cudaEventDestroy(c->ss.fork);
-  }
   for (cudaEvent_t e : c->ext_events) cudaEventDestroy(e);
   delete c;
 }
@@ -601,8 +589,8 @@ static void camera_basis(const rtb_camera& c, DevCamera& f, DevCameraF64& g) {  
 static int ensure_pool(Lane& c, uint32_t n) {
   if (c.pool_n >= n) return RTB_OK;
   CU(c.ray.resize((size_t)n * 2)); CU(c.st.resize((size_t)n * 2)); CU(c.hit.resize(n));
-  CU(c.q_ext0.resize(n)); CU(c.q_ext1.resize(n)); CU(c.q_dead.resize(n));
-  for (int k = 0; k < (int)Q_COUNT; ++k) CU(c.q_mat[k].resize(n));
+  const size_t chunks = ((size_t)n + RTB_CHUNK - 1) / RTB_CHUNK;
+  CU(c.cls.resize(chunks * RTB_CHUNK)); CU(c.cursor.resize(chunks));
   c.pool_n = n;
   return RTB_OK;
 }
@@ -654,14 +642,18 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     const uint32_t cnt = p->spp / n_lanes + ((uint32_t)k < p->spp % n_lanes ? 1u : 0u);
     LaneRun& R = run[k];
     R.total = npix * cnt;
+    // Pools are a whole number of "units" (one RTB_CHUNK-slot chunk per resident shade warp) so that every warp of a
+    // shade kernel gets the same number of chunks; small renders get a pool no larger than their path count.
     uint32_t pool_n = std::max(1024u, pool_total / (uint32_t)n_lanes);
+    const uint32_t unit = s->lc.pool_unit;
+    if (!p->pool_paths && unit) pool_n = std::max(1u, (pool_n + unit / 2) / unit) * unit;
     if ((unsigned long long)pool_n > R.total) pool_n = (uint32_t)std::max<unsigned long long>(1024ull, R.total);
     rc = ensure_pool(L, pool_n);
     if (rc) return rc;
     R.pool.n = pool_n;
     R.pool.ray = L.ray.p; R.pool.st = L.st.p; R.pool.hit = L.hit.p;
-    R.pool.q_ext[0] = L.q_ext0.p; R.pool.q_ext[1] = L.q_ext1.p; R.pool.q_dead = L.q_dead.p;
-    for (int q = 0; q < (int)Q_COUNT; ++q) R.pool.q_mat[q] = L.q_mat[q].p;
+    R.pool.n_chunks = (pool_n + RTB_CHUNK - 1) / RTB_CHUNK;
+    R.pool.cls = L.cls.p; R.pool.cursor = L.cursor.p;
     R.pool.c = L.counters.p;
     DevParams& prm = R.prm;
     prm.width = p->width; prm.height = p->height; prm.spp = cnt; prm.sample_offset = p->sample_offset + first_sample;
@@ -677,7 +669,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     first_sample += cnt;
     R.active = true;
     R.iters = 0;
-    R.iter_cap = (uint64_t)(R.total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
+    R.iter_cap = 2 * (uint64_t)(R.total / pool_n + 2) * (uint64_t)(p->max_depth + 2) + 64;
   }
 
   uint64_t launches = 0, extend_launches = 0;
@@ -695,7 +687,6 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
   const uint32_t check_every = 8;
-  static const bool serial_shade = getenv("RTB_CONCURRENT_SHADE") == nullptr;  // fork/join measured: no gain (profiles/)
   size_t ev_used = 0;
   int n_active = n_lanes;
   while (n_active > 0) {
@@ -718,7 +709,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
           CU(cudaEventRecord(c->ext_events[ev_used + 1], ls));
           ev_used += 2;
         }
-        launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls, serial_shade ? nullptr : &c->ss);
+        launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls);
         launch_advance(run[k].pool, ls);
         launches += 2 + n_shade;
         extend_launches += 1;
@@ -733,7 +724,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
       CU(cudaStreamSynchronize(c->lanes[k].stream));
       run[k].iters += check_every;
       const DevCounters* h = c->lanes[k].h_counters;
-      if (h->n_ext[h->cur] == 0) {
+      if (h->last_rays == 0) {
         run[k].active = false;
         --n_active;
       } else if (run[k].iters > run[k].iter_cap) {
@@ -754,7 +745,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     for (int k = 0; k < n_lanes; ++k) {
       const DevCounters* h = c->lanes[k].h_counters;
-      stats->paths += std::min<unsigned long long>(h->next_path, run[k].total);
+      stats->paths += run[k].total;  // a render always runs to completion: every path number was started exactly once
       stats->segments += h->segments;
       stats->rejected += h->rejected;
       stats->iterations = std::max<uint64_t>(stats->iterations, h->iter);

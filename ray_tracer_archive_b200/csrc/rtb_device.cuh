@@ -63,28 +63,40 @@ struct DevCamera {  // camera.rs:6-17, basis computed on the host in f64
 };
 
 struct DevCounters {
-  uint32_t n_ext[2];
-  uint32_t n_mat[Q_COUNT];
-  uint32_t n_dead;
-  uint32_t cur;       // which n_ext/q_ext is being extended this iteration
+  uint32_t iter_rays;   // rays extended in the current iteration (one atomicAdd per extend warp at kernel end)
+  uint32_t last_rays;   // ... in the previous iteration: 0 = the pool has drained (host check)
   uint32_t iter;
-  uint32_t ext_cursor;  // next unclaimed entry of the extend queue (dynamic ray fetch)
-  uint32_t _pad;
-  unsigned long long next_path, total_paths;
-  unsigned long long segments, rejected, paths_started;
+  uint32_t ext_cursor;  // next unclaimed slot batch (dynamic ray fetch)
+  unsigned long long total_paths;
+  unsigned long long segments, rejected;
   unsigned long long nodes_visited, prims_tested;
 };
 
-struct DevPool {  // wavefront path state, SoA over `n` slots
-  uint32_t n;
-  float4* ray;     // [2s] origin xyz, time ; [2s+1] direction xyz (un-normalised, ray.rs), 0   — one 32-byte sector
-  float4* st;      // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
-  float4* hit;     // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
-  uint32_t* q_ext[2];
-  uint32_t* q_mat[Q_COUNT];
-  uint32_t* q_dead;
+// Path pool of one wavefront instance ("lane").  SLOT-STABLE: a path lives in slot i until it terminates, and slot i is
+// then restarted in place with a new camera path.  There are NO global work queues: `extend` walks the slots in order
+// (coalesced ray loads), writes the hit record and the slot's shade class; every per-material shade kernel walks the
+// class bytes in chunks of RTB_CHUNK slots per warp and compacts the matching slots warp-locally (ballot/scan into a
+// shared-memory list).  Path numbers for restarted slots come from a per-chunk cursor over the chunk's own sequence of
+// 32-path blocks, so no kernel issues a contended global atomic (the queue-compacting version spent 77 % of
+// k_shade_terminal's stall samples on two same-address atomics per warp, profiles/r2_ab.md §3).
+#define RTB_CHUNK 256u
+enum SlotClass : uint32_t { CLS_NEW = 6, CLS_DEAD = 7 };  // 0..4 = Queue of the slot's current hit
+struct DevPool {
+  uint32_t n;         // slots
+  uint32_t n_chunks;  // ceil(n / RTB_CHUNK)
+  float4* ray;        // [2s] origin xyz, time ; [2s+1] direction xyz (un-normalised, ray.rs), 0   — one 32-byte sector
+  float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
+  float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
+  uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
+  unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence
   DevCounters* c;
 };
+
+// m-th path number of chunk `chunk`: the chunk owns the 32-path blocks chunk, chunk + n_chunks, chunk + 2 n_chunks, ...
+// (consecutive numbers are neighbouring pixels of one 8x4 tile, so slots restarted together get coherent primary rays)
+__device__ __forceinline__ unsigned long long chunk_path(unsigned long long m, uint32_t chunk, uint32_t n_chunks) {
+  return (((m >> 5) * n_chunks + chunk) << 5) | (m & 31ull);
+}
 
 struct DevParams {
   uint32_t width, height, spp, sample_offset;

@@ -16,36 +16,8 @@
 
 namespace rtb {
 
-// ---- queue helpers ----------------------------------------------------------------------------------------------
-// must be executed by all 32 lanes of a converged warp
-__device__ __forceinline__ void warp_enqueue(uint32_t* __restrict__ q, uint32_t* counter, bool pred, uint32_t value) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, pred);
-  if (mask == 0) return;
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t leader = __ffs(mask) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) q[base + __popc(mask & ((1u << lane) - 1u))] = value;
-}
-
-// Append `value` to per-material queue `queue` (Q_COUNT = none).  Lanes are grouped by queue with one MATCH.ANY; the
-// leader of every group issues its atomicAdd in the SAME instruction, so a warp whose rays go to 3-4 different queues
-// pays one atomic round trip instead of one per queue (the five serial ballot+atomic+shuffle rounds were 17 % of the
-// extend kernel's stall samples, profiles/r1d_c1_ncu_summary.md).  Must be executed by all 32 lanes.
-__device__ __forceinline__ void warp_enqueue_mat(const DevPool& pool, DevCounters* c, uint32_t queue, uint32_t value) {
-  const uint32_t peers = __match_any_sync(0xffffffffu, queue);
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t leader = __ffs(peers) - 1;
-  const bool live = queue < Q_COUNT;
-  uint32_t base = 0;
-  if (live && lane == leader) base = atomicAdd(&c->n_mat[queue], (uint32_t)__popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (live) pool.q_mat[queue][base + __popc(peers & ((1u << lane) - 1u))] = value;
-}
-
+// ---- helpers ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -68,22 +40,82 @@ __device__ __forceinline__ void stage_nodes(const DevScene& sc, uint4* snodes, u
   __syncthreads();
 }
 
+// media + classification + result write of one finished ray (Material trait dispatch, material.rs:11-21): the info word
+// carries material | face mode | shade queue, resolved on the host, so no material fetch is needed here
+__device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t slot,
+                                           float3 o, float3 d, Closest best) {
+  if (sc.n_media) {
+    const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
+    const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
+    intersect_media(sc, o, d, RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+  }
+  uint32_t queue = Q_TERMINAL, minfo = 0;
+  if (best.ref != REF_MISS) {
+    const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
+    minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
+    queue = RTB_MINFO_QUEUE(minfo);
+  }
+  pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
+  pool.cls[slot] = (uint8_t)queue;
+}
+
+// ---- warp-local chunk lists -------------------------------------------------------------------------------------------
+// A warp owns RTB_CHUNK consecutive slots; lane l holds the class bytes of slots 8l..8l+7 (`cw`).  append_class() appends
+// the chunk-relative indices of the slots whose class is `key` to the warp's shared-memory list (ascending slot order)
+// and returns the new list length.  Must be executed by all 32 lanes.
+__device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t* list, uint32_t len, uint32_t lane) {
+  // bytes equal to key -> 0xFF (SIMD-in-a-word compare), one bit per matching slot
+  const uint32_t e0 = __vcmpeq4(cw.x, key * 0x01010101u), e1 = __vcmpeq4(cw.y, key * 0x01010101u);
+  const uint32_t cnt = (__popc(e0) + __popc(e1)) >> 3;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total) {
+    uint32_t pos = len + incl - cnt;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j)
+      if (((j < 4 ? e0 : e1) >> (8 * (j & 3))) & 1u) list[pos++] = (uint8_t)(8u * lane + j);
+  }
+  return len + total;
+}
+
+// extend's order of a chunk: the live slots sorted by the kernel that produced their ray — restarted slots (new camera
+// rays: consecutive path numbers = neighbouring pixels of one tile) first, then the Lambertian bounces, metal, glass,
+// media.  Rays of one kind share warps, so the coherent primary rays are not diluted by incoherent bounce rays
+// (slot order alone: C1 extend 27.2 -> 32.3 ms, C3 68.6 -> 86.0 ms, profiles/r2_ab.md §4).
+__device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint32_t chunk, uint8_t* list, uint32_t lane) {
+  const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + chunk * RTB_CHUNK + 8u * lane);
+  uint32_t len = 0;
+  len = append_class(cw, CLS_NEW, list, len, lane);
+  len = append_class(cw, Q_TERMINAL, list, len, lane);
+  len = append_class(cw, Q_LAMBERT, list, len, lane);
+  len = append_class(cw, Q_METAL, list, len, lane);
+  len = append_class(cw, Q_DIELECTRIC, list, len, lane);
+  len = append_class(cw, Q_ISOTROPIC, list, len, lane);
+  __syncwarp();
+  return len;
+}
+
 // ---- extend ------------------------------------------------------------------------------------------------------
-// Persistent warps with dynamic ray fetch.  Every lane owns one in-flight ray and advances it by ONE node visit (or
-// stack pop) per loop iteration, so the 32 lanes execute the node-decode code together.  Rays finish after different
-// numbers of visits; instead of idling until the slowest lane of the warp is done (17 of 32 lanes active in the
-// one-ray-per-thread version, profiles/r1_c1_ncu_summary.md) a finished lane immediately swaps its ray:
-//   * rays are PREFETCHED 32 at a time by the whole warp (coalesced queue read, ray fetch, 1/d) into a per-warp
-//     shared-memory buffer; an idle lane takes the next prepared ray with three LDS.128;
-//   * results are pushed to a per-warp shared-memory buffer and WRITTEN OUT 32 at a time by the whole warp
-//     (media, material classification, hit record, per-material queues).
-// So the expensive set-up / tear-down code always runs with full warps and only the swap itself is divergent.
-// Work is claimed from a device-side cursor, one atomic per 32 rays.
+// Dynamic-fetch variant (deep trees).  Persistent warps: every lane owns one in-flight ray and advances it by ONE node
+// visit per loop iteration, so the 32 lanes execute the node-decode code together.  Rays finish after different
+// numbers of visits; instead of idling until the slowest lane of the warp is done a finished lane immediately swaps
+// its ray:
+//   * rays are PREFETCHED 32 slots at a time by the whole warp (coalesced class + ray loads, 1/d, the scene's global
+//     primitives) into a per-warp shared-memory buffer; an idle lane takes the next prepared ray with four LDS.128;
+//   * results are pushed to a per-warp shared-memory buffer and WRITTEN OUT 32 at a time by the whole warp.
+// So the set-up / tear-down code always runs with full warps and only the swap itself is divergent.
+// Work is claimed from a device-side cursor one chunk (RTB_CHUNK slots) at a time; the chunk's live slots are ordered by
+// ray kind (build_extend_list) and handed out 32 at a time.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
 // extend runs 2 CTAs/SM (configure_launch) with at most 80 registers: 2 x 256 x 80 = 41 K of the 64 K registers, so a
-// 256-thread shade CTA (72 registers) of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476,
-// 80: 4497, 88: 4326, 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
+// 256-thread shade CTA of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476, 80: 4497, 88: 4326,
+// 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
 struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, gid, group word) after the global primitives
 struct ExtOut { float t; uint32_t ref, gid, slot; };
@@ -95,49 +127,35 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ ExtIn s_in[RTB_EXTEND_WARPS][32];
   __shared__ ExtOut s_out[RTB_EXTEND_WARPS][32];
+  __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   DevCounters* c = pool.c;
-  const uint32_t cur = c->cur;
-  const uint32_t n = c->n_ext[cur];
-  if (n == 0) return;
   stage_nodes(sc, snodes, n_snodes);
-  const uint32_t* __restrict__ q = pool.q_ext[cur];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   ExtIn* in = s_in[warp];
   ExtOut* out = s_out[warp];
+  uint8_t* list = s_list[warp];
   enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
   uint32_t state = EMPTY, slot = 0;
   uint32_t in_head = 0, in_count = 0, out_count = 0;  // warp-uniform
-  bool exhausted = false;                              // warp-uniform: the queue has no more rays
+  uint32_t chunk_base = 0, list_pos = 0, list_len = 0;  // warp-uniform: the claimed chunk's ordered slot list
+  bool exhausted = false;                              // warp-uniform: no more chunks to claim
+  uint32_t n_rays = 0;                                 // warp-uniform
   Trav tv;
   uint2 stack[RTB_STACK];
   uint32_t nv = 0, nt = 0;
 
   auto flush = [&]() {  // executed by the whole warp
     __syncwarp();
-    uint32_t queue = Q_COUNT, oslot = 0;
     if (lane < out_count) {
       const ExtOut h = out[lane];
-      oslot = h.slot;
-      Closest best{h.t, h.ref, h.gid};
+      float3 o = f3(0.f, 0.f, 0.f), d = o;
       if (sc.n_media) {
-        const float4 ro = pool.ray[2 * oslot], rd = pool.ray[2 * oslot + 1];
-        const uint32_t pixel = __float_as_uint(pool.st[2 * oslot].w);
-        const uint32_t st = __float_as_uint(pool.st[2 * oslot + 1].w);
-        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+        o = xyz(pool.ray[2 * h.slot]);
+        d = xyz(pool.ray[2 * h.slot + 1]);
       }
-      // classify by material (Material trait dispatch, material.rs:11-21): the info word carries material | face mode |
-      // shade queue, resolved on the host
-      queue = Q_TERMINAL;
-      uint32_t minfo = 0;
-      if (best.ref != REF_MISS) {
-        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
-        queue = RTB_MINFO_QUEUE(minfo);
-      }
-      pool.hit[oslot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
+      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.ref, h.gid});
     }
-    warp_enqueue_mat(pool, c, queue, oslot);
     out_count = 0;
     __syncwarp();
   };
@@ -146,26 +164,39 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     // ---- idle lanes take prepared rays ----------------------------------------------------------------------------
     const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
     if (empty) {
-      if (in_head == in_count && !exhausted) {  // prefetch the next 32 rays with the whole warp
-        uint32_t first = 0;
-        if (lane == 0) first = atomicAdd(&c->ext_cursor, 32u);
-        first = __shfl_sync(0xffffffffu, first, 0);
-        exhausted = first + 32u >= n;
+      while (in_head == in_count && !(exhausted && list_pos == list_len)) {  // prepare the next 32 rays
+        if (list_pos == list_len) {  // claim the next chunk and order its live slots by ray kind
+          uint32_t ch = 0;
+          if (lane == 0) ch = atomicAdd(&c->ext_cursor, 1u);
+          ch = __shfl_sync(0xffffffffu, ch, 0);
+          if (ch >= pool.n_chunks) {
+            exhausted = true;
+            break;
+          }
+          chunk_base = ch * RTB_CHUNK;
+          list_len = build_extend_list(pool, ch, list, lane);
+          list_pos = 0;
+          n_rays += list_len;
+          if (list_len == 0) continue;
+        }
+        const bool live = list_pos + lane < list_len;
+        const uint32_t sl = chunk_base + (live ? list[list_pos + lane] : 0u);
         in_head = 0;
-        in_count = first < n ? min(32u, n - first) : 0u;
+        in_count = min(32u, list_len - list_pos);
+        list_pos += in_count;
         __syncwarp();
-        if (lane < in_count) {
-          const uint32_t sl = q[first + lane];
+        if (live) {
           const float4 ro = pool.ray[2 * sl], rd = pool.ray[2 * sl + 1];
           // set-up runs here with the whole warp: 1/d, and the scene's global primitives (tested before the tree)
           Trav t0;
           trav_init(t0, xyz(ro), xyz(rd), ro.w);
           trav_globals<COUNT>(sc, t0, RTB_TMIN, nt);
-          in[lane].o_time = ro;
-          in[lane].d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
-          in[lane].idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
-          in[lane].best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.best.gid),
-                                      __uint_as_float(t0.grp.y));
+          ExtIn& e = in[lane];
+          e.o_time = ro;
+          e.d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
+          e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
+          e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.best.gid),
+                               __uint_as_float(t0.grp.y));
         }
         __syncwarp();
       }
@@ -188,7 +219,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
     if (__ballot_sync(0xffffffffu, state == RUNNING) == 0u) {
       if (out_count) flush();
-      if (exhausted && in_head == in_count) break;
+      if (exhausted && list_pos == list_len && in_head == in_count) break;
       continue;
     }
     // ---- one node visit (or pop) per lane ---------------------------------------------------------------------------
@@ -206,6 +237,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
       out_count += __popc(done);
     }
   }
+  if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
   if (COUNT) {
     nv = __reduce_add_sync(0xffffffffu, nv);
     nt = __reduce_add_sync(0xffffffffu, nt);
@@ -216,62 +248,45 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   }
 }
 
-// The first version: one ray per thread to completion, grid-stride (kept for A/B measurements, RTB_EXTEND_MODE=static).
+// One ray per thread to completion (small trees: all lanes start at the root together, so root-level work stays
+// converged).  Slot-stable pool: a warp takes one chunk of RTB_CHUNK slots at a time, orders its live slots by ray kind
+// (build_extend_list) and traces them 32 at a time; the next round's ray sectors are prefetched into L1 during the
+// current traversal.  No queue, no atomics apart from one ray-count add per warp at the end.
 template <bool COUNT>
 __global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
+  __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   DevCounters* c = pool.c;
-  const uint32_t cur = c->cur;
-  const uint32_t n = c->n_ext[cur];
-  if (n == 0) return;
   stage_nodes(sc, snodes, n_snodes);
-  const uint32_t* __restrict__ q = pool.q_ext[cur];
-  const uint32_t stride = gridDim.x * blockDim.x;
-  // Software pipeline over the grid-stride loop: the queue entry is read two rays ahead and the ray's 32-byte sector
-  // is prefetched into L1 one ray ahead, so the dependent q[i] -> ray[slot] DRAM gather (11.5 % of the kernel's stall
-  // samples when issued at the point of use) is in flight during the previous ray's traversal.
-  const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t slot_cur = i0 < n ? q[i0] : 0u;
-  uint32_t slot_nxt = i0 + stride < n ? q[i0 + stride] : 0u;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
-    const uint32_t i = base + threadIdx.x;
-    const bool valid = i < n;
-    const uint32_t slot = slot_cur;
-    uint32_t queue = Q_COUNT;
-    uint32_t nv = 0, nt = 0;
-    slot_cur = slot_nxt;
-    if (i + stride < n && !(prm.opt & 2u)) prefetch_l1(pool.ray + 2 * (size_t)slot_cur);
-    slot_nxt = i + 2 * stride < n ? q[i + 2 * stride] : 0u;
-    if (valid) {
-      const float4 ro = pool.ray[2 * slot];
-      const float4 rd = pool.ray[2 * slot + 1];
-      Closest best{INFINITY, REF_MISS, 0u};
-      traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
-      if (sc.n_media) {
-        const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
-        const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
-        intersect_media(sc, xyz(ro), xyz(rd), RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* list = s_list[warp];
+  const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
+  uint32_t n_rays = 0, nv = 0, nt = 0;
+  for (uint32_t chunk = blockIdx.x * RTB_EXTEND_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
+    const uint32_t base = chunk * RTB_CHUNK;
+    const uint32_t total = build_extend_list(pool, chunk, list, lane);
+    n_rays += total;
+    for (uint32_t r = 0; r < total; r += 32) {
+      if (r + 32 + lane < total) prefetch_l1(pool.ray + 2 * (size_t)(base + list[r + 32 + lane]));
+      if (r + lane < total) {
+        const uint32_t slot = base + list[r + lane];
+        const float4 ro = pool.ray[2 * slot];
+        const float4 rd = pool.ray[2 * slot + 1];
+        Closest best{INFINITY, REF_MISS, 0u};
+        traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+        finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
       }
-      // classify by material (Material trait dispatch, material.rs:11-21): the info word carries material | face mode |
-      // shade queue, resolved on the host
-      queue = Q_TERMINAL;
-      uint32_t minfo = 0;
-      if (best.ref != REF_MISS) {
-        const uint32_t type = best.ref >> REF_TYPE_SHIFT, idx = best.ref & REF_INDEX_MASK;
-        minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
-        queue = RTB_MINFO_QUEUE(minfo);
-      }
-      pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
     }
-    warp_enqueue_mat(pool, c, queue, slot);
-    if (COUNT) {
-      nv = __reduce_add_sync(0xffffffffu, nv);
-      nt = __reduce_add_sync(0xffffffffu, nt);
-      if ((threadIdx.x & 31u) == 0) {
-        atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-        atomicAdd(&c->prims_tested, (unsigned long long)nt);
-      }
+    __syncwarp();  // the list is rewritten for the next chunk
+  }
+  if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
+  if (COUNT) {
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if (lane == 0) {
+      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+      atomicAdd(&c->prims_tested, (unsigned long long)nt);
     }
   }
 }
@@ -554,83 +569,70 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
   pool.st[2 * slot + 1] = make_float4(0.f, 0.f, 0.f, __uint_as_float(sample << 8));
 }
 
-// (An L2 prefetch of the next path's state sectors one iteration ahead was measured and removed: it doubled the
-// request count of a request-bound kernel, C1 57.9 -> 62.3 ms single-lane, profiles/r2_ab.md.)
-#define RTB_SHADE_LOOP_HEAD(QID)                                                         \
-  DevCounters* c = pool.c;                                                               \
-  const uint32_t n = c->n_mat[QID];                                                      \
-  if (n == 0) return;                                                                    \
-  const uint32_t nxt = c->cur ^ 1u;                                                      \
-  const unsigned long long total_paths = c->total_paths;                                 \
-  const uint32_t* __restrict__ q = pool.q_mat[QID];                                      \
-  const uint32_t stride = gridDim.x * blockDim.x;                                        \
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {              \
-    const uint32_t i = base + threadIdx.x;                                               \
-    const bool valid = i < n;                                                            \
-    bool alive = false;                                                                  \
-    const uint32_t slot = valid ? q[i] : 0u;
-#define RTB_SHADE_LOOP_BEGIN(QID) RTB_SHADE_LOOP_HEAD(QID) if (valid) {
+// ---- the shade loop: warp-local compaction of one chunk of slots, shading, in-place restart ---------------------------
+// One warp owns one chunk of RTB_CHUNK consecutive slots at a time.  Lane l reads the class bytes of slots 8l..8l+7 (one
+// coalesced 256-byte read per warp), the slots of class QID are compacted into a per-warp shared-memory list with a
+// warp scan, and the list is processed 32 entries at a time.  `body(slot)` shades one path and returns true if it
+// continues (its next ray is in the pool).  A finished path's slot is restarted immediately with the chunk's next path
+// number (fused regeneration); when the chunk's numbers are used up the slot is marked CLS_DEAD.
+// (An L2 prefetch of the next path's state sectors was measured and removed: it doubled the request count of a
+// request-bound kernel, profiles/r2_ab.md §2.)
+#define RTB_SHADE_WARPS (RTB_SHADE_THREADS / 32)
 
-/* terminated paths are restarted in place (fused regeneration): one 64-bit atomic per warp claims path numbers */  \
-#define RTB_SHADE_LOOP_END                                                               \
-    }                                                                                    \
-    {                                                                                    \
-      const bool dead = valid && !alive;                                                 \
-      const uint32_t dmask = __ballot_sync(0xffffffffu, dead);                           \
-      if (dmask) {                                                                       \
-        const uint32_t lane = threadIdx.x & 31u, leader = __ffs(dmask) - 1;              \
-        unsigned long long first = 0;                                                    \
-        if (lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(dmask)); \
-        first = __shfl_sync(0xffffffffu, first, leader);                                 \
-        if (dead) {                                                                      \
-          const unsigned long long path = first + __popc(dmask & ((1u << lane) - 1u));   \
-          if (path < total_paths) {                                                      \
-            start_path(pool, prm, cam, slot, path);                                      \
-            alive = true;                                                                \
-          }                                                                              \
-        }                                                                                \
-      }                                                                                  \
-    }                                                                                    \
-    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);                          \
+template <uint32_t QID, class Body>
+__device__ __forceinline__ void shade_loop(const DevPool& pool, const DevParams& prm, const DevCamera& cam, Body&& body) {
+  __shared__ uint8_t s_list[RTB_SHADE_WARPS][RTB_CHUNK];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint8_t* list = s_list[warp];
+  const unsigned long long total_paths = pool.c->total_paths;
+  const uint32_t n_warps = gridDim.x * RTB_SHADE_WARPS;
+  for (uint32_t chunk = blockIdx.x * RTB_SHADE_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
+    const uint32_t base = chunk * RTB_CHUNK;
+    const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + base + 8u * lane);
+    const uint32_t total = append_class(cw, QID, list, 0u, lane);
+    if (total == 0) continue;
+    __syncwarp();
+    unsigned long long m_cur = pool.cursor[chunk];
+    const unsigned long long m_first = m_cur;
+    for (uint32_t r = 0; r < total; r += 32) {
+      const bool valid = r + lane < total;
+      const uint32_t slot = base + (valid ? list[r + lane] : 0u);
+      bool alive = false;
+      if (valid) alive = body(slot);
+      const bool dead = valid && !alive;
+      const uint32_t dmask = __ballot_sync(0xffffffffu, dead);
+      if (dead) {
+        const unsigned long long path = chunk_path(m_cur + __popc(dmask & lt_mask), chunk, pool.n_chunks);
+        if (path < total_paths) start_path(pool, prm, cam, slot, path);
+        else pool.cls[slot] = (uint8_t)CLS_DEAD;
+      }
+      m_cur += __popc(dmask);
+    }
+    if (lane == 0 && m_cur != m_first) pool.cursor[chunk] = m_cur;
+    __syncwarp();  // the list is rewritten for the next chunk
   }
+}
 
 // miss -> background (main.rs:74-76); DiffuseLight -> emitted iff front_face, no scatter (material.rs:184-190, main.rs:85-87)
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_terminal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_HEAD(Q_TERMINAL)
-    // Every path of this queue ends here, so the replacement path numbers are claimed FIRST: the atomic's round trip
-    // overlaps the state loads below instead of following them.
-    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-    const uint32_t lane = threadIdx.x & 31u, leader = (__ffs(vmask) - 1) & 31u;
-    unsigned long long first = 0;
-    const bool late = (prm.opt & 4u) != 0;
-    if (!late && vmask && lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(vmask));
-    if (valid) {
-      // a miss needs only the throughput/radiance sector; the ray is fetched for emitters alone
-      const float4 h = pool.hit[slot], b = pool.st[2 * slot], r = pool.st[2 * slot + 1];
-      float3 L = xyz(r);
-      const float3 beta = xyz(b);
-      const uint32_t ref = __float_as_uint(h.y);
-      if (ref == REF_MISS) {
-        L = L + beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
-      } else {
-        const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
-        const Surf s = surface_at(sc, ref, __float_as_uint(h.z), xyz(ro), xyz(rd), ro.w, h.x);
-        const float4 m = __ldg(&sc.materials[2 * s.mat]);
-        if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front) L = L + beta * tex_value(sc, m, s.mat, s);
-      }
-      deposit(prm, c, __float_as_uint(b.w), L);
+  shade_loop<Q_TERMINAL>(pool, prm, cam, [&](uint32_t slot) {
+    // a miss needs only the throughput/radiance sector; the ray is fetched for emitters alone
+    const float4 h = pool.hit[slot], b = pool.st[2 * slot], r = pool.st[2 * slot + 1];
+    float3 L = xyz(r);
+    const float3 beta = xyz(b);
+    const uint32_t ref = __float_as_uint(h.y);
+    if (ref == REF_MISS) {
+      L = L + beta * f3(prm.bg[0], prm.bg[1], prm.bg[2]);
+    } else {
+      const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
+      const Surf s = surface_at(sc, ref, __float_as_uint(h.z), xyz(ro), xyz(rd), ro.w, h.x);
+      const float4 m = __ldg(&sc.materials[2 * s.mat]);
+      if (__float_as_uint(m.x) == RTB_MAT_DIFFUSE_LIGHT && s.front) L = L + beta * tex_value(sc, m, s.mat, s);
     }
-    if (late && vmask && lane == leader) first = atomicAdd(&c->next_path, (unsigned long long)__popc(vmask));
-    first = __shfl_sync(0xffffffffu, first, leader);
-    if (valid) {  // fused regeneration: restart the slot with the next camera path
-      const unsigned long long path = first + __popc(vmask & ((1u << lane) - 1u));
-      if (path < total_paths) {
-        start_path(pool, prm, cam, slot, path);
-        alive = true;
-      }
-    }
-    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);
-  }
+    deposit(prm, pool.c, __float_as_uint(b.w), L);
+    return false;
+  });
 }
 
 // Lambertian (material.rs:48-71) / Isotropic through the mixture pdf of main.rs:94-138
@@ -675,20 +677,16 @@ __device__ __forceinline__ bool shade_diffuse(const DevScene& sc, const DevPool&
 }
 
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_lambert(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_BEGIN(Q_LAMBERT)
-      alive = shade_diffuse<false>(sc, pool, prm, slot);
-  RTB_SHADE_LOOP_END
+  shade_loop<Q_LAMBERT>(pool, prm, cam, [&](uint32_t slot) { return shade_diffuse<false>(sc, pool, prm, slot); });
 }
 
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_isotropic(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_BEGIN(Q_ISOTROPIC)
-      alive = shade_diffuse<true>(sc, pool, prm, slot);
-  RTB_SHADE_LOOP_END
+  shade_loop<Q_ISOTROPIC>(pool, prm, cam, [&](uint32_t slot) { return shade_diffuse<true>(sc, pool, prm, slot); });
 }
 
 // Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_metal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_BEGIN(Q_METAL)
+  shade_loop<Q_METAL>(pool, prm, cam, [&](uint32_t slot) {
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
       const float4 m = __ldg(&sc.materials[2 * s.mat]);
@@ -704,13 +702,13 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
         dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
       }
       io.beta = io.beta * tex_value(sc, m, s.mat, s);
-      alive = finish_bounce(pool, prm, io, true, s.p, dir, 0.0f, ua.x);
-  RTB_SHADE_LOOP_END
+      return finish_bounce(pool, prm, io, true, s.p, dir, 0.0f, ua.x);
+  });
 }
 
 // Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
 __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  RTB_SHADE_LOOP_BEGIN(Q_DIELECTRIC)
+  shade_loop<Q_DIELECTRIC>(pool, prm, cam, [&](uint32_t slot) {
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
       const float ir = __ldg(&sc.materials[2 * s.mat]).z;
@@ -732,63 +730,50 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
         const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
         dir = fma3(par, s.n, perp);
       }
-      alive = finish_bounce(pool, prm, io, true, s.p, dir, io.time, ua.x);
-  RTB_SHADE_LOOP_END
+      return finish_bounce(pool, prm, io, true, s.p, dir, io.time, ua.x);
+  });
 }
 
-// ---- generate (initial fill of the pool; afterwards terminated slots are restarted inside the shade kernels) ----
+// ---- generate: initial fill — every chunk starts its first paths (afterwards slots are restarted inside shade_loop) ----
 __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, DevParams prm, DevCamera cam) {
-  __shared__ unsigned long long s_first;
-  DevCounters* c = pool.c;
-  const uint32_t n = c->n_dead;
-  if (n == 0) return;
-  const unsigned long long total = c->total_paths;
-  if (c->next_path >= total) return;  // nothing left to start: terminated slots stay dead
-  const uint32_t nxt = c->cur ^ 1u;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
-    const uint32_t cnt = min(blockDim.x, n - base);
-    __syncthreads();
-    if (threadIdx.x == 0) s_first = atomicAdd(&c->next_path, (unsigned long long)cnt);
-    __syncthreads();
-    const unsigned long long path = s_first + threadIdx.x;
-    const bool alive = threadIdx.x < cnt && path < total;
-    uint32_t slot = 0;
-    if (alive) {
-      slot = pool.q_dead[base + threadIdx.x];
-      start_path(pool, prm, cam, slot, path);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned long long total = pool.c->total_paths;
+  const uint32_t n_warps = gridDim.x * RTB_SHADE_WARPS;
+  for (uint32_t chunk = blockIdx.x * RTB_SHADE_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
+    const uint32_t base = chunk * RTB_CHUNK;
+    const uint32_t cnt = min(RTB_CHUNK, pool.n - base);
+    for (uint32_t m = lane; m < cnt; m += 32) {
+      const unsigned long long path = chunk_path(m, chunk, pool.n_chunks);
+      if (path < total) {
+        start_path(pool, prm, cam, base + m, path);
+        pool.cls[base + m] = (uint8_t)CLS_NEW;
+      }
     }
-    warp_enqueue(pool.q_ext[nxt], &c->n_ext[nxt], alive, slot);
+    if (lane == 0) pool.cursor[chunk] = cnt;
   }
 }
 
 __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < pool.n) pool.q_dead[i] = i;
+  if (i < pool.n_chunks * RTB_CHUNK) pool.cls[i] = (uint8_t)CLS_DEAD;
+  if (i < pool.n_chunks) pool.cursor[i] = 0ull;
   if (i == 0) {
     DevCounters* c = pool.c;
-    c->n_ext[0] = c->n_ext[1] = 0;
-    for (int k = 0; k < (int)Q_COUNT; ++k) c->n_mat[k] = 0;
-    c->n_dead = pool.n;
-    c->cur = 0;
+    c->iter_rays = c->last_rays = 0;
     c->iter = 0;
-    c->next_path = 0;
     c->ext_cursor = 0;
     c->total_paths = total_paths;
-    c->segments = c->rejected = c->paths_started = 0;
+    c->segments = c->rejected = 0;
     c->nodes_visited = c->prims_tested = 0;
   }
 }
 
 __global__ void k_advance(DevPool pool) {
   DevCounters* c = pool.c;
-  const uint32_t cur = c->cur;
-  c->segments += c->n_ext[cur];
-  c->n_ext[cur] = 0;
-  for (int k = 0; k < (int)Q_COUNT; ++k) c->n_mat[k] = 0;
-  c->n_dead = 0;
+  c->segments += c->iter_rays;
+  c->last_rays = c->iter_rays;
+  c->iter_rays = 0;
   c->ext_cursor = 0;
-  c->cur = cur ^ 1u;
   c->iter += 1;
 }
 
@@ -848,7 +833,7 @@ __global__ void k_primary_rays(DevCameraF64 cam, uint32_t W, uint32_t H, float* 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st) {
-  k_init_pool<<<cdiv(pool.n, 256), 256, 0, st>>>(pool, total_paths);
+  k_init_pool<<<cdiv(pool.n_chunks * RTB_CHUNK, 256), 256, 0, st>>>(pool, total_paths);
 }
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st) {
   k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
@@ -868,39 +853,15 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
   if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
   else k_extend<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
 }
-// The per-material kernels of one iteration are independent (they only append to the next extend queue), so they are
-// forked onto side streams after `extend` and joined before `advance`: the small queues (terminal, metal, dielectric)
-// overlap the large one instead of each paying its own ramp-up and tail.
+// The per-material kernels of one iteration run back to back on the lane's stream; they touch disjoint slots (each
+// slot has exactly one class per iteration) and each chunk's path cursor is updated by one warp per kernel.
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
-                  const DevCamera& cam, uint32_t present, cudaStream_t st, const ShadeStreams* ss) {
-  const bool fork = ss != nullptr;
-  int k = 0;
-  if (fork) cudaEventRecord(ss->fork, st);
-  auto side = [&](void (*kern)(DevScene, DevPool, DevParams, DevCamera)) {
-    if (!fork) {
-      kern<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-      return;
-    }
-    cudaStream_t s2 = ss->side[k];
-    cudaStreamWaitEvent(s2, ss->fork, 0);
-    kern<<<lc.shade_grid, RTB_SHADE_THREADS, 0, s2>>>(sc, pool, prm, cam);
-    cudaEventRecord(ss->join[k], s2);
-    ++k;
-  };
-  // the (usually) largest queue stays on the main stream
-  if (present & (1u << RTB_MAT_LAMBERTIAN)) {
-    side(k_shade_terminal);
-    if (present & (1u << RTB_MAT_METAL)) side(k_shade_metal);
-    if (present & (1u << RTB_MAT_DIELECTRIC)) side(k_shade_dielectric);
-    if (present & (1u << RTB_MAT_ISOTROPIC)) side(k_shade_isotropic);
-    k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  } else {
-    if (present & (1u << RTB_MAT_METAL)) side(k_shade_metal);
-    if (present & (1u << RTB_MAT_DIELECTRIC)) side(k_shade_dielectric);
-    if (present & (1u << RTB_MAT_ISOTROPIC)) side(k_shade_isotropic);
-    k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  }
-  for (int j = 0; j < k; ++j) cudaStreamWaitEvent(st, ss->join[j], 0);
+                  const DevCamera& cam, uint32_t present, cudaStream_t st) {
+  k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
 }
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
   k_finalize<<<cdiv(npix, 256), 256, 0, st>>>(accum, rgb, npix, inv_spp);
@@ -947,6 +908,12 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (occ2 < 1) occ2 = 1;
   if (getenv("RTB_SHADE_OCC")) occ2 = std::max(1, std::min(occ2, atoi(getenv("RTB_SHADE_OCC"))));
   lc.shade_grid = (uint32_t)(sm_count * occ2);
+  {  // smallest pool that gives every resident extend warp AND every resident shade warp a whole number of chunks
+    uint32_t a = lc.extend_grid * RTB_EXTEND_WARPS, b = lc.shade_grid * RTB_SHADE_WARPS, x = a, y = b;
+    while (y) { const uint32_t t = x % y; x = y; y = t; }
+    const uint64_t lcm = (uint64_t)a / x * b;
+    lc.pool_unit = lcm * RTB_CHUNK <= (1ull << 23) ? (uint32_t)(lcm * RTB_CHUNK) : b * RTB_CHUNK;
+  }
   return 0;
 }
 

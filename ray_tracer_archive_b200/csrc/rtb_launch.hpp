@@ -25,11 +25,8 @@ struct DevCameraF64 {  // camera.rs:6-17 in f64, for the parity probe's primary 
 struct LaunchCfg {
   uint32_t extend_grid = 0, shade_grid = 0, extend_smem = 0, n_snodes = 0;
   bool dynamic_fetch = false;
-};
-
-struct ShadeStreams {  // fork/join of the per-material kernels
-  cudaStream_t side[4];
-  cudaEvent_t fork, join[4];
+  // slots that give every resident shade warp exactly one chunk: pools are sized in multiples of this
+  uint32_t pool_unit = 0;
 };
 
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
@@ -39,7 +36,7 @@ void launch_advance(const DevPool& pool, cudaStream_t st);
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st);
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
-                  const DevCamera& cam, uint32_t present, cudaStream_t st, const ShadeStreams* ss);
+                  const DevCamera& cam, uint32_t present, cudaStream_t st);
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st);
 void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
                   uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st);
