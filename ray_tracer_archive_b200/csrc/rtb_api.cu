@@ -685,7 +685,8 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     launches += 3;
   }
   const uint32_t present = s->present_materials;
-  const uint32_t n_shade = 1 + __builtin_popcount(present & ~(1u << RTB_MAT_DIFFUSE_LIGHT));
+  const uint32_t n_shade = 1 + ((present >> RTB_MAT_LAMBERTIAN) & 1u) + ((present >> RTB_MAT_ISOTROPIC) & 1u) +
+                           ((present & ((1u << RTB_MAT_METAL) | (1u << RTB_MAT_DIELECTRIC))) ? 1u : 0u);
   const uint32_t check_every = 8;
   size_t ev_used = 0;
   int n_active = n_lanes;

@@ -187,13 +187,22 @@ __device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint
 struct Closest {
   float t;        // current t_max (closest_so_far, hittable_list.rs:42)
   uint32_t ref;   // type << 29 | leaf index
-  uint32_t gid;   // primitive id, for the "later primitive wins equal t" rule (hittable_list.rs:44-47)
 };
 
-__device__ __forceinline__ void consider(Closest& best, float t, uint32_t ref, uint32_t gid) {
+// primitive id of a hit reference (list order of the reference's scene graph).  Needed only for the "later primitive
+// wins equal t" rule (hittable_list.rs:44-47) and by the parity probe, so it is fetched lazily: an accepted hit does
+// not pay the dependent info load (1-5 % of extend's stall samples, profiles/r2e_ncu_summary.md).
+__device__ __forceinline__ uint32_t ref_gid(const DevScene& sc, uint32_t ref) {
+  const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+  return type == PT_MEDIUM ? sc.media[idx].prim_id : __ldg(&sc.info[type][idx].x);
+}
+
+__device__ __forceinline__ void consider(const DevScene& sc, Closest& best, float t, uint32_t ref) {
   if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
-  if (t < best.t || (t == best.t && (best.ref == REF_MISS || gid > best.gid))) {
-    best.t = t; best.ref = ref; best.gid = gid;
+  if (t < best.t) {
+    best.t = t; best.ref = ref;
+  } else if (t == best.t && (best.ref == REF_MISS || ref_gid(sc, ref) > ref_gid(sc, best.ref))) {
+    best.ref = ref;
   }
 }
 
@@ -327,8 +336,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     float3 c = fma3(time, xyz(b), xyz(a));
     if (!sphere_roots(o, d, c, a.w, tmin, best.t, t)) return;
   }
-  uint32_t gid = __ldg(&sc.info[type][idx].x);
-  consider(best, t, (type << REF_TYPE_SHIFT) | idx, gid);
+  consider(sc, best, t, (type << REF_TYPE_SHIFT) | idx);
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
@@ -363,7 +371,7 @@ __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float ti
   tv.octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
   tv.sp = 0;
-  tv.best = Closest{INFINITY, REF_MISS, 0u};
+  tv.best = Closest{INFINITY, REF_MISS};
 }
 
 // returns false when the traversal is complete
@@ -529,7 +537,7 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
     float hd = md.neg_inv_density * log_fast(xi);
     if (hd > inside) continue;
     float t = t1 + hd * rcp_fast(len);
-    consider(best, t, ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m, md.prim_id);
+    consider(sc, best, t, ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m);
   }
 }
 

@@ -117,8 +117,8 @@ __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint3
 // 256-thread shade CTA of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476, 80: 4497, 88: 4326,
 // 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
-struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, gid, group word) after the global primitives
-struct ExtOut { float t; uint32_t ref, gid, slot; };
+struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, -) after the global primitives
+struct ExtOut { float t; uint32_t ref, slot, _pad; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
 template <bool COUNT>
@@ -154,7 +154,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         o = xyz(pool.ray[2 * h.slot]);
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
-      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.ref, h.gid});
+      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.ref});
     }
     out_count = 0;
     __syncwarp();
@@ -195,8 +195,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           e.o_time = ro;
           e.d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
           e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
-          e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.best.gid),
-                               __uint_as_float(t0.grp.y));
+          e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.grp.y), 0.f);
         }
         __syncwarp();
       }
@@ -209,9 +208,9 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
           tv.idx = r.idir_oct.x; tv.idy = r.idir_oct.y; tv.idz = r.idir_oct.z;
           tv.octinv = __float_as_uint(r.idir_oct.w);
-          tv.grp = make_uint2(0u, __float_as_uint(r.best.w));
+          tv.grp = make_uint2(0u, __float_as_uint(r.best.z));
           tv.sp = 0;
-          tv.best = Closest{r.best.x, __float_as_uint(r.best.y), __float_as_uint(r.best.z)};
+          tv.best = Closest{r.best.x, __float_as_uint(r.best.y)};
           state = RUNNING;
         }
         in_head += min((uint32_t)__popc(empty), avail);
@@ -231,7 +230,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
       if (state == DONE) {
-        out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, tv.best.gid, slot};
+        out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, 0u};
         state = EMPTY;
       }
       out_count += __popc(done);
@@ -273,7 +272,7 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const uint32_t slot = base + list[r + lane];
         const float4 ro = pool.ray[2 * slot];
         const float4 rd = pool.ray[2 * slot + 1];
-        Closest best{INFINITY, REF_MISS, 0u};
+        Closest best{INFINITY, REF_MISS};
         traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
         finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
       }
@@ -579,7 +578,7 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
 // request-bound kernel, profiles/r2_ab.md §2.)
 #define RTB_SHADE_WARPS (RTB_SHADE_THREADS / 32)
 
-template <uint32_t QID, class Body>
+template <uint32_t QID, uint32_t QID2 = QID, class Body>
 __device__ __forceinline__ void shade_loop(const DevPool& pool, const DevParams& prm, const DevCamera& cam, Body&& body) {
   __shared__ uint8_t s_list[RTB_SHADE_WARPS][RTB_CHUNK];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -590,7 +589,8 @@ __device__ __forceinline__ void shade_loop(const DevPool& pool, const DevParams&
   for (uint32_t chunk = blockIdx.x * RTB_SHADE_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
     const uint32_t base = chunk * RTB_CHUNK;
     const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + base + 8u * lane);
-    const uint32_t total = append_class(cw, QID, list, 0u, lane);
+    uint32_t total = append_class(cw, QID, list, 0u, lane);
+    if (QID2 != QID) total = append_class(cw, QID2, list, total, lane);  // a second (small) class shares the kernel
     if (total == 0) continue;
     __syncwarp();
     unsigned long long m_cur = pool.cursor[chunk];
@@ -684,53 +684,51 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
   shade_loop<Q_ISOTROPIC>(pool, prm, cam, [&](uint32_t slot) { return shade_diffuse<true>(sc, pool, prm, slot); });
 }
 
-// Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_metal(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  shade_loop<Q_METAL>(pool, prm, cam, [&](uint32_t slot) {
+// The two specular materials share one kernel (their classes are small: 10 % and 7 % of C1's hits; as separate kernels
+// each paid a launch, a scan of the class bytes and a tail, profiles/r2e_ncu_summary.md).  A chunk's metal slots come
+// first in the warp's list, then its glass slots, so only one round per chunk mixes the two branches.
+//   Metal::scatter, material.rs:95-107: reflect(unit(d), n) + fuzz * (uniform ball); specular; ray time reset to 0
+//   Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
+__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_specular(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
+  shade_loop<Q_METAL, Q_DIELECTRIC>(pool, prm, cam, [&](uint32_t slot) {
       PathIO io = load_path(pool, slot);
       const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
       const float4 m = __ldg(&sc.materials[2 * s.mat]);
-      const float fuzz = fminf(m.z, 1.0f);
       const float3 ud = unit(io.d);
-      float3 dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);  // reflect, vec3.rs:115-117
-      const float4 ua = philox_u(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed);
-      if (fuzz > 0.f) {  // random_in_unit_sphere (vec3.rs:78-86) in closed form: uniform direction * cbrt(xi)
-        const float z = 1.0f - 2.0f * ua.y, phi = 2.0f * RTB_PI * ua.z, rad = cbrtf(ua.w);
-        const float r = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
-        float sn, cs;
-        __sincosf(phi, &sn, &cs);
-        dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
-      }
-      io.beta = io.beta * tex_value(sc, m, s.mat, s);
-      return finish_bounce(pool, prm, io, true, s.p, dir, 0.0f, ua.x);
-  });
-}
-
-// Dielectric::scatter, material.rs:123-155 (+ reflectance :118-122, refract vec3.rs:246-251)
-__global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_shade_dielectric(DevScene sc, DevPool pool, DevParams prm, DevCamera cam) {
-  shade_loop<Q_DIELECTRIC>(pool, prm, cam, [&](uint32_t slot) {
-      PathIO io = load_path(pool, slot);
-      const Surf s = surface_at(sc, io.ref, io.minfo, io.o, io.d, io.time, io.t);
-      const float ir = __ldg(&sc.materials[2 * s.mat]).z;
-      const float ratio = s.front ? rcp_fast(ir) : ir;
-      const float3 ud = unit(io.d);
-      const float cos_theta = fminf(-dot(ud, s.n), 1.0f);
-      const float sin_theta = sqrt_fast(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
-      const bool cannot_refract = ratio * sin_theta > 1.0f;
-      float r0 = (1.0f - ratio) * rcp_fast(1.0f + ratio);
-      r0 *= r0;
-      const float om = 1.0f - cos_theta;
-      const float reflectance = r0 + (1.0f - r0) * (om * om) * (om * om) * om;
       const float4 ua = philox_u(io.pixel, io.sample, BLK_AUX, io.segs, prm.seed);
       float3 dir;
-      if (cannot_refract || reflectance > ua.y) {
-        dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);
+      float ntime = io.time;
+      if (__float_as_uint(m.x) == RTB_MAT_METAL) {
+        const float fuzz = fminf(m.z, 1.0f);
+        dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);  // reflect, vec3.rs:115-117
+        if (fuzz > 0.f) {  // random_in_unit_sphere (vec3.rs:78-86) in closed form: uniform direction * cbrt(xi)
+          const float z = 1.0f - 2.0f * ua.y, phi = 2.0f * RTB_PI * ua.z, rad = cbrtf(ua.w);
+          const float r = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
+          float sn, cs;
+          __sincosf(phi, &sn, &cs);
+          dir = fma3(fuzz * rad, f3(r * cs, r * sn, z), dir);
+        }
+        io.beta = io.beta * tex_value(sc, m, s.mat, s);
+        ntime = 0.0f;  // material.rs:101
       } else {
-        const float3 perp = ratio * fma3(cos_theta, s.n, ud);
-        const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
-        dir = fma3(par, s.n, perp);
+        const float ir = m.z;
+        const float ratio = s.front ? rcp_fast(ir) : ir;
+        const float cos_theta = fminf(-dot(ud, s.n), 1.0f);
+        const float sin_theta = sqrt_fast(fmaxf(0.f, 1.0f - cos_theta * cos_theta));
+        const bool cannot_refract = ratio * sin_theta > 1.0f;
+        float r0 = (1.0f - ratio) * rcp_fast(1.0f + ratio);
+        r0 *= r0;
+        const float om = 1.0f - cos_theta;
+        const float reflectance = r0 + (1.0f - r0) * (om * om) * (om * om) * om;
+        if (cannot_refract || reflectance > ua.y) {
+          dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);
+        } else {
+          const float3 perp = ratio * fma3(cos_theta, s.n, ud);
+          const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
+          dir = fma3(par, s.n, perp);
+        }
       }
-      return finish_bounce(pool, prm, io, true, s.p, dir, io.time, ua.x);
+      return finish_bounce(pool, prm, io, true, s.p, dir, ntime, ua.x);
   });
 }
 
@@ -803,11 +801,11 @@ k_probe(DevScene sc, const float* __restrict__ org, const float* __restrict__ di
   if (i >= n) return;
   const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
   const float tm = time ? time[i] : 0.f;
-  Closest best{INFINITY, REF_MISS, 0u};
+  Closest best{INFINITY, REF_MISS};
   uint32_t nv = 0, nt = 0;
   traverse<true>(sc, snodes, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
   if (sc.n_media) intersect_media(sc, o, d, RTB_TMIN, best, 0, 0, 0, 0, false);
-  id_out[i] = best.ref == REF_MISS ? RTB_NONE : best.gid;
+  id_out[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
   t_out[i] = best.t;
   if (c) {
     atomicAdd(&c->nodes_visited, (unsigned long long)nv);
@@ -859,8 +857,8 @@ void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, 
                   const DevCamera& cam, uint32_t present, cudaStream_t st) {
   k_shade_terminal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
   if (present & (1u << RTB_MAT_LAMBERTIAN)) k_shade_lambert<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_METAL)) k_shade_metal<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
-  if (present & (1u << RTB_MAT_DIELECTRIC)) k_shade_dielectric<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
+  if (present & ((1u << RTB_MAT_METAL) | (1u << RTB_MAT_DIELECTRIC)))
+    k_shade_specular<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
   if (present & (1u << RTB_MAT_ISOTROPIC)) k_shade_isotropic<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(sc, pool, prm, cam);
 }
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
