@@ -106,7 +106,7 @@ struct DevParams {
   const uint32_t* pix_order;  // tile-ordered pixel indices
   double inv_npix;
   float inv_wm1, inv_hm1;     // 1/(W-1), 1/(H-1)
-  uint32_t opt;               // A/B switches (env RTB_OPT; 0 in production): 1 no shade prefetch, 2 no ray prefetch, 4 late claim
+  uint32_t opt;               // A/B switch bits for experiments (env RTB_OPT; 0 in production, currently unused)
   float4* accum;
 };
 
