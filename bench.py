@@ -367,6 +367,10 @@ def main():
             "algorithmic": {"nodes_per_segment": nodes_per_seg, "prims_per_segment": prims_per_seg,
                             "flops_per_segment": flops_seg, "bytes_per_segment": bytes_seg,
                             "segments_per_launch": seg_per_launch},
+            # scenes whose nodes + primitives fit the kernel's shared-memory stage / L1 never send these bytes to L2: the
+            # BASELINE.json roofline (bytes at L2 bandwidth) is then a definition, not a physical bound, and `frac` can
+            # exceed 1 (C2: 13 primitives in the constant bank); the FP32 figure is the one that binds there
+            "on_chip_scene": bool(scene_bytes <= 56 * 1024),
             "extend_ms_per_launch": avg_launch_ms, "extend_launches_per_step": n_ext,
             "extend_share_of_step": ext_ms / stt["ms_total"],
             "roofline_mrays_s": 1.0 / max(t_flops, t_bytes) / 1e6,
