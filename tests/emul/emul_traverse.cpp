@@ -65,3 +65,8 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   if (prims_tested) *prims_tested = nt_total;
   return 0;
 }
+
+// path numbering of the slot-stable pool (rtb_device.cuh: chunk_path), exposed for tests/test_pool_numbering.py
+extern "C" unsigned long long emul_chunk_path(unsigned long long m, uint32_t chunk, uint32_t n_chunks) {
+  return chunk_path(m, chunk, n_chunks);
+}

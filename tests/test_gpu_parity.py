@@ -366,6 +366,25 @@ def test_d1_sample_split_matches_single_call(rtb, ctx):
     assert st1["segments"] > 0
 
 
+@pytest.mark.parametrize("pool", [1024, 1025, 1279, 4097, 60000, 1 << 20])
+def test_slot_stable_pool_any_size_renders_every_path_once(rtb, ctx, pool):
+    """The pool is walked in 256-slot chunks and path numbers come from per-chunk cursors: ragged last chunks, pools
+    smaller / larger than the path count and pools that are not a multiple of anything must all start every (pixel,
+    sample) exactly once — the image equals the default-pool image up to f32 summation order and the segment count is
+    identical (paths are deterministic functions of (pixel, sample, seed))."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_random_spheres()
+    dev = rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights))
+    W, Hh, spp = 96, 54, 24  # 124 416 paths
+    ref, st0 = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=4))
+    acc, st = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=4, pool_paths=pool))
+    assert st["paths"] == W * Hh * spp and st["segments"] == st0["segments"] and st["rejected"] == 0
+    np.testing.assert_allclose(acc, ref, rtol=3e-4, atol=1e-4)
+    # the sum of the weights deposited per pixel is the sample count: with a constant background and a white
+    # furnace-like check we cannot count deposits directly, so check the luminance moments instead
+    assert abs(acc[..., :3].sum() / ref[..., :3].sum() - 1.0) < 1e-5
+
+
 def test_finalize_rgb8_matches_write_color(rtb, orc, ctx):
     from ray_tracer_archive_b200 import scenes
     cfg = scenes.config_cornell()
