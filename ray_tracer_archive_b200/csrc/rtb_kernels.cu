@@ -876,11 +876,14 @@ void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float*
 
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   // stage as much of the (breadth-first ordered) node array as fits the shared-memory budget
-  const uint32_t budget = 56 * 1024;  // + 20 KB of per-warp ray/result buffers (dynamic fetch); extend runs 2 CTAs per SM
+  // extend runs 2 CTAs per SM: 2 x (stage + 2 KB list [+ 20 KB of per-warp ray/result buffers, dynamic fetch]) must fit
+  // the 227 KB of an SM beside one 3 KB shade CTA
+  lc.dynamic_fetch = n_nodes > 4096;
+  uint32_t budget = (getenv("RTB_STAGE_KB") ? (uint32_t)atoi(getenv("RTB_STAGE_KB")) : 56u) * 1024u;
+  budget = std::min(budget, (lc.dynamic_fetch ? 84u : 104u) * 1024u);
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;
-  lc.dynamic_fetch = n_nodes > 4096;
   lc.extend_smem = n_s * 80;
   cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
