@@ -149,7 +149,7 @@ typedef struct rtb_params {
   uint32_t rr_start_depth; /* Russian roulette after this many segments; 0 = off (reference behaviour) */
   uint32_t seed;
   float background[3];     /* main.rs:692 */
-  uint32_t pool_paths;     /* wavefront pool size; 0 = default */
+  uint32_t pool_paths;     /* path-pool slots, all wavefront lanes together; 0 = default (sized to the device) */
   uint32_t flags;          /* RTB_RENDER_* */
 } rtb_params;
 #define RTB_RENDER_ACCUMULATE 1u  /* add into the accumulation buffer instead of clearing it first */

@@ -1,10 +1,11 @@
-// rtb_kernels.cu — the wavefront path-tracing pipeline (sm_100a).  One iteration =
-//   extend (wide-BVH closest hit + media, classify into per-material queues)
-//   shade_terminal / shade_lambert / shade_metal / shade_dielectric / shade_isotropic (one kernel per material)
-//   generate (refill terminated slots with new camera paths)  ->  advance (swap queues)
+// rtb_kernels.cu — the wavefront path-tracing pipeline (sm_100a) over a SLOT-STABLE path pool.  One iteration =
+//   extend (wide-BVH closest hit + media; writes the hit record and the slot's shade class)
+//   shade_terminal / shade_lambert / shade_specular / shade_isotropic (one kernel per material family; a finished
+//   path's slot is restarted in place with the next camera path)  ->  advance (rotates the iteration counters)
 // replacing the reference's recursive ray_color (main.rs:63-139) and its per-pixel sample loop (main.rs:731-784).
-// Queues are compacted with warp ballots + one atomic per warp.  Tensor cores are not used: nothing here is a
-// dense contraction.
+// There are no global work queues: every kernel walks the pool in 256-slot chunks, one warp per chunk, and compacts the
+// slots it wants warp-locally (byte compares + warp scan into a shared-memory list).  No kernel issues a contended
+// atomic.  Tensor cores are not used: nothing here is a dense contraction.
 #include <cuda_runtime.h>
 
 #include <algorithm>
