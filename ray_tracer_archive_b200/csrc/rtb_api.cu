@@ -430,6 +430,31 @@ int rtb_scene_commit(rtb_scene* s) {
   d.n_global = (uint32_t)s->bvh.global_refs.size();
   d.tree_empty = (d.n_global == (uint32_t)s->hs.prims.size()) ? 1u : 0u;
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
+  {
+    // a global sphere whose radius is >= 16 extents of everything else can only be hit at distances < r/16 from
+    // points ~r away from its centre — exactly where sphere_roots() rejects its f32 result — so it is tested in f64
+    // directly.  Extent = diagonal of the union box of the primitives that are in the tree.
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // global refs point at the END of their type's leaf-ordered arrays; recover radius / centre from the geometry words
+    for (const HostPrim& p : hs.prims) {
+      bool glob = false;
+      for (uint32_t k = 0; k < d.n_global && !glob; ++k) {
+        const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+        glob = type == p.type && s->bvh.info[type][2 * idx] == p.prim_id;
+      }
+      if (glob) continue;
+      for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.lo[a]); hi[a] = std::max(hi[a], p.hi[a]); }
+    }
+    double diag2 = 0;
+    for (int a = 0; a < 3; ++a) if (hi[a] > lo[a]) diag2 += (double)(hi[a] - lo[a]) * (hi[a] - lo[a]);
+    const double extent = std::sqrt(diag2);
+    for (uint32_t k = 0; k < d.n_global && !d.tree_empty; ++k) {
+      const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+      if (type != PT_SPHERE || extent <= 0) continue;
+      const float r = s->bvh.geom[PT_SPHERE][4 * idx + 3];
+      if ((double)r >= 16.0 * extent) d.global_f64 |= 1u << k;
+    }
+  }
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)

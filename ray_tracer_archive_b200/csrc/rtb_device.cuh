@@ -46,6 +46,8 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t n_global;    // primitives tested for every ray before the traversal (kept out of the tree)
   uint32_t tree_empty;  // all primitives are global (tiny scene): skip the traversal
   uint32_t global_ref[RTB_MAX_GLOBALS];
+  uint32_t global_f64;  // bit k: global k is a sphere so large next to the rest of the scene (radius >= 16 scene
+                        // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
@@ -468,7 +470,14 @@ template <bool COUNT>
 __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float tmin, uint32_t& n_tests) {
   for (uint32_t k = 0; k < sc.n_global; ++k) {
     const uint32_t ref = sc.global_ref[k];
-    intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+    if ((sc.global_f64 >> k) & 1u) {  // the r = 1000 ground sphere of book 1: skip the f32 attempt (~100 instructions per ray)
+      if (COUNT) ++n_tests;
+      const float4 s = __ldg(sc.geom[PT_SPHERE] + (ref & REF_INDEX_MASK));
+      float t;
+      if (sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, tv.best.t, t)) consider(sc, tv.best, t, ref);
+    } else {
+      intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+    }
   }
   if (sc.tree_empty) tv.grp.y = 0u;  // nothing left to traverse: the first trav_step returns false
 }
