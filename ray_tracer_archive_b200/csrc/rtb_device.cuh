@@ -376,9 +376,23 @@ __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float ti
   tv.best = Closest{INFINITY, REF_MISS};
 }
 
-// returns false when the traversal is complete
-template <bool COUNT>
-__device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
+// 128-bit load from the shared-memory node stage.  On the device the stage is addressed through a 32-bit shared-space
+// address computed ONCE per kernel (`sbase`): through the generic pointer ptxas re-derives the shared window base
+// (S2R CgaCtaId, MOV, LEA) at every node visit.
+__device__ __forceinline__ uint4 lds_node_word(const uint4* __restrict__ snodes, uint32_t sbase, uint32_t node, uint32_t w) {
+#ifdef __CUDA_ARCH__
+  uint4 r;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(sbase + node * 80u + w * 16u));
+  return r;
+#else
+  return snodes[5 * node + w];
+#endif
+}
+
+// returns false when the traversal is complete.  ALL_STAGED: every node of the tree is in the shared-memory stage (small
+// scenes), so the global-memory fetch path and its five predicated loads + register moves are compiled out.
+template <bool COUNT, bool ALL_STAGED = false>
+__device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                           Trav& tv, uint2* __restrict__ stack, float tmin,
                                           uint32_t& n_nodes_visited, uint32_t& n_tests) {
   if (!(tv.grp.y & 0xFF00u)) {  // group exhausted: pop (stack entries always have hits left) and visit in the same step
@@ -395,9 +409,10 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   if (hits) stack[tv.sp++] = make_uint2(tv.grp.x, (hits << 8) | gmask);
   if (COUNT) ++n_nodes_visited;
   uint4 w0, w1, w2, w3, w4;
-  if (node < n_snodes) {
-    const uint4* p = snodes + 5 * node;
-    w0 = p[0]; w1 = p[1]; w2 = p[2]; w3 = p[3]; w4 = p[4];
+  if (ALL_STAGED || node < n_snodes) {
+    w0 = lds_node_word(snodes, sbase, node, 0); w1 = lds_node_word(snodes, sbase, node, 1);
+    w2 = lds_node_word(snodes, sbase, node, 2); w3 = lds_node_word(snodes, sbase, node, 3);
+    w4 = lds_node_word(snodes, sbase, node, 4);
   } else {
     const uint4* p = sc.nodes + 5 * (size_t)node;
     w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2); w3 = __ldg(p + 3); w4 = __ldg(p + 4);
@@ -482,8 +497,8 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
   if (sc.tree_empty) tv.grp.y = 0u;  // nothing left to traverse: the first trav_step returns false
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t n_snodes,
+template <bool COUNT, bool ALL_STAGED = false>
+__device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
   Trav tv;
@@ -491,7 +506,7 @@ __device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __rest
   trav_init(tv, o, d, time);
   tv.best = best;
   trav_globals<COUNT>(sc, tv, tmin, n_tests);
-  while (trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
+  while (trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
 }
 

@@ -131,6 +131,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   ExtIn* in = s_in[warp];
@@ -224,7 +226,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
     // ---- one node visit (or pop) per lane ---------------------------------------------------------------------------
     if (state == RUNNING) {
-      if (!trav_step<COUNT>(sc, snodes, n_snodes, tv, stack, RTB_TMIN, nv, nt)) state = DONE;
+      if (!trav_step<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt)) state = DONE;
     }
     // ---- finished lanes push their result -------------------------------------------------------------------------
     const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
@@ -252,13 +254,15 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
 // converged).  Slot-stable pool: a warp takes one chunk of RTB_CHUNK slots at a time, orders its live slots by ray kind
 // (build_extend_list) and traces them 32 at a time; the next round's ray sectors are prefetched into L1 during the
 // current traversal.  No queue, no atomics apart from one ray-count add per warp at the end.
-template <bool COUNT>
+template <bool COUNT, bool ALL_STAGED>
 __global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* list = s_list[warp];
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
@@ -274,7 +278,7 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const float4 ro = pool.ray[2 * slot];
         const float4 rd = pool.ray[2 * slot + 1];
         Closest best{INFINITY, REF_MISS};
-        traverse<COUNT>(sc, snodes, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+        traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
         finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
       }
     }
@@ -798,13 +802,15 @@ k_probe(DevScene sc, const float* __restrict__ org, const float* __restrict__ di
         uint32_t n, uint32_t n_snodes, uint32_t* __restrict__ id_out, float* __restrict__ t_out, DevCounters* c) {
   extern __shared__ uint4 snodes[];
   stage_nodes(sc, snodes, n_snodes);
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
   const float tm = time ? time[i] : 0.f;
   Closest best{INFINITY, REF_MISS};
   uint32_t nv = 0, nt = 0;
-  traverse<true>(sc, snodes, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
+  traverse<true>(sc, snodes, sbase, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
   if (sc.n_media) intersect_media(sc, o, d, RTB_TMIN, best, 0, 0, 0, 0, false);
   id_out[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
   t_out[i] = best.t;
@@ -845,8 +851,9 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
   static const char* mode = getenv("RTB_EXTEND_MODE");
   const bool use_static = mode ? !strcmp(mode, "static") : !lc.dynamic_fetch;
   if (use_static) {
-    if (count) k_extend_static<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
-    else k_extend_static<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    if (count) k_extend_static<true, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    else if (lc.all_staged) k_extend_static<false, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    else k_extend_static<false, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
     return;
   }
   if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
@@ -885,14 +892,17 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
   lc.n_snodes = n_s;
+  lc.all_staged = n_s == n_nodes && !(getenv("RTB_ALL_STAGED") && atoi(getenv("RTB_ALL_STAGED")) == 0);
   lc.extend_smem = n_s * 80;
   cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_extend_static<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  e = cudaFuncSetAttribute(k_extend_static<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_extend_static<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  e = cudaFuncSetAttribute(k_extend_static<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_extend_static<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;

@@ -25,6 +25,7 @@ struct DevCameraF64 {  // camera.rs:6-17 in f64, for the parity probe's primary 
 struct LaunchCfg {
   uint32_t extend_grid = 0, shade_grid = 0, extend_smem = 0, n_snodes = 0;
   bool dynamic_fetch = false;
+  bool all_staged = false;  // every BVH node fits the shared-memory stage: the kernel without a global node path is used
   // slots that give every resident shade warp exactly one chunk: pools are sized in multiples of this
   uint32_t pool_unit = 0;
 };

@@ -55,7 +55,7 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   for (uint32_t i = 0; i < n; ++i) {
     Closest best{INFINITY, REF_MISS};
     uint32_t nv = 0, nt = 0;
-    traverse<true>(sc, (const uint4*)nodes, n_snodes < n_nodes ? n_snodes : n_nodes, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
+    traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
                    f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
     ids[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
     ts[i] = best.t;
