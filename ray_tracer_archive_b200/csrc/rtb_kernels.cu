@@ -138,8 +138,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   ExtIn* in = s_in[warp];
   ExtOut* out = s_out[warp];
   uint8_t* list = s_list[warp];
-  enum { EMPTY = 0, RUNNING = 1, DONE = 2 };
-  uint32_t state = EMPTY, slot = 0;
+  uint32_t idle = 0xffffffffu;  // warp-uniform: lanes without a ray in flight
+  uint32_t slot = 0;
   uint32_t in_head = 0, in_count = 0, out_count = 0;  // warp-uniform
   uint32_t chunk_base = 0, list_pos = 0, list_len = 0;  // warp-uniform: the claimed chunk's ordered slot list
   bool exhausted = false;                              // warp-uniform: no more chunks to claim
@@ -147,6 +147,9 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   Trav tv;
   uint2 stack[RTB_STACK];
   uint32_t nv = 0, nt = 0;
+  // idle lanes are refilled when at least this many wait (or nobody runs): a swap costs the whole warp ~40 issue slots
+  // however few lanes take part (C4 ext_ms: 1 -> 21.6, 4 -> 21.2, 8 -> 21.1, 16 -> 21.7; profiles/r2_ab.md §7)
+  const uint32_t refill_min = 8u;
 
   auto flush = [&]() {  // executed by the whole warp
     __syncwarp();
@@ -165,8 +168,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
 
   for (;;) {
     // ---- idle lanes take prepared rays ----------------------------------------------------------------------------
-    const uint32_t empty = __ballot_sync(0xffffffffu, state == EMPTY);
-    if (empty) {
+    const uint32_t n_idle = __popc(idle);
+    if (n_idle >= refill_min || idle == 0xffffffffu) {
       while (in_head == in_count && !(exhausted && list_pos == list_len)) {  // prepare the next 32 rays
         if (list_pos == list_len) {  // claim the next chunk and order its live slots by ray kind
           uint32_t ch = 0;
@@ -204,8 +207,9 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
       }
       const uint32_t avail = in_count - in_head;
       if (avail) {
-        const uint32_t rank = __popc(empty & lt_mask);
-        if (state == EMPTY && rank < avail) {
+        const uint32_t rank = __popc(idle & lt_mask);
+        const bool take = ((idle >> lane) & 1u) && rank < avail;
+        if (take) {
           const ExtIn r = in[in_head + rank];
           tv.o = xyz(r.o_time); tv.time = r.o_time.w;
           tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
@@ -214,29 +218,26 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.grp = make_uint2(0u, __float_as_uint(r.best.z));
           tv.sp = 0;
           tv.best = Closest{r.best.x, __float_as_uint(r.best.y)};
-          state = RUNNING;
         }
-        in_head += min((uint32_t)__popc(empty), avail);
+        idle &= ~__ballot_sync(0xffffffffu, take);
+        in_head += min(n_idle, avail);
       }
     }
-    if (__ballot_sync(0xffffffffu, state == RUNNING) == 0u) {
+    if (idle == 0xffffffffu) {  // nobody runs and nothing could be taken
       if (out_count) flush();
       if (exhausted && list_pos == list_len && in_head == in_count) break;
       continue;
     }
-    // ---- one node visit (or pop) per lane ---------------------------------------------------------------------------
-    if (state == RUNNING) {
-      if (!trav_step<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt)) state = DONE;
-    }
+    // ---- one node visit (or pop) per running lane -------------------------------------------------------------------
+    bool finished = false;
+    if (!((idle >> lane) & 1u)) finished = !trav_step<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
     // ---- finished lanes push their result -------------------------------------------------------------------------
-    const uint32_t done = __ballot_sync(0xffffffffu, state == DONE);
+    const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (state == DONE) {
-        out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, 0u};
-        state = EMPTY;
-      }
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, 0u};
       out_count += __popc(done);
+      idle |= done;
     }
   }
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
