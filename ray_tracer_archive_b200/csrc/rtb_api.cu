@@ -649,8 +649,11 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
   // per-launch timings / counters describe the kernel alone)
-  static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 3;
-  int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(env_lanes, RTB_MAX_LANES));
+  // 4 lanes for trees that use the static extend scheduler, 3 for deep trees (dynamic fetch): C1 7696 -> 7882, C3 +1.4 %,
+  // C4 -1.5 % with 4 (profiles/r2_ab.md)
+  static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 0;
+  const int want_lanes = env_lanes > 0 ? env_lanes : (s->lc.dynamic_fetch ? 3 : 4);
+  int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(want_lanes, RTB_MAX_LANES));
   if ((uint32_t)n_lanes > p->spp) n_lanes = (int)p->spp;
   uint32_t pool_total = p->pool_paths ? p->pool_paths : (1u << 22);  // all lanes together; 112 B per slot
   int rc = ensure_pix_order(c, p->width, p->height, st);
