@@ -14,7 +14,9 @@
 #include <cstring>
 #include <chrono>
 #include <cstdio>
+#include <atomic>
 #include <future>
+#include <thread>
 #include <cstdlib>
 #include <numeric>
 
@@ -405,11 +407,20 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
 
   float open_min_rel = 1.0f / 8.0f;
   if (const char* e = getenv("RTB_OPEN_MIN_REL")) open_min_rel = (float)atof(e);
-  while (qhead < queue.size()) {
-    Pending pd = queue[qhead++];
+
+  // One wide node: gather up to 8 children of binary node pd.bin_node, assign slots, quantise, append its leaf
+  // primitives and allocate its internal children — into `sk` (the global arrays, or a subtree-local set).
+  struct Sink {
+    std::vector<Node8>* nodes;
+    std::vector<float>* geom;      // [PT_COUNT]
+    std::vector<uint32_t>* info;   // [PT_COUNT]
+    std::vector<Pending>* queue;
+    uint32_t max_depth = 0;
+  };
+  auto process = [&](const Pending& pd, Sink& sk, std::string& perr) -> bool {
     Builder& b = *trees[pd.tree].b;
     const uint32_t type = trees[pd.tree].type;
-    if (pd.depth > out.max_depth) out.max_depth = pd.depth;
+    if (pd.depth > sk.max_depth) sk.max_depth = pd.depth;
     // gather up to 8 children by opening the largest internal child
     int cand[8];
     int nc = 0;
@@ -457,33 +468,104 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     std::memset(&n, 0, sizeof(n));
     as.quantise(n, ch, slot_of, nc);
     const uint32_t gw = geom_words(type);
-    const uint32_t prim_base = (uint32_t)(out.info[type].size() / 2);
-    if (prim_base > REF_INDEX_MASK) { err = "too many primitives of one type"; cleanup(); return RTB_ERR_INVALID; }
+    const uint32_t prim_base = (uint32_t)(sk.info[type].size() / 2);
+    if (prim_base > REF_INDEX_MASK) { perr = "too many primitives of one type"; return false; }
     n.prim_base = (type << REF_TYPE_SHIFT) | prim_base;
-    n.child_base = (uint32_t)out.nodes.size();
+    n.child_base = (uint32_t)sk.nodes->size();
     uint32_t off = 0;
     for (int k = 0; k < nc; ++k) {
       int i = idx[k];
       int s = slot_of[i];
       if (ch[i].leaf) {
         const BinNode& lf = b.bin[ch[i].bin_node];
-        if (lf.count > 3 || off + lf.count > 24) { err = "internal: leaf too large"; cleanup(); return RTB_ERR_INVALID; }
+        if (lf.count > 3 || off + lf.count > 24) { perr = "internal: leaf too large"; return false; }
         n.meta[s] = (uint8_t)((lf.count << 5) | off);
         for (uint32_t q = 0; q < lf.count; ++q) {
           const HostPrim& p = hs.prims[b.recs[lf.first + q].prim];
-          for (uint32_t w = 0; w < gw; ++w) out.geom[type].push_back(p.g[w]);
-          out.info[type].push_back(p.prim_id);
-          out.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
+          for (uint32_t w = 0; w < gw; ++w) sk.geom[type].push_back(p.g[w]);
+          sk.info[type].push_back(p.prim_id);
+          sk.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
         }
         off += lf.count;
       } else {
         n.imask |= (uint8_t)(1u << s);
-        uint32_t child_node = (uint32_t)out.nodes.size();
-        out.nodes.emplace_back();
-        queue.push_back(Pending{child_node, pd.tree, ch[i].bin_node, pd.depth + 1});
+        uint32_t child_node = (uint32_t)sk.nodes->size();
+        sk.nodes->emplace_back();
+        sk.queue->push_back(Pending{child_node, pd.tree, ch[i].bin_node, pd.depth + 1});
       }
     }
-    out.nodes[pd.node] = n;
+    (*sk.nodes)[pd.node] = n;
+    return true;
+  };
+
+  // Serial breadth-first phase: the top of the tree (at least the prefix the extend kernel stages in shared memory)
+  // stays in pure breadth-first order.  Large trees then hand the pending subtrees to worker threads.
+  Sink top{&out.nodes, out.geom, out.info, &queue, 0};
+  const bool parallel = np >= 50000 && !(getenv("RTB_BVH_PAR") && atoi(getenv("RTB_BVH_PAR")) == 0);
+  while (qhead < queue.size()) {
+    if (parallel && out.nodes.size() >= 1024 && queue.size() - qhead >= 64) break;
+    Pending pd = queue[qhead++];
+    if (!process(pd, top, err)) { cleanup(); return RTB_ERR_INVALID; }
+  }
+  out.max_depth = top.max_depth;
+  if (qhead < queue.size()) {
+    // Parallel phase: every pending subtree is collapsed into its own node / primitive arrays (breadth-first inside the
+    // subtree, indices local), then the subtrees are appended in pending order with their indices rebased, so the
+    // layout does not depend on thread timing.  Deep nodes of one subtree end up contiguous in memory.
+    struct Sub {
+      std::vector<Node8> nodes;
+      std::vector<float> geom[PT_COUNT];
+      std::vector<uint32_t> info[PT_COUNT];
+      uint32_t max_depth = 0;
+      std::string err;
+      bool ok = true;
+    };
+    const size_t n_sub = queue.size() - qhead;
+    std::vector<Sub> subs(n_sub);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+      std::vector<Pending> lq;
+      for (;;) {
+        const size_t k = next.fetch_add(1);
+        if (k >= n_sub) break;
+        Sub& sb = subs[k];
+        const Pending root = queue[qhead + k];
+        sb.nodes.emplace_back();  // local node 0 = the subtree root (its global index was allocated by its parent)
+        lq.clear();
+        lq.push_back(Pending{0u, root.tree, root.bin_node, root.depth});
+        Sink sk{&sb.nodes, sb.geom, sb.info, &lq, 0};
+        for (size_t h = 0; h < lq.size() && sb.ok; ++h) {
+          const Pending pd = lq[h];  // copy: process() appends to lq
+          sb.ok = process(pd, sk, sb.err);
+        }
+        sb.max_depth = sk.max_depth;
+      }
+    };
+    unsigned n_thr = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    if (const char* e = getenv("RTB_BVH_THREADS")) n_thr = (unsigned)std::max(1, atoi(e));
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+    for (size_t k = 0; k < n_sub; ++k) {
+      Sub& sb = subs[k];
+      if (!sb.ok) { err = sb.err; cleanup(); return RTB_ERR_INVALID; }
+      const Pending root = queue[qhead + k];
+      const uint32_t type = trees[root.tree].type;
+      const uint32_t node_base = (uint32_t)out.nodes.size();          // local node i >= 1  ->  node_base + i - 1
+      const uint32_t prim_off = (uint32_t)(out.info[type].size() / 2);  // local primitive j ->  prim_off + j
+      if ((uint64_t)prim_off + sb.info[type].size() / 2 > REF_INDEX_MASK) { err = "too many primitives of one type"; cleanup(); return RTB_ERR_INVALID; }
+      for (size_t i = 0; i < sb.nodes.size(); ++i) {
+        Node8 n = sb.nodes[i];
+        n.child_base = node_base + n.child_base - 1u;  // a local child index is always >= 1
+        n.prim_base = (type << REF_TYPE_SHIFT) | ((n.prim_base & REF_INDEX_MASK) + prim_off);
+        if (i == 0) out.nodes[root.node] = n;
+        else out.nodes.push_back(n);
+      }
+      out.geom[type].insert(out.geom[type].end(), sb.geom[type].begin(), sb.geom[type].end());
+      out.info[type].insert(out.info[type].end(), sb.info[type].begin(), sb.info[type].end());
+      if (sb.max_depth > out.max_depth) out.max_depth = sb.max_depth;
+    }
   }
   cleanup();
   if (timing) {

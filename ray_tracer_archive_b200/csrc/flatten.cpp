@@ -4,6 +4,7 @@
 // boxes.rs:19-68 Box, hittable_list.rs:43-49 list order) is resolved here once.
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 #include "rtb_internal.hpp"
 
@@ -167,16 +168,40 @@ struct Walker {
         uint32_t mid = (uint32_t)p[0];
         if (mid >= hs.meshes.size() || hs.meshes[mid].idx.empty()) { ok = fail("mesh id was not set"); break; }
         const HostScene::Mesh& m = hs.meshes[mid];
-        hs.prims.reserve(hs.prims.size() + m.idx.size() / 3);
-        for (size_t k = 0; k + 2 < m.idx.size(); k += 3) {
-          double v[3][3];
-          for (int q = 0; q < 3; ++q) {
-            const float* f = &m.verts[3 * (size_t)m.idx[k + q]];
-            double d[3] = {f[0], f[1], f[2]};
-            x.point(d, v[q]);
+        // triangles take consecutive primitive ids in index order; large meshes are packed by several threads
+        const size_t ntri = m.idx.size() / 3, first = hs.prims.size();
+        const uint32_t id0 = hs.n_prim_ids;
+        hs.prims.resize(first + ntri);
+        hs.n_prim_ids += (uint32_t)ntri;
+        const uint32_t material = n.material;
+        auto pack_range = [&](size_t t0, size_t t1) {
+          for (size_t t = t0; t < t1; ++t) {
+            double v[3][3];
+            for (int q = 0; q < 3; ++q) {
+              const float* f = &m.verts[3 * (size_t)m.idx[3 * t + q]];
+              double d[3] = {f[0], f[1], f[2]};
+              x.point(d, v[q]);
+            }
+            HostPrim& pr = hs.prims[first + t];
+            std::memset(&pr, 0, sizeof(pr));
+            pr.type = PT_TRI;
+            pr.prim_id = id0 + (uint32_t)t;
+            pr.material = material;
+            pr.face_mode = fm;
+            pack_tri(pr, v[0], v[1], v[2]);
           }
-          HostPrim& pr = emit(PT_TRI, n.material, fm);
-          pack_tri(pr, v[0], v[1], v[2]);
+        };
+        unsigned n_thr = ntri >= 100000 ? std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)) : 1u;
+        if (n_thr <= 1) {
+          pack_range(0, ntri);
+        } else {
+          std::vector<std::thread> pool;
+          const size_t per = (ntri + n_thr - 1) / n_thr;
+          for (unsigned t = 0; t < n_thr; ++t) {
+            const size_t t0 = std::min(ntri, t * per), t1 = std::min(ntri, t0 + per);
+            if (t0 < t1) pool.emplace_back(pack_range, t0, t1);
+          }
+          for (std::thread& th : pool) th.join();
         }
         break;
       }

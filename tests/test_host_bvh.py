@@ -157,3 +157,54 @@ def test_oracle_bvh_mode_is_bit_identical_to_linear_scan(rtb, orc):
         acc2, seg2, _ = osc.render(cfg.camera, prm)
         assert np.array_equal(a_ids, b_ids) and np.array_equal(a_t, b_t), cfg.name
         assert np.array_equal(acc1, acc2) and seg1 == seg2, cfg.name
+
+
+def test_parallel_subtree_collapse_large_mesh(rtb, orc, emul, monkeypatch):
+    """Trees of >= 50 000 primitives collapse their subtrees on worker threads (bvh_build.cpp): the result must be
+    independent of the thread count (byte-identical nodes), give the same closest hits as the serial breadth-first
+    layout, and keep its first 1024 nodes in pure breadth-first order (every child index of that prefix lies after its
+    parent, levels contiguous) — that prefix is what the extend kernel stages in shared memory."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_mesh(nx=180, nz=180)  # 64 800 triangles + the Cornell walls
+    cs = rtb.compile_scene(cfg.world, cfg.lights)
+
+    def build(env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        hs = rtb.Scene(None, cs)
+        hs.build_bvh()
+        nodes, prims = hs.export_bvh()
+        for k in env:
+            monkeypatch.delenv(k)
+        return hs, nodes.tobytes(), prims
+
+    hs_par, n_par, p_par = build({})
+    hs_one, n_one, _ = build({"RTB_BVH_THREADS": "1"})
+    hs_ser, n_ser, p_ser = build({"RTB_BVH_PAR": "0"})
+    assert hs_par.info()["n_prims"] >= 50000
+    assert n_par == n_one  # layout does not depend on the number of worker threads
+    assert len(n_par) == len(n_ser)  # same tree, different node order
+    # same closest hits as the serial layout, and as the oracle
+    o, d = H.primary_rays(cfg.camera, 96, 54)
+    rng = np.random.default_rng(5)
+    o2 = rng.uniform((70, 160, 70), (480, 500, 480), (4000, 3))
+    d2 = rng.normal(0, 1, (4000, 3)) * 50
+    o32 = np.concatenate([o, o2]).astype(np.float32)
+    d32 = np.concatenate([d, d2]).astype(np.float32)
+    a = H.emul_trace(emul, hs_par, o32, d32)
+    b = H.emul_trace(emul, hs_ser, o32, d32)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    osc = orc.OracleScene(cs)
+    osc.attach_bvh(hs_par)
+    oid, ot = osc.trace_rays(o32.astype(np.float64), d32.astype(np.float64), np.zeros(len(o32)))
+    assert (a[0] != oid).sum() <= 3
+    # breadth-first prefix: children of node i (i < 1024) start after every child block of the nodes before it
+    nd = np.frombuffer(n_par, dtype=np.dtype([("o", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"),
+                                              ("prim_base", "<u4"), ("meta", "u1", 8), ("q", "u1", 48)]))
+    nxt = 1
+    for i in range(min(1024, len(nd))):
+        k = bin(int(nd["imask"][i])).count("1")
+        if k == 0 or nxt >= 1024:
+            continue
+        assert int(nd["child_base"][i]) == nxt, i
+        nxt += k
