@@ -18,6 +18,7 @@
 #include <future>
 #include <thread>
 #include <cstdlib>
+#include <new>
 #include <numeric>
 
 #include "rtb_internal.hpp"
@@ -59,9 +60,44 @@ struct Builder {
   explicit Builder(const HostScene& h) : hs(h) {}
   const HostScene& hs;
   std::vector<Rec> recs;            // the current type's primitives, partitioned in place
-  std::vector<BinNode> bin;
+  // binary nodes, indexed by the ranges build_at() hands out; raw storage: only reachable nodes are ever written, so the
+  // 2n-node array (104 MB for 1 M triangles) is not initialised
+  BinNode* bin = nullptr;
+  ~Builder() { std::free(bin); }
+  Builder(const Builder&) = delete;
+  Builder& operator=(const Builder&) = delete;
   uint32_t max_leaf = 1;            // primitives per leaf slot (1..3)
   int par_depth = 5;                // levels of the tree whose halves are built concurrently
+
+  // SAH sweep over the 16 bins of every valid axis
+  static void best_split(const Box3 (&bb)[3][16], const uint32_t (&bc)[3][16], const bool (&valid)[3], int& best_axis,
+                         int& best_bin) {
+    const int NB = 16;
+    float best_cost = INFINITY;
+    best_axis = best_bin = -1;
+    for (int a = 0; a < 3; ++a) {
+      if (!valid[a]) continue;
+      float right_area[NB];
+      uint32_t right_cnt[NB];
+      Box3 acc;
+      uint32_t cnt = 0;
+      for (int b = NB - 1; b > 0; --b) {
+        acc.grow(bb[a][b]);
+        cnt += bc[a][b];
+        right_area[b] = acc.area();
+        right_cnt[b] = cnt;
+      }
+      Box3 accl;
+      uint32_t cl = 0;
+      for (int b = 0; b < NB - 1; ++b) {
+        accl.grow(bb[a][b]);
+        cl += bc[a][b];
+        if (cl == 0 || right_cnt[b + 1] == 0) continue;
+        const float cost = accl.area() * (float)cl + right_area[b + 1] * (float)right_cnt[b + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+      }
+    }
+  }
 
   // binned SAH split of order[first, first+count): fills the node's bounds; returns false for a leaf
   bool split(uint32_t first, uint32_t count, BinNode& node, uint32_t& mid) {
@@ -100,30 +136,8 @@ struct Builder {
         bc[a][b]++;
       }
     }
-    float best_cost = INFINITY;
     int best_axis = -1, best_bin = -1;
-    for (int a = 0; a < 3; ++a) {
-      if (!valid[a]) continue;
-      float right_area[NB];
-      uint32_t right_cnt[NB];
-      Box3 acc;
-      uint32_t cnt = 0;
-      for (int b = NB - 1; b > 0; --b) {
-        acc.grow(bb[a][b]);
-        cnt += bc[a][b];
-        right_area[b] = acc.area();
-        right_cnt[b] = cnt;
-      }
-      Box3 accl;
-      uint32_t cl = 0;
-      for (int b = 0; b < NB - 1; ++b) {
-        accl.grow(bb[a][b]);
-        cl += bc[a][b];
-        if (cl == 0 || right_cnt[b + 1] == 0) continue;
-        const float cost = accl.area() * (float)cl + right_area[b + 1] * (float)right_cnt[b + 1];
-        if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
-      }
-    }
+    best_split(bb, bc, valid, best_axis, best_bin);
     if (best_axis < 0) {
       mid = first + count / 2;  // all centroids coincide: split the range
     } else {
@@ -140,41 +154,166 @@ struct Builder {
     return true;
   }
 
-  // builds the subtree of order[first, first+count) into `v` and returns its root index in `v`.  Large subtrees near
-  // the top are built concurrently: the two halves touch disjoint ranges of `order`, the left half goes to its own
-  // node vector and is spliced in afterwards.
-  int build_into(std::vector<BinNode>& v, uint32_t first, uint32_t count, int depth) {
-    const int me = (int)v.size();
-    v.emplace_back();
-    BinNode nd;
-    uint32_t mid = 0;
-    const bool inner = split(first, count, nd, mid);
-    v[me] = nd;
-    if (!inner) return me;
-    int l, r;
-    if (count >= 32768 && depth < par_depth) {
-      std::vector<BinNode> lv;
-      lv.reserve(2 * (size_t)(mid - first) / max_leaf + 16);
-      auto fut = std::async(std::launch::async, [&]() { build_into(lv, first, mid - first, depth + 1); });
-      r = build_into(v, mid, first + count - mid, depth + 1);
-      fut.get();
-      const int off = (int)v.size();
-      for (BinNode n : lv) {
-        if (n.left >= 0) { n.left += off; n.right += off; }
-        v.push_back(n);
+  // Multi-threaded version of split() for the few huge ranges at the top of the tree (the serial passes over 1 M
+  // records made the first three levels cost as much as all the others together): per-thread partial bounds / bins are
+  // merged, and the partition is a stable two-way scatter through `tmp` with per-thread prefix offsets.
+  std::vector<Rec> tmp;
+  bool split_par(uint32_t first, uint32_t count, BinNode& node, uint32_t& mid, unsigned T) {
+    const int NB = 16;
+    struct Part { Box3 box, cbox; Box3 bb[3][NB]; uint32_t bc[3][NB]; uint32_t n_left; };
+    std::vector<Part> part(T);
+    const uint32_t per = (count + T - 1) / T;
+    auto run = [&](auto&& fn) {
+      std::vector<std::thread> pool;
+      for (unsigned t = 1; t < T; ++t) pool.emplace_back([&, t]() { fn(t); });
+      fn(0u);
+      for (std::thread& th : pool) th.join();
+    };
+    auto range = [&](unsigned t, uint32_t& a, uint32_t& b) {
+      a = first + std::min(count, t * per);
+      b = first + std::min(count, t * per + per);
+    };
+    run([&](unsigned t) {
+      uint32_t a, b;
+      range(t, a, b);
+      Part& P = part[t];
+      for (uint32_t i = a; i < b; ++i) {
+        const Rec& p = recs[i];
+        P.box.grow(p.lo, p.hi);
+        const float c[3] = {p.centroid(0), p.centroid(1), p.centroid(2)};
+        P.cbox.grow_pt(c);
       }
-      l = off;  // the left subtree's root was lv[0]
-    } else {
-      l = build_into(v, first, mid - first, depth + 1);
-      r = build_into(v, mid, first + count - mid, depth + 1);
+    });
+    Box3 box, cbox;
+    for (unsigned t = 0; t < T; ++t) { box.grow(part[t].box); cbox.grow(part[t].cbox); }
+    node.box = box;
+    node.first = first;
+    node.count = count;
+    node.left = node.right = -1;
+    node.nleaves = 1;
+    if (count <= max_leaf) return false;
+    float k[3], lo[3];
+    bool valid[3];
+    for (int a = 0; a < 3; ++a) {
+      const float ext = cbox.hi[a] - cbox.lo[a];
+      valid[a] = ext > 0.f;
+      k[a] = valid[a] ? NB / ext : 0.f;
+      lo[a] = cbox.lo[a];
     }
-    v[me].left = l;
-    v[me].right = r;
-    v[me].nleaves = v[l].nleaves + v[r].nleaves;
-    return me;
+    run([&](unsigned t) {
+      uint32_t a0, b0;
+      range(t, a0, b0);
+      Part& P = part[t];
+      std::memset(P.bc, 0, sizeof(P.bc));
+      for (uint32_t i = a0; i < b0; ++i) {
+        const Rec& p = recs[i];
+        for (int a = 0; a < 3; ++a) {
+          if (!valid[a]) continue;
+          int b = (int)((p.centroid(a) - lo[a]) * k[a]);
+          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+          P.bb[a][b].grow(p.lo, p.hi);
+          P.bc[a][b]++;
+        }
+      }
+    });
+    Box3 bb[3][NB];
+    uint32_t bc[3][NB] = {{0}};
+    for (unsigned t = 0; t < T; ++t)
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < NB; ++b) { bb[a][b].grow(part[t].bb[a][b]); bc[a][b] += part[t].bc[a][b]; }
+    int best_axis = -1, best_bin = -1;
+    best_split(bb, bc, valid, best_axis, best_bin);
+    if (best_axis < 0) {
+      mid = first + count / 2;  // all centroids coincide: split the range
+      return true;
+    }
+    const float kk = k[best_axis], l0 = lo[best_axis];
+    const int ba = best_axis;
+    auto goes_left = [&](const Rec& p) {
+      int b = (int)((p.centroid(ba) - l0) * kk);
+      b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+      return b <= best_bin;
+    };
+    run([&](unsigned t) {
+      uint32_t a, b;
+      range(t, a, b);
+      uint32_t n = 0;
+      for (uint32_t i = a; i < b; ++i) n += goes_left(recs[i]) ? 1u : 0u;
+      part[t].n_left = n;
+    });
+    uint32_t total_left = 0;
+    for (unsigned t = 0; t < T; ++t) total_left += part[t].n_left;
+    if (total_left == 0 || total_left == count) {
+      mid = first + count / 2;
+      return true;
+    }
+    // `tmp` mirrors `recs` index for index: concurrent splits work on disjoint ranges of both
+    std::vector<uint32_t> loff(T), roff(T);
+    uint32_t l = 0, r = total_left;
+    for (unsigned t = 0; t < T; ++t) {
+      uint32_t a, b;
+      range(t, a, b);
+      loff[t] = l; roff[t] = r;
+      l += part[t].n_left;
+      r += (b - a) - part[t].n_left;
+    }
+    run([&](unsigned t) {
+      uint32_t a, b;
+      range(t, a, b);
+      uint32_t li = first + loff[t], ri = first + roff[t];
+      for (uint32_t i = a; i < b; ++i) {
+        if (goes_left(recs[i])) tmp[li++] = recs[i];
+        else tmp[ri++] = recs[i];
+      }
+    });
+    run([&](unsigned t) {
+      uint32_t a, b;
+      range(t, a, b);
+      if (b > a) std::memcpy(&recs[a], &tmp[a], (size_t)(b - a) * sizeof(Rec));
+    });
+    mid = first + total_left;
+    return true;
   }
 
-  int build_range(uint32_t first, uint32_t count) { return build_into(bin, first, count, 0); }
+  // Builds the subtree of recs[first, first+count) with its root at bin[me].  A subtree of n records has at most 2n-1
+  // nodes, so it owns the index range [me, me + 2n - 1): the left child is bin[me+1], the right child starts after the
+  // left subtree's range.  Ranges of concurrently built subtrees are disjoint — no splicing, no reallocation (`bin` is
+  // sized 2n up front; unused slots stay empty).  Large subtrees near the top are built concurrently and their splits
+  // are themselves multi-threaded.
+  void build_at(int me, uint32_t first, uint32_t count, int depth) {
+    BinNode nd;
+    uint32_t mid = 0;
+    unsigned T = 1;
+    if (count >= 131072 && par_depth > 0) {
+      const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+      T = std::max(1u, hw >> std::min(depth, 5));
+    }
+    const bool inner = T > 1 ? split_par(first, count, nd, mid, T) : split(first, count, nd, mid);
+    bin[me] = nd;
+    if (!inner) return;
+    const int l = me + 1, r = me + 2 * (int)(mid - first);
+    if (count >= 32768 && depth < par_depth) {
+      auto fut = std::async(std::launch::async, [&]() { build_at(l, first, mid - first, depth + 1); });
+      build_at(r, mid, first + count - mid, depth + 1);
+      fut.get();
+    } else {
+      build_at(l, first, mid - first, depth + 1);
+      build_at(r, mid, first + count - mid, depth + 1);
+    }
+    bin[me].left = l;
+    bin[me].right = r;
+    bin[me].nleaves = bin[l].nleaves + bin[r].nleaves;
+  }
+
+  int build_range(uint32_t first, uint32_t count) {
+    std::free(bin);
+    bin = static_cast<BinNode*>(std::malloc(2 * (size_t)count * sizeof(BinNode)));
+    if (!bin) throw std::bad_alloc();
+    if (count >= 131072 && par_depth > 0) tmp.resize(recs.size());
+    build_at(0, first, count, 0);
+    std::vector<Rec>().swap(tmp);
+    return 0;
+  }
 };
 
 struct WideChild {
@@ -319,6 +458,9 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   auto t_start = now();
   // --- per-type binary trees ---------------------------------------------------------------------------------
   struct TypedTree { Builder* b; int root; uint32_t type; };
+  size_t type_count[PT_COUNT] = {0, 0, 0, 0};
+  for (size_t i = 0; i < np; ++i)
+    if (!is_global[i] && hs.prims[i].type < PT_COUNT) type_count[hs.prims[i].type]++;
   std::vector<Builder*> builders;
   std::vector<TypedTree> trees;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
@@ -328,6 +470,8 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     b->max_leaf = (t == PT_TRI) ? 2u : 1u;
     if (const char* e = getenv("RTB_MAX_LEAF")) b->max_leaf = (uint32_t)std::max(1, std::min(3, atoi(e)));
     builders.push_back(b);
+    if (type_count[t] == 0) continue;
+    b->recs.reserve(type_count[t]);
     for (size_t i = 0; i < np; ++i)
       if (hs.prims[i].type == t && !is_global[i]) {
         Rec r;
@@ -335,9 +479,9 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
         r.prim = (uint32_t)i;
         b->recs.push_back(r);
       }
-    if (b->recs.empty()) continue;
+    if (timing) std::fprintf(stderr, "[rtb200]   type %u: %zu records filled at %.3f s\n", t, b->recs.size(),
+                             std::chrono::duration<double>(now() - t_start).count());
     if (const char* e = getenv("RTB_BVH_PAR")) b->par_depth = atoi(e);
-    b->bin.reserve(2 * b->recs.size());
     int root = b->build_range(0, (uint32_t)b->recs.size());
     trees.push_back(TypedTree{b, root, t});
   }
