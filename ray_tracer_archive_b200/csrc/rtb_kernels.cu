@@ -888,7 +888,11 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   // extend runs 2 CTAs per SM: 2 x (stage + 2 KB list [+ 20 KB of per-warp ray/result buffers, dynamic fetch]) must fit
   // the 227 KB of an SM beside one 3 KB shade CTA
   lc.dynamic_fetch = n_nodes > 4096;
-  uint32_t budget = (getenv("RTB_STAGE_KB") ? (uint32_t)atoi(getenv("RTB_STAGE_KB")) : 56u) * 1024u;
+  // 12 KB (153 nodes = the top two to three levels).  Larger stages do not speed extend up (deeper nodes hit L1 anyway:
+  // one-lane ext_ms C3 66.3 at 12 KB vs 68.5 at 56 KB, C4 20.8 vs 21.1) and cost the multi-lane pipeline its overlap —
+  // with <= ~62 KB per CTA a third extend CTA (of another lane) fits an SM: C4 2748 -> 3268 Mrays/s, C3 3585 -> 3694
+  // (profiles/r2_ab.md §9).
+  uint32_t budget = (getenv("RTB_STAGE_KB") ? (uint32_t)atoi(getenv("RTB_STAGE_KB")) : 12u) * 1024u;
   budget = std::min(budget, (lc.dynamic_fetch ? 84u : 104u) * 1024u);
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;
@@ -913,7 +917,8 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (occ < 1) occ = 1;
   // two extend CTAs per SM (of the three that fit): leaves a third of the register file to the shade kernels of the
   // other wavefront lanes, which then really run beside extend (measured +8 % on C1, profiles/r1_ab_extend.md)
-  occ = std::min(occ, getenv("RTB_EXTEND_OCC") ? std::max(1, atoi(getenv("RTB_EXTEND_OCC"))) : 2);
+  // (512 resident extend threads per SM whatever the CTA size: RTB_EXTEND_THREADS is a build-time knob)
+  occ = std::min(occ, getenv("RTB_EXTEND_OCC") ? std::max(1, atoi(getenv("RTB_EXTEND_OCC"))) : std::max(1, 512 / RTB_EXTEND_THREADS));
   lc.extend_grid = (uint32_t)(sm_count * occ);
   int occ2 = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_shade_lambert, RTB_SHADE_THREADS, 0);

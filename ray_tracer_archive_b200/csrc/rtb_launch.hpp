@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef RTB_EXTEND_THREADS
 #define RTB_EXTEND_THREADS 256
+#endif
 #define RTB_SHADE_THREADS 256
 #ifndef RTB_SHADE_MIN_BLOCKS
 #define RTB_SHADE_MIN_BLOCKS 3
