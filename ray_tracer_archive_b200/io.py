@@ -44,3 +44,30 @@ def save_image(path: str, rgb8: np.ndarray) -> None:
         return
     from PIL import Image  # PNG / JPEG (quality 100 like main.rs:720) when available
     Image.fromarray(a).save(path, quality=100)
+
+
+# ---- checkpoint / resume of the accumulation buffer ("resume = add more spp") -----------------------
+# The accumulation buffer holds SUMS over samples (main.rs:767-781) and samples are keyed by their global index, so a
+# render can be continued later — or on another GPU — by loading the sums, passing sample_offset = samples already
+# done and RTB_RENDER_ACCUMULATE to rtb_render_device.
+def save_checkpoint(path: str, accum: np.ndarray, spp_done: int, seed: int, **meta) -> None:
+    """accum: (H, W, 4) float32 sums (ΣR, ΣG, ΣB, ΣY²) as returned by rtb_render / read back from the device buffer."""
+    a = np.ascontiguousarray(accum, dtype=np.float32)
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("accum must have shape (H, W, 4)")
+    np.savez(path, accum=a, spp_done=np.int64(spp_done), seed=np.int64(seed),
+             meta=np.array(repr(sorted(meta.items()))))
+
+
+def load_checkpoint(path: str, width: int | None = None, height: int | None = None, seed: int | None = None):
+    """-> (accum (H, W, 4) float32, spp_done).  Raises if the image size or seed does not match the render being resumed
+    (a different seed is a different sample set: its sums must not be mixed with this one's sample indices)."""
+    with np.load(path if path.endswith(".npz") else path + ".npz") as z:
+        a, done, sd = z["accum"], int(z["spp_done"]), int(z["seed"])
+    if a.ndim != 3 or a.shape[2] != 4:
+        raise ValueError("not an rtb200 checkpoint")
+    if (height is not None and a.shape[0] != height) or (width is not None and a.shape[1] != width):
+        raise ValueError(f"checkpoint is {a.shape[1]}x{a.shape[0]}, render is {width}x{height}")
+    if seed is not None and sd != seed:
+        raise ValueError(f"checkpoint was rendered with seed {sd}, not {seed}")
+    return np.ascontiguousarray(a, dtype=np.float32), done

@@ -111,3 +111,21 @@ def test_obj_loader_and_ppm_writer(rtb, tmp_path):
     assert raw.startswith(b"P6\n5 4\n255\n") and raw[-60:] == img.tobytes()
     with pytest.raises(ValueError):
         io.load_obj(["v 0 0 0", "f 1 2 3"], mesh.mat)
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """io.save_checkpoint / load_checkpoint: sums, sample count and the guards against resuming the wrong render."""
+    import numpy as np
+    import pytest
+    from ray_tracer_archive_b200 import io
+    acc = np.random.default_rng(3).random((5, 7, 4)).astype(np.float32)
+    p = str(tmp_path / "ck")
+    io.save_checkpoint(p, acc, spp_done=48, seed=9, scene="cornell")
+    got, done = io.load_checkpoint(p, width=7, height=5, seed=9)
+    assert done == 48 and got.dtype == np.float32 and np.array_equal(got, acc)
+    with pytest.raises(ValueError):
+        io.load_checkpoint(p, width=8, height=5)
+    with pytest.raises(ValueError):
+        io.load_checkpoint(p, seed=10)
+    with pytest.raises(ValueError):
+        io.save_checkpoint(p, acc[..., :3], 1, 1)

@@ -385,6 +385,27 @@ def test_slot_stable_pool_any_size_renders_every_path_once(rtb, ctx, pool):
     assert abs(acc[..., :3].sum() / ref[..., :3].sum() - 1.0) < 1e-5
 
 
+def test_checkpoint_resume_adds_samples(rtb, ctx, tmp_path):
+    """Resume = add more spp: 16 spp, checkpoint to disk, load into a NEW device buffer, 16 more spp with
+    sample_offset 16 + RTB_RENDER_ACCUMULATE  ==  one 32-spp render (same global sample indices)."""
+    import torch
+    from ray_tracer_archive_b200 import scenes, io
+    cfg = scenes.config_cornell()
+    dev = rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights))
+    W = Hh = 48
+    ref, _ = dev.render(cfg.camera, rtb.make_params(W, Hh, 32, seed=6))
+    a = torch.zeros((Hh, W, 4), dtype=torch.float32, device="cuda")
+    dev.render_device(cfg.camera, rtb.make_params(W, Hh, 16, seed=6, total_spp=32), a.data_ptr())
+    torch.cuda.synchronize()
+    io.save_checkpoint(str(tmp_path / "half"), a.cpu().numpy(), spp_done=16, seed=6)
+    acc, done = io.load_checkpoint(str(tmp_path / "half"), width=W, height=Hh, seed=6)
+    b = torch.from_numpy(acc).cuda()
+    dev.render_device(cfg.camera, rtb.make_params(W, Hh, 32 - done, seed=6, sample_offset=done, total_spp=32,
+                                                  flags=rtb._ffi.RENDER_ACCUMULATE), b.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(b.cpu().numpy(), ref, rtol=2e-4, atol=1e-4)
+
+
 def test_finalize_rgb8_matches_write_color(rtb, orc, ctx):
     from ray_tracer_archive_b200 import scenes
     cfg = scenes.config_cornell()
