@@ -649,8 +649,8 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
   // per-launch timings / counters describe the kernel alone)
-  // 4 lanes for trees that use the static extend scheduler, 3 for deep trees (dynamic fetch): C1 7696 -> 7882, C3 +1.4 %,
-  // C4 -1.5 % with 4 (profiles/r2_ab.md)
+  // 4 lanes for trees that use the static extend scheduler, 3 for deep trees (dynamic fetch): C1 7696 -> 7882, C3 +2.6 %
+  // with 4; C4 +0.9 % only, not worth a fourth 147 MB pool (profiles/r2_ab.md)
   static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 0;
   const int want_lanes = env_lanes > 0 ? env_lanes : (s->lc.dynamic_fetch ? 3 : 4);
   int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(want_lanes, RTB_MAX_LANES));
