@@ -18,6 +18,7 @@
 #include <future>
 #include <thread>
 #include <cstdlib>
+#include <emmintrin.h>
 #include <new>
 #include <numeric>
 
@@ -50,10 +51,29 @@ struct BinNode {  // binary tree node
   uint32_t nleaves = 1;       // leaf nodes in this subtree
 };
 
-struct Rec {  // one primitive's padded bounds; the records themselves are partitioned, so every range the builder
-  float lo[3], hi[3];  // touches is contiguous in memory (index-only partitioning made the build DRAM-latency-bound)
-  uint32_t prim;
+struct alignas(16) Rec {  // one primitive's padded bounds; the records themselves are partitioned, so every range the
+  float lo[3];             // builder touches is contiguous in memory (index-only partitioning made the build
+  uint32_t prim_enc;       // DRAM-latency-bound).  Two 16-byte halves: (lo, prim) and (hi, 0) load as SSE vectors; the
+  float hi[3];             // primitive index carries bit 30 so that, read as a float, lane 3 is a normal number (no
+  uint32_t _pad;           // denormal assists in the vector arithmetic that ignores it)
   float centroid(int a) const { return 0.5f * (lo[a] + hi[a]); }
+  uint32_t prim() const { return prim_enc & 0x3FFFFFFFu; }
+};
+static_assert(sizeof(Rec) == 32, "Rec must be two SSE vectors");
+
+// SSE accumulation of bounds: lanes 0-2 = x, y, z; lane 3 carries the record's integer fields and is ignored
+struct Box4 {
+  __m128 lo = _mm_set1_ps(INFINITY), hi = _mm_set1_ps(-INFINITY);
+  void grow(__m128 l, __m128 h) { lo = _mm_min_ps(lo, l); hi = _mm_max_ps(hi, h); }
+  void grow(const Box4& b) { grow(b.lo, b.hi); }
+  Box3 box3() const {
+    alignas(16) float l[4], h[4];
+    _mm_store_ps(l, lo);
+    _mm_store_ps(h, hi);
+    Box3 b;
+    for (int a = 0; a < 3; ++a) { b.lo[a] = l[a]; b.hi[a] = h[a]; }
+    return b;
+  }
 };
 
 struct Builder {
@@ -68,6 +88,45 @@ struct Builder {
   Builder& operator=(const Builder&) = delete;
   uint32_t max_leaf = 1;            // primitives per leaf slot (1..3)
   int par_depth = 5;                // levels of the tree whose halves are built concurrently
+
+  // bounds of the records [a, b) and of their centroids (SSE: one min + one max per record and box)
+  void range_bounds(uint32_t a, uint32_t b, Box3& box, Box3& cbox) const {
+    Box4 bx, cb;
+    const __m128 half = _mm_set1_ps(0.5f);
+    for (uint32_t i = a; i < b; ++i) {
+      const __m128 l = _mm_load_ps(recs[i].lo), h = _mm_load_ps(recs[i].hi);
+      bx.grow(l, h);
+      const __m128 c = _mm_mul_ps(half, _mm_add_ps(l, h));
+      cb.grow(c, c);
+    }
+    box = bx.box3();
+    cbox = cb.box3();
+  }
+
+  // 16-bin histograms of the records [a, b) on the three axes: bin = clamp(int((centroid - lo) * k)), exactly the
+  // expression the partition step evaluates
+  void range_bins(uint32_t a, uint32_t b, const float lo[3], const float k[3], const bool valid[3], Box3 (&bb)[3][16],
+                  uint32_t (&bc)[3][16]) const {
+    const int NB = 16;
+    Box4 acc[3][NB];
+    const __m128 half = _mm_set1_ps(0.5f);
+    const __m128 lo4 = _mm_set_ps(0.f, lo[2], lo[1], lo[0]), k4 = _mm_set_ps(0.f, k[2], k[1], k[0]);
+    for (uint32_t i = a; i < b; ++i) {
+      const __m128 l = _mm_load_ps(recs[i].lo), h = _mm_load_ps(recs[i].hi);
+      const __m128 c = _mm_mul_ps(half, _mm_add_ps(l, h));
+      alignas(16) int32_t bi[4];
+      _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, lo4), k4)));
+      for (int ax = 0; ax < 3; ++ax) {
+        if (!valid[ax]) continue;
+        int q = bi[ax];
+        q = q < 0 ? 0 : (q >= NB ? NB - 1 : q);
+        acc[ax][q].grow(l, h);
+        bc[ax][q]++;
+      }
+    }
+    for (int ax = 0; ax < 3; ++ax)
+      for (int q = 0; q < NB; ++q) bb[ax][q] = acc[ax][q].box3();
+  }
 
   // SAH sweep over the 16 bins of every valid axis
   static void best_split(const Box3 (&bb)[3][16], const uint32_t (&bc)[3][16], const bool (&valid)[3], int& best_axis,
@@ -102,12 +161,7 @@ struct Builder {
   // binned SAH split of order[first, first+count): fills the node's bounds; returns false for a leaf
   bool split(uint32_t first, uint32_t count, BinNode& node, uint32_t& mid) {
     Box3 box, cbox;
-    for (uint32_t i = first; i < first + count; ++i) {
-      const Rec& p = recs[i];
-      box.grow(p.lo, p.hi);
-      const float c[3] = {p.centroid(0), p.centroid(1), p.centroid(2)};
-      cbox.grow_pt(c);
-    }
+    range_bounds(first, first + count, box, cbox);
     node.box = box;
     node.first = first;
     node.count = count;
@@ -126,16 +180,7 @@ struct Builder {
       k[a] = valid[a] ? NB / ext : 0.f;
       lo[a] = cbox.lo[a];
     }
-    for (uint32_t i = first; i < first + count; ++i) {
-      const Rec& p = recs[i];
-      for (int a = 0; a < 3; ++a) {
-        if (!valid[a]) continue;
-        int b = (int)((p.centroid(a) - lo[a]) * k[a]);
-        b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-        bb[a][b].grow(p.lo, p.hi);
-        bc[a][b]++;
-      }
-    }
+    range_bins(first, first + count, lo, k, valid, bb, bc);
     int best_axis = -1, best_bin = -1;
     best_split(bb, bc, valid, best_axis, best_bin);
     if (best_axis < 0) {
@@ -160,7 +205,7 @@ struct Builder {
   std::vector<Rec> tmp;
   bool split_par(uint32_t first, uint32_t count, BinNode& node, uint32_t& mid, unsigned T) {
     const int NB = 16;
-    struct Part { Box3 box, cbox; Box3 bb[3][NB]; uint32_t bc[3][NB]; uint32_t n_left; };
+    struct Part { Box3 box, cbox; Box3 bb[3][16]; uint32_t bc[3][16]; uint32_t n_left; };
     std::vector<Part> part(T);
     const uint32_t per = (count + T - 1) / T;
     auto run = [&](auto&& fn) {
@@ -176,13 +221,7 @@ struct Builder {
     run([&](unsigned t) {
       uint32_t a, b;
       range(t, a, b);
-      Part& P = part[t];
-      for (uint32_t i = a; i < b; ++i) {
-        const Rec& p = recs[i];
-        P.box.grow(p.lo, p.hi);
-        const float c[3] = {p.centroid(0), p.centroid(1), p.centroid(2)};
-        P.cbox.grow_pt(c);
-      }
+      range_bounds(a, b, part[t].box, part[t].cbox);
     });
     Box3 box, cbox;
     for (unsigned t = 0; t < T; ++t) { box.grow(part[t].box); cbox.grow(part[t].cbox); }
@@ -205,16 +244,7 @@ struct Builder {
       range(t, a0, b0);
       Part& P = part[t];
       std::memset(P.bc, 0, sizeof(P.bc));
-      for (uint32_t i = a0; i < b0; ++i) {
-        const Rec& p = recs[i];
-        for (int a = 0; a < 3; ++a) {
-          if (!valid[a]) continue;
-          int b = (int)((p.centroid(a) - lo[a]) * k[a]);
-          b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-          P.bb[a][b].grow(p.lo, p.hi);
-          P.bc[a][b]++;
-        }
-      }
+      range_bins(a0, b0, lo, k, valid, P.bb, P.bc);
     });
     Box3 bb[3][NB];
     uint32_t bc[3][NB] = {{0}};
@@ -474,9 +504,9 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     b->recs.reserve(type_count[t]);
     for (size_t i = 0; i < np; ++i)
       if (hs.prims[i].type == t && !is_global[i]) {
-        Rec r;
+        Rec r{};
         for (int a = 0; a < 3; ++a) { r.lo[a] = hs.prims[i].lo[a]; r.hi[a] = hs.prims[i].hi[a]; }
-        r.prim = (uint32_t)i;
+        r.prim_enc = (uint32_t)i | 0x40000000u;
         b->recs.push_back(r);
       }
     if (timing) std::fprintf(stderr, "[rtb200]   type %u: %zu records filled at %.3f s\n", t, b->recs.size(),
@@ -625,7 +655,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
         if (lf.count > 3 || off + lf.count > 24) { perr = "internal: leaf too large"; return false; }
         n.meta[s] = (uint8_t)((lf.count << 5) | off);
         for (uint32_t q = 0; q < lf.count; ++q) {
-          const HostPrim& p = hs.prims[b.recs[lf.first + q].prim];
+          const HostPrim& p = hs.prims[b.recs[lf.first + q].prim()];
           for (uint32_t w = 0; w < gw; ++w) sk.geom[type].push_back(p.g[w]);
           sk.info[type].push_back(p.prim_id);
           sk.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
