@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1u
+#define RTB_ABI_VERSION 2u
 #define RTB_NONE 0xFFFFFFFFu
 
 typedef enum rtb_status {
@@ -220,6 +220,8 @@ typedef struct rtb_scene_info {
   uint32_t bvh_width;
   uint32_t bvh_max_depth;
   uint64_t bvh_bytes, prim_bytes;
+  uint32_t global_f64_mask; /* bit k: global primitive k is a sphere so large next to the rest of the scene that it is tested in f64 */
+  uint32_t _pad;
 } rtb_scene_info;
 int rtb_scene_get_info(rtb_scene* s, rtb_scene_info* out);
 /* copies out the leaf-ordered device layout: geometry as float4 words + (prim_id, material|flags<<24) pairs */
@@ -228,6 +230,12 @@ int rtb_scene_export_bvh(rtb_scene* s, void* nodes_80B, size_t cap_bytes);
 int rtb_scene_export_globals(rtb_scene* s, uint32_t* refs, uint32_t cap, uint32_t* n_out);
 int rtb_scene_export_prims(rtb_scene* s, uint32_t type /*0 sphere 1 moving 2 quad 3 triangle*/, float* geom,
                            size_t geom_cap_bytes, uint32_t* info_pairs, size_t info_cap_bytes);
+/* leaf-ordered reference-exact records (16 doubles per sphere / moving sphere / quad; none for triangles): the
+ * constructor's f64 arguments + its Translate/RotateY chain, on which the device re-decides every closest-hit
+ * comparison that f32 rounding leaves open (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176).  Also the
+ * two rounding scales of the f32 quad test.  Any pointer may be NULL. */
+int rtb_scene_export_exact(rtb_scene* s, uint32_t type, double* records, size_t cap_bytes, float* coord_max,
+                           float* eps_ab);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------ */
 /* Renders params->spp samples of every pixel into the context's float4 accumulation buffer

@@ -4,6 +4,7 @@
 // ray_color.  All arithmetic f64 (vec3.rs:7).
 #include "rt_oracle.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <functional>
 #include <cstring>
@@ -469,11 +470,11 @@ struct Scene {
         l->objects.push_back(rect(0, p[1], p[4], p[2], p[5], p[0]));
         return l;
       }
-      case RTB_NODE_TRIANGLE: {
+      case RTB_NODE_TRIANGLE: {  // vertices are single precision by contract (include/rtb200.h), like mesh vertices
         auto t = std::make_shared<Triangle>();
-        t->v0 = V3(p[0], p[1], p[2]);
-        t->e1 = V3(p[3], p[4], p[5]) - t->v0;
-        t->e2 = V3(p[6], p[7], p[8]) - t->v0;
+        t->v0 = V3((float)p[0], (float)p[1], (float)p[2]);
+        t->e1 = V3((float)p[3], (float)p[4], (float)p[5]) - t->v0;
+        t->e2 = V3((float)p[6], (float)p[7], (float)p[8]) - t->v0;
         t->mat = (int)n.material; t->id = new_id();
         register_prim(t->id, t);
         return t;
@@ -928,14 +929,18 @@ int orc_primary_hits(orc_scene* o, const rtb_camera* cam, uint32_t W, uint32_t H
 int orc_trace_rays(orc_scene* o, const double* org, const double* dir, const double* time, uint32_t n, uint32_t* ids,
                    double* ts) {
   if (!o->s.build()) return -1;
-  for (uint32_t i = 0; i < n; ++i) {
-    Ray r{V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
-          time ? time[i] : 0.0};
-    HitRecord rec;
-    bool h = world_hit(o->s, r, 0.001, INF, rec, HitCtx());
-    ids[i] = h ? rec.prim : RTB_NONE;
-    ts[i] = h ? rec.t : INF;
-  }
+  const uint32_t block = 4096;
+  parallel_rows((n + block - 1) / block, n >= 8 * block ? 0 : 1, [&](uint32_t b) {
+    const uint32_t end = std::min<uint64_t>(n, (uint64_t)(b + 1) * block);
+    for (uint32_t i = b * block; i < end; ++i) {
+      Ray r{V3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]),
+            time ? time[i] : 0.0};
+      HitRecord rec;
+      bool h = world_hit(o->s, r, 0.001, INF, rec, HitCtx());
+      ids[i] = h ? rec.prim : RTB_NONE;
+      ts[i] = h ? rec.t : INF;
+    }
+  });
   return 0;
 }
 

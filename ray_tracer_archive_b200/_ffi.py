@@ -70,7 +70,8 @@ class SceneInfo(C.Structure):
                 ("n_triangles", C.c_uint32), ("n_media", C.c_uint32), ("n_lights", C.c_uint32),
                 ("n_materials", C.c_uint32), ("n_textures", C.c_uint32), ("n_prims", C.c_uint32),
                 ("n_bvh_nodes", C.c_uint32), ("bvh_width", C.c_uint32), ("bvh_max_depth", C.c_uint32),
-                ("bvh_bytes", C.c_uint64), ("prim_bytes", C.c_uint64)]
+                ("bvh_bytes", C.c_uint64), ("prim_bytes", C.c_uint64), ("global_f64_mask", C.c_uint32),
+                ("_pad", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -104,6 +105,7 @@ SIGNATURES = {
     "rtb_scene_export_bvh": (_I, [_VP, _VP, _SZ]),
     "rtb_scene_export_globals": (_I, [_VP, _VP, _U32, C.POINTER(C.c_uint32)]),
     "rtb_scene_export_prims": (_I, [_VP, _U32, _VP, _SZ, _VP, _SZ]),
+    "rtb_scene_export_exact": (_I, [_VP, _U32, _VP, _SZ, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "rtb_render": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _VP, C.POINTER(Stats)]),
     "rtb_render_device": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _VP, _VP, C.POINTER(Stats)]),
     "rtb_finalize_rgb8": (_I, [_VP, _VP, _U32, _U32, _U32, _VP]),

@@ -58,6 +58,14 @@ void set_bounds(HostPrim& p, const double lo[3], const double hi[3]) {
   }
 }
 
+// the wrapper chain in the form the reference evaluates it per ray; `canonical` = at most one Translate outside at most
+// one RotateY (every reference scene: main.rs:398-422,507-516,630-641).  Other nestings are flattened to world space:
+// still f64 on the exact path, but the reference's per-wrapper rounding sequence is not reproduced bit for bit.
+struct Chain {
+  ExactXform x;
+  bool canonical = true;
+};
+
 struct Walker {
   HostScene& hs;
   const rtb_node* nodes;
@@ -77,7 +85,15 @@ struct Walker {
     p.prim_id = hs.n_prim_ids++;
     p.material = material;
     p.face_mode = face_mode;
+    p.exact = RTB_NONE;
     return p;
+  }
+
+  // header of a non-canonical chain: no per-ray transform (parameters are world-space), total rotation kept for uv
+  static ExactXform world_header(const Xform& x) {
+    ExactXform h;
+    h.sin_t = x.s; h.cos_t = x.c;
+    return h;
   }
 
   bool check_mat(uint32_t m) {
@@ -85,7 +101,8 @@ struct Walker {
     return true;
   }
 
-  void rect(int axis, double a0, double a1, double b0, double b1, double k, uint32_t mat, const Xform& x, uint32_t fm) {
+  void rect(int axis, double a0, double a1, double b0, double b1, double k, uint32_t mat, const Xform& x, uint32_t fm,
+            const Chain& ch) {
     // aarect.rs: XyRect axis 2 (a=x,b=y), XzRect axis 1 (a=x,b=z), YzRect axis 0 (a=y,b=z); outward normal = +axis
     int ia = axis == 0 ? 1 : 0, ib = axis == 2 ? 1 : 2;
     double Q[3], U[3] = {0, 0, 0}, V[3] = {0, 0, 0}, N[3] = {0, 0, 0};
@@ -97,9 +114,16 @@ struct Walker {
     x.point(Q, Qw); x.vec(U, Uw); x.vec(V, Vw); x.vec(N, Nw);
     HostPrim& p = emit(PT_QUAD, mat, fm);
     pack_quad(p, Qw, Uw, Vw, Nw);
+    if (ch.canonical) {
+      const double prm[5] = {k, a0, a1, b0, b1};
+      p.exact = add_exact(hs, ch.x, (uint32_t)axis, prm, 5);
+    } else {
+      const double prm[9] = {Qw[0], Qw[1], Qw[2], Uw[0], Uw[1], Uw[2], Vw[0], Vw[1], Vw[2]};
+      p.exact = add_exact(hs, world_header(x), EX_QUAD_GENERAL, prm, 9);
+    }
   }
 
-  bool walk(uint32_t ni, const Xform& x, uint32_t fm) {
+  bool walk(uint32_t ni, const Xform& x, uint32_t fm, const Chain& ch) {
     if (ni >= n_nodes) return fail("node index out of range");
     if (++depth > 256) return fail("scene graph too deep (cycle?)");
     const rtb_node& n = nodes[ni];
@@ -113,17 +137,18 @@ struct Walker {
     switch (n.type) {
       case RTB_NODE_SPHERE: {
         if (!check_mat(n.material)) { ok = false; break; }
-        if (!x.identity_rot && hs.materials[n.material].type != RTB_MAT_DIELECTRIC) {
-          // uv are object-space (sphere.rs:32-37); only an image texture reads them
-          uint32_t t = hs.materials[n.material].texture;
-          if (t < hs.textures.size() && hs.textures[t].type == RTB_TEX_IMAGE) {
-            ok = fail("image-textured sphere under RotateY is not supported"); break;
-          }
-        }
+        // uv are object-space (sphere.rs:32-37): the record keeps the rotation, surface_uv() rotates the normal back
         double c[3];
         x.point(p, c);
         HostPrim& pr = emit(PT_SPHERE, n.material, fm);
         pack_sphere(pr, c, p[3]);
+        if (ch.canonical) {
+          const double prm[4] = {p[0], p[1], p[2], p[3]};
+          pr.exact = add_exact(hs, ch.x, 0, prm, 4);
+        } else {
+          const double prm[4] = {c[0], c[1], c[2], p[3]};
+          pr.exact = add_exact(hs, world_header(x), 0, prm, 4);
+        }
         break;
       }
       case RTB_NODE_MOVING_SPHERE: {
@@ -132,25 +157,34 @@ struct Walker {
         x.point(p, c0); x.point(p + 3, c1);
         HostPrim& pr = emit(PT_MOVING, n.material, fm);
         pack_moving(pr, c0, c1, p[6], p[7], p[8]);
+        if (ch.canonical) {
+          const double prm[9] = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+          pr.exact = add_exact(hs, ch.x, 0, prm, 9);
+        } else {
+          const double prm[9] = {c0[0], c0[1], c0[2], c1[0], c1[1], c1[2], p[6], p[7], p[8]};
+          pr.exact = add_exact(hs, world_header(x), 0, prm, 9);
+        }
         break;
       }
-      case RTB_NODE_XY_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(2, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
-      case RTB_NODE_XZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(1, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
-      case RTB_NODE_YZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(0, p[0], p[1], p[2], p[3], p[4], n.material, x, fm); break;
+      case RTB_NODE_XY_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(2, p[0], p[1], p[2], p[3], p[4], n.material, x, fm, ch); break;
+      case RTB_NODE_XZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(1, p[0], p[1], p[2], p[3], p[4], n.material, x, fm, ch); break;
+      case RTB_NODE_YZ_RECT: if (!check_mat(n.material)) { ok = false; break; } rect(0, p[0], p[1], p[2], p[3], p[4], n.material, x, fm, ch); break;
       case RTB_NODE_BOX: {  // boxes.rs:19-68: XY(z1) XY(z0) XZ(y1) XZ(y0) YZ(x1) YZ(x0)
         if (!check_mat(n.material)) { ok = false; break; }
-        rect(2, p[0], p[3], p[1], p[4], p[5], n.material, x, fm);
-        rect(2, p[0], p[3], p[1], p[4], p[2], n.material, x, fm);
-        rect(1, p[0], p[3], p[2], p[5], p[4], n.material, x, fm);
-        rect(1, p[0], p[3], p[2], p[5], p[1], n.material, x, fm);
-        rect(0, p[1], p[4], p[2], p[5], p[3], n.material, x, fm);
-        rect(0, p[1], p[4], p[2], p[5], p[0], n.material, x, fm);
+        rect(2, p[0], p[3], p[1], p[4], p[5], n.material, x, fm, ch);
+        rect(2, p[0], p[3], p[1], p[4], p[2], n.material, x, fm, ch);
+        rect(1, p[0], p[3], p[2], p[5], p[4], n.material, x, fm, ch);
+        rect(1, p[0], p[3], p[2], p[5], p[1], n.material, x, fm, ch);
+        rect(0, p[1], p[4], p[2], p[5], p[3], n.material, x, fm, ch);
+        rect(0, p[1], p[4], p[2], p[5], p[0], n.material, x, fm, ch);
         break;
       }
       case RTB_NODE_TRIANGLE: {
         if (!check_mat(n.material)) { ok = false; break; }
-        double a[3], b[3], c[3];
-        x.point(p, a); x.point(p + 3, b); x.point(p + 6, c);
+        // triangle vertices are single precision by contract (include/rtb200.h): rounded before the transform
+        double pf[9], a[3], b[3], c[3];
+        for (int q = 0; q < 9; ++q) pf[q] = (double)(float)p[q];
+        x.point(pf, a); x.point(pf + 3, b); x.point(pf + 6, c);
         HostPrim& pr = emit(PT_TRI, n.material, fm);
         pack_tri(pr, a, b, c);
         break;
@@ -161,6 +195,12 @@ struct Walker {
         x.point(p, Q); x.vec(p + 3, U); x.vec(p + 6, V);
         HostPrim& pr = emit(PT_QUAD, n.material, fm);
         pack_quad(pr, Q, U, V, nullptr);
+        if (ch.canonical) {
+          pr.exact = add_exact(hs, ch.x, EX_QUAD_GENERAL, p, 9);
+        } else {
+          const double prm[9] = {Q[0], Q[1], Q[2], U[0], U[1], U[2], V[0], V[1], V[2]};
+          pr.exact = add_exact(hs, world_header(x), EX_QUAD_GENERAL, prm, 9);
+        }
         break;
       }
       case RTB_NODE_MESH: {
@@ -188,6 +228,7 @@ struct Walker {
             pr.prim_id = id0 + (uint32_t)t;
             pr.material = material;
             pr.face_mode = fm;
+            pr.exact = RTB_NONE;
             pack_tri(pr, v[0], v[1], v[2]);
           }
         };
@@ -212,7 +253,14 @@ struct Walker {
         double off[3];
         x.vec(p, off);
         for (int a = 0; a < 3; ++a) y.t[a] += off[a];
-        ok = walk(c, y, compose_face(fm, FACE_TRUE));
+        Chain c2 = ch;
+        if (ch.canonical && ch.x.flags == 0) {
+          c2.x.flags = EX_TRANSLATE;
+          for (int a = 0; a < 3; ++a) c2.x.off[a] = p[a];
+        } else {
+          c2.canonical = false;  // Translate inside RotateY / inside another Translate
+        }
+        ok = walk(c, y, compose_face(fm, FACE_TRUE), c2);
         break;
       }
       case RTB_NODE_ROTATE_Y: {
@@ -223,13 +271,21 @@ struct Walker {
         double rad = y.angle_deg * kPi / 180.0;  // hittable.rs:108
         y.c = std::cos(rad); y.s = std::sin(rad);
         y.identity_rot = false;
-        ok = walk(c, y, compose_face(fm, FACE_TRUE));
+        Chain c2 = ch;
+        if (ch.canonical && !(ch.x.flags & EX_ROTATE)) {
+          const double r1 = p[0] * kPi / 180.0;  // hittable.rs:108
+          c2.x.flags |= EX_ROTATE;
+          c2.x.sin_t = std::sin(r1); c2.x.cos_t = std::cos(r1);
+        } else {
+          c2.canonical = false;
+        }
+        ok = walk(c, y, compose_face(fm, FACE_TRUE), c2);
         break;
       }
       case RTB_NODE_FLIP_FACE: {
         uint32_t c;
         if (!child(0, c)) { ok = false; break; }
-        ok = walk(c, x, compose_face(fm, FACE_FLIPPED));
+        ok = walk(c, x, compose_face(fm, FACE_FLIPPED), ch);
         break;
       }
       case RTB_NODE_CONSTANT_MEDIUM: {
@@ -287,7 +343,7 @@ struct Walker {
         for (uint32_t k = 0; k < n.n_children && ok; ++k) {
           uint32_t c;
           if (!child(k, c)) { ok = false; break; }
-          ok = walk(c, x, fm);
+          ok = walk(c, x, fm, ch);
         }
         break;
       }
@@ -299,6 +355,19 @@ struct Walker {
 };
 
 }  // namespace
+
+uint32_t add_exact(HostScene& hs, const ExactXform& x, uint32_t subtype, const double* params, int n_params) {
+  ExactRec r;
+  std::memset(&r, 0, sizeof(r));
+  const uint64_t bits = (uint64_t)x.flags | ((uint64_t)subtype << 8);
+  std::memcpy(&r.v[0], &bits, 8);
+  for (int a = 0; a < 3; ++a) r.v[1 + a] = x.off[a];
+  r.v[4] = x.sin_t;
+  r.v[5] = x.cos_t;
+  for (int k = 0; k < n_params && 6 + k < RTB_EXACT_STRIDE; ++k) r.v[6 + k] = params[k];
+  hs.exact.push_back(r);
+  return (uint32_t)(hs.exact.size() - 1);
+}
 
 void pack_sphere(HostPrim& p, const double c[3], double r) {
   p.g[0] = (float)c[0]; p.g[1] = (float)c[1]; p.g[2] = (float)c[2]; p.g[3] = (float)r;
@@ -377,10 +446,12 @@ int flatten_graph(HostScene& hs, const rtb_node* nodes, uint32_t n_nodes, const 
                   uint32_t n_child_index, uint32_t root, std::string& err) {
   hs.prims.clear();
   hs.media.clear();
+  hs.exact.clear();
   hs.n_prim_ids = 0;
   Walker w{hs, nodes, n_nodes, child_index, n_child_index, err};
   Xform id;
-  if (!w.walk(root, id, FACE_NATURAL)) return RTB_ERR_INVALID;
+  Chain ch;
+  if (!w.walk(root, id, FACE_NATURAL, ch)) return RTB_ERR_INVALID;
   return RTB_OK;
 }
 

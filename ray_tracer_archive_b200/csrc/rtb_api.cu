@@ -90,6 +90,7 @@ struct rtb_scene {
   DevBuf<uint4> d_nodes;
   DevBuf<float4> d_geom[PT_COUNT];
   DevBuf<uint2> d_info[PT_COUNT];
+  DevBuf<double> d_exact[PT_COUNT];
   DevBuf<float4> d_materials;
   DevBuf<DevTexture> d_textures;
   DevBuf<float4> d_perlin_vec[RTB_MAX_TABLES];
@@ -289,6 +290,7 @@ static HostPrim& add_flat(rtb_scene* s, uint32_t type, const uint32_t* mat, cons
   p.type = type;
   p.material = mat[i];
   p.face_mode = flags ? face_mode_of(flags[i]) : FACE_NATURAL;
+  p.exact = RTB_NONE;
   p.prim_id = id ? id[i] : s->hs.n_prim_ids;
   s->hs.n_prim_ids = std::max(s->hs.n_prim_ids, p.prim_id + 1);
   return p;
@@ -302,6 +304,9 @@ int rtb_scene_set_spheres(rtb_scene* s, const float* cr, const uint32_t* mat, co
     HostPrim& p = add_flat(s, PT_SPHERE, mat, flags, id, i);
     double c[3] = {cr[4 * i], cr[4 * i + 1], cr[4 * i + 2]};
     pack_sphere(p, c, cr[4 * i + 3]);
+    const double prm[4] = {c[0], c[1], c[2], cr[4 * i + 3]};
+    const uint32_t ex = add_exact(s->hs, ExactXform(), 0, prm, 4);  // (may reallocate hs.exact, not hs.prims)
+    s->hs.prims.back().exact = ex;
   }
   s->built = s->committed = false;
   return RTB_OK;
@@ -314,6 +319,8 @@ int rtb_scene_set_moving_spheres(rtb_scene* s, const float* c0r, const float* c1
     HostPrim& p = add_flat(s, PT_MOVING, mat, flags, id, i);
     double a[3] = {c0r[4 * i], c0r[4 * i + 1], c0r[4 * i + 2]}, b[3] = {c1[3 * i], c1[3 * i + 1], c1[3 * i + 2]};
     pack_moving(p, a, b, t01[2 * i], t01[2 * i + 1], c0r[4 * i + 3]);
+    const double prm[9] = {a[0], a[1], a[2], b[0], b[1], b[2], t01[2 * i], t01[2 * i + 1], c0r[4 * i + 3]};
+    s->hs.prims.back().exact = add_exact(s->hs, ExactXform(), 0, prm, 9);
   }
   s->built = s->committed = false;
   return RTB_OK;
@@ -327,6 +334,8 @@ int rtb_scene_set_quads(rtb_scene* s, const float* q, const float* u, const floa
     double Q[3] = {q[3 * i], q[3 * i + 1], q[3 * i + 2]}, U[3] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]},
            V[3] = {v[3 * i], v[3 * i + 1], v[3 * i + 2]};
     pack_quad(p, Q, U, V, nullptr);
+    const double prm[9] = {Q[0], Q[1], Q[2], U[0], U[1], U[2], V[0], V[1], V[2]};
+    s->hs.prims.back().exact = add_exact(s->hs, ExactXform(), EX_QUAD_GENERAL, prm, 9);
   }
   s->built = s->committed = false;
   return RTB_OK;
@@ -395,6 +404,61 @@ int rtb_scene_build_bvh(rtb_scene* s) {
   std::string err;
   int rc = build_bvh8(hs, s->bvh, err);
   if (rc != RTB_OK) return set_err(rc, err);
+  {
+    const uint32_t n_global = (uint32_t)s->bvh.global_refs.size();
+    s->bvh.global_f64 = 0;
+    // a global sphere whose radius is >= 16 extents of everything else can only be hit at distances < r/16 from
+    // points ~r away from its centre — exactly where sphere_roots() rejects its f32 result — so it is tested in f64
+    // directly.  Extent = diagonal of the union box of the primitives that are in the tree.
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // global refs point at the END of their type's leaf-ordered arrays; recover radius / centre from the geometry words
+    for (const HostPrim& p : hs.prims) {
+      bool glob = false;
+      for (uint32_t k = 0; k < n_global && !glob; ++k) {
+        const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+        glob = type == p.type && s->bvh.info[type][2 * idx] == p.prim_id;
+      }
+      if (glob) continue;
+      for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.lo[a]); hi[a] = std::max(hi[a], p.hi[a]); }
+    }
+    double diag2 = 0;
+    for (int a = 0; a < 3; ++a) if (hi[a] > lo[a]) diag2 += (double)(hi[a] - lo[a]) * (hi[a] - lo[a]);
+    const double extent = std::sqrt(diag2);
+    for (uint32_t k = 0; k < n_global ; ++k) {
+      const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+      if (type != PT_SPHERE || extent <= 0) continue;
+      const float r = s->bvh.geom[PT_SPHERE][4 * idx + 3];
+      if ((double)r >= 16.0 * extent) s->bvh.global_f64 |= 1u << k;
+    }
+  }
+  {  // leaf-ordered exact records + the rounding scales of the f32 quad test
+    HostBvh& bvh = s->bvh;
+    std::vector<uint32_t> by_id(hs.n_prim_ids, RTB_NONE);
+    for (size_t i = 0; i < hs.prims.size(); ++i)
+      if (hs.prims[i].prim_id < by_id.size()) by_id[hs.prims[i].prim_id] = (uint32_t)i;
+    double pmax = 0.0, wmax = 0.0;
+    for (uint32_t t = 0; t < PT_COUNT; ++t) {
+      bvh.exact[t].clear();
+      if (t == PT_TRI) continue;
+      const size_t n = bvh.info[t].size() / 2;
+      bvh.exact[t].assign(n * RTB_EXACT_STRIDE, 0.0);
+      for (size_t k = 0; k < n; ++k) {
+        const uint32_t pid = bvh.info[t][2 * k];
+        const uint32_t pi = pid < by_id.size() ? by_id[pid] : RTB_NONE;
+        if (pi == RTB_NONE || hs.prims[pi].type != t || hs.prims[pi].exact >= hs.exact.size())
+          return set_err(RTB_ERR_INVALID, "primitive ids must be unique (exact record lookup failed)");
+        std::memcpy(&bvh.exact[t][k * RTB_EXACT_STRIDE], hs.exact[hs.prims[pi].exact].v, sizeof(ExactRec));
+      }
+    }
+    for (const HostPrim& p : hs.prims) {
+      if (p.type != PT_QUAD) continue;
+      for (int a = 0; a < 3; ++a) pmax = std::max(pmax, (double)std::max(std::fabs(p.lo[a]), std::fabs(p.hi[a])));
+      wmax = std::max(wmax, (double)(std::fabs(p.g[4]) + std::fabs(p.g[5]) + std::fabs(p.g[6]) + std::fabs(p.g[8]) +
+                                     std::fabs(p.g[9]) + std::fabs(p.g[10])));
+    }
+    bvh.coord_max = (float)(2.0 * pmax);
+    bvh.eps_ab = (float)(std::ldexp(1.0, -20) * wmax * pmax + 1e-7);
+  }
   s->built = true;
   return RTB_OK;
 }
@@ -430,31 +494,7 @@ int rtb_scene_commit(rtb_scene* s) {
   d.n_global = (uint32_t)s->bvh.global_refs.size();
   d.tree_empty = (d.n_global == (uint32_t)s->hs.prims.size()) ? 1u : 0u;
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
-  {
-    // a global sphere whose radius is >= 16 extents of everything else can only be hit at distances < r/16 from
-    // points ~r away from its centre — exactly where sphere_roots() rejects its f32 result — so it is tested in f64
-    // directly.  Extent = diagonal of the union box of the primitives that are in the tree.
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    // global refs point at the END of their type's leaf-ordered arrays; recover radius / centre from the geometry words
-    for (const HostPrim& p : hs.prims) {
-      bool glob = false;
-      for (uint32_t k = 0; k < d.n_global && !glob; ++k) {
-        const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
-        glob = type == p.type && s->bvh.info[type][2 * idx] == p.prim_id;
-      }
-      if (glob) continue;
-      for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p.lo[a]); hi[a] = std::max(hi[a], p.hi[a]); }
-    }
-    double diag2 = 0;
-    for (int a = 0; a < 3; ++a) if (hi[a] > lo[a]) diag2 += (double)(hi[a] - lo[a]) * (hi[a] - lo[a]);
-    const double extent = std::sqrt(diag2);
-    for (uint32_t k = 0; k < d.n_global && !d.tree_empty; ++k) {
-      const uint32_t ref = s->bvh.global_refs[k], type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
-      if (type != PT_SPHERE || extent <= 0) continue;
-      const float r = s->bvh.geom[PT_SPHERE][4 * idx + 3];
-      if ((double)r >= 16.0 * extent) d.global_f64 |= 1u << k;
-    }
-  }
+  d.global_f64 = d.tree_empty ? 0u : s->bvh.global_f64;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
@@ -464,7 +504,11 @@ int rtb_scene_commit(rtb_scene* s) {
     CU(cudaStreamSynchronize(0));  // `info` is a temporary
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
+    CU(s->d_exact[t].upload(s->bvh.exact[t].data(), s->bvh.exact[t].size()));
+    d.exact[t] = s->d_exact[t].p;
   }
+  d.coord_max = s->bvh.coord_max;
+  d.eps_ab = s->bvh.eps_ab;
   std::vector<float4> mats(hs.materials.size() * 2);
   for (size_t i = 0; i < hs.materials.size(); ++i) {
     uint32_t ty = hs.materials[i].type, tx = hs.materials[i].texture, tt = 0xFFu;
@@ -547,6 +591,7 @@ int rtb_scene_get_info(rtb_scene* s, rtb_scene_info* o) {
   o->bvh_bytes = (uint64_t)s->bvh.nodes.size() * sizeof(Node8);
   o->prim_bytes = 0;
   for (uint32_t t = 0; t < PT_COUNT; ++t) o->prim_bytes += s->bvh.geom[t].size() * 4 + s->bvh.info[t].size() * 4;
+  o->global_f64_mask = (s->bvh.global_refs.size() == s->hs.prims.size()) ? 0u : s->bvh.global_f64;
   return RTB_OK;
 }
 int rtb_scene_export_bvh(rtb_scene* s, void* nodes, size_t cap) {
@@ -565,6 +610,16 @@ int rtb_scene_export_globals(rtb_scene* s, uint32_t* refs, uint32_t cap, uint32_
     if (cap < *n_out) return set_err(RTB_ERR_INVALID, "buffer too small");
     for (uint32_t k = 0; k < *n_out; ++k) refs[k] = s->bvh.global_refs[k];
   }
+  return RTB_OK;
+}
+int rtb_scene_export_exact(rtb_scene* s, uint32_t type, double* out, size_t cap_bytes, float* coord_max, float* eps_ab) {
+  if (!s || type >= PT_COUNT) return set_err(RTB_ERR_INVALID, "bad argument");
+  if (!s->built) return set_err(RTB_ERR_STATE, "BVH not built (call rtb_scene_build_bvh or rtb_scene_commit)");
+  const size_t bytes = s->bvh.exact[type].size() * sizeof(double);
+  if (out && cap_bytes < bytes) return set_err(RTB_ERR_INVALID, "buffer too small");
+  if (out && bytes) std::memcpy(out, s->bvh.exact[type].data(), bytes);
+  if (coord_max) *coord_max = s->bvh.coord_max;
+  if (eps_ab) *eps_ab = s->bvh.eps_ab;
   return RTB_OK;
 }
 int rtb_scene_export_prims(rtb_scene* s, uint32_t type, float* geom, size_t gcap, uint32_t* info, size_t icap) {

@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+#include <cstring>
+
 #include "rtb_internal.hpp"
 
 namespace rtb {
@@ -50,6 +53,9 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
                         // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
+  const double* exact[PT_COUNT];  // reference-exact f64 records (RTB_EXACT_STRIDE doubles each; none for triangles)
+  float coord_max;                // 2 x the largest |coordinate| of the scene box: scale of the plane-test rounding bound
+  float eps_ab;                   // rounding bound of a quad's in-plane coordinates (alpha, beta), see intersect_prim
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
   const DevTexture* textures;
   const float4* perlin_vec[RTB_MAX_TABLES];
@@ -186,10 +192,24 @@ __device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint
 }
 
 // ---- closest-hit record -----------------------------------------------------------------------------------------
+// Parity contract (BASELINE.json: primary-ray primitive ids bit-exact against the f64 reference): every f32 primitive
+// test returns its hit distance WITH a bound on |t_f32 - t_ref| and knows whether each of its own decisions (inside /
+// outside, t against t_min) was certain under f32 rounding.  A candidate is accepted or rejected in f32 only when its
+// interval [t - e, t + e] does not overlap the current closest hit's; everything else — edge-grazing hits, two
+// surfaces meeting at the hit point, exact ties — is decided by exact_hit(): the reference's literal f64 arithmetic
+// (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176, same operation order, no FMA contraction) on the
+// constructor's own f64 arguments.  So on identical rays the device returns the id the f64 linear scan returns.
 struct Closest {
-  float t;        // current t_max (closest_so_far, hittable_list.rs:42)
+  float t;        // f32 distance of `ref` (closest_so_far, hittable_list.rs:42)
+  float hi;       // upper bound of ref's exact distance (t + error bound): the traversal's t_max
   uint32_t ref;   // type << 29 | leaf index
+  uint32_t ref2;  // second contender whose interval overlaps ref's (then [2t - hi, hi] is the union), or REF_MISS
 };
+#define RTB_U20 9.5367432e-7f   // 2^-20
+#define RTB_U21 4.7683716e-7f
+#define RTB_U22 2.3841858e-7f
+#define RTB_U23 1.1920929e-7f
+enum HitStatus : int { HIT_MISS = 0, HIT_CERTAIN = 1, HIT_AMBIGUOUS = 2 };
 
 // primitive id of a hit reference (list order of the reference's scene graph).  Needed only for the "later primitive
 // wins equal t" rule (hittable_list.rs:44-47) and by the parity probe, so it is fetched lazily: an accepted hit does
@@ -199,104 +219,313 @@ __device__ __forceinline__ uint32_t ref_gid(const DevScene& sc, uint32_t ref) {
   return type == PT_MEDIUM ? sc.media[idx].prim_id : __ldg(&sc.info[type][idx].x);
 }
 
-__device__ __forceinline__ void consider(const DevScene& sc, Closest& best, float t, uint32_t ref) {
-  if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
-  if (t < best.t) {
-    best.t = t; best.ref = ref;
-  } else if (t == best.t && (best.ref == REF_MISS || ref_gid(sc, ref) > ref_gid(sc, best.ref))) {
-    best.ref = ref;
-  }
+__device__ __forceinline__ float abs1(float3 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z); }
+
+// ---- the reference's f64 arithmetic, operation by operation (no contraction: Rust does not fuse) ------------------
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ uint32_t exact_bits(double v) { return (uint32_t)__double_as_longlong(v); }
+#else  // host build (tests/emul), compiled with -ffp-contract=off
+__host__ __device__ inline double dadd(double a, double b) { return a + b; }
+__host__ __device__ inline double dsub(double a, double b) { return a - b; }
+__host__ __device__ inline double dmul(double a, double b) { return a * b; }
+__host__ __device__ inline double ddiv(double a, double b) { return a / b; }
+__host__ __device__ inline double dsqrt(double a) { return sqrt(a); }
+__host__ __device__ inline uint32_t exact_bits(double v) { unsigned long long u; memcpy(&u, &v, 8); return (uint32_t)u; }
+#endif
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 d3sub(D3 a, D3 b) { return D3{dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)}; }
+__device__ __forceinline__ double d3dot(D3 a, D3 b) {  // vec3.rs:64-66: a.x*b.x + a.y*b.y + a.z*b.z
+  return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z));
+}
+__device__ __forceinline__ D3 d3cross(D3 u, D3 v) {    // vec3.rs:68-76
+  return D3{dsub(dmul(u.y, v.z), dmul(u.z, v.y)), -dsub(dmul(u.x, v.z), dmul(u.z, v.x)), dsub(dmul(u.x, v.y), dmul(u.y, v.x))};
+}
+__device__ __forceinline__ D3 d3at(D3 o, double t, D3 d) {  // ray.rs: origin + t * direction
+  return D3{dadd(o.x, dmul(t, d.x)), dadd(o.y, dmul(t, d.y)), dadd(o.z, dmul(t, d.z))};
 }
 
-// Sphere::hit, sphere.rs:41-65, literally, in f64: used only where the f32 form below is ill-conditioned
-// (grazing rays, or an origin much farther from the centre than from the hit — the r=1000 ground sphere).
-static __device__ __noinline__ bool sphere_roots_f64(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+// Sphere::hit root selection (sphere.rs:47-57) with t_max = +inf: the primitive's own first root >= t_min
+__device__ __forceinline__ bool exact_sphere(D3 o, D3 d, D3 c, double r, double tmin, double& t) {
+  const D3 oc = d3sub(o, c);
+  const double a = d3dot(d, d), half_b = d3dot(oc, d);
+  const double cc = dsub(d3dot(oc, oc), dmul(r, r));
+  const double det = dsub(dmul(half_b, half_b), dmul(a, cc));
+  if (det < 0.0) return false;
+  const double sqrtd = dsqrt(det);
+  double root = ddiv(dsub(-half_b, sqrtd), a);
+  if (root < tmin) {
+    root = ddiv(dadd(-half_b, sqrtd), a);
+    if (root < tmin) return false;
+  }
+  t = root;
+  return root < (double)INFINITY;
+}
+
+// The reference's own evaluation of primitive `ref` for the ray (o, d, time), t_min = 0.001 (main.rs:74), t_max = inf.
+static __device__ __noinline__ bool exact_hit(const DevScene& sc, uint32_t ref, float3 of, float3 df, float timef, double& t_out) {
+  const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+  const double tmin = 0.001;
+  D3 o{(double)of.x, (double)of.y, (double)of.z}, d{(double)df.x, (double)df.y, (double)df.z};
+  if (type == PT_TRI) {  // Moller-Trumbore on the f32 vertices (the oracle's Triangle::hit)
+    const float4 a4 = __ldg(sc.geom[PT_TRI] + 3 * idx), b4 = __ldg(sc.geom[PT_TRI] + 3 * idx + 1), c4 = __ldg(sc.geom[PT_TRI] + 3 * idx + 2);
+    const D3 v0{(double)a4.x, (double)a4.y, (double)a4.z};
+    const D3 e1 = d3sub(D3{(double)b4.x, (double)b4.y, (double)b4.z}, v0), e2 = d3sub(D3{(double)c4.x, (double)c4.y, (double)c4.z}, v0);
+    const D3 pv = d3cross(d, e2);
+    const double det = d3dot(e1, pv);
+    if (det == 0.0) return false;
+    const double inv = ddiv(1.0, det);
+    const D3 tv = d3sub(o, v0);
+    const double u = dmul(d3dot(tv, pv), inv);
+    if (u < 0.0 || u > 1.0) return false;
+    const D3 qv = d3cross(tv, e1);
+    const double v = dmul(d3dot(d, qv), inv);
+    if (v < 0.0 || dadd(u, v) > 1.0) return false;
+    const double t = dmul(d3dot(e2, qv), inv);
+    if (!(t >= tmin && t < (double)INFINITY)) return false;
+    t_out = t;
+    return true;
+  }
+  const double* e = sc.exact[type] + (size_t)idx * RTB_EXACT_STRIDE;
+  const uint32_t bits = exact_bits(e[0]);
+  if (bits & EX_TRANSLATE) o = d3sub(o, D3{e[1], e[2], e[3]});  // Translate::hit, hittable.rs:77
+  if (bits & EX_ROTATE) {                                       // RotateY::hit, hittable.rs:150-156
+    const double sn = e[4], cs = e[5];
+    const double ox = dsub(dmul(cs, o.x), dmul(sn, o.z)), oz = dadd(dmul(sn, o.x), dmul(cs, o.z));
+    const double dx = dsub(dmul(cs, d.x), dmul(sn, d.z)), dz = dadd(dmul(sn, d.x), dmul(cs, d.z));
+    o.x = ox; o.z = oz; d.x = dx; d.z = dz;
+  }
+  if (type == PT_SPHERE) return exact_sphere(o, d, D3{e[6], e[7], e[8]}, e[9], tmin, t_out);
+  if (type == PT_MOVING) {  // moving_sphere.rs:36-39: c0 + ((time - t0) / (t1 - t0)) * (c1 - c0)
+    const double s = ddiv(dsub((double)timef, e[12]), dsub(e[13], e[12]));
+    const D3 dc = d3sub(D3{e[9], e[10], e[11]}, D3{e[6], e[7], e[8]});
+    const D3 c{dadd(e[6], dmul(s, dc.x)), dadd(e[7], dmul(s, dc.y)), dadd(e[8], dmul(s, dc.z))};
+    return exact_sphere(o, d, c, e[14], tmin, t_out);
+  }
+  const uint32_t sub = (bits >> 8) & 0xFFu;
+  if (sub < 3u) {  // XyRect / XzRect / YzRect::hit, aarect.rs:31-48,81-98,150-167
+    const double oa[3] = {o.x, o.y, o.z}, da[3] = {d.x, d.y, d.z};
+    const uint32_t ia = sub == 0u ? 1u : 0u, ib = sub == 2u ? 1u : 2u;
+    const double t = ddiv(dsub(e[6], oa[sub]), da[sub]);
+    if (!(t >= tmin && t < (double)INFINITY)) return false;
+    const double a = dadd(oa[ia], dmul(t, da[ia])), b = dadd(oa[ib], dmul(t, da[ib]));
+    if (a < e[7] || a > e[8] || b < e[9] || b > e[10]) return false;
+    t_out = t;
+    return true;
+  }
+  // general quad(Q, u, v) (the oracle's Quad::hit)
+  const D3 Q{e[6], e[7], e[8]}, u{e[9], e[10], e[11]}, v{e[12], e[13], e[14]};
+  const D3 n = d3cross(u, v);
+  const double nn = d3dot(n, n), denom = d3dot(n, d);
+  if (denom == 0.0) return false;
+  const double t = ddiv(d3dot(n, d3sub(Q, o)), denom);
+  if (!(t >= tmin && t < (double)INFINITY)) return false;
+  const D3 pl = d3sub(d3at(o, t, d), Q);
+  const double alpha = ddiv(d3dot(n, d3cross(pl, v)), nn), beta = ddiv(d3dot(n, d3cross(u, pl)), nn);
+  if (alpha < 0.0 || alpha > 1.0 || beta < 0.0 || beta > 1.0) return false;
+  t_out = t;
+  return true;
+}
+
+#ifdef RTB_EMUL_STATS
+static unsigned long long g_exact_calls[8];
+#endif
+// Two contenders whose intervals overlap: decided exactly; equal t goes to the larger primitive id
+// (hittable_list.rs:44-47).  Both were certain hits (or exact hits) when they were recorded.
+static __device__ __noinline__ void resolve_pair(const DevScene& sc, float3 o, float3 d, float time, Closest& best) {
+#ifdef RTB_EMUL_STATS
+  ++g_exact_calls[4];
+#endif
+  double ta = 0.0, tb = 0.0;
+  const bool ha = exact_hit(sc, best.ref, o, d, time, ta), hb = exact_hit(sc, best.ref2, o, d, time, tb);
+  if (ha || hb) {
+    const bool second = hb && (!ha || tb < ta || (tb == ta && ref_gid(sc, best.ref2) > ref_gid(sc, best.ref)));
+    const float tf = (float)(second ? tb : ta);
+    best.t = tf;
+    best.hi = tf * (1.0f + RTB_U22);
+    if (second) best.ref = best.ref2;
+  }
+  best.ref2 = REF_MISS;
+}
+
+// closest-hit update with a certain hit at t, |t - t_exact| <= e.  Accept / reject in f32 when the intervals are
+// disjoint; an overlapping candidate becomes the second contender (the pair is decided exactly at the end of the
+// traversal, or as soon as a third one overlaps — most overlaps are superseded by a closer hit before that).
+__device__ __forceinline__ void consider(const DevScene& sc, float3 o, float3 d, float time, Closest& best, float t, float e, uint32_t ref) {
+  if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
+  const float hi = t + e, lo = t - e;
+  if (best.ref == REF_MISS || hi < best.t - (best.hi - best.t)) {
+    best.t = t; best.hi = hi; best.ref = ref; best.ref2 = REF_MISS;
+    return;
+  }
+  if (lo > best.hi) return;
+  if (best.ref2 != REF_MISS) {  // third contender: settle the pending pair first
+    resolve_pair(sc, o, d, time, best);
+    if (hi < best.t - (best.hi - best.t)) { best.t = t; best.hi = hi; best.ref = ref; return; }
+    if (lo > best.hi) return;
+  }
+  const float L = fminf(lo, best.t - (best.hi - best.t)), H = fmaxf(hi, best.hi);
+  best.t = 0.5f * (L + H);
+  best.hi = H;
+  best.ref2 = ref;
+}
+
+// a candidate whose own f32 test was ambiguous (edge-grazing, t next to t_min, ill-conditioned sphere): evaluated
+// exactly, then treated as a certain hit known to 1 ulp
+static __device__ __noinline__ void consider_exact(const DevScene& sc, float3 o, float3 d, float time, Closest& best, uint32_t ref) {
+#ifdef RTB_EMUL_STATS
+  ++g_exact_calls[ref >> REF_TYPE_SHIFT];
+#endif
+  double tc;
+  if (!exact_hit(sc, ref, o, d, time, tc)) return;
+  const float tf = (float)tc;
+  consider(sc, o, d, time, best, tf, RTB_U22 * tf, ref);
+}
+
+// end of a traversal: a still-pending pair is decided now
+__device__ __forceinline__ void settle(const DevScene& sc, float3 o, float3 d, float time, Closest& best) {
+  if (best.ref2 != REF_MISS) resolve_pair(sc, o, d, time, best);
+}
+
+// t against t_min = 0.001 (main.rs:74): certain unless within the error bound AND within a quarter of t_min (the
+// self-intersection of a bounce ray sits at |t| ~ 1e-5, far below the band; the band keeps the slow path off it)
+__device__ __forceinline__ int tmin_status(float t, float e, float tmin) {
+  const float band = fminf(e, 0.25f * tmin);
+  return t > tmin + band ? HIT_CERTAIN : (t < tmin - band ? HIT_MISS : HIT_AMBIGUOUS);
+}
+
+// Sphere::hit, sphere.rs:41-65, in f64 with MUFU-seeded Newton sqrt / reciprocal (~1e-14 relative): used for the
+// "global" sphere whose f32 test can never be trusted (book 1's r = 1000 ground sphere is hit at distances << r from
+// points ~r from its centre).  Its own decisions are certain unless within 1e-12 of the threshold.
+static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c, float r, float tmin, float& t_out) {
   const double ox = (double)o.x - (double)c.x, oy = (double)o.y - (double)c.y, oz = (double)o.z - (double)c.z;
   const double dx = d.x, dy = d.y, dz = d.z;
   const double a = dx * dx + dy * dy + dz * dz;
   const double hb = ox * dx + oy * dy + oz * dz;
-  const double cc = ox * ox + oy * oy + oz * oz - (double)r * (double)r;
+  const double oo = ox * ox + oy * oy + oz * oz, rr = (double)r * (double)r;
+  const double cc = oo - rr;
   const double det = hb * hb - a * cc;
-  if (det < 0.0) return false;
+  if (fabs(det) <= 1e-12 * (hb * hb + a * (oo + rr))) return HIT_AMBIGUOUS;
+  if (det < 0.0) return HIT_MISS;
 #ifdef __CUDA_ARCH__
   // sqrt(det) and 1/a to ~1e-14 relative: f32 MUFU seed + one Newton step in f64 (the result is rounded to f32)
-  double sq = 0.0;
-  if (det > 0.0) {
-    const double y = (double)rsqrtf((float)det);
-    sq = det * y;
-    sq = fma(0.5 * y, fma(-sq, sq, det), sq);
-  }
+  const double y = (double)rsqrtf((float)det);
+  double sq = det * y;
+  sq = fma(0.5 * y, fma(-sq, sq, det), sq);
   double inv_a = (double)rcp_fast((float)a);
   inv_a = inv_a * fma(-a, inv_a, 2.0);
 #else
   const double sq = sqrt(det);
   const double inv_a = 1.0 / a;
 #endif
+  const double band = 1e-12 * (fabs(hb) + sq) * inv_a;
   double root = (-hb - sq) * inv_a;
-  if (root < (double)tmin || (double)tmax < root) {
+  if (fabs(root - (double)tmin) <= band + 1e-10) return HIT_AMBIGUOUS;
+  if (root < (double)tmin) {
     root = (-hb + sq) * inv_a;
-    if (root < (double)tmin || (double)tmax < root) return false;
+    if (fabs(root - (double)tmin) <= band + 1e-10) return HIT_AMBIGUOUS;
+    if (root < (double)tmin) return HIT_MISS;
   }
   t_out = (float)root;
-  return true;
+  return HIT_CERTAIN;
 }
 
 // Sphere::hit in f32, in the cancellation-free form  disc' = r^2 - |oc - (oc.d/a) d|^2  (= det/a): the reference's
-// c = |oc|^2 - r^2 loses all bits in f32 for large spheres.  Falls back to f64 when the sign of disc' or the root
-// cannot be trusted to ~1e-6.
-__device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+// c = |oc|^2 - r^2 loses all bits in f32 for large spheres.  Error model (position space): every intermediate carries
+// at most epos = 2^-21 (|oc|_1 + r) + cerr (cerr: the f32 rounding of the stored centre / radius against the f64
+// constructor arguments); half-chord h = sqrt(disc'); a root moves by <= epos/|d| (1 + 2r/h) — the 1/h term is the
+// grazing amplification.  HIT_AMBIGUOUS when a decision (disc' sign, root against t_min) is inside its bound or when
+// the bound exceeds RTB_SPHERE_REL_MAX t (the reported t must hold 1e-5 relative).
+#define RTB_SPHERE_REL_MAX 5.0e-5f
+__device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out) {
   const float3 oc = o - c;
   const float a = dot(d, d);
   const float hb = dot(oc, d);
-  const float oo = dot(oc, oc);
   const float inv_a = rcp_fast(a);
   const float3 l = fma3(-hb * inv_a, d, oc);
   const float disc = fmaf(r, r, -dot(l, l));
-  bool need64 = disc * disc < 1e-9f * r * r * oo;  // |disc| within ~3e-5 r|oc| of zero: grazing
-  if (!need64) {
-    if (disc < 0.0f) return false;
-    const float sq = sqrt_fast(a * disc);
-    float root = (-hb - sq) * inv_a;
-    if (root < tmin || tmax < root) {
-      root = (-hb + sq) * inv_a;
-      if (root < tmin || tmax < root) return false;
-    }
-    // f32 is accurate to ~1e-6 relative when the origin-to-centre distance is <= 16 hit distances and the rounding of
-    // disc' (~4e-7 r|oc|) moves the root by < 1e-6 t:  dt = d(disc')/(2 sqrt(a disc'))
-    const float tta = root * root * a;
-    if (oo <= 256.0f * tta && r * r * oo <= 25.0f * tta * disc) {
-      t_out = root;
-      return true;
-    }
+  const float epos = fmaf(RTB_U21, abs1(oc) + fabsf(r), RTB_U23 * (abs1(c) + fabsf(r)));
+  const float edisc = 4.0f * fabsf(r) * epos;
+  if (disc < -edisc) return HIT_MISS;
+  if (disc <= edisc) return HIT_AMBIGUOUS;
+#ifdef __CUDA_ARCH__
+  const float inv_d = rsqrtf(a), rh = rsqrtf(disc);
+#else
+  const float inv_d = 1.0f / sqrtf(a), rh = 1.0f / sqrtf(disc);
+#endif
+  const float sq = (disc * rh) * (a * inv_d);  // sqrt(a disc')
+  const float ebase = epos * inv_d * fmaf(2.0f * fabsf(r), rh, 1.0f);
+  float root = (-hb - sq) * inv_a;
+  float e = fmaf(RTB_U21, fabsf(root), ebase);
+  int st = tmin_status(root, e, tmin);
+  if (st == HIT_MISS) {
+    root = (-hb + sq) * inv_a;
+    e = fmaf(RTB_U21, fabsf(root), ebase);
+    st = tmin_status(root, e, tmin);
+    if (st == HIT_MISS) return HIT_MISS;
   }
-  return sphere_roots_f64(o, d, c, r, tmin, tmax, t_out);
+  if (root - e > tmax_hi) return HIT_MISS;
+  if (st == HIT_AMBIGUOUS || e > RTB_SPHERE_REL_MAX * root) return HIT_AMBIGUOUS;
+  t_out = root; e_out = e;
+  return HIT_CERTAIN;
+}
+
+// shade-side sphere root (light pdf, sphere.rs:75-84): f32, f64 only when grazing; no closest-hit decision hangs on it
+__device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
+  float t, e;
+  int st = sphere_fast(o, d, c, r, tmin, tmax, t, e);
+  if (st == HIT_AMBIGUOUS) st = sphere_roots_f64(o, d, c, r, tmin, t);
+  if (st == HIT_MISS || (st == HIT_CERTAIN && t > tmax)) return false;
+  if (st == HIT_AMBIGUOUS) return false;  // within 1e-12 of tangency / t_min: measure zero for a pdf
+  t_out = t;
+  return true;
 }
 
 template <bool COUNT>
 __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
                                                float time, float tmin, Closest& best, uint32_t& n_tests) {
   if (COUNT) ++n_tests;
-  float t;
+  const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
+  float t, e;
   if (type == PT_SPHERE) {
-    float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
-    if (!sphere_roots(o, d, xyz(s), s.w, tmin, best.t, t)) return;
+    const float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
+    const int st = sphere_fast(o, d, xyz(s), s.w, tmin, best.hi, t, e);
+    if (st == HIT_MISS) return;
+    if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
   } else if (type == PT_QUAD) {
-    // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square
-    float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
-    float denom = dot(xyz(w0), d);
-    t = (w0.w - dot(xyz(w0), o)) * rcp_fast(denom);
-    if (!(t >= tmin && t <= best.t)) return;
-    float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
-    float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
-    float3 p = fma3(t, d, o);
-    float alpha = dot(xyz(w1), p) - w1.w;
-    float beta = dot(xyz(w2), p) - w2.w;
-    if (alpha < 0.0f || alpha > 1.0f || beta < 0.0f || beta > 1.0f) return;
+    // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square.
+    // Numerator error <= 2^-22 (|o|_1 + coord_max) (three FMAs on |n_i| <= 1, the stored n.Q); denominator error <=
+    // 2^-22 |d|_1; alpha / beta inherit t's error through wa.d, wb.d plus eps_ab (rounding of p and of the plane words).
+    const float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
+    const float nd = dot(xyz(w0), d);
+    const float inv = rcp_fast(nd);
+    t = (w0.w - dot(xyz(w0), o)) * inv;
+    e = fmaf(fabsf(inv), fmaf(RTB_U22 * abs1(d), fabsf(t), RTB_U22 * (abs1(o) + sc.coord_max)), RTB_U21 * fabsf(t));
+    if (!(t - e <= best.hi)) return;  // also rejects NaN
+    int st = tmin_status(t, e, tmin);
+    if (st == HIT_MISS) return;
+    const float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
+    const float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
+    const float3 p = fma3(t, d, o);
+    const float alpha = dot(xyz(w1), p) - w1.w;
+    const float beta = dot(xyz(w2), p) - w2.w;
+    const float ea = fmaf(e, fabsf(dot(xyz(w1), d)), fmaf(RTB_U20, fabsf(alpha), sc.eps_ab));
+    const float eb = fmaf(e, fabsf(dot(xyz(w2), d)), fmaf(RTB_U20, fabsf(beta), sc.eps_ab));
+    const float ma = fminf(alpha, 1.0f - alpha), mb = fminf(beta, 1.0f - beta);
+    if (ma < -ea || mb < -eb) return;
+    if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { consider_exact(sc, o, d, time, best, ref); return; }
   } else if (type == PT_TRI) {
     // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
     // Watertight edge functions (Woop, Benthin, Wald 2013): vertices are translated to the ray origin and sheared so
     // the ray runs along +z; the edge function of a shared edge is computed from the SAME two translated vertices by
     // both triangles (exact negatives, no FMA contraction), so f32 rounding can never open a crack in a mesh.
+    // An edge function within its rounding bound of zero (the ray passes within ~1e-6 of an edge or vertex) sends the
+    // triangle to the exact f64 test, so on a shared edge BOTH neighbours are decided — and tie-broken — as the
+    // reference decides them.
     const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx));
     const float3 v1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1));
     const float3 v2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
@@ -305,6 +534,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     // (kx, ky, kz) cyclic; swapped when d[kz] < 0 to keep the winding
     float3 dp = kz == 0 ? f3(d.y, d.z, d.x) : (kz == 1 ? f3(d.z, d.x, d.y) : d);
     float3 A = v0 - o, B = v1 - o, C = v2 - o;
+    const float amax = fmaxf(fmaxf(abs1(A), abs1(B)), abs1(C));
     A = kz == 0 ? f3(A.y, A.z, A.x) : (kz == 1 ? f3(A.z, A.x, A.y) : A);
     B = kz == 0 ? f3(B.y, B.z, B.x) : (kz == 1 ? f3(B.z, B.x, B.y) : B);
     C = kz == 0 ? f3(C.y, C.z, C.x) : (kz == 1 ? f3(C.z, C.x, C.y) : C);
@@ -319,26 +549,39 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float Ax = __fsub_rn(A.x, __fmul_rn(Sx, A.z)), Ay = __fsub_rn(A.y, __fmul_rn(Sy, A.z));
     const float Bx = __fsub_rn(B.x, __fmul_rn(Sx, B.z)), By = __fsub_rn(B.y, __fmul_rn(Sy, B.z));
     const float Cx = __fsub_rn(C.x, __fmul_rn(Sx, C.z)), Cy = __fsub_rn(C.y, __fmul_rn(Sy, C.z));
-    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
-    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
-    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
-    if (U == 0.0f || V == 0.0f || W == 0.0f) {  // exactly on an edge in f32: decide in f64 (products are exact there)
-      U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-      V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-      W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
-    }
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return;
+    const float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    const float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    const float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    // a sheared coordinate is off by <= 2^-22 amax (translate + shear roundings, 1 ulp of 1/d_z included), so an edge
+    // function by <= m
+    const float m = (RTB_U21 * amax) * (fabsf(Ax) + fabsf(Ay) + fabsf(Bx) + fabsf(By) + fabsf(Cx) + fabsf(Cy));
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (mn < -m && mx > m) return;  // certainly outside
     const float det = U + V + W;
-    if (det == 0.0f) return;
-    t = (U * (Sz * A.z) + V * (Sz * B.z) + W * (Sz * C.z)) * rcp_fast(det);
-    if (!(t >= tmin && t <= best.t)) return;
+    const float idet = rcp_fast(det), za = Sz * A.z, zb = Sz * B.z, zc = Sz * C.z;
+    t = (U * za + V * zb + W * zc) * idet;
+    // t is the (U, V, W)-weighted mean of the vertex depths: the weights' error m/|det| moves it by at most the depth
+    // spread of the triangle
+    e = fmaf(RTB_U20, fabsf(t), 4.0f * m * fabsf(idet) * (fmaxf(fmaxf(za, zb), zc) - fminf(fminf(za, zb), zc)));
+    const bool inside_certain = mn > m || mx < -m;
+    if (inside_certain) {
+      if (!(t - e <= best.hi)) return;
+      const int st = tmin_status(t, e, tmin);
+      if (st == HIT_MISS) return;
+      if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
+    } else {
+      consider_exact(sc, o, d, time, best, ref);  // on an edge / vertex / degenerate: t itself may be meaningless
+      return;
+    }
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
-    float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
-    float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
-    float3 c = fma3(time, xyz(b), xyz(a));
-    if (!sphere_roots(o, d, c, a.w, tmin, best.t, t)) return;
+    const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
+    const float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
+    const float3 c = fma3(time, xyz(b), xyz(a));
+    const int st = sphere_fast(o, d, c, a.w, tmin, best.hi, t, e);
+    if (st == HIT_MISS) return;
+    if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
   }
-  consider(sc, best, t, (type << REF_TYPE_SHIFT) | idx);
+  consider(sc, o, d, time, best, t, e, ref);
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
@@ -373,7 +616,7 @@ __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float ti
   tv.octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
   tv.sp = 0;
-  tv.best = Closest{INFINITY, REF_MISS};
+  tv.best = Closest{INFINITY, INFINITY, REF_MISS, REF_MISS};
 }
 
 // 128-bit load from the shared-memory node stage.  On the device the stage is addressed through a 32-bit shared-space
@@ -443,7 +686,8 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   // 6.4 (2 FMNMX, 2 FMNMX3, FSETP, SEL, IADD3/3) — the node test is ALU-pipe bound (profiles/r1d_c1_ncu_summary.md).
   uint32_t missmask = 0;
   const uint32_t magic = sc.prmt_magic;  // 0x43000000, read from the constant bank (ptxas cannot fold it into the PRMT)
-  const float tmax = tv.best.t;
+  const float tmax = tv.best.hi;  // upper bound of the closest hit's exact distance: a subtree is culled only if it
+                                  // cannot hold a hit at or before it (equal t must still reach the id tie-break)
 #pragma unroll
   for (int i = 7; i >= 0; --i) {
     const uint32_t sel = 0x7044u | ((uint32_t)(i & 3) << 8);
@@ -489,7 +733,9 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
       if (COUNT) ++n_tests;
       const float4 s = __ldg(sc.geom[PT_SPHERE] + (ref & REF_INDEX_MASK));
       float t;
-      if (sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, tv.best.t, t)) consider(sc, tv.best, t, ref);
+      const int st = sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, t);
+      if (st == HIT_CERTAIN) consider(sc, tv.o, tv.d, tv.time, tv.best, t, RTB_U22 * t, ref);
+      else if (st == HIT_AMBIGUOUS) consider_exact(sc, tv.o, tv.d, tv.time, tv.best, ref);
     } else {
       intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
     }
@@ -507,6 +753,7 @@ __device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __rest
   tv.best = best;
   trav_globals<COUNT>(sc, tv, tmin, n_tests);
   while (trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
+  settle(sc, o, d, time, tv.best);
   best = tv.best;
 }
 
@@ -561,7 +808,10 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
     float hd = md.neg_inv_density * log_fast(xi);
     if (hd > inside) continue;
     float t = t1 + hd * rcp_fast(len);
-    consider(sc, best, t, ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m);
+    // a sampled (continuous) distance: accepted iff closer than the closest surface / earlier medium, no tie rule needed
+    if (t < INFINITY && (best.ref == REF_MISS || t < best.t)) {
+      best.t = t; best.hi = t; best.ref = ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m; best.ref2 = REF_MISS;
+    }
   }
 }
 

@@ -28,7 +28,19 @@ struct HostPrim {      // one flattened primitive, any type
   uint32_t face_mode;  // FaceMode
   float g[12];         // device geometry words: sphere (c,r); moving (A,r)(B,0); quad plane form; triangle v0,v1,v2
   float lo[3], hi[3];  // bounds (padded)
+  uint32_t exact;      // index into HostScene::exact (RTB_NONE for triangles: their f32 vertices ARE the exact record)
 };
+
+// Reference-exact record of one sphere / moving sphere / quad: the constructor's own f64 arguments in OBJECT space plus
+// the wrapper chain the reference evaluates per ray (Translate outside RotateY, hittable.rs:76-85,147-176).  The device
+// falls back to the reference's literal f64 arithmetic on these whenever an f32 decision is within its rounding bound
+// (exact_hit, rtb_device.cuh), so closest-hit ids equal the f64 linear scan's on identical rays.
+// Layout (16 doubles): [0] bits: xform flags | subtype << 8 ; [1..3] Translate offset ; [4] sin ; [5] cos ;
+//   sphere [6..8] c [9] r ; moving [6..8] c0 [9..11] c1 [12] t0 [13] t1 [14] r ;
+//   rect (subtype = normal axis 0..2) [6] k [7] a0 [8] a1 [9] b0 [10] b1 ; general quad (subtype 3) [6..8] Q [9..11] u [12..14] v
+#define RTB_EXACT_STRIDE 16
+enum ExactFlags : uint32_t { EX_TRANSLATE = 1u, EX_ROTATE = 2u, EX_QUAD_GENERAL = 3u };
+struct ExactRec { double v[RTB_EXACT_STRIDE]; };
 
 struct HostMedium {
   uint32_t boundary_type, material, prim_id;
@@ -60,6 +72,11 @@ struct HostBvh {
   std::vector<uint32_t> info[PT_COUNT];
   uint32_t max_depth = 0;
   std::vector<uint32_t> global_refs;  // type << 29 | leaf index of the primitives tested before the traversal
+  // leaf-ordered reference-exact records (RTB_EXACT_STRIDE doubles per sphere / moving sphere / quad) and the scene's
+  // rounding scales of the f32 quad test (rtb_device.cuh: DevScene::coord_max, eps_ab)
+  std::vector<double> exact[PT_COUNT];
+  float coord_max = 0.f, eps_ab = 0.f;
+  uint32_t global_f64 = 0;  // bit k: global k is a sphere tested in f64 directly (DevScene::global_f64)
 };
 
 static inline uint32_t geom_words(uint32_t type) { return type == PT_SPHERE ? 4u : (type == PT_MOVING ? 8u : 12u); }
@@ -76,12 +93,16 @@ struct HostScene {
   std::vector<Perlin> perlins;
   struct Mesh { std::vector<float> verts; std::vector<uint32_t> idx; };
   std::vector<Mesh> meshes;
+  std::vector<ExactRec> exact;
   uint32_t n_prim_ids = 0;
 };
 
 // flatten.cpp
 int flatten_graph(HostScene& hs, const rtb_node* nodes, uint32_t n_nodes, const uint32_t* child_index,
                   uint32_t n_child_index, uint32_t root, std::string& err);
+// wrapper chain of a primitive as the reference evaluates it: [Translate(offset)] outside [RotateY(sin, cos)]
+struct ExactXform { uint32_t flags = 0; double off[3] = {0, 0, 0}; double sin_t = 0, cos_t = 1; };
+uint32_t add_exact(HostScene& hs, const ExactXform& x, uint32_t subtype, const double* params, int n_params);
 void pack_sphere(HostPrim& p, const double c[3], double r);
 void pack_moving(HostPrim& p, const double c0[3], const double c1[3], double t0, double t1, double r);
 void pack_quad(HostPrim& p, const double Q[3], const double u[3], const double v[3], const double* outward_or_null);

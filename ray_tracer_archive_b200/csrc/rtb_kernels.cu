@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint3
 // 256-thread shade CTA of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476, 80: 4497, 88: 4326,
 // 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
-struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, -) after the global primitives
+struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, t upper bound) after the global primitives
 struct ExtOut { float t; uint32_t ref, slot, _pad; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
@@ -160,7 +160,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         o = xyz(pool.ray[2 * h.slot]);
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
-      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.ref});
+      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref, REF_MISS});
     }
     out_count = 0;
     __syncwarp();
@@ -197,11 +197,12 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           Trav t0;
           trav_init(t0, xyz(ro), xyz(rd), ro.w);
           trav_globals<COUNT>(sc, t0, RTB_TMIN, nt);
+          settle(sc, t0.o, t0.d, t0.time, t0.best);  // the hand-over record carries one contender
           ExtIn& e = in[lane];
           e.o_time = ro;
           e.d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
           e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
-          e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.grp.y), 0.f);
+          e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.grp.y), t0.best.hi);
         }
         __syncwarp();
       }
@@ -217,7 +218,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.octinv = __float_as_uint(r.idir_oct.w);
           tv.grp = make_uint2(0u, __float_as_uint(r.best.z));
           tv.sp = 0;
-          tv.best = Closest{r.best.x, __float_as_uint(r.best.y)};
+          tv.best = Closest{r.best.x, r.best.w, __float_as_uint(r.best.y), REF_MISS};
         }
         idle &= ~__ballot_sync(0xffffffffu, take);
         in_head += min(n_idle, avail);
@@ -235,6 +236,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
+      if (finished) settle(sc, tv.o, tv.d, tv.time, tv.best);
       if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, 0u};
       out_count += __popc(done);
       idle |= done;
@@ -278,7 +280,7 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const uint32_t slot = base + list[r + lane];
         const float4 ro = pool.ray[2 * slot];
         const float4 rd = pool.ray[2 * slot + 1];
-        Closest best{INFINITY, REF_MISS};
+        Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
         traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
         finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
       }
@@ -809,7 +811,7 @@ k_probe(DevScene sc, const float* __restrict__ org, const float* __restrict__ di
   if (i >= n) return;
   const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
   const float tm = time ? time[i] : 0.f;
-  Closest best{INFINITY, REF_MISS};
+  Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
   uint32_t nv = 0, nt = 0;
   traverse<true>(sc, snodes, sbase, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
   if (sc.n_media) intersect_media(sc, o, d, RTB_TMIN, best, 0, 0, 0, 0, false);

@@ -111,6 +111,19 @@ class Scene:
             prims.append((g, inf))
         return nodes, prims
 
+    def export_exact(self):
+        """([records of spheres, moving spheres, quads] as float64 arrays of 16 per primitive, coord_max, eps_ab)"""
+        info = self.info()
+        counts = [info["n_spheres"], info["n_moving"], info["n_quads"]]
+        cm, ea = C.c_float(), C.c_float()
+        out = []
+        for t in range(3):
+            a = np.zeros(counts[t] * 16, dtype=np.float64)
+            F.check(self.lib.rtb_scene_export_exact(self.h, t, F.ptr(a) if counts[t] else None, a.nbytes, C.byref(cm),
+                                                    C.byref(ea)))
+            out.append(a)
+        return out, cm.value, ea.value
+
     def export_globals(self):
         """refs (type << 29 | index) of the primitives that are tested for every ray instead of living in the tree"""
         refs = np.zeros(64, dtype=np.uint32)

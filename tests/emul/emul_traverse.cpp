@@ -12,6 +12,8 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+#undef __host__
+#define __host__
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
@@ -30,13 +32,15 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 #undef __forceinline__
 #define __forceinline__ inline
 
+#define RTB_EMUL_STATS 1
 #include "../../ray_tracer_archive_b200/csrc/rtb_device.cuh"
 
 using namespace rtb;
 
 extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
                           const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
-                          const float* geom3, const uint32_t* info3, const uint32_t* globals, uint32_t n_globals,
+                          const float* geom3, const uint32_t* info3, const double* exact0, const double* exact1,
+                          const double* exact2, float coord_max, float eps_ab, uint32_t global_f64, const uint32_t* globals, uint32_t n_globals,
                           uint32_t tree_empty, uint32_t n_snodes, const float* org,
                           const float* dir, const float* time, uint32_t n, uint32_t* ids, float* ts,
                           uint64_t* nodes_visited, uint64_t* prims_tested) {
@@ -51,9 +55,11 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   const float* g[4] = {geom0, geom1, geom2, geom3};
   const uint32_t* inf[4] = {info0, info1, info2, info3};
   for (int t = 0; t < 4; ++t) { sc.geom[t] = (const float4*)g[t]; sc.info[t] = (const uint2*)inf[t]; }
+  sc.exact[0] = exact0; sc.exact[1] = exact1; sc.exact[2] = exact2; sc.exact[3] = nullptr;
+  sc.coord_max = coord_max; sc.eps_ab = eps_ab; sc.global_f64 = global_f64;
   uint64_t nv_total = 0, nt_total = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    Closest best{INFINITY, REF_MISS};
+    Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
     uint32_t nv = 0, nt = 0;
     traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
                    f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
@@ -64,6 +70,11 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   if (nodes_visited) *nodes_visited = nv_total;
   if (prims_tested) *prims_tested = nt_total;
   return 0;
+}
+
+// exact-path call counts per primitive type since the last call (sphere, moving, quad, triangle) + pair resolutions
+extern "C" void emul_exact_calls(unsigned long long* out4) {
+  for (int i = 0; i < 5; ++i) { out4[i] = rtb::g_exact_calls[i]; rtb::g_exact_calls[i] = 0; }
 }
 
 // path numbering of the slot-stable pool (rtb_device.cuh: chunk_path), exposed for tests/test_pool_numbering.py

@@ -42,11 +42,12 @@ def build_emul():
     csrc = os.path.join(ROOT, "ray_tracer_archive_b200", "csrc")
     deps = [src, os.path.join(ROOT, "include", "rtb200.h")] + [os.path.join(csrc, f) for f in ("rtb_device.cuh", "rtb_internal.hpp")]
     if not os.path.exists(out) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(out):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-attributes", "-D__noinline__=",
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-attributes", "-D__noinline__=",
                                "-I/usr/local/cuda/include", "-o", out, src])
     lib = C.CDLL(out)
     VP = C.c_void_p
-    lib.emul_trace.argtypes = [VP, C.c_uint32] + [VP] * 8 + [VP, C.c_uint32, C.c_uint32, C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP]
+    lib.emul_trace.argtypes = ([VP, C.c_uint32] + [VP] * 8 + [VP] * 3 + [C.c_float, C.c_float, C.c_uint32] +
+                               [VP, C.c_uint32, C.c_uint32, C.c_uint32, VP, VP, VP, C.c_uint32, VP, VP, VP, VP])
     return lib
 
 
@@ -67,6 +68,8 @@ def emul_trace(lib, host_scene, origin, direction, time=None, n_snodes=10 ** 6):
     args = [_p(nodes), info["n_bvh_nodes"]]
     for g, inf in prims:
         args += [_p(g), _p(inf)]
+    exact, coord_max, eps_ab = host_scene.export_exact()
+    args += [_p(x) for x in exact] + [coord_max, eps_ab, info["global_f64_mask"]]
     glob = host_scene.export_globals()
     args += [_p(glob), len(glob), 1 if len(glob) == info["n_spheres"] + info["n_moving"] + info["n_quads"] + info["n_triangles"] else 0]
     lib.emul_trace(*args, n_snodes, _p(o), _p(d), _p(tm), n, _p(ids), _p(ts), C.byref(nv), C.byref(nt))

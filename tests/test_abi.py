@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported_and_bound(rtb):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in rtb200.h but not exported by librtb200.so"
         assert n in rtb._ffi.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.rtb_abi_version() == 1
+    assert lib.rtb_abi_version() == 2
 
 
 def test_struct_layouts_match_header(rtb):

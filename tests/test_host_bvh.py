@@ -42,8 +42,9 @@ def test_emulated_device_traversal_matches_oracle(rtb, orc, emul, name, cfg, W, 
     else:
         surf = np.ones(len(oid), bool)
     mism = (ids != oid) & surf
-    # knife-edge rays (exact shared edges / symmetric corner lines) may differ; they must be very rare
-    assert mism.sum() <= max(2, 2e-3 * len(oid)), f"{mism.sum()} mismatches of {len(oid)}"
+    # identical rays -> identical ids, knife-edge rays included (exact shared edges, the Cornell box's symmetric corner
+    # line): every decision f32 rounding leaves open is re-made with the reference's own f64 arithmetic (exact_hit)
+    assert mism.sum() == 0, f"{mism.sum()} mismatches of {len(oid)}"
     ok = surf & ~mism & (oid != H.NONE)
     rel = np.abs(ts[ok] - ot[ok]) / ot[ok]
     assert np.quantile(rel, 0.999) < 1e-5 and rel.max() < 2e-4
