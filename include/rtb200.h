@@ -167,6 +167,7 @@ typedef struct rtb_stats {
   double ms_extend;        /* summed device time of the extend launches (RTB_RENDER_TIME_EXTEND, else 0) */
   uint64_t nodes_visited;  /* BVH nodes fetched / primitives tested by extend (RTB_RENDER_COUNT or the probes, else 0) */
   uint64_t prims_tested;
+  uint64_t exact_rays;     /* rays whose closest hit f32 rounding left open and that were re-traced with the reference's f64 arithmetic */
 } rtb_stats;
 
 typedef struct rtb_context rtb_context;
@@ -258,6 +259,35 @@ int rtb_primary_hits(rtb_context* ctx, rtb_scene* scene, const rtb_camera* cam, 
 /* closest hit of caller-supplied rays (origin xyz, direction xyz, time): unit-level probe of `extend`. */
 int rtb_trace_rays(rtb_context* ctx, rtb_scene* scene, const float* origin_3, const float* direction_3,
                    const float* time, uint32_t n, uint32_t* prim_id_out, float* t_out, rtb_stats* stats);
+
+/* the f32 rays rtb_primary_hits traces (generated in f64 like camera.rs:60-70, rounded once): lets a checker trace
+ * exactly the same rays.  origin_3 / direction_3: W*H*3 floats, time: W*H floats (host). */
+int rtb_primary_rays(rtb_context* ctx, const rtb_camera* cam, uint32_t width, uint32_t height, float* origin_3,
+                     float* direction_3, float* time);
+
+/* ---- tier-U2 test hook: evaluates ONE device function per item on caller-supplied inputs ----------------------- */
+/* in / out are raw 32-bit words (floats by bit pattern).  scene may be NULL for ops that need no tables; cam / params may
+ * be NULL except for RTB_KAT_CAMERA_RAY.  See rtb_kernels.cu:k_kat for each op's word layout. */
+typedef enum rtb_kat_op {
+  RTB_KAT_PHILOX = 0,        /* rt_weekend.rs:8-19 replacement: Philox4x32-10 words, bit-exact against the oracle      */
+  RTB_KAT_SPHERE = 1,        /* sphere.rs:41-65 (f32 form + error bound)                                                */
+  RTB_KAT_SPHERE_F64 = 2,    /* sphere.rs:41-65 (f64 form used for global spheres)                                      */
+  RTB_KAT_LIGHTS_PDF = 3,    /* hittable_list.rs:73-80, aarect.rs:107-117, sphere.rs:75-84                              */
+  RTB_KAT_LIGHTS_RANDOM = 4, /* hittable_list.rs:81-84, aarect.rs:118-125, sphere.rs:85-90, pdf.rs:82-91                */
+  RTB_KAT_PERLIN_NOISE = 5,  /* perlin.rs:26-52,67-85                                                                   */
+  RTB_KAT_PERLIN_TURB = 6,   /* perlin.rs:86-98                                                                         */
+  RTB_KAT_Q2F = 7,           /* BVH plane-byte decode                                                                   */
+  RTB_KAT_ONB = 8,           /* onb.rs:19-30                                                                            */
+  RTB_KAT_REFLECT = 9,       /* vec3.rs:115-117                                                                         */
+  RTB_KAT_REFRACT = 10,      /* vec3.rs:246-251                                                                         */
+  RTB_KAT_CAMERA_RAY = 11,   /* camera.rs:60-70 + main.rs:752-753                                                       */
+  RTB_KAT_MEDIA = 12,        /* constant_medium.rs:31-71                                                                */
+  RTB_KAT_TEXTURE = 13,      /* texture.rs:61-68,91-95,118-140                                                          */
+  RTB_KAT_EXACT = 14         /* the reference-exact f64 primitive test (exact_hit)                                      */
+} rtb_kat_op;
+int rtb_device_kat(rtb_context* ctx, rtb_scene* scene, const rtb_camera* cam, const rtb_params* params, uint32_t op,
+                   const uint32_t* in_words, uint32_t n_items, uint32_t in_stride, uint32_t* out_words,
+                   uint32_t out_stride);
 
 #ifdef __cplusplus
 }

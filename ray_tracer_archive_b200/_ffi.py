@@ -20,6 +20,8 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = 0,
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = 0, 1, 2, 3
 LIGHT_XZ_RECT, LIGHT_SPHERE = 0, 1
 RENDER_ACCUMULATE, RENDER_COUNT, RENDER_TIME_EXTEND = 1, 2, 4
+(KAT_PHILOX, KAT_SPHERE, KAT_SPHERE_F64, KAT_LIGHTS_PDF, KAT_LIGHTS_RANDOM, KAT_PERLIN_NOISE, KAT_PERLIN_TURB, KAT_Q2F, KAT_ONB,
+ KAT_REFLECT, KAT_REFRACT, KAT_CAMERA_RAY, KAT_MEDIA, KAT_TEXTURE, KAT_EXACT) = range(15)
 
 NODE_DTYPE = np.dtype([("type", "<u4"), ("material", "<u4"), ("first_child", "<u4"), ("n_children", "<u4"),
                        ("p", "<f8", (12,))])
@@ -59,7 +61,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("rejected", C.c_uint64),
                 ("iterations", C.c_uint64), ("launches", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("nodes_visited", C.c_uint64),
-                ("prims_tested", C.c_uint64)]
+                ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -111,6 +113,8 @@ SIGNATURES = {
     "rtb_finalize_rgb8": (_I, [_VP, _VP, _U32, _U32, _U32, _VP]),
     "rtb_primary_hits": (_I, [_VP, _VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, C.POINTER(Stats)]),
     "rtb_trace_rays": (_I, [_VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP, C.POINTER(Stats)]),
+    "rtb_primary_rays": (_I, [_VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, _VP]),
+    "rtb_device_kat": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _U32, _VP, _U32, _U32, _VP, _U32]),
 }
 
 _lib = None

@@ -52,6 +52,7 @@ struct Lane {
   uint32_t pool_n = 0;
   DevBuf<float4> ray, st, hit;
   DevBuf<uint8_t> cls;                    // per-slot shade class
+  DevBuf<uint32_t> redo;                  // slots queued for the exact pass
   DevBuf<unsigned long long> cursor;      // per-chunk path cursor
   DevBuf<DevCounters> counters;
   DevCounters* h_counters = nullptr;  // pinned
@@ -91,6 +92,7 @@ struct rtb_scene {
   DevBuf<float4> d_geom[PT_COUNT];
   DevBuf<uint2> d_info[PT_COUNT];
   DevBuf<double> d_exact[PT_COUNT];
+  DevBuf<ExactTab> d_xtab;
   DevBuf<float4> d_materials;
   DevBuf<DevTexture> d_textures;
   DevBuf<float4> d_perlin_vec[RTB_MAX_TABLES];
@@ -505,7 +507,6 @@ int rtb_scene_commit(rtb_scene* s) {
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
     CU(s->d_exact[t].upload(s->bvh.exact[t].data(), s->bvh.exact[t].size()));
-    d.exact[t] = s->d_exact[t].p;
   }
   d.coord_max = s->bvh.coord_max;
   d.eps_ab = s->bvh.eps_ab;
@@ -563,6 +564,17 @@ int rtb_scene_commit(rtb_scene* s) {
     for (int k = 0; k < 6; ++k) o.p[k] = m.p[k];
     o.sin_t = m.sin_t; o.cos_t = m.cos_t;
     for (int k = 0; k < 3; ++k) o.off[k] = m.offset[k];
+  }
+  {
+    ExactTab xt;
+    std::memset(&xt, 0, sizeof(xt));
+    xt.tri = s->d_geom[PT_TRI].p;
+    for (int t = 0; t < 3; ++t) xt.exact[t] = s->d_exact[t].p;
+    for (uint32_t t = 0; t < PT_COUNT; ++t) xt.info[t] = s->d_info[t].p;
+    for (size_t i = 0; i < hs.media.size() && i < RTB_MAX_MEDIA; ++i) xt.media_prim_id[i] = hs.media[i].prim_id;
+    CU(s->d_xtab.upload(&xt, 1));
+    CU(cudaStreamSynchronize(0));  // `xt` is a temporary
+    d.xtab = s->d_xtab.p;
   }
   int e = configure_launch(s->lc, d.n_nodes, s->ctx->prop.multiProcessorCount);
   if (e != 0) return set_err(RTB_ERR_CUDA, std::string("configure_launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -671,8 +683,19 @@ static int ensure_pool(Lane& c, uint32_t n) {
   CU(c.ray.resize((size_t)n * 2)); CU(c.st.resize((size_t)n * 2)); CU(c.hit.resize(n));
   const size_t chunks = ((size_t)n + RTB_CHUNK - 1) / RTB_CHUNK;
   CU(c.cls.resize(chunks * RTB_CHUNK)); CU(c.cursor.resize(chunks));
+  CU(c.redo.resize(n));
   c.pool_n = n;
   return RTB_OK;
+}
+
+static DevPool lane_pool(Lane& L, uint32_t n) {
+  DevPool p;
+  p.n = n;
+  p.n_chunks = (n + RTB_CHUNK - 1) / RTB_CHUNK;
+  p.ray = L.ray.p; p.st = L.st.p; p.hit = L.hit.p;
+  p.cls = L.cls.p; p.redo = L.redo.p; p.cursor = L.cursor.p;
+  p.c = L.counters.p;
+  return p;
 }
 
 static int ensure_pix_order(rtb_context* c, uint32_t W, uint32_t H, cudaStream_t st) {
@@ -733,11 +756,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     if ((unsigned long long)pool_n > R.total) pool_n = (uint32_t)std::max<unsigned long long>(1024ull, R.total);
     rc = ensure_pool(L, pool_n);
     if (rc) return rc;
-    R.pool.n = pool_n;
-    R.pool.ray = L.ray.p; R.pool.st = L.st.p; R.pool.hit = L.hit.p;
-    R.pool.n_chunks = (pool_n + RTB_CHUNK - 1) / RTB_CHUNK;
-    R.pool.cls = L.cls.p; R.pool.cursor = L.cursor.p;
-    R.pool.c = L.counters.p;
+    R.pool = lane_pool(L, pool_n);
     DevParams& prm = R.prm;
     prm.width = p->width; prm.height = p->height; prm.spp = cnt; prm.sample_offset = p->sample_offset + first_sample;
     prm.max_depth = p->max_depth; prm.rr_start = p->rr_start_depth; prm.seed = p->seed;
@@ -764,7 +783,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     CU(cudaStreamWaitEvent(ls, c->ev_fork, 0));
     launch_init_pool(run[k].pool, run[k].total, ls);
     launch_generate(s->lc, run[k].pool, run[k].prm, dcam, ls);
-    launch_advance(run[k].pool, ls);
+    launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // nothing queued yet: rotates the counters
     launches += 3;
   }
   const uint32_t present = s->present_materials;
@@ -793,8 +812,8 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
           CU(cudaEventRecord(c->ext_events[ev_used + 1], ls));
           ev_used += 2;
         }
+        launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // exact pass over the queued rays + counter rotation
         launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls);
-        launch_advance(run[k].pool, ls);
         launches += 2 + n_shade;
         extend_launches += 1;
       }
@@ -832,6 +851,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
       stats->paths += run[k].total;  // a render always runs to completion: every path number was started exactly once
       stats->segments += h->segments;
       stats->rejected += h->rejected;
+      stats->exact_rays += h->redone;
       stats->iterations = std::max<uint64_t>(stats->iterations, h->iter);
       stats->nodes_visited += h->nodes_visited;
       stats->prims_tested += h->prims_tested;
@@ -874,29 +894,46 @@ int rtb_finalize_rgb8(rtb_context* c, const void* d_accum, uint32_t W, uint32_t 
   return RTB_OK;
 }
 
+// The probes run the PRODUCTION kernels: the rays are written into a path pool, one extend launch (the variant the
+// scene's renders use) + k_fixup trace them, and the hit records are read back.
 static int run_probe(rtb_context* c, rtb_scene* s, uint32_t n, uint32_t* id_out, float* t_out, rtb_stats* stats) {
   CU(c->p_id.resize(n));
   CU(c->p_t.resize(n));
-  CU(cudaMemsetAsync(c->counters.p, 0, sizeof(DevCounters), 0));
-  CU(cudaEventRecord(c->ev0, 0));
-  launch_probe(s->lc, s->dev, c->p_org.p, c->p_dir.p, c->p_time.p, n, c->p_id.p, c->p_t.p, c->counters.p, 0);
-  CU(cudaEventRecord(c->ev1, 0));
-  CU(cudaMemcpy(id_out, c->p_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(t_out, c->p_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(c->h_counters, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost));
+  Lane& L = c->lanes[0];
+  int rc = ensure_pool(L, std::max(n, 1024u));
+  if (rc) return rc;
+  const DevPool pool = lane_pool(L, n);
+  DevParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.opt = RTB_OPT_PROBE;
+  float ms = 0;
+  for (int pass = 0; pass < (stats ? 2 : 1); ++pass) {  // pass 1: the instrumented variant, for the counters only
+    launch_init_pool(pool, 0ull, 0);
+    launch_probe_fill(pool, c->p_org.p, c->p_dir.p, c->p_time.p, n, 0);
+    CU(cudaEventRecord(c->ev0, 0));
+    launch_extend(s->lc, s->dev, pool, prm, pass == 1, 0);
+    launch_fixup(s->lc, s->dev, pool, prm, 0);
+    CU(cudaEventRecord(c->ev1, 0));
+    if (pass == 0) {
+      launch_probe_collect(s->dev, pool, n, c->p_id.p, c->p_t.p, 0);
+      CU(cudaMemcpy(id_out, c->p_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(t_out, c->p_t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    }
+  }
+  CU(cudaMemcpy(c->h_counters, L.counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost));
   CU(cudaGetLastError());
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     stats->paths = n;
     stats->segments = n;
-    stats->launches = 1;
+    stats->launches = 2;
     stats->extend_launches = 1;
     stats->ms_total = ms;
     stats->ms_extend = ms;
     stats->nodes_visited = c->h_counters->nodes_visited;
     stats->prims_tested = c->h_counters->prims_tested;
+    stats->exact_rays = c->h_counters->redone;
   }
   return RTB_OK;
 }
@@ -914,6 +951,55 @@ int rtb_primary_hits(rtb_context* c, rtb_scene* s, const rtb_camera* cam, uint32
   camera_basis(*cam, f, g);
   launch_primary_rays(g, W, H, c->p_org.p, c->p_dir.p, c->p_time.p, 0);
   return run_probe(c, s, n, id_out, t_out, stats);
+}
+
+int rtb_primary_rays(rtb_context* c, const rtb_camera* cam, uint32_t W, uint32_t H, float* org, float* dir, float* time) {
+  if (!c || !cam || !org || !dir) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (W < 2 || H < 2) return set_err(RTB_ERR_INVALID, "image must be at least 2x2");
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)W * H;
+  CU(c->p_org.resize(n * 3)); CU(c->p_dir.resize(n * 3)); CU(c->p_time.resize(n));
+  DevCamera f;
+  DevCameraF64 g;
+  camera_basis(*cam, f, g);
+  launch_primary_rays(g, W, H, c->p_org.p, c->p_dir.p, c->p_time.p, 0);
+  CU(cudaMemcpy(org, c->p_org.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(dir, c->p_dir.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (time) CU(cudaMemcpy(time, c->p_time.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return RTB_OK;
+}
+
+int rtb_device_kat(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rtb_params* p, uint32_t op,
+                   const uint32_t* in, uint32_t n, uint32_t in_stride, uint32_t* out, uint32_t out_stride) {
+  if (!c || !in || !out || !n || !in_stride || !out_stride) return set_err(RTB_ERR_INVALID, "bad argument");
+  if (s && !s->committed) return set_err(RTB_ERR_STATE, "scene not committed (call rtb_scene_commit)");
+  if (op == RTB_KAT_CAMERA_RAY && (!cam || !p || p->width < 2 || p->height < 2)) return set_err(RTB_ERR_INVALID, "camera op needs cam and params");
+  if (!s && (op == RTB_KAT_LIGHTS_PDF || op == RTB_KAT_LIGHTS_RANDOM || op == RTB_KAT_PERLIN_NOISE || op == RTB_KAT_PERLIN_TURB ||
+             op == RTB_KAT_MEDIA || op == RTB_KAT_TEXTURE || op == RTB_KAT_EXACT))
+    return set_err(RTB_ERR_INVALID, "this op reads the scene's tables");
+  CU(cudaSetDevice(c->device));
+  DevBuf<uint32_t> d_in, d_out;
+  CU(d_in.upload(in, (size_t)n * in_stride));
+  CU(d_out.resize((size_t)n * out_stride));
+  CU(cudaMemsetAsync(d_out.p, 0, (size_t)n * out_stride * 4, 0));
+  DevScene dev;
+  if (s) dev = s->dev;
+  else { std::memset(&dev, 0, sizeof(dev)); dev.prmt_magic = 0x43000000u; }
+  DevCamera dcam;
+  DevCameraF64 dcam64;
+  std::memset(&dcam, 0, sizeof(dcam));
+  if (cam) camera_basis(*cam, dcam, dcam64);
+  DevParams prm;
+  std::memset(&prm, 0, sizeof(prm));
+  if (p) {
+    prm.width = p->width; prm.height = p->height; prm.seed = p->seed;
+    if (p->width > 1) prm.inv_wm1 = (float)(1.0 / (double)(p->width - 1));
+    if (p->height > 1) prm.inv_hm1 = (float)(1.0 / (double)(p->height - 1));
+  }
+  launch_kat(dev, dcam, prm, op, d_in.p, n, in_stride, d_out.p, out_stride, 0);
+  CU(cudaMemcpy(out, d_out.p, (size_t)n * out_stride * 4, cudaMemcpyDeviceToHost));
+  CU(cudaGetLastError());
+  return RTB_OK;
 }
 
 int rtb_trace_rays(rtb_context* c, rtb_scene* s, const float* org, const float* dir, const float* time, uint32_t n,

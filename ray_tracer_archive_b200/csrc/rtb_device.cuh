@@ -41,6 +41,15 @@ struct DevMedium {
 };
 struct DevImage { const uint8_t* data; uint32_t w, h; };
 
+// Everything the (rare, out-of-line) exact path reads, in device memory: the out-of-line functions get ONE pointer, so the
+// kernel's parameter block never has to be materialised in local memory to be passed by reference.
+struct ExactTab {
+  const float4* tri;              // triangle vertices (their f32 values are the exact record)
+  const double* exact[3];         // sphere / moving sphere / quad records, RTB_EXACT_STRIDE doubles each
+  const uint2* info[PT_COUNT];    // (primitive id, material word) per leaf entry
+  uint32_t media_prim_id[RTB_MAX_MEDIA];
+};
+
 struct DevScene {  // passed by value as a kernel parameter (constant bank)
   const uint4* nodes;
   uint32_t n_nodes;
@@ -53,7 +62,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
                         // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
-  const double* exact[PT_COUNT];  // reference-exact f64 records (RTB_EXACT_STRIDE doubles each; none for triangles)
+  const ExactTab* xtab;           // tables of the exact path (device memory)
   float coord_max;                // 2 x the largest |coordinate| of the scene box: scale of the plane-test rounding bound
   float eps_ab;                   // rounding bound of a quad's in-plane coordinates (alpha, beta), see intersect_prim
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
@@ -75,6 +84,9 @@ struct DevCounters {
   uint32_t last_rays;   // ... in the previous iteration: 0 = the pool has drained (host check)
   uint32_t iter;
   uint32_t ext_cursor;  // next unclaimed slot batch (dynamic ray fetch)
+  uint32_t redo_count;  // rays of this iteration that need the exact pass (k_fixup)
+  uint32_t fix_ticket;  // CTAs of k_fixup that have finished (the last one rotates the counters)
+  unsigned long long redone;  // total rays re-traced exactly
   unsigned long long total_paths;
   unsigned long long segments, rejected;
   unsigned long long nodes_visited, prims_tested;
@@ -96,6 +108,7 @@ struct DevPool {
   float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
   float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
   uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
+  uint32_t* redo;     // [n] slots whose closest hit f32 could not decide (filled by extend, consumed by k_fixup)
   unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence
   DevCounters* c;
 };
@@ -193,17 +206,21 @@ __device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint
 
 // ---- closest-hit record -----------------------------------------------------------------------------------------
 // Parity contract (BASELINE.json: primary-ray primitive ids bit-exact against the f64 reference): every f32 primitive
-// test returns its hit distance WITH a bound on |t_f32 - t_ref| and knows whether each of its own decisions (inside /
-// outside, t against t_min) was certain under f32 rounding.  A candidate is accepted or rejected in f32 only when its
-// interval [t - e, t + e] does not overlap the current closest hit's; everything else — edge-grazing hits, two
-// surfaces meeting at the hit point, exact ties — is decided by exact_hit(): the reference's literal f64 arithmetic
-// (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176, same operation order, no FMA contraction) on the
-// constructor's own f64 arguments.  So on identical rays the device returns the id the f64 linear scan returns.
+// test returns its hit distance WITH a bound e on |t_f32 - t_ref| and knows whether each of its own decisions (inside /
+// outside, t against t_min) was certain under f32 rounding.  The hot kernels accept or reject a candidate in f32 only
+// when that is certain.  Anything f32 leaves open — an edge-grazing hit, two surfaces meeting at the hit point (their
+// intervals [t - e, t + e] overlap), an exact tie, an ill-conditioned sphere — lowers the ray's AMBIGUITY HORIZON
+// `amb` = the smallest distance at which an undecided candidate may lie.  A later hit that is certainly closer makes
+// the open question irrelevant; if at the end of the traversal amb <= the closest hit's upper bound, the ray is
+// re-traced by traverse_exact(): the same BVH, every candidate evaluated with the reference's literal f64 arithmetic
+// (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176; same operation order, no FMA contraction) on the
+// constructor's own f64 arguments, equal t going to the larger primitive id (hittable_list.rs:44-47).  That happens
+// for 0.03-0.3 % of the rays and runs in a separate small kernel (k_fixup), so the hot loop contains no call and no
+// f64.  On identical rays the device therefore returns the primitive id the reference's f64 linear scan returns.
 struct Closest {
   float t;        // f32 distance of `ref` (closest_so_far, hittable_list.rs:42)
-  float hi;       // upper bound of ref's exact distance (t + error bound): the traversal's t_max
+  float hi;       // upper bound of the exact distance of the closest hit (t + error bound): the traversal's t_max
   uint32_t ref;   // type << 29 | leaf index
-  uint32_t ref2;  // second contender whose interval overlaps ref's (then [2t - hi, hi] is the union), or REF_MISS
 };
 #define RTB_U20 9.5367432e-7f   // 2^-20
 #define RTB_U21 4.7683716e-7f
@@ -217,6 +234,11 @@ enum HitStatus : int { HIT_MISS = 0, HIT_CERTAIN = 1, HIT_AMBIGUOUS = 2 };
 __device__ __forceinline__ uint32_t ref_gid(const DevScene& sc, uint32_t ref) {
   const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
   return type == PT_MEDIUM ? sc.media[idx].prim_id : __ldg(&sc.info[type][idx].x);
+}
+
+__device__ __forceinline__ uint32_t tab_gid(const ExactTab* tab, uint32_t ref) {
+  const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+  return type == PT_MEDIUM ? tab->media_prim_id[idx] : __ldg(&tab->info[type][idx].x);
 }
 
 __device__ __forceinline__ float abs1(float3 a) { return fabsf(a.x) + fabsf(a.y) + fabsf(a.z); }
@@ -250,47 +272,46 @@ __device__ __forceinline__ D3 d3at(D3 o, double t, D3 d) {  // ray.rs: origin + 
 }
 
 // Sphere::hit root selection (sphere.rs:47-57) with t_max = +inf: the primitive's own first root >= t_min
-__device__ __forceinline__ bool exact_sphere(D3 o, D3 d, D3 c, double r, double tmin, double& t) {
+#define RTB_EXACT_MISS (-1.0)
+__device__ __forceinline__ double exact_sphere(D3 o, D3 d, D3 c, double r, double tmin) {
   const D3 oc = d3sub(o, c);
   const double a = d3dot(d, d), half_b = d3dot(oc, d);
   const double cc = dsub(d3dot(oc, oc), dmul(r, r));
   const double det = dsub(dmul(half_b, half_b), dmul(a, cc));
-  if (det < 0.0) return false;
+  if (det < 0.0) return RTB_EXACT_MISS;
   const double sqrtd = dsqrt(det);
   double root = ddiv(dsub(-half_b, sqrtd), a);
   if (root < tmin) {
     root = ddiv(dadd(-half_b, sqrtd), a);
-    if (root < tmin) return false;
+    if (root < tmin) return RTB_EXACT_MISS;
   }
-  t = root;
-  return root < (double)INFINITY;
+  return root < (double)INFINITY ? root : RTB_EXACT_MISS;
 }
 
 // The reference's own evaluation of primitive `ref` for the ray (o, d, time), t_min = 0.001 (main.rs:74), t_max = inf.
-static __device__ __noinline__ bool exact_hit(const DevScene& sc, uint32_t ref, float3 of, float3 df, float timef, double& t_out) {
+// Returns the hit distance, or RTB_EXACT_MISS.
+static __device__ __noinline__ double exact_hit(const ExactTab* __restrict__ tab, uint32_t ref, float3 of, float3 df, float timef) {
   const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
   const double tmin = 0.001;
   D3 o{(double)of.x, (double)of.y, (double)of.z}, d{(double)df.x, (double)df.y, (double)df.z};
   if (type == PT_TRI) {  // Moller-Trumbore on the f32 vertices (the oracle's Triangle::hit)
-    const float4 a4 = __ldg(sc.geom[PT_TRI] + 3 * idx), b4 = __ldg(sc.geom[PT_TRI] + 3 * idx + 1), c4 = __ldg(sc.geom[PT_TRI] + 3 * idx + 2);
+    const float4 a4 = __ldg(tab->tri + 3 * idx), b4 = __ldg(tab->tri + 3 * idx + 1), c4 = __ldg(tab->tri + 3 * idx + 2);
     const D3 v0{(double)a4.x, (double)a4.y, (double)a4.z};
     const D3 e1 = d3sub(D3{(double)b4.x, (double)b4.y, (double)b4.z}, v0), e2 = d3sub(D3{(double)c4.x, (double)c4.y, (double)c4.z}, v0);
     const D3 pv = d3cross(d, e2);
     const double det = d3dot(e1, pv);
-    if (det == 0.0) return false;
+    if (det == 0.0) return RTB_EXACT_MISS;
     const double inv = ddiv(1.0, det);
     const D3 tv = d3sub(o, v0);
     const double u = dmul(d3dot(tv, pv), inv);
-    if (u < 0.0 || u > 1.0) return false;
+    if (u < 0.0 || u > 1.0) return RTB_EXACT_MISS;
     const D3 qv = d3cross(tv, e1);
     const double v = dmul(d3dot(d, qv), inv);
-    if (v < 0.0 || dadd(u, v) > 1.0) return false;
+    if (v < 0.0 || dadd(u, v) > 1.0) return RTB_EXACT_MISS;
     const double t = dmul(d3dot(e2, qv), inv);
-    if (!(t >= tmin && t < (double)INFINITY)) return false;
-    t_out = t;
-    return true;
+    return (t >= tmin && t < (double)INFINITY) ? t : RTB_EXACT_MISS;
   }
-  const double* e = sc.exact[type] + (size_t)idx * RTB_EXACT_STRIDE;
+  const double* e = tab->exact[type] + (size_t)idx * RTB_EXACT_STRIDE;
   const uint32_t bits = exact_bits(e[0]);
   if (bits & EX_TRANSLATE) o = d3sub(o, D3{e[1], e[2], e[3]});  // Translate::hit, hittable.rs:77
   if (bits & EX_ROTATE) {                                       // RotateY::hit, hittable.rs:150-156
@@ -299,100 +320,57 @@ static __device__ __noinline__ bool exact_hit(const DevScene& sc, uint32_t ref, 
     const double dx = dsub(dmul(cs, d.x), dmul(sn, d.z)), dz = dadd(dmul(sn, d.x), dmul(cs, d.z));
     o.x = ox; o.z = oz; d.x = dx; d.z = dz;
   }
-  if (type == PT_SPHERE) return exact_sphere(o, d, D3{e[6], e[7], e[8]}, e[9], tmin, t_out);
+  if (type == PT_SPHERE) return exact_sphere(o, d, D3{e[6], e[7], e[8]}, e[9], tmin);
   if (type == PT_MOVING) {  // moving_sphere.rs:36-39: c0 + ((time - t0) / (t1 - t0)) * (c1 - c0)
     const double s = ddiv(dsub((double)timef, e[12]), dsub(e[13], e[12]));
     const D3 dc = d3sub(D3{e[9], e[10], e[11]}, D3{e[6], e[7], e[8]});
     const D3 c{dadd(e[6], dmul(s, dc.x)), dadd(e[7], dmul(s, dc.y)), dadd(e[8], dmul(s, dc.z))};
-    return exact_sphere(o, d, c, e[14], tmin, t_out);
+    return exact_sphere(o, d, c, e[14], tmin);
   }
   const uint32_t sub = (bits >> 8) & 0xFFu;
   if (sub < 3u) {  // XyRect / XzRect / YzRect::hit, aarect.rs:31-48,81-98,150-167
-    const double oa[3] = {o.x, o.y, o.z}, da[3] = {d.x, d.y, d.z};
-    const uint32_t ia = sub == 0u ? 1u : 0u, ib = sub == 2u ? 1u : 2u;
-    const double t = ddiv(dsub(e[6], oa[sub]), da[sub]);
-    if (!(t >= tmin && t < (double)INFINITY)) return false;
-    const double a = dadd(oa[ia], dmul(t, da[ia])), b = dadd(oa[ib], dmul(t, da[ib]));
-    if (a < e[7] || a > e[8] || b < e[9] || b > e[10]) return false;
-    t_out = t;
-    return true;
+    // normal axis `sub`; in-plane axes (ia, ib) = (sub == 0 ? y : x, sub == 2 ? y : z), selected without local arrays
+    const double on = sub == 0u ? o.x : (sub == 1u ? o.y : o.z), dn = sub == 0u ? d.x : (sub == 1u ? d.y : d.z);
+    const double oia = sub == 0u ? o.y : o.x, dia = sub == 0u ? d.y : d.x;
+    const double oib = sub == 2u ? o.y : o.z, dib = sub == 2u ? d.y : d.z;
+    const double t = ddiv(dsub(e[6], on), dn);
+    if (!(t >= tmin && t < (double)INFINITY)) return RTB_EXACT_MISS;
+    const double a = dadd(oia, dmul(t, dia)), b = dadd(oib, dmul(t, dib));
+    if (a < e[7] || a > e[8] || b < e[9] || b > e[10]) return RTB_EXACT_MISS;
+    return t;
   }
   // general quad(Q, u, v) (the oracle's Quad::hit)
   const D3 Q{e[6], e[7], e[8]}, u{e[9], e[10], e[11]}, v{e[12], e[13], e[14]};
   const D3 n = d3cross(u, v);
   const double nn = d3dot(n, n), denom = d3dot(n, d);
-  if (denom == 0.0) return false;
+  if (denom == 0.0) return RTB_EXACT_MISS;
   const double t = ddiv(d3dot(n, d3sub(Q, o)), denom);
-  if (!(t >= tmin && t < (double)INFINITY)) return false;
+  if (!(t >= tmin && t < (double)INFINITY)) return RTB_EXACT_MISS;
   const D3 pl = d3sub(d3at(o, t, d), Q);
   const double alpha = ddiv(d3dot(n, d3cross(pl, v)), nn), beta = ddiv(d3dot(n, d3cross(u, pl)), nn);
-  if (alpha < 0.0 || alpha > 1.0 || beta < 0.0 || beta > 1.0) return false;
-  t_out = t;
-  return true;
+  if (alpha < 0.0 || alpha > 1.0 || beta < 0.0 || beta > 1.0) return RTB_EXACT_MISS;
+  return t;
 }
 
-#ifdef RTB_EMUL_STATS
-static unsigned long long g_exact_calls[8];
-#endif
-// Two contenders whose intervals overlap: decided exactly; equal t goes to the larger primitive id
-// (hittable_list.rs:44-47).  Both were certain hits (or exact hits) when they were recorded.
-static __device__ __noinline__ void resolve_pair(const DevScene& sc, float3 o, float3 d, float time, Closest& best) {
-#ifdef RTB_EMUL_STATS
-  ++g_exact_calls[4];
-#endif
-  double ta = 0.0, tb = 0.0;
-  const bool ha = exact_hit(sc, best.ref, o, d, time, ta), hb = exact_hit(sc, best.ref2, o, d, time, tb);
-  if (ha || hb) {
-    const bool second = hb && (!ha || tb < ta || (tb == ta && ref_gid(sc, best.ref2) > ref_gid(sc, best.ref)));
-    const float tf = (float)(second ? tb : ta);
-    best.t = tf;
-    best.hi = tf * (1.0f + RTB_U22);
-    if (second) best.ref = best.ref2;
-  }
-  best.ref2 = REF_MISS;
-}
-
-// closest-hit update with a certain hit at t, |t - t_exact| <= e.  Accept / reject in f32 when the intervals are
-// disjoint; an overlapping candidate becomes the second contender (the pair is decided exactly at the end of the
-// traversal, or as soon as a third one overlaps — most overlaps are superseded by a closer hit before that).
-__device__ __forceinline__ void consider(const DevScene& sc, float3 o, float3 d, float time, Closest& best, float t, float e, uint32_t ref) {
+// closest-hit update with a certain hit at t, |t - t_exact| <= e
+__device__ __forceinline__ void consider(Closest& best, float& amb, float t, float e, uint32_t ref) {
   if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
   const float hi = t + e, lo = t - e;
-  if (best.ref == REF_MISS || hi < best.t - (best.hi - best.t)) {
-    best.t = t; best.hi = hi; best.ref = ref; best.ref2 = REF_MISS;
-    return;
+  if (lo > best.hi) return;                     // certainly farther (best.hi = inf while nothing is hit)
+  if (best.ref != REF_MISS) {
+    const float blo = best.t - (best.hi - best.t);
+    if (!(hi < blo)) amb = fminf(amb, fminf(lo, blo));  // the two intervals overlap: which is closer is open
   }
-  if (lo > best.hi) return;
-  if (best.ref2 != REF_MISS) {  // third contender: settle the pending pair first
-    resolve_pair(sc, o, d, time, best);
-    if (hi < best.t - (best.hi - best.t)) { best.t = t; best.hi = hi; best.ref = ref; return; }
-    if (lo > best.hi) return;
-  }
-  const float L = fminf(lo, best.t - (best.hi - best.t)), H = fmaxf(hi, best.hi);
-  best.t = 0.5f * (L + H);
-  best.hi = H;
-  best.ref2 = ref;
+  if (t < best.t) { best.t = t; best.ref = ref; }
+  best.hi = fminf(best.hi, hi);                 // the closer of the two exact distances is <= both upper bounds
 }
-
-// a candidate whose own f32 test was ambiguous (edge-grazing, t next to t_min, ill-conditioned sphere): evaluated
-// exactly, then treated as a certain hit known to 1 ulp
-static __device__ __noinline__ void consider_exact(const DevScene& sc, float3 o, float3 d, float time, Closest& best, uint32_t ref) {
-#ifdef RTB_EMUL_STATS
-  ++g_exact_calls[ref >> REF_TYPE_SHIFT];
-#endif
-  double tc;
-  if (!exact_hit(sc, ref, o, d, time, tc)) return;
-  const float tf = (float)tc;
-  consider(sc, o, d, time, best, tf, RTB_U22 * tf, ref);
-}
-
-// end of a traversal: a still-pending pair is decided now
-__device__ __forceinline__ void settle(const DevScene& sc, float3 o, float3 d, float time, Closest& best) {
-  if (best.ref2 != REF_MISS) resolve_pair(sc, o, d, time, best);
+// a candidate that may or may not be a hit, at a distance >= lo
+__device__ __forceinline__ void undecided(const Closest& best, float& amb, float lo) {
+  if (!(lo > best.hi)) amb = fminf(amb, lo);
 }
 
 // t against t_min = 0.001 (main.rs:74): certain unless within the error bound AND within a quarter of t_min (the
-// self-intersection of a bounce ray sits at |t| ~ 1e-5, far below the band; the band keeps the slow path off it)
+// self-intersection of a bounce ray sits at |t| ~ 1e-5, far below the band; the band keeps the exact path off it)
 __device__ __forceinline__ int tmin_status(float t, float e, float tmin) {
   const float band = fminf(e, 0.25f * tmin);
   return t > tmin + band ? HIT_CERTAIN : (t < tmin - band ? HIT_MISS : HIT_AMBIGUOUS);
@@ -422,12 +400,12 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
   const double sq = sqrt(det);
   const double inv_a = 1.0 / a;
 #endif
-  const double band = 1e-12 * (fabs(hb) + sq) * inv_a;
+  const double band = 1e-12 * (fabs(hb) + sq) * inv_a + 1e-10;
   double root = (-hb - sq) * inv_a;
-  if (fabs(root - (double)tmin) <= band + 1e-10) return HIT_AMBIGUOUS;
+  if (fabs(root - (double)tmin) <= band) return HIT_AMBIGUOUS;
   if (root < (double)tmin) {
     root = (-hb + sq) * inv_a;
-    if (fabs(root - (double)tmin) <= band + 1e-10) return HIT_AMBIGUOUS;
+    if (fabs(root - (double)tmin) <= band) return HIT_AMBIGUOUS;
     if (root < (double)tmin) return HIT_MISS;
   }
   t_out = (float)root;
@@ -436,10 +414,11 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
 
 // Sphere::hit in f32, in the cancellation-free form  disc' = r^2 - |oc - (oc.d/a) d|^2  (= det/a): the reference's
 // c = |oc|^2 - r^2 loses all bits in f32 for large spheres.  Error model (position space): every intermediate carries
-// at most epos = 2^-21 (|oc|_1 + r) + cerr (cerr: the f32 rounding of the stored centre / radius against the f64
-// constructor arguments); half-chord h = sqrt(disc'); a root moves by <= epos/|d| (1 + 2r/h) — the 1/h term is the
-// grazing amplification.  HIT_AMBIGUOUS when a decision (disc' sign, root against t_min) is inside its bound or when
-// the bound exceeds RTB_SPHERE_REL_MAX t (the reported t must hold 1e-5 relative).
+// at most epos = 2^-21 (|oc|_1 + r) + 2^-23 (|c|_1 + r) (the second term: f32 rounding of the stored centre / radius
+// against the f64 constructor arguments); half-chord h = sqrt(disc'); a root moves by <= epos/|d| (1 + 2r/h) — the 1/h
+// term is the grazing amplification.  HIT_AMBIGUOUS (t_out = a lower bound of the possible hit distance) when a
+// decision (disc' sign, root against t_min) is inside its bound or when the bound exceeds RTB_SPHERE_REL_MAX t: the
+// bound is ~8x pessimistic, and the reported t must hold 1e-5 relative.
 #define RTB_SPHERE_REL_MAX 5.0e-5f
 __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out) {
   const float3 oc = o - c;
@@ -451,11 +430,19 @@ __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r
   const float epos = fmaf(RTB_U21, abs1(oc) + fabsf(r), RTB_U23 * (abs1(c) + fabsf(r)));
   const float edisc = 4.0f * fabsf(r) * epos;
   if (disc < -edisc) return HIT_MISS;
-  if (disc <= edisc) return HIT_AMBIGUOUS;
 #ifdef __CUDA_ARCH__
-  const float inv_d = rsqrtf(a), rh = rsqrtf(disc);
+  const float inv_d = rsqrtf(a);
 #else
-  const float inv_d = 1.0f / sqrtf(a), rh = 1.0f / sqrtf(disc);
+  const float inv_d = 1.0f / sqrtf(a);
+#endif
+  if (disc <= edisc) {  // grazing: any hit lies within sqrt(2 edisc)/|d| of the closest approach -hb/a
+    t_out = fmaf(-hb, inv_a, -(sqrt_fast(2.0f * edisc) * inv_d + RTB_U20 * fabsf(hb * inv_a)));
+    return HIT_AMBIGUOUS;
+  }
+#ifdef __CUDA_ARCH__
+  const float rh = rsqrtf(disc);
+#else
+  const float rh = 1.0f / sqrtf(disc);
 #endif
   const float sq = (disc * rh) * (a * inv_d);  // sqrt(a disc')
   const float ebase = epos * inv_d * fmaf(2.0f * fabsf(r), rh, 1.0f);
@@ -469,25 +456,27 @@ __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r
     if (st == HIT_MISS) return HIT_MISS;
   }
   if (root - e > tmax_hi) return HIT_MISS;
-  if (st == HIT_AMBIGUOUS || e > RTB_SPHERE_REL_MAX * root) return HIT_AMBIGUOUS;
   t_out = root; e_out = e;
+  if (st == HIT_AMBIGUOUS || e > RTB_SPHERE_REL_MAX * root) {
+    t_out = fmaxf(root - e, 0.0f);
+    return HIT_AMBIGUOUS;
+  }
   return HIT_CERTAIN;
 }
 
-// shade-side sphere root (light pdf, sphere.rs:75-84): f32, f64 only when grazing; no closest-hit decision hangs on it
+// shade-side sphere root (light pdf, sphere.rs:75-84): f32, f64 only when ill-conditioned; no closest-hit decision hangs on it
 __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
   float t, e;
   int st = sphere_fast(o, d, c, r, tmin, tmax, t, e);
   if (st == HIT_AMBIGUOUS) st = sphere_roots_f64(o, d, c, r, tmin, t);
-  if (st == HIT_MISS || (st == HIT_CERTAIN && t > tmax)) return false;
-  if (st == HIT_AMBIGUOUS) return false;  // within 1e-12 of tangency / t_min: measure zero for a pdf
+  if (st != HIT_CERTAIN || t > tmax) return false;  // (within 1e-12 of tangency / t_min: measure zero for a pdf)
   t_out = t;
   return true;
 }
 
 template <bool COUNT>
 __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
-                                               float time, float tmin, Closest& best, uint32_t& n_tests) {
+                                               float time, float tmin, Closest& best, float& amb, uint32_t& n_tests) {
   if (COUNT) ++n_tests;
   const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
   float t, e;
@@ -495,7 +484,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
     const int st = sphere_fast(o, d, xyz(s), s.w, tmin, best.hi, t, e);
     if (st == HIT_MISS) return;
-    if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
+    if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
   } else if (type == PT_QUAD) {
     // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square.
     // Numerator error <= 2^-22 (|o|_1 + coord_max) (three FMAs on |n_i| <= 1, the stored n.Q); denominator error <=
@@ -506,7 +495,7 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     t = (w0.w - dot(xyz(w0), o)) * inv;
     e = fmaf(fabsf(inv), fmaf(RTB_U22 * abs1(d), fabsf(t), RTB_U22 * (abs1(o) + sc.coord_max)), RTB_U21 * fabsf(t));
     if (!(t - e <= best.hi)) return;  // also rejects NaN
-    int st = tmin_status(t, e, tmin);
+    const int st = tmin_status(t, e, tmin);
     if (st == HIT_MISS) return;
     const float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
     const float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
@@ -517,15 +506,14 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float eb = fmaf(e, fabsf(dot(xyz(w2), d)), fmaf(RTB_U20, fabsf(beta), sc.eps_ab));
     const float ma = fminf(alpha, 1.0f - alpha), mb = fminf(beta, 1.0f - beta);
     if (ma < -ea || mb < -eb) return;
-    if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { consider_exact(sc, o, d, time, best, ref); return; }
+    if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { undecided(best, amb, fmaxf(t - e, 0.0f)); return; }
   } else if (type == PT_TRI) {
     // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
     // Watertight edge functions (Woop, Benthin, Wald 2013): vertices are translated to the ray origin and sheared so
     // the ray runs along +z; the edge function of a shared edge is computed from the SAME two translated vertices by
     // both triangles (exact negatives, no FMA contraction), so f32 rounding can never open a crack in a mesh.
-    // An edge function within its rounding bound of zero (the ray passes within ~1e-6 of an edge or vertex) sends the
-    // triangle to the exact f64 test, so on a shared edge BOTH neighbours are decided — and tie-broken — as the
-    // reference decides them.
+    // An edge function within its rounding bound of zero (the ray passes within ~1e-6 of an edge or vertex) leaves the
+    // triangle undecided, so on a shared edge BOTH neighbours are decided — and tie-broken — by the exact pass.
     const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx));
     const float3 v1 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1));
     const float3 v2 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2));
@@ -559,29 +547,28 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     if (mn < -m && mx > m) return;  // certainly outside
     const float det = U + V + W;
     const float idet = rcp_fast(det), za = Sz * A.z, zb = Sz * B.z, zc = Sz * C.z;
+    const float zlo = fminf(fminf(za, zb), zc), zhi = fmaxf(fmaxf(za, zb), zc);
+    if (!(mn > m || mx < -m)) {  // on an edge / vertex / edge-on: any hit lies within the triangle's depth range
+      if (zhi >= tmin) undecided(best, amb, fmaxf(zlo - RTB_U20 * fabsf(zlo), 0.0f));
+      return;
+    }
     t = (U * za + V * zb + W * zc) * idet;
     // t is the (U, V, W)-weighted mean of the vertex depths: the weights' error m/|det| moves it by at most the depth
     // spread of the triangle
-    e = fmaf(RTB_U20, fabsf(t), 4.0f * m * fabsf(idet) * (fmaxf(fmaxf(za, zb), zc) - fminf(fminf(za, zb), zc)));
-    const bool inside_certain = mn > m || mx < -m;
-    if (inside_certain) {
-      if (!(t - e <= best.hi)) return;
-      const int st = tmin_status(t, e, tmin);
-      if (st == HIT_MISS) return;
-      if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
-    } else {
-      consider_exact(sc, o, d, time, best, ref);  // on an edge / vertex / degenerate: t itself may be meaningless
-      return;
-    }
+    e = fmaf(RTB_U20, fabsf(t), 4.0f * m * fabsf(idet) * (zhi - zlo));
+    if (!(t - e <= best.hi)) return;
+    const int st = tmin_status(t, e, tmin);
+    if (st == HIT_MISS) return;
+    if (st == HIT_AMBIGUOUS) { undecided(best, amb, fmaxf(t - e, 0.0f)); return; }
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
     const float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
     const float3 c = fma3(time, xyz(b), xyz(a));
     const int st = sphere_fast(o, d, c, a.w, tmin, best.hi, t, e);
     if (st == HIT_MISS) return;
-    if (st == HIT_AMBIGUOUS) { consider_exact(sc, o, d, time, best, ref); return; }
+    if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
   }
-  consider(sc, o, d, time, best, t, e, ref);
+  consider(best, amb, t, e, ref);
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
@@ -605,7 +592,10 @@ struct Trav {
   uint2 grp;        // current node group: x = first child node, y = hit-priority mask << 8 | internal mask
   int sp;
   Closest best;
+  float amb;        // ambiguity horizon: smallest distance at which an undecided candidate may lie (inf = none)
 };
+// the ray must be re-traced exactly: something undecided may lie at or before the closest certain hit
+__device__ __forceinline__ bool needs_exact(const Closest& best, float amb) { return amb < INFINITY && amb <= best.hi; }
 
 __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float time) {
   const float tiny = 1e-30f;
@@ -616,7 +606,8 @@ __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float ti
   tv.octinv = 7u ^ ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
   tv.sp = 0;
-  tv.best = Closest{INFINITY, INFINITY, REF_MISS, REF_MISS};
+  tv.best = Closest{INFINITY, INFINITY, REF_MISS};
+  tv.amb = INFINITY;
 }
 
 // 128-bit load from the shared-memory node stage.  On the device the stage is addressed through a 32-bit shared-space
@@ -634,10 +625,11 @@ __device__ __forceinline__ uint4 lds_node_word(const uint4* __restrict__ snodes,
 
 // returns false when the traversal is complete.  ALL_STAGED: every node of the tree is in the shared-memory stage (small
 // scenes), so the global-memory fetch path and its five predicated loads + register moves are compiled out.
-template <bool COUNT, bool ALL_STAGED = false>
+// `leaf(type, index)` tests one primitive (the hot kernels: intersect_prim; the exact pass: exact_hit).
+template <bool COUNT, bool ALL_STAGED, class Leaf>
 __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                           Trav& tv, uint2* __restrict__ stack, float tmin,
-                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
+                                          uint32_t& n_nodes_visited, Leaf&& leaf_fn) {
   if (!(tv.grp.y & 0xFF00u)) {  // group exhausted: pop (stack entries always have hits left) and visit in the same step
     if (tv.sp == 0) return false;
     tv.grp = stack[--tv.sp];
@@ -711,8 +703,7 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     leaf &= leaf - 1;
     const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
     const uint32_t cnt = m >> 5, first = pbase + (m & 31u);
-    for (uint32_t k = 0; k < cnt; ++k)
-      intersect_prim<COUNT>(sc, ptype, first + k, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+    for (uint32_t k = 0; k < cnt; ++k) leaf_fn(ptype, first + k);
   }
   // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
   uint32_t ih = hitmask & imask;
@@ -734,27 +725,66 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
       const float4 s = __ldg(sc.geom[PT_SPHERE] + (ref & REF_INDEX_MASK));
       float t;
       const int st = sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, t);
-      if (st == HIT_CERTAIN) consider(sc, tv.o, tv.d, tv.time, tv.best, t, RTB_U22 * t, ref);
-      else if (st == HIT_AMBIGUOUS) consider_exact(sc, tv.o, tv.d, tv.time, tv.best, ref);
+      if (st == HIT_CERTAIN) consider(tv.best, tv.amb, t, RTB_U22 * t, ref);
+      else if (st == HIT_AMBIGUOUS) tv.amb = 0.0f;  // within 1e-12 of tangency / t_min: exact pass
     } else {
-      intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, n_tests);
+      intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, n_tests);
     }
   }
   if (sc.tree_empty) tv.grp.y = 0u;  // nothing left to traverse: the first trav_step returns false
 }
 
+// one hot-path step: the leaf primitives go through the f32 tests
 template <bool COUNT, bool ALL_STAGED = false>
-__device__ __forceinline__ void traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
+__device__ __forceinline__ bool trav_step_fast(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
+                                               Trav& tv, uint2* __restrict__ stack, float tmin,
+                                               uint32_t& n_nodes_visited, uint32_t& n_tests) {
+  return trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited,
+                                      [&](uint32_t type, uint32_t idx) {
+                                        intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, n_tests);
+                                      });
+}
+
+// returns true when the ray has to go through traverse_exact()
+template <bool COUNT, bool ALL_STAGED = false>
+__device__ __forceinline__ bool traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
   Trav tv;
   uint2 stack[RTB_STACK];
   trav_init(tv, o, d, time);
-  tv.best = best;
   trav_globals<COUNT>(sc, tv, tmin, n_tests);
-  while (trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
-  settle(sc, o, d, time, tv.best);
+  while (trav_step_fast<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
+  return needs_exact(tv.best, tv.amb);
+}
+
+// The exact pass: the same BVH (its conservative boxes cull against the closest exact distance so far), every candidate
+// evaluated by exact_hit(), min t with equal t going to the larger primitive id = HittableList::hit
+// (hittable_list.rs:39-51) in f64.  Nodes come from global memory (n_snodes = 0).
+__device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, float3 d, float time) {
+  Trav tv;
+  uint2 stack[RTB_STACK];
+  trav_init(tv, o, d, time);
+  double bt = 0.0;
+  const ExactTab* tab = sc.xtab;
+  auto leaf = [&](uint32_t type, uint32_t idx) {
+    const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
+    const double tc = exact_hit(tab, ref, tv.o, tv.d, tv.time);
+    if (tc < 0.0) return;
+    if (tv.best.ref == REF_MISS || tc < bt || (tc == bt && tab_gid(tab, ref) > tab_gid(tab, tv.best.ref))) {
+      bt = tc;
+      const float tf = (float)tc;
+      tv.best.t = tf;
+      tv.best.hi = tf * (1.0f + RTB_U22);
+      tv.best.ref = ref;
+    }
+  };
+  for (uint32_t k = 0; k < sc.n_global; ++k) leaf(sc.global_ref[k] >> REF_TYPE_SHIFT, sc.global_ref[k] & REF_INDEX_MASK);
+  if (sc.tree_empty) tv.grp.y = 0u;
+  uint32_t nv = 0;
+  while (trav_step<false, false>(sc, nullptr, 0u, 0u, tv, stack, RTB_TMIN, nv, leaf)) {}
+  return tv.best;
 }
 
 // ConstantMedium::hit, constant_medium.rs:31-71, for the (few) media of the scene; the boundary interval is found
@@ -810,7 +840,7 @@ __device__ __forceinline__ void intersect_media(const DevScene& sc, float3 o, fl
     float t = t1 + hd * rcp_fast(len);
     // a sampled (continuous) distance: accepted iff closer than the closest surface / earlier medium, no tie rule needed
     if (t < INFINITY && (best.ref == REF_MISS || t < best.t)) {
-      best.t = t; best.hi = t; best.ref = ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m; best.ref2 = REF_MISS;
+      best.t = t; best.hi = t; best.ref = ((uint32_t)PT_MEDIUM << REF_TYPE_SHIFT) | m;
     }
   }
 }

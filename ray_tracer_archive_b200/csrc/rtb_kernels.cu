@@ -48,7 +48,7 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
   if (sc.n_media) {
     const uint32_t pixel = __float_as_uint(pool.st[2 * slot].w);
     const uint32_t st = __float_as_uint(pool.st[2 * slot + 1].w);
-    intersect_media(sc, o, d, RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, true);
+    intersect_media(sc, o, d, RTB_TMIN, best, pixel, st >> 8, (st & 0xFFu) + 1u, prm.seed, !(prm.opt & RTB_OPT_PROBE));
   }
   uint32_t queue = Q_TERMINAL, minfo = 0;
   if (best.ref != REF_MISS) {
@@ -58,6 +58,12 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
   }
   pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
   pool.cls[slot] = (uint8_t)queue;
+}
+
+// a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
+// the one atomic per entry is uncontended in practice)
+__device__ __forceinline__ void queue_exact(const DevPool& pool, uint32_t slot) {
+  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] = slot;
 }
 
 // ---- warp-local chunk lists -------------------------------------------------------------------------------------------
@@ -119,7 +125,7 @@ __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint3
 // 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
 struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, t upper bound) after the global primitives
-struct ExtOut { float t; uint32_t ref, slot, _pad; };
+struct ExtOut { float t; uint32_t ref, slot, redo; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
 template <bool COUNT>
@@ -160,7 +166,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         o = xyz(pool.ray[2 * h.slot]);
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
-      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref, REF_MISS});
+      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
+      if (h.redo) queue_exact(pool, h.slot);
     }
     out_count = 0;
     __syncwarp();
@@ -197,11 +204,11 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           Trav t0;
           trav_init(t0, xyz(ro), xyz(rd), ro.w);
           trav_globals<COUNT>(sc, t0, RTB_TMIN, nt);
-          settle(sc, t0.o, t0.d, t0.time, t0.best);  // the hand-over record carries one contender
           ExtIn& e = in[lane];
           e.o_time = ro;
           e.d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
-          e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv));
+          // (an ambiguity among the global primitives is handed over as "undecided from distance 0": bit 8)
+          e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv | (t0.amb < INFINITY ? 256u : 0u)));
           e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.grp.y), t0.best.hi);
         }
         __syncwarp();
@@ -215,10 +222,11 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.o = xyz(r.o_time); tv.time = r.o_time.w;
           tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
           tv.idx = r.idir_oct.x; tv.idy = r.idir_oct.y; tv.idz = r.idir_oct.z;
-          tv.octinv = __float_as_uint(r.idir_oct.w);
+          tv.octinv = __float_as_uint(r.idir_oct.w) & 7u;
+          tv.amb = (__float_as_uint(r.idir_oct.w) & 256u) ? 0.0f : INFINITY;
           tv.grp = make_uint2(0u, __float_as_uint(r.best.z));
           tv.sp = 0;
-          tv.best = Closest{r.best.x, r.best.w, __float_as_uint(r.best.y), REF_MISS};
+          tv.best = Closest{r.best.x, r.best.w, __float_as_uint(r.best.y)};
         }
         idle &= ~__ballot_sync(0xffffffffu, take);
         in_head += min(n_idle, avail);
@@ -231,13 +239,12 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
     // ---- one node visit (or pop) per running lane -------------------------------------------------------------------
     bool finished = false;
-    if (!((idle >> lane) & 1u)) finished = !trav_step<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
+    if (!((idle >> lane) & 1u)) finished = !trav_step_fast<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
     // ---- finished lanes push their result -------------------------------------------------------------------------
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (finished) settle(sc, tv.o, tv.d, tv.time, tv.best);
-      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, 0u};
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, needs_exact(tv.best, tv.amb) ? 1u : 0u};
       out_count += __popc(done);
       idle |= done;
     }
@@ -280,9 +287,10 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const uint32_t slot = base + list[r + lane];
         const float4 ro = pool.ray[2 * slot];
         const float4 rd = pool.ray[2 * slot + 1];
-        Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
-        traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+        Closest best;
+        const bool redo = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
         finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+        if (redo) queue_exact(pool, slot);
       }
     }
     __syncwarp();  // the list is rewritten for the next chunk
@@ -340,9 +348,13 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uin
 __device__ __forceinline__ void surface_uv(const DevScene& sc, const Surf& s, float& u, float& v) {
   const uint32_t type = s.ref >> REF_TYPE_SHIFT, idx = s.ref & REF_INDEX_MASK;
   u = v = 0.f;  // MovingSphere / ConstantMedium leave u,v stale in the reference; defined 0
-  if (type == PT_SPHERE) {  // sphere.rs:32-37
-    const float theta = acosf(fminf(fmaxf(-s.outward.y, -1.f), 1.f));
-    const float phi = atan2f(-s.outward.z, s.outward.x) + RTB_PI;
+  if (type == PT_SPHERE) {  // sphere.rs:32-37, on the OBJECT-space outward normal: a sphere under RotateY gets its
+    // world-space normal rotated back (hittable.rs:150-156 maps world -> object; the record keeps that sin / cos)
+    const double* ex = sc.xtab->exact[PT_SPHERE] + (size_t)idx * RTB_EXACT_STRIDE;
+    const float sn = (float)ex[4], cs = (float)ex[5];
+    const float3 on = f3(cs * s.outward.x - sn * s.outward.z, s.outward.y, sn * s.outward.x + cs * s.outward.z);
+    const float theta = acosf(fminf(fmaxf(-on.y, -1.f), 1.f));
+    const float phi = atan2f(-on.z, on.x) + RTB_PI;
     u = phi / (2.0f * RTB_PI);
     v = theta / RTB_PI;
   } else if (type == PT_QUAD) {
@@ -383,6 +395,17 @@ __device__ float perlin_noise(const float4* __restrict__ vec, const uint8_t* __r
   return accum;
 }
 
+__device__ float perlin_turb(const float4* __restrict__ vec, const uint8_t* __restrict__ perm, float3 p) {  // perlin.rs:86-98
+  float accum = 0.f, weight = 1.f;
+  float3 tp = p;
+  for (int i = 0; i < 7; ++i) {
+    accum += weight * perlin_noise(vec, perm, tp);
+    weight *= 0.5f;
+    tp = 2.0f * tp;
+  }
+  return fabsf(accum);
+}
+
 __device__ float3 tex_value_slow(const DevScene& sc, uint32_t tex, const Surf& s) {
   DevTexture t = sc.textures[tex];
   if (t.type == RTB_TEX_CHECKER) {  // texture.rs:60-69, on the world-space point
@@ -390,16 +413,7 @@ __device__ float3 tex_value_slow(const DevScene& sc, uint32_t tex, const Surf& s
     t = sc.textures[sines < 0.f ? t.odd : t.even];
   }
   if (t.type == RTB_TEX_NOISE) {  // texture.rs:90-96
-    const float4* vec = sc.perlin_vec[t.table];
-    const uint8_t* perm = sc.perlin_perm[t.table];
-    float accum = 0.f, weight = 1.f;
-    float3 tp = s.p;
-    for (int i = 0; i < 7; ++i) {
-      accum += weight * perlin_noise(vec, perm, tp);
-      weight *= 0.5f;
-      tp = 2.0f * tp;
-    }
-    const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * fabsf(accum)));
+    const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * perlin_turb(sc.perlin_vec[t.table], sc.perlin_perm[t.table], s.p)));
     return f3(g, g, g);
   }
   if (t.type == RTB_TEX_IMAGE) {  // texture.rs:118-140: nearest texel, v flipped
@@ -486,6 +500,14 @@ __device__ float3 lights_random(const DevScene& sc, float3 o, float pick, float 
   float sn, cs;
   __sincosf(phi, &sn, &cs);
   return Onb(dir).local(f3(cs * s, sn * s, z));
+}
+
+__device__ __forceinline__ float3 reflect3(float3 v, float3 n) { return fma3(-2.0f * dot(v, n), n, v); }  // vec3.rs:115-117
+__device__ __forceinline__ float3 refract3(float3 uv, float3 n, float ratio) {                               // vec3.rs:246-251
+  const float cos_theta = fminf(-dot(uv, n), 1.0f);
+  const float3 perp = ratio * fma3(cos_theta, n, uv);
+  const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
+  return fma3(par, n, perp);
 }
 
 // ---- common shade prologue/epilogue --------------------------------------------------------------------------------
@@ -708,7 +730,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
       float ntime = io.time;
       if (__float_as_uint(m.x) == RTB_MAT_METAL) {
         const float fuzz = fminf(m.z, 1.0f);
-        dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);  // reflect, vec3.rs:115-117
+        dir = reflect3(ud, s.n);
         if (fuzz > 0.f) {  // random_in_unit_sphere (vec3.rs:78-86) in closed form: uniform direction * cbrt(xi)
           const float z = 1.0f - 2.0f * ua.y, phi = 2.0f * RTB_PI * ua.z, rad = cbrtf(ua.w);
           const float r = sqrt_fast(fmaxf(0.f, 1.0f - z * z));
@@ -728,13 +750,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS, RTB_SHADE_MIN_BLOCKS) k_sha
         r0 *= r0;
         const float om = 1.0f - cos_theta;
         const float reflectance = r0 + (1.0f - r0) * (om * om) * (om * om) * om;
-        if (cannot_refract || reflectance > ua.y) {
-          dir = fma3(-2.0f * dot(ud, s.n), s.n, ud);
-        } else {
-          const float3 perp = ratio * fma3(cos_theta, s.n, ud);
-          const float par = -sqrt_fast(fabsf(1.0f - dot(perp, perp)));
-          dir = fma3(par, s.n, perp);
-        }
+        dir = (cannot_refract || reflectance > ua.y) ? reflect3(ud, s.n) : refract3(ud, s.n, ratio);
       }
       return finish_bounce(pool, prm, io, true, s.p, dir, ntime, ua.x);
   });
@@ -768,19 +784,44 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
     c->iter_rays = c->last_rays = 0;
     c->iter = 0;
     c->ext_cursor = 0;
+    c->redo_count = c->fix_ticket = 0;
+    c->redone = 0;
     c->total_paths = total_paths;
     c->segments = c->rejected = 0;
     c->nodes_visited = c->prims_tested = 0;
   }
 }
 
-__global__ void k_advance(DevPool pool) {
+// ---- the exact pass + iteration bookkeeping (runs after extend, before the shade kernels) ---------------------------
+// Every ray `extend` queued (its closest hit was undecidable in f32) is re-traced with traverse_exact() and its hit
+// record rewritten; the last CTA to finish then rotates the iteration counters (what a one-thread kernel did before).
+#define RTB_FIXUP_THREADS 128
+__global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPool pool, DevParams prm) {
   DevCounters* c = pool.c;
-  c->segments += c->iter_rays;
-  c->last_rays = c->iter_rays;
-  c->iter_rays = 0;
-  c->ext_cursor = 0;
-  c->iter += 1;
+  const uint32_t n = c->redo_count;
+  for (uint32_t i = blockIdx.x * RTB_FIXUP_THREADS + threadIdx.x; i < n; i += gridDim.x * RTB_FIXUP_THREADS) {
+    const uint32_t slot = pool.redo[i];
+    const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
+    const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w);
+    finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+  }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&c->fix_ticket, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    c->segments += c->iter_rays;
+    c->redone += n;
+    c->last_rays = c->iter_rays;
+    c->iter_rays = 0;
+    c->ext_cursor = 0;
+    c->redo_count = 0;
+    c->fix_ticket = 0;
+    c->iter += 1;
+  }
 }
 
 // ---- write_color, main.rs:141-169 ----------------------------------------------------------------------------------
@@ -799,28 +840,28 @@ __global__ void k_finalize(const float4* __restrict__ accum, uint8_t* __restrict
   }
 }
 
-// ---- parity probes: the same traverse<> the extend kernel runs --------------------------------------------------------
-__global__ void __launch_bounds__(RTB_EXTEND_THREADS)
-k_probe(DevScene sc, const float* __restrict__ org, const float* __restrict__ dir, const float* __restrict__ time,
-        uint32_t n, uint32_t n_snodes, uint32_t* __restrict__ id_out, float* __restrict__ t_out, DevCounters* c) {
-  extern __shared__ uint4 snodes[];
-  stage_nodes(sc, snodes, n_snodes);
-  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
-  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
+// ---- parity probes: the PRODUCTION kernels (extend + k_fixup) run over a pool filled with the caller's rays ---------
+__global__ void k_probe_fill(DevPool pool, const float* __restrict__ org, const float* __restrict__ dir,
+                             const float* __restrict__ time, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pool.n_chunks * RTB_CHUNK) return;
+  if (i < n) {
+    pool.ray[2 * i] = make_float4(org[3 * i], org[3 * i + 1], org[3 * i + 2], time ? time[i] : 0.f);
+    pool.ray[2 * i + 1] = make_float4(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], 0.f);
+    pool.st[2 * i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    pool.st[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pool.cls[i] = (uint8_t)CLS_NEW;
+  } else {
+    pool.cls[i] = (uint8_t)CLS_DEAD;
+  }
+}
+__global__ void k_probe_collect(DevScene sc, DevPool pool, uint32_t n, uint32_t* __restrict__ id_out, float* __restrict__ t_out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
-  const float tm = time ? time[i] : 0.f;
-  Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
-  uint32_t nv = 0, nt = 0;
-  traverse<true>(sc, snodes, sbase, n_snodes, o, d, tm, RTB_TMIN, best, nv, nt);
-  if (sc.n_media) intersect_media(sc, o, d, RTB_TMIN, best, 0, 0, 0, 0, false);
-  id_out[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
-  t_out[i] = best.t;
-  if (c) {
-    atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-    atomicAdd(&c->prims_tested, (unsigned long long)nt);
-  }
+  const float4 h = pool.hit[i];
+  const uint32_t ref = __float_as_uint(h.y);
+  id_out[i] = ref == REF_MISS ? RTB_NONE : ref_gid(sc, ref);
+  t_out[i] = h.x;
 }
 
 // pixel-centre primary rays, generated in f64 like the reference's camera (camera.rs:60-70) and rounded once
@@ -837,6 +878,73 @@ __global__ void k_primary_rays(DevCameraF64 cam, uint32_t W, uint32_t H, float* 
   time[i] = (float)cam.time0;
 }
 
+// ---- tier U2: the device functions themselves, evaluated on known-answer inputs (tests/test_gpu_kat.py) ---------------
+// in / out are raw 32-bit words (floats by bit pattern, integers as they are); one thread per item.
+__global__ void k_kat(DevScene sc, DevCamera cam, DevParams prm, uint32_t op, const uint32_t* __restrict__ in, uint32_t n,
+                      uint32_t in_stride, uint32_t* __restrict__ out, uint32_t out_stride) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* a = in + (size_t)i * in_stride;
+  uint32_t* o = out + (size_t)i * out_stride;
+  auto F = [&](uint32_t k) { return __uint_as_float(a[k]); };
+  auto V = [&](uint32_t k) { return f3(__uint_as_float(a[k]), __uint_as_float(a[k + 1]), __uint_as_float(a[k + 2])); };
+  auto put = [&](uint32_t k, float v) { o[k] = __float_as_uint(v); };
+  auto put3 = [&](uint32_t k, float3 v) { put(k, v.x); put(k + 1, v.y); put(k + 2, v.z); };
+  switch (op) {
+    case RTB_KAT_PHILOX: {  // (pixel, sample, block, bounce, seed) -> 4 words
+      const uint4 r = philox4(a[0], a[1], a[2], a[3], a[4]);
+      o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+      break;
+    }
+    case RTB_KAT_SPHERE: {  // (c, r, o, d, tmin, tmax) -> (status, t, e): the f32 sphere test with its error bound
+      float t = 0.f, e = 0.f;
+      const int st = sphere_fast(V(4), V(7), V(0), F(3), F(10), F(11), t, e);
+      o[0] = (uint32_t)st; put(1, t); put(2, e);
+      break;
+    }
+    case RTB_KAT_SPHERE_F64: {  // same inputs -> (status, t): the Newton-refined f64 form used for "global" spheres
+      float t = 0.f;
+      const int st = sphere_roots_f64(V(4), V(7), V(0), F(3), F(10), t);
+      o[0] = (uint32_t)st; put(1, t);
+      break;
+    }
+    case RTB_KAT_LIGHTS_PDF: put(0, lights_pdf(sc, V(0), V(3))); break;                      // (o, v) -> pdf over sc.lights
+    case RTB_KAT_LIGHTS_RANDOM: put3(0, lights_random(sc, V(0), F(3), F(4), F(5))); break;   // (o, pick, r1, r2) -> direction
+    case RTB_KAT_PERLIN_NOISE: put(0, perlin_noise(sc.perlin_vec[a[0]], sc.perlin_perm[a[0]], V(1))); break;  // (table, p)
+    case RTB_KAT_PERLIN_TURB: put(0, perlin_turb(sc.perlin_vec[a[0]], sc.perlin_perm[a[0]], V(1))); break;
+    case RTB_KAT_Q2F: put(0, q2f(a[0], sc.prmt_magic, 0x7044u | ((a[1] & 3u) << 8))); break;  // (plane word, byte) -> 128 + q
+    case RTB_KAT_ONB: { const Onb b(V(0)); put3(0, b.u); put3(3, b.v); put3(6, b.w); break; }
+    case RTB_KAT_REFLECT: put3(0, reflect3(V(0), V(3))); break;
+    case RTB_KAT_REFRACT: put3(0, refract3(V(0), V(3), F(6))); break;
+    case RTB_KAT_CAMERA_RAY: {  // (pixel, sample) -> (o, d, time) of camera_ray(), drawn from the path's own Philox blocks
+      float3 ro, rd;
+      float tm;
+      camera_ray(cam, prm, a[0], a[1], ro, rd, tm);
+      put3(0, ro); put3(3, rd); put(6, tm);
+      break;
+    }
+    case RTB_KAT_MEDIA: {  // (o, d, t_max) -> (hit, t, medium index) of intersect_media() at xi = 0.5
+      Closest best{F(6), F(6), REF_MISS};
+      intersect_media(sc, V(0), V(3), RTB_TMIN, best, 0, 0, 0, 0, false);
+      o[0] = best.ref != REF_MISS ? 1u : 0u; put(1, best.t); o[2] = best.ref & REF_INDEX_MASK;
+      break;
+    }
+    case RTB_KAT_TEXTURE: {  // (texture id, p, outward normal of a unit sphere at the origin) -> rgb of tex_value_slow()
+      Surf s;
+      s.p = V(1); s.outward = s.n = V(4); s.front = true; s.mat = 0; s.ref = ((uint32_t)PT_SPHERE << REF_TYPE_SHIFT) | a[7];
+      put3(0, tex_value_slow(sc, a[0], s));
+      break;
+    }
+    case RTB_KAT_EXACT: {  // (ref, o, d, time) -> exact_hit() as (hi word, lo word) of the f64 distance (-1: miss)
+      const double t = exact_hit(sc.xtab, a[0], V(1), V(4), F(7));
+      const unsigned long long b = (unsigned long long)__double_as_longlong(t);
+      o[0] = (uint32_t)(b >> 32); o[1] = (uint32_t)b;
+      break;
+    }
+    default: break;
+  }
+}
+
 // ================================================= launchers ========================================================
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -846,7 +954,9 @@ void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaS
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st) {
   k_generate<<<lc.shade_grid, RTB_SHADE_THREADS, 0, st>>>(pool, prm, cam);
 }
-void launch_advance(const DevPool& pool, cudaStream_t st) { k_advance<<<1, 1, 0, st>>>(pool); }
+void launch_fixup(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st) {
+  k_fixup<<<lc.fixup_grid, RTB_FIXUP_THREADS, 0, st>>>(sc, pool, prm);
+}
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
   // one-ray-per-thread wins on small trees (all lanes start at the root together); dynamic fetch wins on deep trees
@@ -875,10 +985,15 @@ void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, 
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st) {
   k_finalize<<<cdiv(npix, 256), 256, 0, st>>>(accum, rgb, npix, inv_spp);
 }
-void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
-                  uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st) {
-  k_probe<<<cdiv(n, RTB_EXTEND_THREADS), RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, org, dir, time, n, lc.n_snodes,
-                                                                                  id_out, t_out, c);
+void launch_probe_fill(const DevPool& pool, const float* org, const float* dir, const float* time, uint32_t n, cudaStream_t st) {
+  k_probe_fill<<<cdiv(pool.n_chunks * RTB_CHUNK, 256), 256, 0, st>>>(pool, org, dir, time, n);
+}
+void launch_probe_collect(const DevScene& sc, const DevPool& pool, uint32_t n, uint32_t* id_out, float* t_out, cudaStream_t st) {
+  k_probe_collect<<<cdiv(n, 256), 256, 0, st>>>(sc, pool, n, id_out, t_out);
+}
+void launch_kat(const DevScene& sc, const DevCamera& cam, const DevParams& prm, uint32_t op, const uint32_t* in, uint32_t n,
+                uint32_t in_stride, uint32_t* out, uint32_t out_stride, cudaStream_t st) {
+  k_kat<<<cdiv(n, 128), 128, 0, st>>>(sc, cam, prm, op, in, n, in_stride, out, out_stride);
 }
 void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
                          cudaStream_t st) {
@@ -911,8 +1026,6 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_extend_static<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-  if (e != cudaSuccess) return (int)e;
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
@@ -928,6 +1041,7 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (occ2 < 1) occ2 = 1;
   if (getenv("RTB_SHADE_OCC")) occ2 = std::max(1, std::min(occ2, atoi(getenv("RTB_SHADE_OCC"))));
   lc.shade_grid = (uint32_t)(sm_count * occ2);
+  lc.fixup_grid = (uint32_t)std::max(1, sm_count / 2);
   {  // smallest pool that gives every resident extend warp AND every resident shade warp a whole number of chunks
     uint32_t a = lc.extend_grid * RTB_EXTEND_WARPS, b = lc.shade_grid * RTB_SHADE_WARPS, x = a, y = b;
     while (y) { const uint32_t t = x % y; x = y; y = t; }

@@ -11,6 +11,8 @@
 #define RTB_SHADE_MIN_BLOCKS 3
 #endif
 
+#define RTB_OPT_PROBE 1u  /* DevParams::opt bit: parity probe (media sampled at xi = 0.5 instead of the path's stream) */
+
 namespace rtb {
 
 struct DevScene;
@@ -25,7 +27,7 @@ struct DevCameraF64 {  // camera.rs:6-17 in f64, for the parity probe's primary 
 };
 
 struct LaunchCfg {
-  uint32_t extend_grid = 0, shade_grid = 0, extend_smem = 0, n_snodes = 0;
+  uint32_t extend_grid = 0, shade_grid = 0, fixup_grid = 0, extend_smem = 0, n_snodes = 0;
   bool dynamic_fetch = false;
   bool all_staged = false;  // every BVH node fits the shared-memory stage: the kernel without a global node path is used
   // slots that give every resident shade warp exactly one chunk: pools are sized in multiples of this
@@ -35,15 +37,17 @@ struct LaunchCfg {
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);
-void launch_advance(const DevPool& pool, cudaStream_t st);
+void launch_fixup(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st);
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st);
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
                   const DevCamera& cam, uint32_t present, cudaStream_t st);
 void launch_finalize(const float4* accum, uint8_t* rgb, uint32_t npix, float inv_spp, cudaStream_t st);
-void launch_probe(const LaunchCfg& lc, const DevScene& sc, const float* org, const float* dir, const float* time,
-                  uint32_t n, uint32_t* id_out, float* t_out, DevCounters* c, cudaStream_t st);
+void launch_probe_fill(const DevPool& pool, const float* org, const float* dir, const float* time, uint32_t n, cudaStream_t st);
+void launch_probe_collect(const DevScene& sc, const DevPool& pool, uint32_t n, uint32_t* id_out, float* t_out, cudaStream_t st);
 void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
                          cudaStream_t st);
+void launch_kat(const DevScene& sc, const DevCamera& cam, const DevParams& prm, uint32_t op, const uint32_t* in, uint32_t n,
+                uint32_t in_stride, uint32_t* out, uint32_t out_stride, cudaStream_t st);
 
 }  // namespace rtb

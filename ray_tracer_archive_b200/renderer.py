@@ -31,6 +31,23 @@ class Context:
         except Exception:
             pass
 
+    def primary_rays(self, cam: F.Camera, width: int, height: int):
+        """The f32 pixel-centre rays rtb_primary_hits traces: (origin (n,3), direction (n,3), time (n,)) float32."""
+        n = width * height
+        o, d, t = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32)
+        F.check(self.lib.rtb_primary_rays(self.h, C.byref(cam), width, height, F.ptr(o), F.ptr(d), F.ptr(t)))
+        return o, d, t
+
+    def kat(self, op: int, words, out_stride: int, scene=None, cam=None, params=None):
+        """Tier-U2 hook (rtb_device_kat): `words` (n, in_stride) uint32 -> (n, out_stride) uint32."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        out = np.zeros((w.shape[0], out_stride), dtype=np.uint32)
+        F.check(self.lib.rtb_device_kat(self.h, scene.h if scene is not None else None,
+                                        C.byref(cam) if cam is not None else None,
+                                        C.byref(params) if params is not None else None, op, F.ptr(w), w.shape[0],
+                                        w.shape[1], F.ptr(out), out_stride))
+        return out
+
     def device_info(self):
         sm, l2, khz = C.c_int(), C.c_int(), C.c_int()
         name = C.create_string_buffer(128)

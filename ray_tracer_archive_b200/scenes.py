@@ -101,8 +101,20 @@ def config_random_spheres(width=1200, height=675, spp=500, seed=1) -> Config:
 
 
 # ---------------------------------------------------------------------------------------------- C3/C5: book-2 final
+def earthmap() -> np.ndarray:
+    """The reference's earthmap.jpg (main.rs:281,601) as raw RGB8 texels (512, 1024, 3): decoded once from
+    /root/reference/earthmap.jpg by tests/golden/make_earthmap.py and committed as tests/golden/earthmap_rgb8.npz
+    (RTB_EARTHMAP overrides the path).  Falls back to the seeded synthetic map only if that file is missing."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.environ.get("RTB_EARTHMAP", os.path.join(os.path.dirname(here), "tests", "golden", "earthmap_rgb8.npz"))
+    if os.path.exists(path):
+        return np.ascontiguousarray(np.load(path)["rgb"], dtype=np.uint8)
+    return synthetic_earth()
+
+
 def synthetic_earth(width=1024, height=512, seed=7) -> np.ndarray:
-    """Stand-in for earthmap.jpg (1024x512 RGB8), which cannot travel to the GPU box: smooth seeded continents."""
+    """Seeded stand-in for an RGB8 map (used by tests that want a second image, and as earthmap()'s fallback)."""
     rng = np.random.default_rng(seed)
     y, x = np.mgrid[0:height, 0:width]
     lon, lat = x / width * 2 * np.pi, (y / height - 0.5) * np.pi
@@ -147,7 +159,7 @@ def final_scene(seed=1, boxes_per_side=20, n_small=1000, earth: Optional[np.ndar
     objects.add(ConstantMedium.construct_color(boundary, 0.2, (0.2, 0.4, 0.9)))
     boundary2 = Sphere.construct((0.0, 0.0, 0.0), 5000.0, Dielectric.construct(1.5))
     objects.add(ConstantMedium.construct_color(boundary2, 0.0001, (1.0, 1.0, 1.0)))
-    img = earth if earth is not None else synthetic_earth()
+    img = earth if earth is not None else earthmap()
     emat = Lambertian.construct_texture(ImageTexture.construct(img, img.shape[1], img.shape[0]))
     objects.add(Sphere.construct((400.0, 200.0, 400.0), 100.0, emat))
     pertext = NoiseTexture.construct(0.1, rng)
@@ -260,7 +272,7 @@ def two_perlin_spheres(seed=1) -> HittableList:  # main.rs:265-279
 
 
 def earth(img: Optional[np.ndarray] = None) -> HittableList:  # main.rs:280-299
-    img = img if img is not None else synthetic_earth()
+    img = img if img is not None else earthmap()
     surface = Lambertian.construct_texture(ImageTexture.construct(img, img.shape[1], img.shape[0]))
     return HittableList.construct(Sphere.construct((0.0, 0.0, 0.0), 2.0, surface))
 

@@ -32,10 +32,10 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 #undef __forceinline__
 #define __forceinline__ inline
 
-#define RTB_EMUL_STATS 1
 #include "../../ray_tracer_archive_b200/csrc/rtb_device.cuh"
 
 using namespace rtb;
+static unsigned long long g_exact_rays = 0;
 
 extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
                           const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
@@ -55,14 +55,24 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   const float* g[4] = {geom0, geom1, geom2, geom3};
   const uint32_t* inf[4] = {info0, info1, info2, info3};
   for (int t = 0; t < 4; ++t) { sc.geom[t] = (const float4*)g[t]; sc.info[t] = (const uint2*)inf[t]; }
-  sc.exact[0] = exact0; sc.exact[1] = exact1; sc.exact[2] = exact2; sc.exact[3] = nullptr;
+  static ExactTab xt;
+  std::memset(&xt, 0, sizeof(xt));
+  xt.tri = (const float4*)geom3;
+  xt.exact[0] = exact0; xt.exact[1] = exact1; xt.exact[2] = exact2;
+  for (int t = 0; t < 4; ++t) xt.info[t] = (const uint2*)inf[t];
+  sc.xtab = &xt;
   sc.coord_max = coord_max; sc.eps_ab = eps_ab; sc.global_f64 = global_f64;
   uint64_t nv_total = 0, nt_total = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    Closest best{INFINITY, INFINITY, REF_MISS, REF_MISS};
+    Closest best;
     uint32_t nv = 0, nt = 0;
-    traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]),
-                   f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
+    const float3 ro = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), rd = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    // the hot path (f32, ambiguity detection), then — as k_fixup does on the device — the exact pass if it asked for one
+    if (traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd, time ? time[i] : 0.f,
+                       RTB_TMIN, best, nv, nt)) {
+      best = traverse_exact(sc, ro, rd, time ? time[i] : 0.f);
+      ++g_exact_rays;
+    }
     ids[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
     ts[i] = best.t;
     nv_total += nv; nt_total += nt;
@@ -72,9 +82,11 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   return 0;
 }
 
-// exact-path call counts per primitive type since the last call (sphere, moving, quad, triangle) + pair resolutions
-extern "C" void emul_exact_calls(unsigned long long* out4) {
-  for (int i = 0; i < 5; ++i) { out4[i] = rtb::g_exact_calls[i]; rtb::g_exact_calls[i] = 0; }
+// rays that went through the exact pass since the last call
+extern "C" unsigned long long emul_exact_rays() {
+  const unsigned long long n = g_exact_rays;
+  g_exact_rays = 0;
+  return n;
 }
 
 // path numbering of the slot-stable pool (rtb_device.cuh: chunk_path), exposed for tests/test_pool_numbering.py

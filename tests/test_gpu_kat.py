@@ -1,0 +1,356 @@
+"""Tier U2 (-m gpu): the DEVICE functions themselves, evaluated by a test kernel (rtb_device_kat -> k_kat) on the U1
+known-answer vectors of tests/golden/kat_vectors.json and against the oracle's own unit entry points.
+
+Integer work is bit-exact (Philox4x32-10 words, the BVH plane-byte decode); floating point within 1e-5 relative
+(SURVEY §4 tier U2) unless a tighter bound is stated.  Reference lines: rt_weekend.rs:8-19 (RNG, replaced by Philox),
+sphere.rs:41-65,75-90, aarect.rs:107-125, perlin.rs:26-98, onb.rs:19-30, vec3.rs:115-117,246-251, camera.rs:60-70,
+constant_medium.rs:31-71, texture.rs:61-68,91-95,118-140."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "kat_vectors.json")) as f:
+    G = json.load(f)
+
+
+def f2w(x):
+    """float32 values -> their 32-bit words"""
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def w2f(w):
+    return np.ascontiguousarray(w, dtype=np.uint32).view(np.float32)
+
+
+def dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_philox_words_bit_exact(rtb, orc, ctx):
+    """The device Philox stream IS the oracle's: golden words, then 20 000 random (pixel, sample, block, bounce, seed)
+    tuples word for word against oracle/rt_oracle.hpp:Philox::gen."""
+    F = rtb._ffi
+    args = np.array([c["args"] for c in G["philox"]], dtype=np.uint32)
+    out = ctx.kat(F.KAT_PHILOX, args, 4)
+    assert np.array_equal(out, np.array([c["expect"] for c in G["philox"]], dtype=np.uint32))
+    rng = np.random.default_rng(11)
+    args = rng.integers(0, 2 ** 32, size=(20000, 5), dtype=np.uint64).astype(np.uint32)
+    args[:4000, 2] = rng.integers(0, 16, 4000)      # the block / bounce ranges the integrator really uses
+    args[:4000, 3] = rng.integers(0, 51, 4000)
+    out = ctx.kat(F.KAT_PHILOX, args, 4)
+    lib = orc.load()
+    exp = np.zeros((len(args), 4), dtype=np.uint32)
+    row = np.zeros(4, dtype=np.uint32)
+    for i, a in enumerate(args):
+        lib.orc_kat_philox(int(a[0]), int(a[1]), int(a[2]), int(a[3]), int(a[4]), dptr(row))
+        exp[i] = row
+    assert np.array_equal(out, exp)
+
+
+def test_q2f_plane_decode_exact(rtb, ctx):
+    """byte q of a plane word -> the float 128 + q, for every q in 0..127 and every byte position."""
+    F = rtb._ffi
+    rows, exp = [], []
+    for b in range(4):
+        for q in range(128):
+            rows.append([(q << (8 * b)) | (0x55AA55AA & ~(0xFF << (8 * b)) & 0xFFFFFFFF), b])
+            exp.append(128.0 + q)
+    out = w2f(ctx.kat(F.KAT_Q2F, np.array(rows, dtype=np.uint32), 1))[:, 0]
+    assert np.array_equal(out, np.array(exp, dtype=np.float32))
+
+
+def _sphere_rows(cases):
+    rows = []
+    for c in cases:
+        tmax = c["tmax"] if math.isfinite(c["tmax"]) else 3.0e38
+        rows.append(list(c["c"]) + list(c["o"]) + list(c["d"]) + [c["tmin"], tmax])
+    return f2w(np.array(rows))
+
+
+def test_sphere_hit_golden(rtb, ctx):
+    """sphere_fast (f32 + error bound) and sphere_roots_f64 on the U1 vectors: same hit / miss, t within 1e-5, and the
+    returned bound really bounds the error."""
+    F = rtb._ffi
+    cases = G["sphere_hit"]
+    rows = _sphere_rows(cases)
+    o32 = ctx.kat(F.KAT_SPHERE, rows, 3)
+    o64 = ctx.kat(F.KAT_SPHERE_F64, rows, 2)
+    n_hit = 0
+    for c, a, b in zip(cases, o32, o64):
+        exp = c["expect"]
+        tmax = c["tmax"] if math.isfinite(c["tmax"]) else 3.0e38
+        st, t, e = int(a[0]), float(w2f(a[1:2])[0]), float(w2f(a[2:3])[0])
+        st64, t64 = int(b[0]), float(w2f(b[1:2])[0])
+        if exp is None:
+            assert st in (0, 2) or t > tmax  # miss, or undecided (grazing) — never a certain hit in range
+            assert st64 in (0, 2) or t64 > tmax
+            continue
+        n_hit += 1
+        assert st64 == 1 and abs(t64 - exp[0]) <= 2e-7 * exp[0] + 1e-7 * np.abs(c["o"]).max() / np.linalg.norm(c["d"])
+        if st == 1:
+            # inputs were rounded to f32: that alone moves t by ~1e-7 |o| / |d|
+            slack = 4e-7 * (np.abs(c["o"]).max() + np.abs(c["c"]).max()) / np.linalg.norm(c["d"])
+            assert abs(t - exp[0]) <= 1e-5 * exp[0]
+            assert abs(t - exp[0]) <= e + slack, (t, exp[0], e)
+        else:
+            assert st == 2  # undecided in f32 -> the exact pass; must not be reported as a miss
+    assert n_hit >= 10
+
+
+def test_sphere_fast_bound_holds_on_random_rays(rtb, orc, ctx):
+    """200 000 random ray / sphere pairs (incl. grazing, origin on the surface, huge radii): whenever the f32 test is
+    certain it agrees with the f64 reference about hit / miss and |t - t_ref| <= its own bound (<= 5e-5 t)."""
+    F = rtb._ffi
+    rng = np.random.default_rng(3)
+    n = 200000
+    c = rng.uniform(-50, 50, (n, 3))
+    r = 10 ** rng.uniform(-1, 3, n)
+    o = c + rng.normal(0, 1, (n, 3)) * (r * rng.uniform(0.2, 4, n))[:, None]
+    on_surface = rng.random(n) < 0.25
+    u = rng.normal(0, 1, (n, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    o[on_surface] = c[on_surface] + u[on_surface] * r[on_surface, None]
+    tgt = c + rng.normal(0, 1, (n, 3)) * (r * rng.uniform(0, 1.3, n))[:, None]
+    d = (tgt - o) * rng.uniform(0.01, 30, n)[:, None]
+    rows = np.concatenate([c, r[:, None], o, d, np.full((n, 1), 0.001), np.full((n, 1), 3e38)], axis=1).astype(np.float32)
+    out = ctx.kat(F.KAT_SPHERE, rows.view(np.uint32), 3)
+    st, t, e = out[:, 0].astype(int), w2f(out[:, 1]), w2f(out[:, 2])
+    # reference on the SAME f32 inputs
+    R = rows.astype(np.float64)
+    cc, rr, oo, dd = R[:, 0:3], R[:, 3], R[:, 4:7], R[:, 7:10]
+    oc = oo - cc
+    a = (dd * dd).sum(1)
+    hb = (oc * dd).sum(1)
+    det = hb * hb - a * ((oc * oc).sum(1) - rr * rr)
+    ok = det >= 0
+    sq = np.sqrt(np.where(ok, det, 0))
+    r1, r2 = (-hb - sq) / a, (-hb + sq) / a
+    tref = np.where(r1 >= 0.001, r1, r2)
+    hit = ok & (tref >= 0.001)
+    certain_hit, certain_miss = st == 1, st == 0
+    assert (certain_hit & ~hit).sum() == 0 and (certain_miss & hit).sum() == 0
+    err = np.abs(t[certain_hit] - tref[certain_hit])
+    assert (err <= e[certain_hit] * 1.0 + 1e-30).all(), float((err / np.maximum(e[certain_hit], 1e-30)).max())
+    assert (e[certain_hit] <= 5.0001e-5 * t[certain_hit]).all()
+    assert certain_hit.sum() > 0.2 * n and (st == 2).mean() < 0.35
+    print(f"sphere_fast: {certain_hit.mean():.3f} certain hits, {certain_miss.mean():.3f} certain misses, {(st == 2).mean():.3f} undecided;"
+          f" max err/bound {float((err / np.maximum(e[certain_hit], 1e-30)).max()):.3f}, max rel err {float((err / tref[certain_hit]).max()):.2e}")
+
+
+def _cornell_scene(rtb, ctx):
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_cornell()
+    return rtb.Scene(ctx, rtb.compile_scene(cfg.world, cfg.lights)), cfg
+
+
+def test_light_pdfs_golden_and_oracle(rtb, orc, ctx):
+    """lights_pdf / lights_random on single-light scenes built from the U1 vectors, then the Cornell light list
+    (XzRect + Sphere, main.rs:669-684) against the oracle's HittableList::pdf_value on random rays."""
+    from ray_tracer_archive_b200 import scene as S
+    F = rtb._ffi
+    lam = S.Lambertian.construct((0.5, 0.5, 0.5))
+    for c in G["xzrect_pdf"]:
+        a = c["abk"]
+        rect = S.XzRect.construct(a[0], a[1], a[2], a[3], a[4], lam)
+        sc = rtb.Scene(ctx, rtb.compile_scene(S.HittableList([rect]), S.HittableList([rect])))
+        got = w2f(ctx.kat(F.KAT_LIGHTS_PDF, f2w([list(c["o"]) + list(c["d"])]), 1, scene=sc))[0, 0]
+        assert got == pytest.approx(c["pdf"], rel=1e-5, abs=1e-7)
+    for c in G["sphere_pdf"]:
+        sp = S.Sphere.construct(tuple(c["c"][:3]), c["c"][3], lam)
+        sc = rtb.Scene(ctx, rtb.compile_scene(S.HittableList([sp]), S.HittableList([sp])))
+        got = w2f(ctx.kat(F.KAT_LIGHTS_PDF, f2w([list(c["o"]) + list(c["d"])]), 1, scene=sc))[0, 0]
+        assert got == pytest.approx(c["pdf"], rel=2e-5, abs=1e-7)
+    dev, cfg = _cornell_scene(rtb, ctx)
+    lib = orc.load()
+    rng = np.random.default_rng(5)
+    n = 4000
+    o = rng.uniform(20, 530, (n, 3)).astype(np.float32)
+    tgt = np.stack([rng.uniform(150, 400, n), np.where(rng.random(n) < 0.5, 554.0, rng.uniform(0, 180, n)), rng.uniform(150, 400, n)], 1)
+    v = (tgt - o).astype(np.float32)
+    got = w2f(ctx.kat(F.KAT_LIGHTS_PDF, np.concatenate([o, v], 1).view(np.uint32), 1, scene=dev))[:, 0]
+    exp = np.zeros(n)
+    rect = np.array([213.0, 343.0, 227.0, 332.0, 554.0])
+    sph = np.array([190.0, 90.0, 190.0, 90.0])
+    for i in range(n):
+        oo, vv = o[i].astype(np.float64), v[i].astype(np.float64)
+        exp[i] = 0.5 * lib.orc_kat_xzrect_pdf(dptr(rect), dptr(oo), dptr(vv)) + 0.5 * lib.orc_kat_sphere_pdf(dptr(sph), dptr(oo), dptr(vv))
+    both = (exp > 0) & (got > 0)
+    assert (exp > 0).sum() > 500
+    # a ray within f32 rounding of a light's edge may be in for one side and out for the other
+    assert ((exp > 0) != (got > 0)).sum() <= 3
+    np.testing.assert_allclose(got[both], exp[both], rtol=3e-5)
+    # lights_random: the sphere light's cone sample against Sphere::random (sphere.rs:85-90), the rect's against aarect.rs:118-125
+    u = rng.random((n, 3)).astype(np.float32)
+    rows = np.concatenate([o, u], 1)
+    got = w2f(ctx.kat(F.KAT_LIGHTS_RANDOM, rows.view(np.uint32), 3, scene=dev))
+    out3 = np.zeros(3)
+    for i in range(0, n, 7):
+        oo = o[i].astype(np.float64)
+        k = min(int(float(u[i, 0]) * 2), 1)
+        if k == 0:
+            exp3 = np.array([213.0 + 130.0 * float(u[i, 1]), 554.0, 227.0 + 105.0 * float(u[i, 2])]) - oo
+        else:
+            lib.orc_kat_sphere_random(dptr(sph), dptr(oo), float(u[i, 1]), float(u[i, 2]), dptr(out3))
+            exp3 = out3.copy()
+        np.testing.assert_allclose(got[i], exp3, rtol=2e-4, atol=2e-4 * np.linalg.norm(exp3))
+
+
+def _perlin_scene(rtb, orc, ctx):
+    from ray_tracer_archive_b200 import scene as S
+    g = G["perlin"]
+    noise = S.Perlin(np.array(g["ranvec"]), *(np.array(x, dtype=np.uint32) for x in g["perm"]))
+    tex = S.NoiseTexture(noise, 4.0)
+    checker = S.CheckerTexture.construct_color((0.2, 0.3, 0.1), (0.9, 0.9, 0.9))
+    img = (np.arange(16 * 8 * 3) % 251).astype(np.uint8).reshape(8, 16, 3)
+    world = S.HittableList([S.Sphere((0, 0, 0), 1.0, S.Lambertian.construct_texture(tex)),
+                            S.Sphere((3, 0, 0), 1.0, S.Lambertian.construct_texture(checker)),
+                            S.Sphere((6, 0, 0), 1.0, S.Lambertian.construct_texture(S.ImageTexture.construct(img, 16, 8)))])
+    cs = rtb.compile_scene(world)
+    return rtb.Scene(ctx, cs), orc.OracleScene(cs), cs
+
+
+def test_perlin_noise_turb_and_textures(rtb, orc, ctx):
+    """perlin_noise / perlin_turb (double Hermite smoothing, perlin.rs:30-32,68-80) on the U1 cases and 5000 random
+    points against the oracle; checker / noise / image texture values through tex_value_slow."""
+    F = rtb._ffi
+    dev, osc, cs = _perlin_scene(rtb, orc, ctx)
+    lib = orc.load()
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([np.array([c["p"] for c in G["perlin"]["cases"]]), rng.uniform(-40, 40, (5000, 3))]).astype(np.float32)
+    rows = np.concatenate([np.zeros((len(pts), 1), np.uint32), pts.view(np.uint32)], 1)
+    noise = w2f(ctx.kat(F.KAT_PERLIN_NOISE, rows, 1, scene=dev))[:, 0]
+    turb = w2f(ctx.kat(F.KAT_PERLIN_TURB, rows, 1, scene=dev))[:, 0]
+    en = np.array([lib.orc_kat_perlin_noise(osc.h, 0, dptr(p.astype(np.float64))) for p in pts])
+    et = np.array([lib.orc_kat_perlin_turb(osc.h, 0, dptr(p.astype(np.float64))) for p in pts])
+    # noise values are O(1) sums of 8 O(1) terms: absolute 1e-5 (a relative bound is meaningless near its zeros)
+    assert np.abs(noise - en).max() < 1e-5 and np.abs(turb - et).max() < 2e-5
+    for k, c in enumerate(G["perlin"]["cases"]):  # the golden values themselves (f64 inputs rounded to f32: 1e-5 abs)
+        assert abs(noise[k] - c["noise"]) < 2e-5 and abs(turb[k] - c["turb"]) < 4e-5
+    # textures: (texture id, p, outward normal, sphere leaf index)
+    types = [int(t["type"]) for t in cs.textures]
+    out3 = np.zeros(3)
+    n = 1500
+    p = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    nrm = rng.normal(0, 1, (n, 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(np.float32)
+    for ttype in (1, 2, 3):
+        ti = types.index(ttype)
+        rows = np.concatenate([np.full((n, 1), ti, np.uint32), p.view(np.uint32), nrm.view(np.uint32), np.zeros((n, 1), np.uint32)], 1)
+        got = w2f(ctx.kat(F.KAT_TEXTURE, rows, 3, scene=dev))
+        bad = 0
+        for i in range(n):
+            nn = nrm[i].astype(np.float64)
+            theta, phi = math.acos(max(-1.0, min(1.0, -nn[1]))), math.atan2(-nn[2], nn[0]) + math.pi  # sphere.rs:32-37
+            lib.orc_kat_texture(osc.h, ti, phi / (2 * math.pi), theta / math.pi, dptr(p[i].astype(np.float64)), dptr(out3))
+            if not np.allclose(got[i], out3, rtol=1e-5, atol=2e-5):
+                bad += 1
+        # checker cells / texel boundaries are knife edges in f32: a handful of points may fall on the other side
+        assert bad <= (6 if ttype != 2 else 0), (ttype, bad)
+
+
+def test_onb_reflect_refract_golden(rtb, ctx):
+    F = rtb._ffi
+    n = np.array([c["n"] for c in G["onb"]])
+    got = w2f(ctx.kat(F.KAT_ONB, f2w(n), 9))
+    np.testing.assert_allclose(got, np.array([c["uvw"] for c in G["onb"]]), rtol=1e-5, atol=2e-6)
+    rr = G["reflect_refract"]
+    rows = np.array([list(c["v"]) + list(c["n"]) + [c["eta"]] for c in rr])
+    got = w2f(ctx.kat(F.KAT_REFLECT, f2w(rows), 3))
+    np.testing.assert_allclose(got, np.array([c["reflect"] for c in rr]), rtol=1e-5, atol=2e-6)
+    got = w2f(ctx.kat(F.KAT_REFRACT, f2w(rows), 3))
+    np.testing.assert_allclose(got, np.array([c["refract"] for c in rr]), rtol=1e-5, atol=3e-6)
+
+
+def test_camera_ray_matches_oracle_stream(rtb, orc, ctx):
+    """camera_ray() for (pixel, sample): jitter, lens sample and time come from the path's Philox blocks — the oracle's
+    get_ray (camera.rs:60-70) fed with the same words must give the same ray."""
+    from ray_tracer_archive_b200 import scenes
+    F = rtb._ffi
+    cfg = scenes.config_random_spheres()
+    lib = orc.load()
+    W, Hh, seed = 240, 135, 17
+    prm = rtb.make_params(W, Hh, 1, seed=seed)
+    rng = np.random.default_rng(2)
+    px = rng.integers(0, W * Hh, 3000).astype(np.uint32)
+    smp = rng.integers(0, 5000, 3000).astype(np.uint32)
+    got = w2f(ctx.kat(F.KAT_CAMERA_RAY, np.stack([px, smp], 1), 7, cam=cfg.camera, params=prm))
+    words = np.zeros(4, dtype=np.uint32)
+    out6 = np.zeros(6)
+    for i in range(0, 3000, 3):
+        lib.orc_kat_philox(int(px[i]), int(smp[i]), 0, 0, seed, dptr(words))
+        u = (words >> 8).astype(np.float64) / 16777216.0
+        row, col = divmod(int(px[i]), W)
+        j = Hh - 1 - row
+        s, t = (col + u[0]) / (W - 1), (j + u[1]) / (Hh - 1)
+        rr, phi = math.sqrt(u[2]), 2 * math.pi * u[3]
+        lib.orc_kat_camera_ray(C.byref(cfg.camera), s, t, rr * math.cos(phi), rr * math.sin(phi), 0.0, dptr(out6))
+        np.testing.assert_allclose(got[i, :6], out6, rtol=2e-5, atol=2e-5)
+        lib.orc_kat_philox(int(px[i]), int(smp[i]), 1, 0, seed, dptr(words))
+        assert got[i, 6] == pytest.approx((int(words[0]) >> 8) / 16777216.0, abs=1e-6)
+
+
+def test_exact_hit_is_bit_identical_to_oracle(rtb, orc, ctx):
+    """exact_hit(): the reference's f64 arithmetic on the device.  For every primitive type of the final scene
+    (spheres under Translate(RotateY), box sides, moving sphere) and the Cornell box (rotated box, walls), the f64
+    distance is BIT-identical to what the oracle computes for the same f32 ray."""
+    from ray_tracer_archive_b200 import scenes
+    F = rtb._ffi
+    for cfg in (scenes.config_final_scene(boxes_per_side=6, n_small=60), scenes.config_cornell()):
+        cs = rtb.compile_scene(cfg.world, cfg.lights)
+        dev, osc = rtb.Scene(ctx, cs), orc.OracleScene(cs)
+        o, d, tm = ctx.primary_rays(cfg.camera, 160, 160)
+        ids, ts, _ = dev.trace_rays(o, d, tm)
+        oid, ot = osc.trace_rays(o.astype(np.float64), d.astype(np.float64), tm.astype(np.float64))
+        nodes, prims = dev.export_bvh()
+        # leaf reference of each primitive id
+        ref_of = {}
+        for t, (g, inf) in enumerate(prims):
+            for k in range(len(inf) // 2):
+                ref_of[int(inf[2 * k])] = (t << 29) | k
+        media = set(int(x) for x in np.unique(oid)) - set(ref_of) - {H.NONE}
+        sel = np.array([i for i in range(len(oid)) if int(oid[i]) in ref_of])
+        rows = np.concatenate([np.array([ref_of[int(oid[i])] for i in sel], np.uint32)[:, None], o[sel].view(np.uint32),
+                               d[sel].view(np.uint32), tm[sel].view(np.uint32)[:, None]], 1)
+        out = ctx.kat(F.KAT_EXACT, rows, 2, scene=dev)
+        bits = (out[:, 0].astype(np.uint64) << np.uint64(32)) | out[:, 1].astype(np.uint64)
+        t64 = bits.view(np.float64)
+        assert len(sel) > 10000 and len(media) <= 2
+        assert np.array_equal(t64, ot[sel]), f"{(t64 != ot[sel]).sum()} of {len(sel)} distances differ in f64"
+        assert np.array_equal(ids[sel], oid[sel])
+
+
+def test_media_interval_matches_oracle(rtb, orc, ctx):
+    """intersect_media (constant_medium.rs:31-71) at xi = 0.5, sphere and rotated-box boundaries, against the oracle's
+    ConstantMedium::hit for the same rays."""
+    from ray_tracer_archive_b200 import scene as S
+    F = rtb._ffi
+    b1 = S.Sphere.construct((0.0, 1.0, 0.0), 1.5, S.Dielectric.construct(1.5))
+    b2 = S.Translate.construct(S.RotateY.construct(S.Box.construct((0, 0, 0), (2, 3, 2), S.Lambertian.construct((1, 1, 1))), 25.0), (4.0, 0.0, -1.0))
+    world = S.HittableList([S.ConstantMedium.construct_color(b1, 0.8, (0.9, 0.9, 0.9)),
+                            S.ConstantMedium.construct_color(b2, 0.5, (0.1, 0.1, 0.1))])
+    cs = rtb.compile_scene(world)
+    dev, osc = rtb.Scene(ctx, cs), orc.OracleScene(cs)
+    rng = np.random.default_rng(4)
+    n = 20000
+    o = rng.uniform((-4, -1, -5), (9, 5, 5), (n, 3)).astype(np.float32)
+    tgt = np.where(rng.random((n, 1)) < 0.5, rng.normal((0, 1, 0), 1.0, (n, 3)), rng.normal((5, 1.5, 0), 1.2, (n, 3)))
+    d = ((tgt - o) * rng.uniform(0.2, 3, (n, 1))).astype(np.float32)
+    rows = np.concatenate([o, d, np.full((n, 1), 3e38, np.float32)], 1)
+    out = ctx.kat(F.KAT_MEDIA, rows.view(np.uint32), 3, scene=dev)
+    hit, t, which = out[:, 0] == 1, w2f(out[:, 1]), out[:, 2]
+    oid, ot = osc.trace_rays(o.astype(np.float64), d.astype(np.float64))
+    ohit = oid != H.NONE
+    assert ohit.sum() > 2000
+    assert (hit != ohit).sum() <= 4  # hit_distance vs distance_inside is a knife edge for a few rays
+    both = hit & ohit
+    assert np.array_equal(which[both], oid[both])
+    np.testing.assert_allclose(t[both], ot[both], rtol=2e-5, atol=2e-6)
