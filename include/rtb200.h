@@ -168,6 +168,7 @@ typedef struct rtb_stats {
   uint64_t nodes_visited;  /* BVH nodes fetched / primitives tested by extend (RTB_RENDER_COUNT or the probes, else 0) */
   uint64_t prims_tested;
   uint64_t exact_rays;     /* rays whose closest hit f32 rounding left open and that were re-traced with the reference's f64 arithmetic */
+  uint64_t refined_rays;   /* certain hits (grazing spheres) whose distance was recomputed in f64 */
 } rtb_stats;
 
 typedef struct rtb_context rtb_context;

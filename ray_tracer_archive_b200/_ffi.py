@@ -61,7 +61,7 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("rejected", C.c_uint64),
                 ("iterations", C.c_uint64), ("launches", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("nodes_visited", C.c_uint64),
-                ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64)]
+                ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64), ("refined_rays", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -851,7 +851,8 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
       stats->paths += run[k].total;  // a render always runs to completion: every path number was started exactly once
       stats->segments += h->segments;
       stats->rejected += h->rejected;
-      stats->exact_rays += h->redone;
+      stats->exact_rays += h->redone - h->refined;
+      stats->refined_rays += h->refined;
       stats->iterations = std::max<uint64_t>(stats->iterations, h->iter);
       stats->nodes_visited += h->nodes_visited;
       stats->prims_tested += h->prims_tested;
@@ -933,7 +934,8 @@ static int run_probe(rtb_context* c, rtb_scene* s, uint32_t n, uint32_t* id_out,
     stats->ms_extend = ms;
     stats->nodes_visited = c->h_counters->nodes_visited;
     stats->prims_tested = c->h_counters->prims_tested;
-    stats->exact_rays = c->h_counters->redone;
+    stats->exact_rays = c->h_counters->redone - c->h_counters->refined;
+    stats->refined_rays = c->h_counters->refined;
   }
   return RTB_OK;
 }

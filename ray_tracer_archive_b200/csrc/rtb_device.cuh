@@ -87,6 +87,7 @@ struct DevCounters {
   uint32_t redo_count;  // rays of this iteration that need the exact pass (k_fixup)
   uint32_t fix_ticket;  // CTAs of k_fixup that have finished (the last one rotates the counters)
   unsigned long long redone;  // total rays re-traced exactly
+  unsigned long long refined; // total hits whose distance was recomputed in f64
   unsigned long long total_paths;
   unsigned long long segments, rejected;
   unsigned long long nodes_visited, prims_tested;
@@ -352,8 +353,11 @@ static __device__ __noinline__ double exact_hit(const ExactTab* __restrict__ tab
   return t;
 }
 
-// closest-hit update with a certain hit at t, |t - t_exact| <= e
-__device__ __forceinline__ void consider(Closest& best, float& amb, float t, float e, uint32_t ref) {
+// closest-hit update with a certain hit at t, |t - t_exact| <= e.  `coarse`: the decision is certain but t itself is only
+// known to ~1e-5 (a grazing sphere hit): if this hit ends up the closest, its distance is recomputed in f64 afterwards
+// (k_fixup, one exact_hit of that primitive — no re-traversal).  The mark lives in bit 8 of the ray's octant word.
+#define RTB_TRAV_COARSE 0x100u
+__device__ __forceinline__ void consider(Closest& best, float& amb, uint32_t& flags, float t, float e, uint32_t ref, bool coarse) {
   if (!(t < INFINITY)) return;  // degenerate rays (0/0, x/0) never produce a hit
   const float hi = t + e, lo = t - e;
   if (lo > best.hi) return;                     // certainly farther (best.hi = inf while nothing is hit)
@@ -361,7 +365,10 @@ __device__ __forceinline__ void consider(Closest& best, float& amb, float t, flo
     const float blo = best.t - (best.hi - best.t);
     if (!(hi < blo)) amb = fminf(amb, fminf(lo, blo));  // the two intervals overlap: which is closer is open
   }
-  if (t < best.t) { best.t = t; best.ref = ref; }
+  if (t < best.t) {
+    best.t = t; best.ref = ref;
+    flags = coarse ? (flags | RTB_TRAV_COARSE) : (flags & ~RTB_TRAV_COARSE);
+  }
   best.hi = fminf(best.hi, hi);                 // the closer of the two exact distances is <= both upper bounds
 }
 // a candidate that may or may not be a hit, at a distance >= lo
@@ -417,10 +424,12 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
 // at most epos = 2^-21 (|oc|_1 + r) + 2^-23 (|c|_1 + r) (the second term: f32 rounding of the stored centre / radius
 // against the f64 constructor arguments); half-chord h = sqrt(disc'); a root moves by <= epos/|d| (1 + 2r/h) — the 1/h
 // term is the grazing amplification.  HIT_AMBIGUOUS (t_out = a lower bound of the possible hit distance) when a
-// decision (disc' sign, root against t_min) is inside its bound or when the bound exceeds RTB_SPHERE_REL_MAX t: the
-// bound is ~8x pessimistic, and the reported t must hold 1e-5 relative.
-#define RTB_SPHERE_REL_MAX 5.0e-5f
-__device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out) {
+// decision (disc' sign, root against t_min) is inside its bound.  `coarse` = the bound exceeds RTB_SPHERE_REL_MAX t
+// (measured: the bound is 50-80x the worst actual error, and the reported t must hold 1e-5 relative): such a hit is
+// certain, only its distance wants an f64 recomputation if it ends up the closest.
+#define RTB_SPHERE_REL_MAX 4.0e-4f
+__device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out,
+                                           bool& coarse) {
   const float3 oc = o - c;
   const float a = dot(d, d);
   const float hb = dot(oc, d);
@@ -457,7 +466,8 @@ __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r
   }
   if (root - e > tmax_hi) return HIT_MISS;
   t_out = root; e_out = e;
-  if (st == HIT_AMBIGUOUS || e > RTB_SPHERE_REL_MAX * root) {
+  coarse = e > RTB_SPHERE_REL_MAX * root;
+  if (st == HIT_AMBIGUOUS) {
     t_out = fmaxf(root - e, 0.0f);
     return HIT_AMBIGUOUS;
   }
@@ -467,8 +477,9 @@ __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r
 // shade-side sphere root (light pdf, sphere.rs:75-84): f32, f64 only when ill-conditioned; no closest-hit decision hangs on it
 __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float r, float tmin, float tmax, float& t_out) {
   float t, e;
-  int st = sphere_fast(o, d, c, r, tmin, tmax, t, e);
-  if (st == HIT_AMBIGUOUS) st = sphere_roots_f64(o, d, c, r, tmin, t);
+  bool coarse = false;
+  int st = sphere_fast(o, d, c, r, tmin, tmax, t, e, coarse);
+  if (st == HIT_AMBIGUOUS || (st == HIT_CERTAIN && coarse)) st = sphere_roots_f64(o, d, c, r, tmin, t);
   if (st != HIT_CERTAIN || t > tmax) return false;  // (within 1e-12 of tangency / t_min: measure zero for a pdf)
   t_out = t;
   return true;
@@ -476,13 +487,14 @@ __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float
 
 template <bool COUNT>
 __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
-                                               float time, float tmin, Closest& best, float& amb, uint32_t& n_tests) {
+                                               float time, float tmin, Closest& best, float& amb, uint32_t& flags, uint32_t& n_tests) {
   if (COUNT) ++n_tests;
   const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
   float t, e;
+  bool coarse = false;
   if (type == PT_SPHERE) {
     const float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
-    const int st = sphere_fast(o, d, xyz(s), s.w, tmin, best.hi, t, e);
+    const int st = sphere_fast(o, d, xyz(s), s.w, tmin, best.hi, t, e, coarse);
     if (st == HIT_MISS) return;
     if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
   } else if (type == PT_QUAD) {
@@ -564,11 +576,11 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
     const float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
     const float3 c = fma3(time, xyz(b), xyz(a));
-    const int st = sphere_fast(o, d, c, a.w, tmin, best.hi, t, e);
+    const int st = sphere_fast(o, d, c, a.w, tmin, best.hi, t, e, coarse);
     if (st == HIT_MISS) return;
     if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
   }
-  consider(best, amb, t, e, ref);
+  consider(best, amb, flags, t, e, ref, coarse);
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
@@ -588,7 +600,7 @@ __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel
 struct Trav {
   float3 o, d;
   float idx, idy, idz, time;
-  uint32_t octinv;  // 7 ^ (sign bits of d): children are visited in descending (slot ^ octinv)
+  uint32_t octinv;  // bits 0-2: 7 ^ (sign bits of d): children are visited in descending (slot ^ octinv); bit 8: RTB_TRAV_COARSE
   uint2 grp;        // current node group: x = first child node, y = hit-priority mask << 8 | internal mask
   int sp;
   Closest best;
@@ -596,6 +608,12 @@ struct Trav {
 };
 // the ray must be re-traced exactly: something undecided may lie at or before the closest certain hit
 __device__ __forceinline__ bool needs_exact(const Closest& best, float amb) { return amb < INFINITY && amb <= best.hi; }
+// what k_fixup has to do for a finished ray: 0 nothing, 1 exact re-trace, 2 recompute the distance of its (certain) hit
+enum FixKind : uint32_t { FIX_NONE = 0, FIX_RETRACE = 1, FIX_REFINE = 2 };
+#define RTB_REDO_REFINE 0x80000000u  /* redo-queue entry: slot | this bit = FIX_REFINE */
+__device__ __forceinline__ uint32_t fix_kind(const Trav& tv) {
+  return needs_exact(tv.best, tv.amb) ? FIX_RETRACE : ((tv.octinv & RTB_TRAV_COARSE) && tv.best.ref != REF_MISS ? FIX_REFINE : FIX_NONE);
+}
 
 __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float time) {
   const float tiny = 1e-30f;
@@ -634,7 +652,7 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     if (tv.sp == 0) return false;
     tv.grp = stack[--tv.sp];
   }
-  const uint32_t octinv = tv.octinv;
+  const uint32_t octinv = tv.octinv & 7u;
   uint32_t hits = tv.grp.y >> 8;
   const uint32_t prio = 31u - __clz(hits);
   hits &= ~(1u << prio);
@@ -725,10 +743,10 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
       const float4 s = __ldg(sc.geom[PT_SPHERE] + (ref & REF_INDEX_MASK));
       float t;
       const int st = sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, t);
-      if (st == HIT_CERTAIN) consider(tv.best, tv.amb, t, RTB_U22 * t, ref);
+      if (st == HIT_CERTAIN) consider(tv.best, tv.amb, tv.octinv, t, RTB_U22 * t, ref, false);
       else if (st == HIT_AMBIGUOUS) tv.amb = 0.0f;  // within 1e-12 of tangency / t_min: exact pass
     } else {
-      intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, n_tests);
+      intersect_prim<COUNT>(sc, ref >> REF_TYPE_SHIFT, ref & REF_INDEX_MASK, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
     }
   }
   if (sc.tree_empty) tv.grp.y = 0u;  // nothing left to traverse: the first trav_step returns false
@@ -741,13 +759,13 @@ __device__ __forceinline__ bool trav_step_fast(const DevScene& sc, const uint4* 
                                                uint32_t& n_nodes_visited, uint32_t& n_tests) {
   return trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited,
                                       [&](uint32_t type, uint32_t idx) {
-                                        intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, n_tests);
+                                        intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
                                       });
 }
 
-// returns true when the ray has to go through traverse_exact()
+// returns the ray's FixKind
 template <bool COUNT, bool ALL_STAGED = false>
-__device__ __forceinline__ bool traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
+__device__ __forceinline__ uint32_t traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
                                          uint32_t& n_nodes_visited, uint32_t& n_tests) {
   Trav tv;
@@ -756,7 +774,14 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, const uint4* __rest
   trav_globals<COUNT>(sc, tv, tmin, n_tests);
   while (trav_step_fast<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
-  return needs_exact(tv.best, tv.amb);
+  return fix_kind(tv);
+}
+
+// FIX_REFINE: the hit is certain, its distance is recomputed with the reference's arithmetic
+__device__ __forceinline__ float refine_hit(const DevScene& sc, uint32_t ref, float3 o, float3 d, float time, float t) {
+  if ((ref >> REF_TYPE_SHIFT) >= PT_COUNT) return t;  // a medium's sampled distance
+  const double tc = exact_hit(sc.xtab, ref, o, d, time);
+  return tc >= 0.0 ? (float)tc : t;
 }
 
 // The exact pass: the same BVH (its conservative boxes cull against the closest exact distance so far), every candidate

@@ -62,8 +62,8 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
 
 // a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
 // the one atomic per entry is uncontended in practice)
-__device__ __forceinline__ void queue_exact(const DevPool& pool, uint32_t slot) {
-  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] = slot;
+__device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind) {
+  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] = slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u);
 }
 
 // ---- warp-local chunk lists -------------------------------------------------------------------------------------------
@@ -167,7 +167,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
       finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
-      if (h.redo) queue_exact(pool, h.slot);
+      if (h.redo) queue_fix(pool, h.slot, h.redo);
     }
     out_count = 0;
     __syncwarp();
@@ -207,8 +207,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           ExtIn& e = in[lane];
           e.o_time = ro;
           e.d_slot = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
-          // (an ambiguity among the global primitives is handed over as "undecided from distance 0": bit 8)
-          e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv | (t0.amb < INFINITY ? 256u : 0u)));
+          // (an ambiguity among the global primitives is handed over as "undecided from distance 0": bit 9)
+          e.idir_oct = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv | (t0.amb < INFINITY ? 0x200u : 0u)));
           e.best = make_float4(t0.best.t, __uint_as_float(t0.best.ref), __uint_as_float(t0.grp.y), t0.best.hi);
         }
         __syncwarp();
@@ -222,8 +222,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.o = xyz(r.o_time); tv.time = r.o_time.w;
           tv.d = xyz(r.d_slot); slot = __float_as_uint(r.d_slot.w);
           tv.idx = r.idir_oct.x; tv.idy = r.idir_oct.y; tv.idz = r.idir_oct.z;
-          tv.octinv = __float_as_uint(r.idir_oct.w) & 7u;
-          tv.amb = (__float_as_uint(r.idir_oct.w) & 256u) ? 0.0f : INFINITY;
+          tv.octinv = __float_as_uint(r.idir_oct.w) & (7u | RTB_TRAV_COARSE);
+          tv.amb = (__float_as_uint(r.idir_oct.w) & 0x200u) ? 0.0f : INFINITY;
           tv.grp = make_uint2(0u, __float_as_uint(r.best.z));
           tv.sp = 0;
           tv.best = Closest{r.best.x, r.best.w, __float_as_uint(r.best.y)};
@@ -244,7 +244,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, needs_exact(tv.best, tv.amb) ? 1u : 0u};
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(tv)};
       out_count += __popc(done);
       idle |= done;
     }
@@ -288,9 +288,9 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         const float4 ro = pool.ray[2 * slot];
         const float4 rd = pool.ray[2 * slot + 1];
         Closest best;
-        const bool redo = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+        const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
         finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-        if (redo) queue_exact(pool, slot);
+        if (fix) queue_fix(pool, slot, fix);
       }
     }
     __syncwarp();  // the list is rewritten for the next chunk
@@ -785,7 +785,7 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
     c->iter = 0;
     c->ext_cursor = 0;
     c->redo_count = c->fix_ticket = 0;
-    c->redone = 0;
+    c->redone = c->refined = 0;
     c->total_paths = total_paths;
     c->segments = c->rejected = 0;
     c->nodes_visited = c->prims_tested = 0;
@@ -799,13 +799,24 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
 __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPool pool, DevParams prm) {
   DevCounters* c = pool.c;
   const uint32_t n = c->redo_count;
+  uint32_t n_refined = 0;
   for (uint32_t i = blockIdx.x * RTB_FIXUP_THREADS + threadIdx.x; i < n; i += gridDim.x * RTB_FIXUP_THREADS) {
-    const uint32_t slot = pool.redo[i];
+    const uint32_t entry = pool.redo[i], slot = entry & ~RTB_REDO_REFINE;
     const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
-    const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w);
-    finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+    if (entry & RTB_REDO_REFINE) {  // certain hit, coarse distance: one f64 evaluation of that primitive
+      const float4 h = pool.hit[slot];
+      pool.hit[slot].x = refine_hit(sc, __float_as_uint(h.y), xyz(ro), xyz(rd), ro.w, h.x);
+      ++n_refined;
+    } else {
+      const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w);
+      finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+    }
   }
   __shared__ bool last;
+  if (n) {
+    n_refined = __reduce_add_sync(0xffffffffu, n_refined);
+    if ((threadIdx.x & 31u) == 0 && n_refined) atomicAdd(&c->refined, (unsigned long long)n_refined);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -814,7 +825,7 @@ __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPoo
   __syncthreads();
   if (last && threadIdx.x == 0) {
     c->segments += c->iter_rays;
-    c->redone += n;
+    c->redone += n;  // (retraces + refinements; the retraces are redone - refined)
     c->last_rays = c->iter_rays;
     c->iter_rays = 0;
     c->ext_cursor = 0;
@@ -898,8 +909,9 @@ __global__ void k_kat(DevScene sc, DevCamera cam, DevParams prm, uint32_t op, co
     }
     case RTB_KAT_SPHERE: {  // (c, r, o, d, tmin, tmax) -> (status, t, e): the f32 sphere test with its error bound
       float t = 0.f, e = 0.f;
-      const int st = sphere_fast(V(4), V(7), V(0), F(3), F(10), F(11), t, e);
-      o[0] = (uint32_t)st; put(1, t); put(2, e);
+      bool coarse = false;
+      const int st = sphere_fast(V(4), V(7), V(0), F(3), F(10), F(11), t, e, coarse);
+      o[0] = (uint32_t)st | (coarse ? 16u : 0u); put(1, t); put(2, e);
       break;
     }
     case RTB_KAT_SPHERE_F64: {  // same inputs -> (status, t): the Newton-refined f64 form used for "global" spheres

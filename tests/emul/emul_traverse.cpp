@@ -35,7 +35,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 #include "../../ray_tracer_archive_b200/csrc/rtb_device.cuh"
 
 using namespace rtb;
-static unsigned long long g_exact_rays = 0;
+static unsigned long long g_exact_rays = 0, g_refined_rays = 0;
 
 extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
                           const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
@@ -68,10 +68,14 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
     uint32_t nv = 0, nt = 0;
     const float3 ro = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), rd = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
     // the hot path (f32, ambiguity detection), then — as k_fixup does on the device — the exact pass if it asked for one
-    if (traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd, time ? time[i] : 0.f,
-                       RTB_TMIN, best, nv, nt)) {
+    const uint32_t fix = traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd,
+                                        time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
+    if (fix == FIX_RETRACE) {
       best = traverse_exact(sc, ro, rd, time ? time[i] : 0.f);
       ++g_exact_rays;
+    } else if (fix == FIX_REFINE) {
+      best.t = refine_hit(sc, best.ref, ro, rd, time ? time[i] : 0.f, best.t);
+      ++g_refined_rays;
     }
     ids[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
     ts[i] = best.t;
@@ -86,6 +90,11 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
 extern "C" unsigned long long emul_exact_rays() {
   const unsigned long long n = g_exact_rays;
   g_exact_rays = 0;
+  return n;
+}
+extern "C" unsigned long long emul_refined_rays() {
+  const unsigned long long n = g_refined_rays;
+  g_refined_rays = 0;
   return n;
 }
 

@@ -323,7 +323,7 @@ def test_exact_hit_is_bit_identical_to_oracle(rtb, orc, ctx):
         out = ctx.kat(F.KAT_EXACT, rows, 2, scene=dev)
         bits = (out[:, 0].astype(np.uint64) << np.uint64(32)) | out[:, 1].astype(np.uint64)
         t64 = bits.view(np.float64)
-        assert len(sel) > 10000 and len(media) <= 2
+        assert len(sel) > 3000 and len(media) <= 2
         assert np.array_equal(t64, ot[sel]), f"{(t64 != ot[sel]).sum()} of {len(sel)} distances differ in f64"
         assert np.array_equal(ids[sel], oid[sel])
 

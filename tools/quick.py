@@ -22,5 +22,5 @@ for arg in sys.argv[1:]:
     _, stc = sc.render(cfg.camera, prm(F.RENDER_COUNT), readback=False)
     print(f"[{tag}] {name} spp={spp}: {best:8.1f} Mrays/s  ext_share={stt['ms_extend'] / stt['ms_total']:.3f} "
           f"ext_ms={stt['ms_extend']:.1f} total_ms={stt['ms_total']:.1f} nodes/seg={stc['nodes_visited'] / stc['segments']:.2f} "
-          f"prims/seg={stc['prims_tested'] / stc['segments']:.2f} iters={st['iterations']}", flush=True)
+          f"prims/seg={stc["prims_tested"] / stc["segments"]:.2f} iters={st["iterations"]} exact_rays={st["exact_rays"] / st["segments"]:.5f} refined={st["refined_rays"] / st["segments"]:.5f}", flush=True)
     sc.close()

@@ -31,7 +31,8 @@ for w in which:
     rel = np.abs(ts[ok] - ot[ok]) / ot[ok]
     import ctypes as C
     emul.emul_exact_rays.restype = C.c_ulonglong
-    print("   rays through the exact pass:", emul.emul_exact_rays(), "of", len(oid))
+    emul.emul_refined_rays.restype = C.c_ulonglong
+    print("   rays through the exact pass:", emul.emul_exact_rays(), "refined:", emul.emul_refined_rays(), "of", len(oid))
     print(w, len(oid), "mismatch", int(mism.sum()), "max rel t", rel.max(), f"oracle {t1-t0:.1f}s emul {t2-t1:.1f}s")
     idx = np.argwhere(mism)[:10, 0]
     for i in idx:
