@@ -4,9 +4,13 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4|C5] [--impl reference]
 
 One "step" = one full render of the workload (every pixel, `spp` samples) on each rank.  N > 1 is launched by
-torchrun (one process per GPU): rank r renders global samples [r*spp, (r+1)*spp) of every pixel (weak scaling: per-GPU
-work fixed), the float4 accumulation buffers are summed onto rank 0 with one NCCL reduce, rank 0 finalises.
+torchrun (one process per GPU): rank r renders global samples [r*spp, (r+1)*spp) of every pixel (WEAK scaling: per-GPU
+work fixed), the float4 accumulation buffers are summed onto rank 0 by the LIBRARY (rtb_render_device with
+RTB_RENDER_REDUCE: one ncclReduce per frame on a communicator the ranks join through rtb_context_comm_init; torch only
+carries the 128-byte id), rank 0 finalises.
 `value` = segments traced by all ranks / max-over-ranks device time of the K steps, scene resident in HBM.
+`strong_scaling` (sub-record, every N): BASELINE.json's scaling config C5 — the book-2 final scene at 3840x2160, a FIXED
+total spp (--strong-spp, stated) SPLIT across the ranks, 133 MB reduce — so the per-N lines give a strong-scaling curve.
 `e2e`   = the same through the host-facing C ABI: scene records handed over from host memory (flatten + BVH build +
           H2D), render, reduce, D2H of the accumulation buffer — every step.
 `--impl reference` times the reference's CPU algorithm (the f64 oracle port: the Rust reference cannot be compiled in
@@ -73,24 +77,12 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows), "window": "warm-up + timed + e2e steps"}
 
 
-def measure_l2_bandwidth(torch):
-    """L2-resident copy (read + write bytes) of 48 MB -> 48 MB (96 MB < 126 MB L2), best of 5 runs of 50 copies.
-    MEASURED_PEAKS.json has no L2 figure (SURVEY §8d asks the builder to measure one)."""
-    n = 48 << 20
-    a = torch.empty(n, dtype=torch.uint8, device="cuda")
-    b = torch.empty(n, dtype=torch.uint8, device="cuda")
-    for _ in range(5):
-        b.copy_(a)
-    best = 0.0
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(50):
-            b.copy_(a)
-        e1.record()
-        torch.cuda.synchronize()
-        best = max(best, 50 * 2 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-    return best
+def measure_bandwidths(ctx, F):
+    """Physical denominators, measured in this run by the library's own microbenchmark (rtb_measure_bandwidth): read-only
+    128-bit ld.global.nc streams over a 48 MB L2-resident buffer and a 2 GB HBM-resident one, and 128-bit shared-memory
+    loads on all SMs.  MEASURED_PEAKS.json has no L2 / shared-memory figure (SURVEY §8d asks the builder to measure one)."""
+    return {"l2_read_gbs": ctx.measure_bandwidth(F.BW_L2_READ), "hbm_read_gbs": ctx.measure_bandwidth(F.BW_HBM_READ),
+            "shared_read_gbs": ctx.measure_bandwidth(F.BW_SHARED_READ)}
 
 
 def bounded_cpu_sample(osc, rtb, cfg, cores, budget_s=12.0):
@@ -182,6 +174,8 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the workload's spp is SPLIT across the ranks (BASELINE config C5) instead of "
                          "rendered by every rank (weak, default)")
+    ap.add_argument("--strong-spp", type=int, default=512,
+                    help="total spp of the C5 strong-scaling sub-record (split across the ranks); 0 = skip it")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,10 +201,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W = max(args.warmup, 3)
+    F = rtb._ffi
 
     cfg = get_config(args.workload, args.spp or None)
     cs = rtb.compile_scene(cfg.world, cfg.lights)
     ctx = rtb.Context(local_rank)
+    if world > 1:  # the library's own communicator: torch.distributed only carries the 128-byte id to the other ranks
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(rtb.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    reduce_flag = F.RENDER_REDUCE if world > 1 else 0
     scene = rtb.Scene(ctx, cs)
     info = scene.info()
     npix = cfg.width * cfg.height
@@ -233,16 +235,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    reduce_events = []
+    reduce_ms_list = []
 
     def step(flags=0):
         flush.zero_()  # flush L2 between steps
-        st = scene.render_device(cfg.camera, params(flags), accum.data_ptr(), stream.cuda_stream)
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(stream)
-        parallel.reduce_accum(accum, dst=0)  # NCCL reduce of the float4 accumulation buffer onto rank 0
-        r1.record(stream)
-        reduce_events.append((r0, r1))
+        # render + (N > 1) the library's ncclReduce of the float4 accumulation buffer onto rank 0, on this stream
+        st = scene.render_device(cfg.camera, params(flags | reduce_flag), accum.data_ptr(), stream.cuda_stream)
+        reduce_ms_list.append(st["ms_nccl"])
         return st
 
     # clocks / throttle reasons are sampled from the first warm-up step to the last e2e step (everything under load)
@@ -253,7 +252,7 @@ def main():
     # ---- timed region: exactly K steps, device time, max over ranks ---------------------------------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reduce_events.clear()
+    reduce_ms_list.clear()
     e0.record(stream)
     segs = launches = 0
     for _ in range(args.steps):
@@ -263,7 +262,7 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    reduce_ms = sum(a.elapsed_time(b) for a, b in reduce_events) / max(len(reduce_events), 1)
+    reduce_ms = sum(reduce_ms_list) / max(len(reduce_ms_list), 1)
     tot = torch.tensor([ms, float(segs), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = tot.clone()
@@ -287,9 +286,8 @@ def main():
         sc2.set_compiled(cs)  # scene records from host memory: tables + flatten ...
         sc2.commit()          # ... + BVH build + H2D
         t1 = time.perf_counter()
-        st = sc2.render_device(cfg.camera, params(), accum.data_ptr(), stream.cuda_stream)
+        st = sc2.render_device(cfg.camera, params(reduce_flag), accum.data_ptr(), stream.cuda_stream)
         t2 = time.perf_counter()
-        parallel.reduce_accum(accum, dst=0)
         if rank == 0:
             host_out.copy_(accum, non_blocking=True)
         torch.cuda.synchronize()
@@ -315,24 +313,62 @@ def main():
     e2e_value = et[1].item() / dt / 1e6
     sampler.stop_flag = True
 
+    # ---- strong scaling on BASELINE.json's scaling config (C5): fixed total spp split across the ranks ---------------
+    strong = None
+    if args.strong_spp > 0 and not args.strong and args.workload == "C1":
+        c5 = get_config("C5", args.strong_spp)
+        first5, cnt5 = parallel.rank_sample_range(c5.spp, rank, world)
+        cs5 = rtb.compile_scene(c5.world, c5.lights)
+        sc5 = rtb.Scene(ctx, cs5)
+        acc5 = torch.zeros((c5.height, c5.width, 4), dtype=torch.float32, device="cuda")
+
+        def step5(spp_override=None):
+            flush.zero_()
+            n_s = cnt5 if spp_override is None else spp_override
+            p5 = rtb.make_params(c5.width, c5.height, max(n_s, 1), c5.max_depth, c5.background, seed=1, sample_offset=first5,
+                                 total_spp=c5.spp, flags=reduce_flag)
+            return sc5.render_device(c5.camera, p5, acc5.data_ptr(), stream.cuda_stream)
+
+        step5(min(cnt5, 8))  # warm-up (pool allocation, caches) at a few spp
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        st5 = step5()
+        s1.record(stream)
+        barrier()
+        t5 = torch.tensor([s0.elapsed_time(s1), float(st5["segments"]), st5["ms_render"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            m5 = t5.clone()
+            dist.all_reduce(m5, op=dist.ReduceOp.MAX)
+            mn5 = t5.clone()
+            dist.all_reduce(mn5, op=dist.ReduceOp.MIN)
+            dist.all_reduce(t5, op=dist.ReduceOp.SUM)
+        else:
+            m5 = mn5 = t5
+        strong = {"workload": c5.name, "width": c5.width, "height": c5.height, "total_spp": c5.spp, "spp_per_gpu": cnt5,
+                  "scaling": "strong", "value": t5[1].item() / (m5[0].item() * 1e-3) / 1e6, "unit": "Mrays/s",
+                  "ms_per_step": m5[0].item(), "ms_render_slowest_rank": m5[2].item(), "ms_render_fastest_rank": mn5[2].item(),
+                  "reduce_bytes": c5.width * c5.height * 16, "reduce_ms_rank0": st5["ms_nccl"],
+                  "reduce_frac_of_step": st5["ms_nccl"] / m5[0].item(), "segments": t5[1].item(),
+                  "note": "efficiency = value(N) / (N x value(1)) across the per-N lines; what limits it is the wavefront drain "
+                          "tail of each rank's shorter render (fewer samples per pixel to refill the path pool from), not the collective"}
+        sc5.close()
+        del acc5
+
     # ---- roofline of the dominant kernel (extend), measured live on rank 0 ------------------------------------------
     roofline = None
     cpu_baseline = None
     cpu_fair = None
     if rank == 0:
-        F = rtb._ffi
         stc = scene.render_device(cfg.camera, params(F.RENDER_COUNT), accum.data_ptr(), stream.cuda_stream)
         stt = scene.render_device(cfg.camera, params(F.RENDER_TIME_EXTEND), accum.data_ptr(), stream.cuda_stream)
         n_seg = stc["segments"]
         nodes_per_seg = stc["nodes_visited"] / n_seg
         prims_per_seg = stc["prims_tested"] / n_seg
-        # primitive mix: weight per-type constants by the scene's primitive counts (tests are type-homogeneous per leaf)
-        cnt = {"sphere": info["n_spheres"], "moving": info["n_moving"], "quad": info["n_quads"], "tri": info["n_triangles"]}
-        tot_p = max(sum(cnt.values()), 1)
-        b_prim = sum(B_PRIM[k] * v for k, v in cnt.items()) / tot_p
-        f_prim = sum(F_PRIM[k] * v for k, v in cnt.items()) / tot_p
-        flops_seg = nodes_per_seg * F_NODE + prims_per_seg * f_prim
-        bytes_seg = nodes_per_seg * B_NODE + prims_per_seg * b_prim
+        # primitive mix: the instrumented kernel counts the tests it EXECUTES per type (not the scene's primitive counts)
+        per_type = dict(zip(("sphere", "moving", "quad", "tri"), (x / n_seg for x in stc["prims_tested_type"])))
+        flops_seg = nodes_per_seg * F_NODE + sum(F_PRIM[k] * v for k, v in per_type.items())
+        bytes_seg = nodes_per_seg * B_NODE + sum(B_PRIM[k] * v for k, v in per_type.items())
         ext_ms, n_ext = stt["ms_extend"], stt["extend_launches"]
         seg_per_launch = stt["segments"] / n_ext
         avg_launch_ms = ext_ms / n_ext
@@ -345,10 +381,18 @@ def main():
         ach_gbs = bytes_seg * seg_per_launch / (avg_launch_ms * 1e-3) / 1e9
         scene_bytes = info["bvh_bytes"] + info["prim_bytes"]
         in_l2 = scene_bytes <= dev["l2_bytes"]
-        # BASELINE.json: roofline = slower of FP32 intersection math at peak and BVH/primitive bytes at L2 bandwidth
-        # (scene <= L2) or HBM bandwidth (scene > L2).  L2 bandwidth: measured here by an L2-resident copy.
-        l2_gbs = measure_l2_bandwidth(torch)
-        mem_gbs, mem_name = (l2_gbs, "l2") if in_l2 else (peaks["hbm_gbs"], "hbm")
+        # where the scene's bytes physically come from decides the memory side of the roofline:
+        #   all nodes staged in shared memory / primitives in the constant bank  -> shared-memory read bandwidth
+        #   scene <= L2 (every other config)                                      -> L2 read bandwidth (read-only 128-bit stream)
+        #   scene >  L2                                                           -> HBM (MEASURED_PEAKS.json)
+        bw = measure_bandwidths(ctx, F)
+        on_chip = bool(scene_bytes <= 56 * 1024)
+        if on_chip:
+            mem_gbs, mem_name = bw["shared_read_gbs"], "shared"
+        elif in_l2:
+            mem_gbs, mem_name = bw["l2_read_gbs"], "l2"
+        else:
+            mem_gbs, mem_name = peaks["hbm_gbs"], "hbm"
         t_flops, t_bytes = flops_seg / (fp32_peak * 1e12), bytes_seg / (mem_gbs * 1e9)
         fp_bound = t_flops >= t_bytes
         roofline = {
@@ -359,20 +403,23 @@ def main():
             "frac": (ach_tflops / fp32_peak) if fp_bound else (ach_gbs / mem_gbs),
             "traffic": ncu_traffic(args.workload),
             "peak_source": f"FP32 = SMs*128*2*f_SM at the median SM clock seen in this run ({sm_mhz:.0f} MHz) = {fp32_peak:.1f} TFLOP/s; "
-                           f"L2 = {l2_gbs:.0f} GB/s measured in this run (L2-resident 2x48 MB copy); HBM {which} {peaks['hbm_gbs']} GB/s",
+                           f"measured in this run by rtb_measure_bandwidth (read-only 128-bit streams): L2 {bw['l2_read_gbs']:.0f} GB/s (48 MB resident), "
+                           f"HBM {bw['hbm_read_gbs']:.0f} GB/s (2 GB), shared memory {bw['shared_read_gbs']:.0f} GB/s; HBM copy {which} {peaks['hbm_gbs']} GB/s (MEASURED_PEAKS.json)",
+            "bandwidths": bw,
             "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_peak, "frac": ach_tflops / fp32_peak},
             "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": ach_gbs / peaks["hbm_gbs"],
                     "scene_bytes": scene_bytes, "scene_fits_l2": bool(in_l2)},
-            "l2": {"achieved_gbs": ach_gbs, "peak_gbs": l2_gbs, "frac": ach_gbs / l2_gbs},
+            "l2": {"achieved_gbs": ach_gbs, "peak_gbs": bw["l2_read_gbs"], "frac": ach_gbs / bw["l2_read_gbs"]},
+            "shared": {"achieved_gbs": ach_gbs, "peak_gbs": bw["shared_read_gbs"], "frac": ach_gbs / bw["shared_read_gbs"]},
             "algorithmic": {"nodes_per_segment": nodes_per_seg, "prims_per_segment": prims_per_seg,
+                            "prim_tests_per_segment_by_type": per_type,
                             "flops_per_segment": flops_seg, "bytes_per_segment": bytes_seg,
                             "segments_per_launch": seg_per_launch},
-            # scenes whose nodes + primitives fit the kernel's shared-memory stage / L1 never send these bytes to L2: the
-            # BASELINE.json roofline (bytes at L2 bandwidth) is then a definition, not a physical bound, and `frac` can
-            # exceed 1 (C2: 13 primitives in the constant bank); the FP32 figure is the one that binds there
-            "on_chip_scene": bool(scene_bytes <= 56 * 1024),
+            # the whole scene sits in the kernel's shared-memory stage / the constant bank: its bytes never reach L2
+            "on_chip_scene": on_chip,
             "extend_ms_per_launch": avg_launch_ms, "extend_launches_per_step": n_ext,
             "extend_share_of_step": ext_ms / stt["ms_total"],
+            "exact_pass": {"rays_retraced_per_segment": stc["exact_rays"] / n_seg, "hits_refined_per_segment": stc["refined_rays"] / n_seg},
             "roofline_mrays_s": 1.0 / max(t_flops, t_bytes) / 1e6,
         }
         if not args.no_cpu_baseline:
@@ -399,8 +446,9 @@ def main():
                        "l2": "L2 flushed (256 MB write) between steps; path-state pool exceeds the 126 MB L2; the scene is cache-resident by design"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(all_launches),
-            "reduce": {"collective": "ncclReduce(sum) of W*H float4 onto rank 0" if world > 1 else "none (1 GPU)",
+            "reduce": {"collective": "ncclReduce(sum) of W*H float4 onto rank 0, issued by librtb200 (RTB_RENDER_REDUCE)" if world > 1 else "none (1 GPU)",
                        "bytes": npix * 16, "ms_per_step_rank0": reduce_ms, "frac_of_step": reduce_ms / (ms / args.steps)},
+            "strong_scaling": strong,
             "clocks": clk,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -155,6 +155,9 @@ typedef struct rtb_params {
 #define RTB_RENDER_ACCUMULATE 1u  /* add into the accumulation buffer instead of clearing it first */
 #define RTB_RENDER_COUNT 2u       /* instrumented extend: fills stats->nodes_visited / prims_tested (slower) */
 #define RTB_RENDER_TIME_EXTEND 4u /* CUDA events around every extend launch: fills stats->ms_extend */
+#define RTB_RENDER_REDUCE 8u      /* rtb_render_device on a context with a communicator (rtb_context_comm_init): after the
+                                     render, the library sums the ranks' accumulation buffers onto rank 0 with ONE
+                                     ncclReduce(float32, 4 W H, sum, root 0) on `stream`; its time goes to stats->ms_nccl */
 
 typedef struct rtb_stats {
   uint64_t paths;          /* camera paths started */
@@ -169,6 +172,11 @@ typedef struct rtb_stats {
   uint64_t prims_tested;
   uint64_t exact_rays;     /* rays whose closest hit f32 rounding left open and that were re-traced with the reference's f64 arithmetic */
   uint64_t refined_rays;   /* certain hits (grazing spheres) whose distance was recomputed in f64 */
+  double ms_nccl;          /* device time of the framebuffer reduce on this rank / on device 0 (0 on one GPU) */
+  double ms_render;        /* multi-device context: slowest device's render time (ms_total = ms_render + ms_nccl) */
+  uint32_t n_devices;      /* GPUs that took part in this call */
+  uint32_t _pad;
+  uint64_t prims_tested_type[4]; /* prims_tested per type: sphere, moving sphere, quad, triangle */
 } rtb_stats;
 
 typedef struct rtb_context rtb_context;
@@ -180,6 +188,22 @@ const char* rtb_last_error(void);
 int rtb_context_create(int device_id, rtb_context** out);
 void rtb_context_destroy(rtb_context* ctx);
 int rtb_context_device_info(rtb_context* ctx, int* sm_count, int* l2_bytes, int* clock_khz, char* name, size_t name_cap);
+
+/* ---- multi-GPU: the only parallelism of the reference is its per-pixel thread fan-out (main.rs:730-778); here the
+ * samples of every pixel are split across the GPUs of one box and the float4 accumulation buffers are summed by the
+ * LIBRARY with one NCCL reduce per frame (NVLink 5 / NVSwitch).  Philox streams are keyed by the GLOBAL sample index, so
+ * the sample set does not depend on the number of GPUs.  NCCL (libnccl.so.2) is bound at run time: single-GPU callers
+ * do not need it.
+ *   (a) one process drives n GPUs: rtb_context_create_multi(ids, n) -> ncclCommInitAll.  The SAME calls then work on that
+ *       context: scenes are uploaded to every device, rtb_render renders spp / n samples on each (remainder to the
+ *       lowest ranks), reduces onto device ids[0] and returns that buffer; stats aggregate all devices.
+ *   (b) one process per GPU (torchrun, MPI): rank 0 calls rtb_comm_unique_id and hands the 128 bytes to the others by
+ *       any means; every rank calls rtb_context_comm_init; rtb_render_device(..., RTB_RENDER_REDUCE) then reduces. */
+#define RTB_COMM_ID_BYTES 128
+int rtb_context_create_multi(const int* device_ids, int n_devices, rtb_context** out);
+int rtb_context_device_count(rtb_context* ctx);
+int rtb_comm_unique_id(uint8_t* id_128_bytes);
+int rtb_context_comm_init(rtb_context* ctx, const uint8_t* id_128_bytes, int rank, int n_ranks);
 
 /* ---- scene: tables ---------------------------------------------------------------------------------------- */
 /* ctx may be NULL: a host-only scene that can be flattened, built and exported but not committed/rendered */
@@ -289,6 +313,15 @@ typedef enum rtb_kat_op {
 int rtb_device_kat(rtb_context* ctx, rtb_scene* scene, const rtb_camera* cam, const rtb_params* params, uint32_t op,
                    const uint32_t* in_words, uint32_t n_items, uint32_t in_stride, uint32_t* out_words,
                    uint32_t out_stride);
+
+/* ---- measurement: the physical bandwidths the extend kernel's roofline is quoted against -------------------------- */
+typedef enum rtb_bw_kind {
+  RTB_BW_L2_READ = 0,     /* 128-bit ld.global.nc over a 48 MB (L2-resident) buffer, read-only */
+  RTB_BW_HBM_READ = 1,    /* the same over a 2 GB buffer (streams from HBM)                    */
+  RTB_BW_SHARED_READ = 2  /* 128-bit shared-memory loads, all SMs (where staged nodes come from) */
+} rtb_bw_kind;
+/* best of `repeats` timed launches, GB/s (1e9 bytes per second) */
+int rtb_measure_bandwidth(rtb_context* ctx, uint32_t kind, uint32_t repeats, double* gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,8 @@ NODE_LIST, NODE_BVH = 32, 33
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = 0, 1, 2, 3, 4
 TEX_SOLID, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = 0, 1, 2, 3
 LIGHT_XZ_RECT, LIGHT_SPHERE = 0, 1
-RENDER_ACCUMULATE, RENDER_COUNT, RENDER_TIME_EXTEND = 1, 2, 4
+RENDER_ACCUMULATE, RENDER_COUNT, RENDER_TIME_EXTEND, RENDER_REDUCE = 1, 2, 4, 8
+BW_L2_READ, BW_HBM_READ, BW_SHARED_READ = 0, 1, 2
 (KAT_PHILOX, KAT_SPHERE, KAT_SPHERE_F64, KAT_LIGHTS_PDF, KAT_LIGHTS_RANDOM, KAT_PERLIN_NOISE, KAT_PERLIN_TURB, KAT_Q2F, KAT_ONB,
  KAT_REFLECT, KAT_REFRACT, KAT_CAMERA_RAY, KAT_MEDIA, KAT_TEXTURE, KAT_EXACT) = range(15)
 
@@ -61,10 +62,12 @@ class Stats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("rejected", C.c_uint64),
                 ("iterations", C.c_uint64), ("launches", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("nodes_visited", C.c_uint64),
-                ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64), ("refined_rays", C.c_uint64)]
+                ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64), ("refined_rays", C.c_uint64),
+                ("ms_nccl", C.c_double), ("ms_render", C.c_double), ("n_devices", C.c_uint32), ("_pad", C.c_uint32),
+                ("prims_tested_type", C.c_uint64 * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "prims_tested_type" else getattr(self, k)) for k, _ in self._fields_}
 
 
 class SceneInfo(C.Structure):
@@ -86,6 +89,10 @@ SIGNATURES = {
     "rtb_last_error": (C.c_char_p, []),
     "rtb_context_create": (_I, [_I, C.POINTER(_VP)]),
     "rtb_context_destroy": (None, [_VP]),
+    "rtb_context_create_multi": (_I, [C.POINTER(C.c_int), _I, C.POINTER(_VP)]),
+    "rtb_context_device_count": (_I, [_VP]),
+    "rtb_comm_unique_id": (_I, [_VP]),
+    "rtb_context_comm_init": (_I, [_VP, _VP, _I, _I]),
     "rtb_context_device_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.c_char_p, _SZ]),
     "rtb_scene_create": (_I, [_VP, C.POINTER(_VP)]),
     "rtb_scene_destroy": (None, [_VP]),
@@ -113,6 +120,7 @@ SIGNATURES = {
     "rtb_finalize_rgb8": (_I, [_VP, _VP, _U32, _U32, _U32, _VP]),
     "rtb_primary_hits": (_I, [_VP, _VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, C.POINTER(Stats)]),
     "rtb_trace_rays": (_I, [_VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP, C.POINTER(Stats)]),
+    "rtb_measure_bandwidth": (_I, [_VP, _U32, _U32, C.POINTER(C.c_double)]),
     "rtb_primary_rays": (_I, [_VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, _VP]),
     "rtb_device_kat": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _U32, _VP, _U32, _U32, _VP, _U32]),
 }

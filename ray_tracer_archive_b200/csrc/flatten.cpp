@@ -290,6 +290,7 @@ struct Walker {
       }
       case RTB_NODE_CONSTANT_MEDIUM: {
         if (!check_mat(n.material)) { ok = false; break; }
+        if (!(p[0] > 0.0) || !std::isfinite(p[0])) { ok = fail("ConstantMedium density must be positive and finite"); break; }
         uint32_t c;
         if (!child(0, c)) { ok = false; break; }
         // resolve the boundary: Sphere or Box under Translate/RotateY wrappers (convex, as the reference requires)

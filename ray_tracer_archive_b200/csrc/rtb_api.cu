@@ -10,8 +10,13 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+#include <memory>
+#include <thread>
+
 #include "rtb_device.cuh"
 #include "rtb_launch.hpp"
+#include "rtb_nccl.hpp"
 
 using namespace rtb;
 
@@ -78,10 +83,19 @@ struct rtb_context {
   DevBuf<uint32_t> p_id;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ext_events;  // pairs around every extend launch when RTB_RENDER_TIME_EXTEND is set
+  // ---- multi-GPU: the framebuffer reduce lives in the library --------------------------------
+  // single process, n devices: `peers` are the contexts of device_ids[1..] (owned), every one with its communicator from
+  // ncclCommInitAll; one process per device: `comm` comes from rtb_context_comm_init (ncclCommInitRank)
+  std::vector<rtb_context*> peers;
+  NcclComm comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  cudaEvent_t ev_n0 = nullptr, ev_n1 = nullptr;
 };
 
 struct rtb_scene {
   rtb_context* ctx = nullptr;
+  int device = -1;                   // ctx's device, kept here: the context may be destroyed before the scene
+  std::vector<rtb_scene*> replicas;  // multi-device context: device copies on the peers (host data stays with this one)
   HostScene hs;
   HostBvh bvh;
   bool built = false;      // host BVH is current
@@ -107,23 +121,11 @@ extern "C" {
 uint32_t rtb_abi_version(void) { return RTB_ABI_VERSION; }
 const char* rtb_last_error(void) { return g_err.c_str(); }
 
-int rtb_context_create(int device_id, rtb_context** out) {
-  if (!out) return set_err(RTB_ERR_INVALID, "out is NULL");
-  *out = nullptr;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0)
-    return set_err(RTB_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
-                                          " (librtb200 has no CPU fallback)");
-  if (device_id < 0 || device_id >= n) return set_err(RTB_ERR_INVALID, "device_id out of range");
+static int context_init(rtb_context* c, int device_id) {
   CU(cudaSetDevice(device_id));
-  rtb_context* c = new rtb_context();
   c->device = device_id;
   CU(cudaGetDeviceProperties(&c->prop, device_id));
-  if (c->prop.major < 10) {
-    delete c;
-    return set_err(RTB_ERR_NO_DEVICE, "librtb200 is built for sm_100a only");
-  }
+  if (c->prop.major < 10) return set_err(RTB_ERR_NO_DEVICE, "librtb200 is built for sm_100a only");
   CU(cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters)));
   for (int k = 0; k < RTB_MAX_LANES; ++k) {
     Lane& L = c->lanes[k];
@@ -135,15 +137,35 @@ int rtb_context_create(int device_id, rtb_context** out) {
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreate(&c->ev0));
   CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreate(&c->ev_n0));
+  CU(cudaEventCreate(&c->ev_n1));
   CU(c->counters.resize(1));
-  *out = c;
+  return RTB_OK;
+}
+
+int rtb_context_create(int device_id, rtb_context** out) {
+  if (!out) return set_err(RTB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_err(RTB_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                          " (librtb200 has no CPU fallback)");
+  if (device_id < 0 || device_id >= n) return set_err(RTB_ERR_INVALID, "device_id out of range");
+  // a partly built context is torn down by its destructor path (streams, events, pinned buffers)
+  std::unique_ptr<rtb_context, void (*)(rtb_context*)> c(new rtb_context(), rtb_context_destroy);
+  const int rc = context_init(c.get(), device_id);
+  if (rc != RTB_OK) return rc;
+  *out = c.release();
   return RTB_OK;
 }
 
 void rtb_context_destroy(rtb_context* c) {
   if (!c) return;
+  for (rtb_context* p : c->peers) rtb_context_destroy(p);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  if (c->comm && nccl_api().ok) nccl_api().CommDestroy(c->comm);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (int k = 0; k < RTB_MAX_LANES; ++k) {
     Lane& L = c->lanes[k];
@@ -154,9 +176,76 @@ void rtb_context_destroy(rtb_context* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_n0) cudaEventDestroy(c->ev_n0);
+  if (c->ev_n1) cudaEventDestroy(c->ev_n1);
   for (cudaEvent_t e : c->ext_events) cudaEventDestroy(e);
   delete c;
 }
+
+// ---- multi-GPU: communicators ---------------------------------------------------------------------------------------
+#define NCCLCHECK(call)                                                                                        \
+  do {                                                                                                         \
+    const int r_ = (call);                                                                                     \
+    if (r_ != kNcclSuccess)                                                                                    \
+      return set_err(RTB_ERR_CUDA, std::string(#call) + ": " + nccl_api().GetErrorString(r_));                  \
+  } while (0)
+
+int rtb_context_create_multi(const int* device_ids, int n_devices, rtb_context** out) {
+  if (!out || !device_ids || n_devices < 1) return set_err(RTB_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b)
+      if (device_ids[a] == device_ids[b]) return set_err(RTB_ERR_INVALID, "device ids must be distinct");
+  rtb_context* root = nullptr;
+  int rc = rtb_context_create(device_ids[0], &root);
+  if (rc != RTB_OK) return rc;
+  std::unique_ptr<rtb_context, void (*)(rtb_context*)> guard(root, rtb_context_destroy);
+  root->n_ranks = n_devices;
+  if (n_devices > 1) {
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return set_err(RTB_ERR_UNSUPPORTED, "multi-GPU needs NCCL: " + api.error);
+    for (int k = 1; k < n_devices; ++k) {
+      rtb_context* p = nullptr;
+      rc = rtb_context_create(device_ids[k], &p);
+      if (rc != RTB_OK) return rc;
+      p->rank = k;
+      p->n_ranks = n_devices;
+      root->peers.push_back(p);
+    }
+    std::vector<NcclComm> comms((size_t)n_devices, nullptr);
+    NCCLCHECK(api.CommInitAll(comms.data(), n_devices, device_ids));  // one communicator per device, ranks = list order
+    root->comm = comms[0];
+    for (int k = 1; k < n_devices; ++k) root->peers[(size_t)k - 1]->comm = comms[(size_t)k];
+  }
+  *out = guard.release();
+  return RTB_OK;
+}
+
+int rtb_comm_unique_id(uint8_t* id128) {
+  if (!id128) return set_err(RTB_ERR_INVALID, "id is NULL");
+  const NcclApi& api = nccl_api();
+  if (!api.ok) return set_err(RTB_ERR_UNSUPPORTED, "multi-GPU needs NCCL: " + api.error);
+  NcclUniqueId id;
+  NCCLCHECK(api.GetUniqueId(&id));
+  std::memcpy(id128, id.internal, RTB_COMM_ID_BYTES);
+  return RTB_OK;
+}
+
+int rtb_context_comm_init(rtb_context* c, const uint8_t* id128, int rank, int n_ranks) {
+  if (!c || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return set_err(RTB_ERR_INVALID, "bad argument");
+  if (!c->peers.empty() || c->comm) return set_err(RTB_ERR_STATE, "context already has a communicator");
+  const NcclApi& api = nccl_api();
+  if (!api.ok) return set_err(RTB_ERR_UNSUPPORTED, "multi-GPU needs NCCL: " + api.error);
+  CU(cudaSetDevice(c->device));
+  NcclUniqueId id;
+  std::memcpy(id.internal, id128, RTB_COMM_ID_BYTES);
+  NCCLCHECK(api.CommInitRank(&c->comm, n_ranks, id, rank));
+  c->rank = rank;
+  c->n_ranks = n_ranks;
+  return RTB_OK;
+}
+
+int rtb_context_device_count(rtb_context* c) { return c ? 1 + (int)c->peers.size() : 0; }
 
 int rtb_context_device_info(rtb_context* c, int* sm_count, int* l2_bytes, int* clock_khz, char* name, size_t cap) {
   if (!c) return set_err(RTB_ERR_INVALID, "ctx is NULL");
@@ -176,15 +265,21 @@ int rtb_scene_create(rtb_context* ctx, rtb_scene** out) {
   if (!out) return set_err(RTB_ERR_INVALID, "NULL argument");
   rtb_scene* s = new rtb_scene();  // ctx == NULL: host-only scene (flatten / BVH build / export; cannot be committed)
   s->ctx = ctx;
+  s->device = ctx ? ctx->device : -1;
+  if (ctx)
+    for (rtb_context* p : ctx->peers) {  // device copies on the other GPUs of a multi-device context
+      rtb_scene* r = new rtb_scene();
+      r->ctx = p;
+      r->device = p->device;
+      s->replicas.push_back(r);
+    }
   *out = s;
   return RTB_OK;
 }
 void rtb_scene_destroy(rtb_scene* s) {
   if (!s) return;
-  if (s->ctx) {
-    cudaSetDevice(s->ctx->device);
-    cudaDeviceSynchronize();
-  }
+  for (rtb_scene* r : s->replicas) rtb_scene_destroy(r);
+  if (s->device >= 0 && cudaSetDevice(s->device) == cudaSuccess) cudaDeviceSynchronize();  // (never touches s->ctx: it may be gone)
   delete s;
 }
 
@@ -202,6 +297,10 @@ int rtb_scene_set_textures(rtb_scene* s, const rtb_texture* tex, uint32_t n) {
     if (tex[i].type > RTB_TEX_IMAGE) return set_err(RTB_ERR_INVALID, "unknown texture type");
     if (tex[i].type == RTB_TEX_CHECKER && (tex[i].even >= n || tex[i].odd >= n))
       return set_err(RTB_ERR_INVALID, "checker child out of range");
+    // the reference's Arc<dyn Texture> children can nest (texture.rs:41-45) but only solid colours are ever constructed
+    // (:52-57); the device resolves ONE checker level, so a checker under a checker is refused instead of rendered black
+    if (tex[i].type == RTB_TEX_CHECKER && (tex[tex[i].even].type == RTB_TEX_CHECKER || tex[tex[i].odd].type == RTB_TEX_CHECKER))
+      return set_err(RTB_ERR_UNSUPPORTED, "a checker texture's children must not be checker textures");
     if (tex[i].type == RTB_TEX_NOISE && tex[i].table >= RTB_MAX_TABLES) return set_err(RTB_ERR_INVALID, "perlin table id too large");
   }
   s->hs.textures.assign(tex, tex + n);
@@ -210,8 +309,11 @@ int rtb_scene_set_textures(rtb_scene* s, const rtb_texture* tex, uint32_t n) {
 }
 int rtb_scene_set_image(rtb_scene* s, uint32_t id, const uint8_t* rgb, uint32_t w, uint32_t h) {
   if (!s || id >= RTB_MAX_TABLES) return set_err(RTB_ERR_INVALID, "image id out of range");
+  if ((!rgb && w && h) || ((size_t)w * h == 0 && rgb)) return set_err(RTB_ERR_INVALID, "image pointer / size mismatch");
+  if (!rgb) w = h = 0;  // an empty image: the texture renders cyan (texture.rs:119-121)
   if (s->hs.images.size() <= id) s->hs.images.resize(id + 1);
-  s->hs.images[id].rgb.assign(rgb, rgb + (size_t)w * h * 3);
+  if (rgb) s->hs.images[id].rgb.assign(rgb, rgb + (size_t)w * h * 3);
+  else s->hs.images[id].rgb.clear();
   s->hs.images[id].w = w;
   s->hs.images[id].h = h;
   s->built = s->committed = false;
@@ -220,6 +322,8 @@ int rtb_scene_set_image(rtb_scene* s, uint32_t id, const uint8_t* rgb, uint32_t 
 int rtb_scene_set_perlin(rtb_scene* s, uint32_t id, const double* ranvec, const uint32_t* px, const uint32_t* py,
                          const uint32_t* pz) {
   if (!s || id >= RTB_MAX_TABLES || !ranvec || !px || !py || !pz) return set_err(RTB_ERR_INVALID, "bad perlin table");
+  for (int i = 0; i < 256; ++i)  // validate before the stored table is touched
+    if (px[i] > 255 || py[i] > 255 || pz[i] > 255) return set_err(RTB_ERR_INVALID, "perm entry > 255");
   if (s->hs.perlins.size() <= id) s->hs.perlins.resize(id + 1);
   HostScene::Perlin& p = s->hs.perlins[id];
   p.ranvec.resize(256 * 4);
@@ -229,7 +333,6 @@ int rtb_scene_set_perlin(rtb_scene* s, uint32_t id, const double* ranvec, const 
     p.ranvec[4 * i + 1] = (float)ranvec[3 * i + 1];
     p.ranvec[4 * i + 2] = (float)ranvec[3 * i + 2];
     p.ranvec[4 * i + 3] = 0.f;
-    if (px[i] > 255 || py[i] > 255 || pz[i] > 255) return set_err(RTB_ERR_INVALID, "perm entry > 255");
     p.perm[i] = (uint8_t)px[i];
     p.perm[256 + i] = (uint8_t)py[i];
     p.perm[512 + i] = (uint8_t)pz[i];
@@ -362,6 +465,7 @@ int rtb_scene_set_media(rtb_scene* s, const rtb_medium* media, uint32_t n) {
   for (uint32_t i = 0; i < n; ++i) {
     const rtb_medium& m = media[i];
     if (m.boundary_type > RTB_BOUNDARY_BOX) return set_err(RTB_ERR_UNSUPPORTED, "medium boundary must be sphere or box");
+    if (!(m.density > 0.0) || !std::isfinite(m.density)) return set_err(RTB_ERR_INVALID, "medium density must be positive and finite");
     HostMedium h;
     std::memset(&h, 0, sizeof(h));
     h.boundary_type = m.boundary_type;
@@ -477,39 +581,36 @@ static uint32_t queue_of_material(const HostScene& hs, uint32_t m) {
   }
 }
 
-int rtb_scene_commit(rtb_scene* s) {
-  if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
-  if (!s->ctx) return set_err(RTB_ERR_STATE, "host-only scene (created without a context) cannot be committed");
-  if (!s->built) {
-    int rc = rtb_scene_build_bvh(s);
-    if (rc != RTB_OK) return rc;
-  }
-  HostScene& hs = s->hs;
+// uploads the flattened scene + BVH of `host` to the device of `s` (s == host, or one of its replicas)
+static int upload_scene(rtb_scene* s, const rtb_scene* host) {
+  const HostScene& hs = host->hs;
+  const HostBvh& bvh = host->bvh;
   CU(cudaSetDevice(s->ctx->device));
+  s->present_materials = host->present_materials;
 
   DevScene& d = s->dev;
   std::memset(&d, 0, sizeof(d));
-  CU(s->d_nodes.upload(reinterpret_cast<const uint4*>(s->bvh.nodes.data()), s->bvh.nodes.size() * 5));
+  CU(s->d_nodes.upload(reinterpret_cast<const uint4*>(bvh.nodes.data()), bvh.nodes.size() * 5));
   d.nodes = s->d_nodes.p;
-  d.n_nodes = (uint32_t)s->bvh.nodes.size();
+  d.n_nodes = (uint32_t)bvh.nodes.size();
   d.prmt_magic = 0x43000000u;
-  d.n_global = (uint32_t)s->bvh.global_refs.size();
-  d.tree_empty = (d.n_global == (uint32_t)s->hs.prims.size()) ? 1u : 0u;
-  for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = s->bvh.global_refs[k];
-  d.global_f64 = d.tree_empty ? 0u : s->bvh.global_f64;
+  d.n_global = (uint32_t)bvh.global_refs.size();
+  d.tree_empty = (d.n_global == (uint32_t)hs.prims.size()) ? 1u : 0u;
+  for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = bvh.global_refs[k];
+  d.global_f64 = d.tree_empty ? 0u : bvh.global_f64;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
-    CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(s->bvh.geom[t].data()), s->bvh.geom[t].size() / 4));
+    CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(bvh.geom[t].data()), bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
-    std::vector<uint32_t> info = s->bvh.info[t];
+    std::vector<uint32_t> info = bvh.info[t];
     for (size_t i = 1; i < info.size(); i += 2) info[i] |= queue_of_material(hs, info[i] & 0xFFFFFFu) << 26;
     CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(info.data()), info.size() / 2));
     CU(cudaStreamSynchronize(0));  // `info` is a temporary
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
-    CU(s->d_exact[t].upload(s->bvh.exact[t].data(), s->bvh.exact[t].size()));
+    CU(s->d_exact[t].upload(bvh.exact[t].data(), bvh.exact[t].size()));
   }
-  d.coord_max = s->bvh.coord_max;
-  d.eps_ab = s->bvh.eps_ab;
+  d.coord_max = bvh.coord_max;
+  d.eps_ab = bvh.eps_ab;
   std::vector<float4> mats(hs.materials.size() * 2);
   for (size_t i = 0; i < hs.materials.size(); ++i) {
     uint32_t ty = hs.materials[i].type, tx = hs.materials[i].texture, tt = 0xFFu;
@@ -582,6 +683,19 @@ int rtb_scene_commit(rtb_scene* s) {
   s->committed = true;
   return RTB_OK;
 }
+
+int rtb_scene_commit(rtb_scene* s) {
+  if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
+  if (!s->ctx) return set_err(RTB_ERR_STATE, "host-only scene (created without a context) cannot be committed");
+  if (!s->built) {
+    int rc = rtb_scene_build_bvh(s);
+    if (rc != RTB_OK) return rc;
+  }
+  int rc = upload_scene(s, s);
+  for (size_t k = 0; k < s->replicas.size() && rc == RTB_OK; ++k) rc = upload_scene(s->replicas[k], s);  // same host data, every GPU
+  return rc;
+}
+
 
 int rtb_scene_get_info(rtb_scene* s, rtb_scene_info* o) {
   if (!s || !o) return set_err(RTB_ERR_INVALID, "NULL argument");
@@ -831,6 +945,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
         run[k].active = false;
         --n_active;
       } else if (run[k].iters > run[k].iter_cap) {
+        for (int q = 0; q < n_lanes; ++q) cudaStreamSynchronize(c->lanes[q].stream);  // nothing may still write d_accum
         return set_err(RTB_ERR_CUDA, "wavefront did not drain (internal error)");
       }
     }
@@ -840,12 +955,27 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     CU(cudaStreamWaitEvent(st, c->lanes[k].done, 0));
   }
   CU(cudaEventRecord(c->ev1, st));
+  float ms_nccl = 0.f;
+  if ((p->flags & RTB_RENDER_REDUCE) && c->n_ranks > 1) {
+    // one ncclReduce(float32, 4 W H, sum, root 0) per frame, in place, on the caller's stream
+    if (!c->comm) return set_err(RTB_ERR_STATE, "RTB_RENDER_REDUCE needs a communicator (rtb_context_comm_init)");
+    CU(cudaEventRecord(c->ev_n0, st));
+    const int r = nccl_api().Reduce(d_accum, d_accum, npix * 4, kNcclFloat32, kNcclSum, 0, c->comm, st);
+    if (r != kNcclSuccess) return set_err(RTB_ERR_CUDA, std::string("ncclReduce: ") + nccl_api().GetErrorString(r));
+    CU(cudaEventRecord(c->ev_n1, st));
+    CU(cudaEventSynchronize(c->ev_n1));
+    cudaEventElapsedTime(&ms_nccl, c->ev_n0, c->ev_n1);
+  }
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaGetLastError());
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    stats->ms_nccl = ms_nccl;
+    stats->ms_render = ms;
+    stats->n_devices = 1;
+    ms += ms_nccl;
     for (int k = 0; k < n_lanes; ++k) {
       const DevCounters* h = c->lanes[k].h_counters;
       stats->paths += run[k].total;  // a render always runs to completion: every path number was started exactly once
@@ -856,6 +986,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
       stats->iterations = std::max<uint64_t>(stats->iterations, h->iter);
       stats->nodes_visited += h->nodes_visited;
       stats->prims_tested += h->prims_tested;
+      for (uint32_t t = 0; t < PT_COUNT; ++t) stats->prims_tested_type[t] += h->prims_tested_type[t];
     }
     stats->launches = launches;
     stats->extend_launches = extend_launches;
@@ -871,11 +1002,97 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   return RTB_OK;
 }
 
+// One process, n GPUs: device k renders its share of the samples of EVERY pixel on its own thread, then all of them join one
+// ncclReduce onto device 0 (replaces the reference's only parallelism, the per-pixel thread fan-out of main.rs:730-778).
+static int render_multi(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rtb_params* p, rtb_stats* stats) {
+  const int n = 1 + (int)c->peers.size();
+  if ((int)s->replicas.size() != n - 1) return set_err(RTB_ERR_STATE, "scene was not created on this multi-device context");
+  const size_t npix = (size_t)p->width * p->height;
+  std::vector<rtb_context*> ctxs{c};
+  std::vector<rtb_scene*> scs{s};
+  for (int k = 1; k < n; ++k) { ctxs.push_back(c->peers[(size_t)k - 1]); scs.push_back(s->replicas[(size_t)k - 1]); }
+  std::vector<int> rc((size_t)n, RTB_OK);
+  std::vector<std::string> msg((size_t)n);
+  std::vector<rtb_stats> st((size_t)n);
+  std::vector<float> ms_nccl((size_t)n, 0.f);
+  std::atomic<int> arrived{0};
+  std::atomic<bool> failed{false};
+  auto work = [&](int k) {
+    rtb_context* ck = ctxs[(size_t)k];
+    auto fail = [&](int code, const std::string& m) { rc[(size_t)k] = code; msg[(size_t)k] = m; failed = true; };
+    std::memset(&st[(size_t)k], 0, sizeof(rtb_stats));
+    const uint32_t base = p->spp / (uint32_t)n, rem = p->spp % (uint32_t)n;
+    const uint32_t cnt = base + ((uint32_t)k < rem ? 1u : 0u), first = (uint32_t)k * base + std::min((uint32_t)k, rem);
+    cudaError_t e = cudaSetDevice(ck->device);
+    if (e == cudaSuccess) e = ck->accum.resize(npix);
+    if (e != cudaSuccess) fail(RTB_ERR_CUDA, cudaGetErrorString(e));
+    if (rc[(size_t)k] == RTB_OK) {
+      if (cnt == 0) {
+        e = (p->flags & RTB_RENDER_ACCUMULATE) ? cudaSuccess : cudaMemset(ck->accum.p, 0, npix * sizeof(float4));
+        if (e != cudaSuccess) fail(RTB_ERR_CUDA, cudaGetErrorString(e));
+      } else {
+        rtb_params pk = *p;
+        pk.spp = cnt;
+        pk.sample_offset = p->sample_offset + first;
+        pk.flags &= ~RTB_RENDER_REDUCE;
+        if (pk.pool_paths) pk.pool_paths = std::max(1024u, pk.pool_paths);
+        const int r = rtb_render_device(ck, scs[(size_t)k], cam, &pk, ck->accum.p, nullptr, &st[(size_t)k]);
+        if (r != RTB_OK) fail(r, g_err);
+      }
+    }
+    // every device finished rendering before the collective starts: ms_nccl is the reduce alone
+    arrived.fetch_add(1);
+    while (arrived.load() < n) std::this_thread::yield();
+    if (failed.load()) return;  // no device enters the collective when one of them failed
+    cudaEventRecord(ck->ev_n0, 0);
+    const int r = nccl_api().Reduce(ck->accum.p, ck->accum.p, npix * 4, kNcclFloat32, kNcclSum, 0, ck->comm, (cudaStream_t)0);
+    cudaEventRecord(ck->ev_n1, 0);
+    e = cudaEventSynchronize(ck->ev_n1);
+    if (r != kNcclSuccess) fail(RTB_ERR_CUDA, std::string("ncclReduce: ") + nccl_api().GetErrorString(r));
+    else if (e != cudaSuccess) fail(RTB_ERR_CUDA, cudaGetErrorString(e));
+    else cudaEventElapsedTime(&ms_nccl[(size_t)k], ck->ev_n0, ck->ev_n1);
+  };
+  std::vector<std::thread> pool;
+  for (int k = 1; k < n; ++k) pool.emplace_back(work, k);
+  work(0);
+  for (std::thread& t : pool) t.join();
+  for (int k = 0; k < n; ++k)
+    if (rc[(size_t)k] != RTB_OK) return set_err(rc[(size_t)k], "device " + std::to_string(ctxs[(size_t)k]->device) + ": " + msg[(size_t)k]);
+  CU(cudaSetDevice(c->device));
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    for (int k = 0; k < n; ++k) {
+      const rtb_stats& q = st[(size_t)k];
+      stats->paths += q.paths; stats->segments += q.segments; stats->rejected += q.rejected;
+      stats->launches += q.launches; stats->extend_launches += q.extend_launches;
+      stats->nodes_visited += q.nodes_visited; stats->prims_tested += q.prims_tested;
+      for (uint32_t t = 0; t < PT_COUNT; ++t) stats->prims_tested_type[t] += q.prims_tested_type[t];
+      stats->exact_rays += q.exact_rays; stats->refined_rays += q.refined_rays;
+      stats->iterations = std::max(stats->iterations, q.iterations);
+      stats->ms_render = std::max(stats->ms_render, q.ms_total);
+      stats->ms_extend = std::max(stats->ms_extend, q.ms_extend);
+    }
+    stats->ms_nccl = ms_nccl[0];
+    stats->ms_total = stats->ms_render + stats->ms_nccl;
+    stats->n_devices = (uint32_t)n;
+  }
+  return RTB_OK;
+}
+
 int rtb_render(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rtb_params* p, float* accum_out,
                rtb_stats* stats) {
   if (!c || !p) return set_err(RTB_ERR_INVALID, "NULL argument");
   CU(cudaSetDevice(c->device));
   const size_t npix = (size_t)p->width * p->height;
+  if (!c->peers.empty()) {
+    if (!s || !cam) return set_err(RTB_ERR_INVALID, "NULL argument");
+    if (!s->committed) return set_err(RTB_ERR_STATE, "scene not committed (call rtb_scene_commit)");
+    if (p->spp == 0) return set_err(RTB_ERR_INVALID, "spp must be > 0");
+    int rc = render_multi(c, s, cam, p, stats);
+    if (rc) return rc;
+    if (accum_out) CU(cudaMemcpy(accum_out, c->accum.p, npix * sizeof(float4), cudaMemcpyDeviceToHost));
+    return RTB_OK;
+  }
   CU(c->accum.resize(npix));
   int rc = rtb_render_device(c, s, cam, p, c->accum.p, nullptr, stats);
   if (rc) return rc;
@@ -934,6 +1151,7 @@ static int run_probe(rtb_context* c, rtb_scene* s, uint32_t n, uint32_t* id_out,
     stats->ms_extend = ms;
     stats->nodes_visited = c->h_counters->nodes_visited;
     stats->prims_tested = c->h_counters->prims_tested;
+    for (uint32_t t = 0; t < PT_COUNT; ++t) stats->prims_tested_type[t] = c->h_counters->prims_tested_type[t];
     stats->exact_rays = c->h_counters->redone - c->h_counters->refined;
     stats->refined_rays = c->h_counters->refined;
   }
@@ -1001,6 +1219,43 @@ int rtb_device_kat(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rt
   launch_kat(dev, dcam, prm, op, d_in.p, n, in_stride, d_out.p, out_stride, 0);
   CU(cudaMemcpy(out, d_out.p, (size_t)n * out_stride * 4, cudaMemcpyDeviceToHost));
   CU(cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_measure_bandwidth(rtb_context* c, uint32_t kind, uint32_t repeats, double* gbs) {
+  if (!c || !gbs || kind > RTB_BW_SHARED_READ) return set_err(RTB_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (repeats == 0) repeats = 5;
+  const uint32_t grid = (uint32_t)c->prop.multiProcessorCount * 8u;
+  DevBuf<uint4> sink, buf;
+  CU(sink.resize(1));
+  double bytes = 0.0;
+  uint32_t reps = 1;
+  size_t n_vec = 0;
+  if (kind == RTB_BW_SHARED_READ) {
+    reps = 1u << 16;
+    bytes = (double)grid * 256.0 * reps * 16.0;
+  } else {
+    const size_t sz = kind == RTB_BW_L2_READ ? ((size_t)48 << 20) : ((size_t)2 << 30);
+    n_vec = sz / 16;
+    CU(buf.resize(n_vec));
+    CU(cudaMemsetAsync(buf.p, 1, sz, 0));
+    reps = kind == RTB_BW_L2_READ ? 64u : 2u;
+    bytes = (double)sz * reps;
+  }
+  double best = 0.0;
+  for (uint32_t r = 0; r < repeats + 1; ++r) {  // first launch = warm-up (fills L2)
+    CU(cudaEventRecord(c->ev0, 0));
+    if (kind == RTB_BW_SHARED_READ) launch_bw_shared(reps, sink.p, grid, 0);
+    else launch_bw_global(buf.p, n_vec, reps, sink.p, grid, 0);
+    CU(cudaEventRecord(c->ev1, 0));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    if (r > 0 && ms > 0.f) best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+  }
+  CU(cudaGetLastError());
+  *gbs = best;
   return RTB_OK;
 }
 

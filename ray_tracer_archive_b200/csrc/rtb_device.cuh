@@ -91,6 +91,7 @@ struct DevCounters {
   unsigned long long total_paths;
   unsigned long long segments, rejected;
   unsigned long long nodes_visited, prims_tested;
+  unsigned long long prims_tested_type[PT_COUNT];  // ... per primitive type (the roofline weights each type's bytes / flops)
 };
 
 // Path pool of one wavefront instance ("lane").  SLOT-STABLE: a path lives in slot i until it terminates, and slot i is
@@ -228,6 +229,7 @@ struct Closest {
 #define RTB_U22 2.3841858e-7f
 #define RTB_U23 1.1920929e-7f
 enum HitStatus : int { HIT_MISS = 0, HIT_CERTAIN = 1, HIT_AMBIGUOUS = 2 };
+struct TestCount { uint32_t n[PT_COUNT]; };  // primitive tests per type (instrumented build only)
 
 // primitive id of a hit reference (list order of the reference's scene graph).  Needed only for the "later primitive
 // wins equal t" rule (hittable_list.rs:44-47) and by the parity probe, so it is fetched lazily: an accepted hit does
@@ -487,8 +489,8 @@ __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float
 
 template <bool COUNT>
 __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
-                                               float time, float tmin, Closest& best, float& amb, uint32_t& flags, uint32_t& n_tests) {
-  if (COUNT) ++n_tests;
+                                               float time, float tmin, Closest& best, float& amb, uint32_t& flags, TestCount& n_tests) {
+  if (COUNT) ++n_tests.n[type];
   const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
   float t, e;
   bool coarse = false;
@@ -735,11 +737,11 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
 // the scene's "global" primitives (huge relative to the scene, kept out of the tree): tested first, which also
 // establishes an early t_max for the traversal
 template <bool COUNT>
-__device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float tmin, uint32_t& n_tests) {
+__device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float tmin, TestCount& n_tests) {
   for (uint32_t k = 0; k < sc.n_global; ++k) {
     const uint32_t ref = sc.global_ref[k];
     if ((sc.global_f64 >> k) & 1u) {  // the r = 1000 ground sphere of book 1: skip the f32 attempt (~100 instructions per ray)
-      if (COUNT) ++n_tests;
+      if (COUNT) ++n_tests.n[PT_SPHERE];
       const float4 s = __ldg(sc.geom[PT_SPHERE] + (ref & REF_INDEX_MASK));
       float t;
       const int st = sphere_roots_f64(tv.o, tv.d, xyz(s), s.w, tmin, t);
@@ -756,7 +758,7 @@ __device__ __forceinline__ void trav_globals(const DevScene& sc, Trav& tv, float
 template <bool COUNT, bool ALL_STAGED = false>
 __device__ __forceinline__ bool trav_step_fast(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                                Trav& tv, uint2* __restrict__ stack, float tmin,
-                                               uint32_t& n_nodes_visited, uint32_t& n_tests) {
+                                               uint32_t& n_nodes_visited, TestCount& n_tests) {
   return trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited,
                                       [&](uint32_t type, uint32_t idx) {
                                         intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
@@ -767,7 +769,7 @@ __device__ __forceinline__ bool trav_step_fast(const DevScene& sc, const uint4* 
 template <bool COUNT, bool ALL_STAGED = false>
 __device__ __forceinline__ uint32_t traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                          float3 o, float3 d, float time, float tmin, Closest& best,
-                                         uint32_t& n_nodes_visited, uint32_t& n_tests) {
+                                         uint32_t& n_nodes_visited, TestCount& n_tests) {
   Trav tv;
   uint2 stack[RTB_STACK];
   trav_init(tv, o, d, time);

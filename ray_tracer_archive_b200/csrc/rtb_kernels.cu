@@ -152,7 +152,8 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   uint32_t n_rays = 0;                                 // warp-uniform
   Trav tv;
   uint2 stack[RTB_STACK];
-  uint32_t nv = 0, nt = 0;
+  uint32_t nv = 0;
+  TestCount nt{};
   // idle lanes are refilled when at least this many wait (or nobody runs): a swap costs the whole warp ~40 issue slots
   // however few lanes take part (C4 ext_ms: 1 -> 21.6, 4 -> 21.2, 8 -> 21.1, 16 -> 21.7; profiles/r2_ab.md §7)
   const uint32_t refill_min = 8u;
@@ -252,10 +253,17 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
   if (COUNT) {
     nv = __reduce_add_sync(0xffffffffu, nv);
-    nt = __reduce_add_sync(0xffffffffu, nt);
+    uint32_t tot = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < PT_COUNT; ++t) {
+      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
+      tot += nt.n[t];
+    }
     if (lane == 0) {
       atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-      atomicAdd(&c->prims_tested, (unsigned long long)nt);
+      atomicAdd(&c->prims_tested, (unsigned long long)tot);
+      for (uint32_t t = 0; t < PT_COUNT; ++t)
+        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
 }
@@ -276,7 +284,8 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* list = s_list[warp];
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
-  uint32_t n_rays = 0, nv = 0, nt = 0;
+  uint32_t n_rays = 0, nv = 0;
+  TestCount nt{};
   for (uint32_t chunk = blockIdx.x * RTB_EXTEND_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
     const uint32_t base = chunk * RTB_CHUNK;
     const uint32_t total = build_extend_list(pool, chunk, list, lane);
@@ -298,10 +307,17 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
   if (COUNT) {
     nv = __reduce_add_sync(0xffffffffu, nv);
-    nt = __reduce_add_sync(0xffffffffu, nt);
+    uint32_t tot = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < PT_COUNT; ++t) {
+      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
+      tot += nt.n[t];
+    }
     if (lane == 0) {
       atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-      atomicAdd(&c->prims_tested, (unsigned long long)nt);
+      atomicAdd(&c->prims_tested, (unsigned long long)tot);
+      for (uint32_t t = 0; t < PT_COUNT; ++t)
+        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
 }
@@ -789,6 +805,7 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
     c->total_paths = total_paths;
     c->segments = c->rejected = 0;
     c->nodes_visited = c->prims_tested = 0;
+    for (uint32_t t = 0; t < PT_COUNT; ++t) c->prims_tested_type[t] = 0;
   }
 }
 
@@ -957,6 +974,35 @@ __global__ void k_kat(DevScene sc, DevCamera cam, DevParams prm, uint32_t op, co
   }
 }
 
+// ---- bandwidth microbenchmarks: the physical denominators of the roofline (bench.py, profiles/) ------------------------
+// Read-only 128-bit loads (ld.global.nc, the instruction the node / primitive fetches use) streaming a buffer `reps` times:
+// a 48 MB buffer stays in the 126 MB L2 (L2 read bandwidth), a 2 GB one does not (HBM read bandwidth).
+__global__ void __launch_bounds__(256) k_bw_global(const uint4* __restrict__ p, size_t n_vec, uint32_t reps, uint4* __restrict__ sink) {
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (uint32_t r = 0; r < reps; ++r)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint4 v = __ldg(p + i);
+      acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345679u) sink[0] = acc;  // keeps the loads alive; practically never true
+}
+// 128-bit shared-memory loads at conflict-free addresses (how the node stage is read): bytes = threads x reps x 16
+__global__ void __launch_bounds__(256) k_bw_shared(uint32_t reps, uint4* __restrict__ sink) {
+  extern __shared__ uint4 sm[];
+  const uint32_t n = 2048;  // 32 KB
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[i] = make_uint4(i, i * 3u, i * 5u, i * 7u);
+  __syncthreads();
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t k = threadIdx.x;
+  for (uint32_t r = 0; r < reps; ++r) {
+    const uint4 v = sm[k];
+    acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    k = (k + 256u) & (n - 1u);
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345679u) sink[0] = acc;
+}
+
 // ================================================= launchers ========================================================
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
@@ -1006,6 +1052,12 @@ void launch_probe_collect(const DevScene& sc, const DevPool& pool, uint32_t n, u
 void launch_kat(const DevScene& sc, const DevCamera& cam, const DevParams& prm, uint32_t op, const uint32_t* in, uint32_t n,
                 uint32_t in_stride, uint32_t* out, uint32_t out_stride, cudaStream_t st) {
   k_kat<<<cdiv(n, 128), 128, 0, st>>>(sc, cam, prm, op, in, n, in_stride, out, out_stride);
+}
+void launch_bw_global(const uint4* p, size_t n_vec, uint32_t reps, uint4* sink, uint32_t grid, cudaStream_t st) {
+  k_bw_global<<<grid, 256, 0, st>>>(p, n_vec, reps, sink);
+}
+void launch_bw_shared(uint32_t reps, uint4* sink, uint32_t grid, cudaStream_t st) {
+  k_bw_shared<<<grid, 256, 32768, st>>>(reps, sink);
 }
 void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
                          cudaStream_t st) {

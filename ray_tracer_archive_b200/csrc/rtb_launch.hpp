@@ -47,6 +47,8 @@ void launch_probe_fill(const DevPool& pool, const float* org, const float* dir, 
 void launch_probe_collect(const DevScene& sc, const DevPool& pool, uint32_t n, uint32_t* id_out, float* t_out, cudaStream_t st);
 void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float* org, float* dir, float* time,
                          cudaStream_t st);
+void launch_bw_global(const uint4* p, size_t n_vec, uint32_t reps, uint4* sink, uint32_t grid, cudaStream_t st);
+void launch_bw_shared(uint32_t reps, uint4* sink, uint32_t grid, cudaStream_t st);
 void launch_kat(const DevScene& sc, const DevCamera& cam, const DevParams& prm, uint32_t op, const uint32_t* in, uint32_t n,
                 uint32_t in_stride, uint32_t* out, uint32_t out_stride, cudaStream_t st);
 

@@ -11,14 +11,37 @@ from .scene import CompiledScene
 
 
 class Context:
-    """One GPU (one process per GPU; multi-GPU runs split samples via Params.sample_offset)."""
+    """One GPU — or, with a list of device ids, several GPUs driven by this process (rtb_context_create_multi: the
+    library splits every render's samples across them and sums the accumulation buffers with one NCCL reduce).
+    With one process per GPU use comm_unique_id() / comm_init() and the RENDER_REDUCE flag instead."""
 
-    def __init__(self, device_id: int = 0):
+    def __init__(self, device_id=0):
         self.lib = F.load()
         h = C.c_void_p()
-        F.check(self.lib.rtb_context_create(device_id, C.byref(h)))
+        if isinstance(device_id, (list, tuple)):
+            ids = (C.c_int * len(device_id))(*device_id)
+            F.check(self.lib.rtb_context_create_multi(ids, len(device_id), C.byref(h)))
+            self.device_id = int(device_id[0])
+        else:
+            F.check(self.lib.rtb_context_create(device_id, C.byref(h)))
+            self.device_id = device_id
         self.h = h
-        self.device_id = device_id
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.rtb_context_device_count(self.h)
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes (ncclGetUniqueId) that rank 0 hands to the other ranks."""
+        buf = (C.c_uint8 * 128)()
+        F.check(F.load().rtb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """Join the communicator (ncclCommInitRank); collective: every rank must call it."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        F.check(self.lib.rtb_context_comm_init(self.h, buf, rank, n_ranks))
 
     def close(self):
         if getattr(self, "h", None):
@@ -47,6 +70,12 @@ class Context:
                                         C.byref(params) if params is not None else None, op, F.ptr(w), w.shape[0],
                                         w.shape[1], F.ptr(out), out_stride))
         return out
+
+    def measure_bandwidth(self, kind: int, repeats: int = 5) -> float:
+        """GB/s of a read-only stream: F.BW_L2_READ (48 MB, L2-resident), F.BW_HBM_READ (2 GB), F.BW_SHARED_READ."""
+        v = C.c_double()
+        F.check(self.lib.rtb_measure_bandwidth(self.h, kind, repeats, C.byref(v)))
+        return v.value
 
     def device_info(self):
         sm, l2, khz = C.c_int(), C.c_int(), C.c_int()

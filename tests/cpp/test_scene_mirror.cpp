@@ -2,8 +2,11 @@
 // with the C++ mirror of its constructors, handed to librtb200 through the C ABI (host-only scene: no GPU needed here).
 // Prints the flattened scene summary and the serialized records so the pytest wrapper can compare them with the Python
 // mirror's.  With a GPU (argv[1] == "render") it also renders 16 spp and prints the segment count.
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../include/rtb200_scene.hpp"
 
@@ -37,6 +40,45 @@ int main(int argc, char** argv) {
   SceneRecords rec;
   rec.set_world(world, lights);
 
+  // "multi N": SURVEY §4 tier D1 through the C ABI — one process, N GPUs (rtb_context_create_multi -> ncclCommInitAll, samples
+  // split inside rtb_render, one ncclReduce) against the same render on one GPU: same sample set, sums equal to f32
+  // summation order
+  if (argc > 2 && !std::strcmp(argv[1], "multi")) {
+    const int n = std::atoi(argv[2]);
+    std::vector<int> ids;
+    for (int k = 0; k < n; ++k) ids.push_back(k);
+    rtb_context *one = nullptr, *many = nullptr;
+    if (rtb_context_create(0, &one) != 0) { std::printf("context: %s\n", rtb_last_error()); return 2; }
+    if (rtb_context_create_multi(ids.data(), n, &many) != 0) { std::printf("multi context: %s\n", rtb_last_error()); return 2; }
+    rtb_camera cam{{278, 278, -800}, {278, 278, 0}, {0, 1, 0}, 40.0, 1.0, 0.0, 10.0, 0.0, 1.0};
+    rtb_params prm{};
+    prm.width = 128; prm.height = 96; prm.spp = 50; prm.total_spp = 50; prm.max_depth = 50; prm.seed = 3;  // 50 % n != 0 for n = 4, 8
+    std::vector<float> a((size_t)prm.width * prm.height * 4), b(a.size());
+    rtb_stats sa, sb;
+    rtb_context* ctxs[2] = {one, many};
+    std::vector<float>* outs[2] = {&a, &b};
+    rtb_stats* sts[2] = {&sa, &sb};
+    for (int q = 0; q < 2; ++q) {
+      rtb_scene* sc = nullptr;
+      if (rtb_scene_create(ctxs[q], &sc) != 0) return 3;
+      rec.upload(sc);
+      if (rtb_scene_commit(sc) != 0) { std::printf("commit: %s\n", rtb_last_error()); return 5; }
+      if (rtb_render(ctxs[q], sc, &cam, &prm, outs[q]->data(), sts[q]) != 0) { std::printf("render: %s\n", rtb_last_error()); return 6; }
+      rtb_scene_destroy(sc);
+    }
+    double sum_a = 0, sum_b = 0, worst = 0;
+    for (size_t i = 0; i < a.size(); ++i) {
+      sum_a += a[i]; sum_b += b[i];
+      const double d = std::fabs((double)a[i] - (double)b[i]) / (std::fabs((double)a[i]) + 1.0);
+      if (d > worst) worst = d;
+    }
+    std::printf("multi devices %u (count %d) segments %llu vs %llu paths %llu vs %llu rel_sum_diff %.3e worst_pixel %.3e ms_nccl %.3f ms_render %.3f\n",
+                sb.n_devices, rtb_context_device_count(many), (unsigned long long)sb.segments, (unsigned long long)sa.segments,
+                (unsigned long long)sb.paths, (unsigned long long)sa.paths, std::fabs(sum_a - sum_b) / sum_a, worst, sb.ms_nccl, sb.ms_render);
+    rtb_context_destroy(many);
+    rtb_context_destroy(one);
+    return 0;
+  }
   const bool render = argc > 1 && !std::strcmp(argv[1], "render");
   rtb_context* ctx = nullptr;
   if (render && rtb_context_create(0, &ctx) != 0) { std::printf("context: %s\n", rtb_last_error()); return 2; }

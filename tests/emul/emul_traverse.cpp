@@ -65,7 +65,8 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
   uint64_t nv_total = 0, nt_total = 0;
   for (uint32_t i = 0; i < n; ++i) {
     Closest best;
-    uint32_t nv = 0, nt = 0;
+    uint32_t nv = 0;
+    TestCount nt{};
     const float3 ro = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), rd = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
     // the hot path (f32, ambiguity detection), then — as k_fixup does on the device — the exact pass if it asked for one
     const uint32_t fix = traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd,
@@ -79,7 +80,7 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
     }
     ids[i] = best.ref == REF_MISS ? RTB_NONE : ref_gid(sc, best.ref);
     ts[i] = best.t;
-    nv_total += nv; nt_total += nt;
+    nv_total += nv; nt_total += nt.n[0] + nt.n[1] + nt.n[2] + nt.n[3];
   }
   if (nodes_visited) *nodes_visited = nv_total;
   if (prims_tested) *prims_tested = nt_total;

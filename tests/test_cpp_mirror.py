@@ -46,3 +46,22 @@ def test_cpp_mirror_renders():
     assert out.returncode == 0, out.stdout + out.stderr
     last = out.stdout.strip().splitlines()[-1].split()
     assert last[0] == "rendered" and int(last[2]) == 64 * 64 * 16 and int(last[4]) > 64 * 64 * 16
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_context_reduces_inside_the_library():
+    """SURVEY §8b/§8e through the C ABI from C++: rtb_context_create_multi over every GPU of the box (ncclCommInitAll),
+    rtb_render splits the samples and issues one ncclReduce; against the same render on one GPU (tier D1: <= 1e-6
+    relative on the sums).  Needs >= 2 GPUs (gpurun --gpus N); skipped on a single-GPU box."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = _run("multi", str(n))
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = out.stdout.strip().splitlines()[-1].split()
+    print(out.stdout.strip().splitlines()[-1])
+    assert f[0] == "multi" and int(f[2]) == n and int(f[4].rstrip(")")) == n
+    assert f[6] == f[8] and f[10] == f[12]                # same paths, same segments: the same sample set
+    assert float(f[14]) <= 1e-6 and float(f[16]) <= 2e-5  # sums equal to f32 summation order
+    assert float(f[18]) > 0.0

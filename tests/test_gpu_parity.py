@@ -367,8 +367,10 @@ def test_rotated_image_textured_sphere(rtb, orc, ctx):
     img = scenes.earthmap()
     globe = S.Sphere.construct((0.0, 0.0, 0.0), 2.0, S.Lambertian.construct_texture(S.ImageTexture.construct(img, img.shape[1], img.shape[0])))
     world = S.HittableList([S.Translate.construct(S.RotateY.construct(globe, 75.0), (0.5, 0.2, -0.3)),
-                            S.RotateY.construct(S.Sphere.construct((4.5, 0.0, 0.0), 1.0, S.Lambertian.construct_texture(
-                                S.ImageTexture.construct(scenes.synthetic_earth(64, 32), 64, 32))), -130.0)])
+                            # (wrapped in a Translate like every rotated object of the reference's scenes: a BARE RotateY
+                            # orients the normal against the object-space ray, hittable.rs:173 — DESIGN §9)
+                            S.Translate.construct(S.RotateY.construct(S.Sphere.construct((4.5, 0.0, 0.0), 1.0, S.Lambertian.construct_texture(
+                                S.ImageTexture.construct(scenes.synthetic_earth(64, 32), 64, 32))), -130.0), (0.0, 0.0, 0.0))])
     cfg = scenes.config_cornell()
     cfg.world, cfg.lights, cfg.name, cfg.background = world, None, "rotated earth", (0.7, 0.8, 1.0)
     cfg.camera = rtb.Camera.new((13, 2, 3), (0, 0, 0), (0, 1, 0), 24.0, 1.5, 0.0, 10.0)
