@@ -645,11 +645,27 @@ __device__ __forceinline__ uint4 lds_node_word(const uint4* __restrict__ snodes,
 
 // returns false when the traversal is complete.  ALL_STAGED: every node of the tree is in the shared-memory stage (small
 // scenes), so the global-memory fetch path and its five predicated loads + register moves are compiled out.
-// `leaf(type, index)` tests one primitive (the hot kernels: intersect_prim; the exact pass: exact_hit).
-template <bool COUNT, bool ALL_STAGED, class Leaf>
+// The leaf children a node visit found: `leaf` = slot mask, (w1y, w1z, w1w) = the node's primitive base word and the
+// eight (count << 5 | offset) bytes.  expand_leaves() walks them in slot order, ONE primitive per loop iteration (a
+// single call site: the lanes of a warp that expand together execute the primitive test together).
+template <class Leaf>
+__device__ __forceinline__ void expand_leaves(uint32_t leaf, uint32_t w1y, uint32_t w1z, uint32_t w1w, Leaf&& leaf_fn) {
+  const uint32_t ptype = w1y >> REF_TYPE_SHIFT, pbase = w1y & REF_INDEX_MASK;
+  uint32_t k = 0;
+  while (leaf) {
+    const uint32_t s = __ffs(leaf) - 1;
+    const uint32_t m = ((s < 4 ? w1z : w1w) >> (8 * (s & 3))) & 0xFFu;
+    leaf_fn(ptype, pbase + (m & 31u) + k);
+    if (++k >= (m >> 5)) { k = 0; leaf &= leaf - 1; }
+  }
+}
+
+// `leaves(leaf mask, w1y, w1z, w1w)` receives the hit leaf children of the visited node: the hot kernels test them at once
+// (intersect_prim) or park them to test many lanes' primitives together; the exact pass runs exact_hit on them.
+template <bool COUNT, bool ALL_STAGED, class Leaves>
 __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                           Trav& tv, uint2* __restrict__ stack, float tmin,
-                                          uint32_t& n_nodes_visited, Leaf&& leaf_fn) {
+                                          uint32_t& n_nodes_visited, Leaves&& leaves_fn) {
   if (!(tv.grp.y & 0xFF00u)) {  // group exhausted: pop (stack entries always have hits left) and visit in the same step
     if (tv.sp == 0) return false;
     tv.grp = stack[--tv.sp];
@@ -715,16 +731,9 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     missmask = __funnelshift_l(neg, missmask, 1);  // (missmask << 1) | sign bit; child 0 ends in bit 0
   }
   const uint32_t hitmask = ~missmask & 0xFFu;
-  // leaf children: intersect now (all primitives of one node share a type)
-  uint32_t leaf = hitmask & ~imask;
-  const uint32_t ptype = w1.y >> REF_TYPE_SHIFT, pbase = w1.y & REF_INDEX_MASK;
-  while (leaf) {
-    const uint32_t s = __ffs(leaf) - 1;
-    leaf &= leaf - 1;
-    const uint32_t m = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu;
-    const uint32_t cnt = m >> 5, first = pbase + (m & 31u);
-    for (uint32_t k = 0; k < cnt; ++k) leaf_fn(ptype, first + k);
-  }
+  // leaf children (all primitives of one node share a type)
+  const uint32_t leaf = hitmask & ~imask;
+  if (leaf) leaves_fn(leaf, w1.y, w1.z, w1.w);
   // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
   uint32_t ih = hitmask & imask;
   if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
@@ -760,9 +769,46 @@ __device__ __forceinline__ bool trav_step_fast(const DevScene& sc, const uint4* 
                                                Trav& tv, uint2* __restrict__ stack, float tmin,
                                                uint32_t& n_nodes_visited, TestCount& n_tests) {
   return trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited,
-                                      [&](uint32_t type, uint32_t idx) {
-                                        intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
+                                      [&](uint32_t leaf, uint32_t w1y, uint32_t w1z, uint32_t w1w) {
+                                        expand_leaves(leaf, w1y, w1z, w1w, [&](uint32_t type, uint32_t idx) {
+                                          intersect_prim<COUNT>(sc, type, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
+                                        });
                                       });
+}
+
+// Deferred leaf tests.  A node visit parks its hit leaves in the lane's shared-memory record instead of testing them; the
+// lane then sits out the node phases (its t_max must see those tests before it descends further) until the warp
+// drains: all parked lanes test their primitives TOGETHER, one primitive type at a time, one primitive per iteration.
+// The per-ray order of node visits and primitive tests is unchanged, so results, counters and the exact-pass set are
+// identical to the inline form; only how many lanes execute a primitive test at once changes (inline: the ~1/3 of the
+// lanes whose node happened to have a leaf hit; drained: >= the threshold).
+template <bool COUNT, bool ALL_STAGED = false>
+__device__ __forceinline__ bool trav_step_park(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
+                                               Trav& tv, uint2* __restrict__ stack, float tmin, uint32_t& n_nodes_visited,
+                                               uint4* __restrict__ park, bool& parked) {
+  return trav_step<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited,
+                                      [&](uint32_t leaf, uint32_t w1y, uint32_t w1z, uint32_t w1w) {
+                                        *park = make_uint4(leaf, w1y, w1z, w1w);
+                                        parked = true;
+                                      });
+}
+// executed by the whole warp; `parked` lanes test what they parked
+template <bool COUNT>
+__device__ __forceinline__ void drain_parked(const DevScene& sc, Trav& tv, float tmin, const uint4* __restrict__ park, bool parked,
+                                             TestCount& n_tests) {
+  uint4 pd = make_uint4(0u, 0u, 0u, 0u);
+  if (parked) pd = *park;
+  const uint32_t mytype = pd.y >> REF_TYPE_SHIFT;
+#pragma unroll
+  for (uint32_t t = 0; t < PT_COUNT; ++t) {  // one type at a time: the type switch inside intersect_prim folds away
+    const bool mine = parked && mytype == t;
+    if (!__any_sync(0xffffffffu, mine)) continue;
+    if (mine)
+      expand_leaves(pd.x, pd.y, pd.z, pd.w, [&](uint32_t, uint32_t idx) {
+        intersect_prim<COUNT>(sc, t, idx, tv.o, tv.d, tv.time, tmin, tv.best, tv.amb, tv.octinv, n_tests);
+      });
+    __syncwarp();
+  }
 }
 
 // returns the ray's FixKind
@@ -810,7 +856,8 @@ __device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, 
   for (uint32_t k = 0; k < sc.n_global; ++k) leaf(sc.global_ref[k] >> REF_TYPE_SHIFT, sc.global_ref[k] & REF_INDEX_MASK);
   if (sc.tree_empty) tv.grp.y = 0u;
   uint32_t nv = 0;
-  while (trav_step<false, false>(sc, nullptr, 0u, 0u, tv, stack, RTB_TMIN, nv, leaf)) {}
+  while (trav_step<false, false>(sc, nullptr, 0u, 0u, tv, stack, RTB_TMIN, nv,
+                                 [&](uint32_t lf, uint32_t w1y, uint32_t w1z, uint32_t w1w) { expand_leaves(lf, w1y, w1z, w1w, leaf); })) {}
   return tv.best;
 }
 

@@ -135,12 +135,16 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   __shared__ ExtIn s_in[RTB_EXTEND_WARPS][32];
   __shared__ ExtOut s_out[RTB_EXTEND_WARPS][32];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
+  __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
+  uint4* park = &s_park[warp][lane];
+  uint32_t parked_mask = 0;  // warp-uniform: lanes with parked leaf primitives
   ExtIn* in = s_in[warp];
   ExtOut* out = s_out[warp];
   uint8_t* list = s_list[warp];
@@ -240,7 +244,19 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
     // ---- one node visit (or pop) per running lane -------------------------------------------------------------------
     bool finished = false;
-    if (!((idle >> lane) & 1u)) finished = !trav_step_fast<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
+    if (park_min == 0u) {
+      if (!((idle >> lane) & 1u)) finished = !trav_step_fast<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
+    } else {
+      bool parked = (parked_mask >> lane) & 1u;
+      if (!(((idle | parked_mask) >> lane) & 1u))
+        finished = !trav_step_park<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, park, parked);
+      parked_mask = __ballot_sync(0xffffffffu, parked);
+      // drain when enough lanes wait, or when nobody is left to visit nodes meanwhile
+      if (parked_mask && ((uint32_t)__popc(parked_mask) >= park_min || (~(idle | parked_mask | __ballot_sync(0xffffffffu, finished))) == 0u)) {
+        drain_parked<COUNT>(sc, tv, RTB_TMIN, park, parked, nt);
+        parked_mask = 0;
+      }
+    }
     // ---- finished lanes push their result -------------------------------------------------------------------------
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
@@ -277,12 +293,15 @@ __global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
+  __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint8_t* list = s_list[warp];
+  const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
+  uint4* park = &s_park[warp][lane];
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
   uint32_t n_rays = 0, nv = 0;
   TestCount nt{};
@@ -292,14 +311,44 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     n_rays += total;
     for (uint32_t r = 0; r < total; r += 32) {
       if (r + 32 + lane < total) prefetch_l1(pool.ray + 2 * (size_t)(base + list[r + 32 + lane]));
-      if (r + lane < total) {
-        const uint32_t slot = base + list[r + lane];
-        const float4 ro = pool.ray[2 * slot];
-        const float4 rd = pool.ray[2 * slot + 1];
-        Closest best;
-        const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
-        finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-        if (fix) queue_fix(pool, slot, fix);
+      if (park_min == 0u) {
+        if (r + lane < total) {
+          const uint32_t slot = base + list[r + lane];
+          const float4 ro = pool.ray[2 * slot];
+          const float4 rd = pool.ray[2 * slot + 1];
+          Closest best;
+          const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+          if (fix) queue_fix(pool, slot, fix);
+        }
+      } else {
+        // the same traversal with the warp in step: node visits by the lanes that can, primitive tests drained together
+        const bool valid = r + lane < total;
+        const uint32_t slot = base + (valid ? list[r + lane] : 0u);
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (valid) { ro = pool.ray[2 * slot]; rd = pool.ray[2 * slot + 1]; }
+        Trav tv;
+        uint2 stack[RTB_STACK];
+        trav_init(tv, xyz(ro), xyz(rd), ro.w);
+        if (valid) trav_globals<COUNT>(sc, tv, RTB_TMIN, nt);
+        bool active = valid, parked = false;
+        uint32_t parked_mask = 0;
+        for (;;) {
+          if (active && !parked) active = trav_step_park<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, park, parked);
+          parked_mask = __ballot_sync(0xffffffffu, parked);
+          const uint32_t active_mask = __ballot_sync(0xffffffffu, active);
+          if (parked_mask && ((uint32_t)__popc(parked_mask) >= park_min || (active_mask & ~parked_mask) == 0u)) {
+            drain_parked<COUNT>(sc, tv, RTB_TMIN, park, parked, nt);
+            parked = false;
+            parked_mask = 0;
+          }
+          if (!active_mask && !parked_mask) break;
+        }
+        if (valid) {
+          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), tv.best);
+          const uint32_t fix = fix_kind(tv);
+          if (fix) queue_fix(pool, slot, fix);
+        }
       }
     }
     __syncwarp();  // the list is rewritten for the next chunk
@@ -979,24 +1028,35 @@ __global__ void k_kat(DevScene sc, DevCamera cam, DevParams prm, uint32_t op, co
 // a 48 MB buffer stays in the 126 MB L2 (L2 read bandwidth), a 2 GB one does not (HBM read bandwidth).
 __global__ void __launch_bounds__(256) k_bw_global(const uint4* __restrict__ p, size_t n_vec, uint32_t reps, uint4* __restrict__ sink) {
   uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (uint32_t r = 0; r < reps; ++r)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // every repetition an SM reads a DIFFERENT slice of the buffer (rotated by a fraction of it), so its 256 KB L1 cannot
+  // serve the re-reads: with a fixed assignment each SM's 1/148 of a 48 MB buffer would partly live in L1
+  const size_t rot = (n_vec / 37) | 1;
+  for (uint32_t r = 0; r < reps; ++r) {
+    size_t i = (tid + (size_t)r * rot) % n_vec;
+    for (size_t k = tid; k < n_vec; k += stride) {
       const uint4 v = __ldg(p + i);
       acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+      i += stride;
+      if (i >= n_vec) i -= n_vec;
     }
+  }
   if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345679u) sink[0] = acc;  // keeps the loads alive; practically never true
 }
-// 128-bit shared-memory loads at conflict-free addresses (how the node stage is read): bytes = threads x reps x 16
+// 128-bit shared-memory loads at conflict-free addresses (how the node stage is read): bytes = threads x reps x 16.
+// (volatile asm: the addresses repeat, a plain load would be hoisted out of the loop)
 __global__ void __launch_bounds__(256) k_bw_shared(uint32_t reps, uint4* __restrict__ sink) {
   extern __shared__ uint4 sm[];
   const uint32_t n = 2048;  // 32 KB
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) sm[i] = make_uint4(i, i * 3u, i * 5u, i * 7u);
   __syncthreads();
   uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm);
   uint32_t k = threadIdx.x;
+#pragma unroll 8
   for (uint32_t r = 0; r < reps; ++r) {
-    const uint4 v = sm[k];
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + k * 16u));
     acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
     k = (k + 256u) & (n - 1u);
   }
