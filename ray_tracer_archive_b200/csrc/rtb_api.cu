@@ -57,7 +57,7 @@ struct Lane {
   uint32_t pool_n = 0;
   DevBuf<float4> ray, st, hit;
   DevBuf<uint8_t> cls;                    // per-slot shade class
-  DevBuf<uint32_t> redo;                  // slots queued for the exact pass
+  DevBuf<uint4> redo;                     // rays queued for the exact pass (slot, distance slab)
   DevBuf<unsigned long long> cursor;      // per-chunk path cursor
   DevBuf<DevCounters> counters;
   DevCounters* h_counters = nullptr;  // pinned
@@ -598,6 +598,10 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
   d.tree_empty = (d.n_global == (uint32_t)hs.prims.size()) ? 1u : 0u;
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = bvh.global_refs[k];
   d.global_f64 = d.tree_empty ? 0u : bvh.global_f64;
+  {
+    static const char* pf = getenv("RTB_PREFETCH");
+    d.prefetch = pf ? (uint32_t)atoi(pf) : 0u;
+  }
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(bvh.geom[t].data()), bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
@@ -877,8 +881,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
     prm.pix_order = c->pix_order.p;
     prm.inv_npix = 1.0 / (double)npix;
-    static const uint32_t env_opt = getenv("RTB_OPT") ? (uint32_t)atoi(getenv("RTB_OPT")) : 0u;
-    prm.opt = env_opt;
+    // leaf-test parking (rtb_device.cuh: drain_parked): on for the dynamic-fetch kernel of deep trees (C4 +7 %), off for
+    // the one-ray-per-thread kernel (C1 / C3 -13 %): profiles/r3_ab.md.  RTB_OPT overrides (experiments).
+    static const char* env_opt = getenv("RTB_OPT");
+    prm.opt = env_opt ? (uint32_t)atoi(env_opt) : (s->lc.dynamic_fetch ? (14u << RTB_OPT_PARK_SHIFT) : 0u);
     prm.inv_wm1 = (float)(1.0 / (double)(p->width - 1));
     prm.inv_hm1 = (float)(1.0 / (double)(p->height - 1));
     prm.accum = (float4*)d_accum;

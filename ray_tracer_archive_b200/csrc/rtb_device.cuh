@@ -57,6 +57,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t prmt_magic;  // = 0x43000000, see q2f()
   uint32_t n_global;    // primitives tested for every ray before the traversal (kept out of the tree)
   uint32_t tree_empty;  // all primitives are global (tiny scene): skip the traversal
+  uint32_t prefetch;    // prefetch the next node to be visited into L1 before the leaf tests of the current one (deep trees)
   uint32_t global_ref[RTB_MAX_GLOBALS];
   uint32_t global_f64;  // bit k: global k is a sphere so large next to the rest of the scene (radius >= 16 scene
                         // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
@@ -110,7 +111,7 @@ struct DevPool {
   float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
   float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
   uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
-  uint32_t* redo;     // [n] slots whose closest hit f32 could not decide (filled by extend, consumed by k_fixup)
+  uint4* redo;        // [n] rays for k_fixup: (slot | RTB_REDO_REFINE, slab lower bound, slab upper bound, -), filled by extend
   unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence
   DevCounters* c;
 };
@@ -554,9 +555,9 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     const float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     const float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
-    // a sheared coordinate is off by <= 2^-22 amax (translate + shear roundings, 1 ulp of 1/d_z included), so an edge
-    // function by <= m
-    const float m = (RTB_U21 * amax) * (fabsf(Ax) + fabsf(Ay) + fabsf(Bx) + fabsf(By) + fabsf(Cx) + fabsf(Cy));
+    // a sheared coordinate is off by <= 1.2 2^-22 |A|_1 (translate: 2^-24 |A.x|; shear S A.z with S = d_x (1/d_z): 2^-22 |A.z|;
+    // the subtraction: 2^-24), so an edge function (two products of one exact and one perturbed factor pair) by <= m
+    const float m = (1.25f * RTB_U22 * amax) * (fabsf(Ax) + fabsf(Ay) + fabsf(Bx) + fabsf(By) + fabsf(Cx) + fabsf(Cy));
     const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
     if (mn < -m && mx > m) return;  // certainly outside
     const float det = U + V + W;
@@ -615,6 +616,12 @@ enum FixKind : uint32_t { FIX_NONE = 0, FIX_RETRACE = 1, FIX_REFINE = 2 };
 #define RTB_REDO_REFINE 0x80000000u  /* redo-queue entry: slot | this bit = FIX_REFINE */
 __device__ __forceinline__ uint32_t fix_kind(const Trav& tv) {
   return needs_exact(tv.best, tv.amb) ? FIX_RETRACE : ((tv.octinv & RTB_TRAV_COARSE) && tv.best.ref != REF_MISS ? FIX_REFINE : FIX_NONE);
+}
+// The distance slab the exact pass has to search: every candidate f32 left open lies at or beyond `amb`, the closest
+// certain hit within [2t - hi, hi], and whatever the traversal culled lies beyond hi.  Nothing closer than the slab can be
+// a hit (a certain candidate entirely below amb would have pulled hi below amb, and the ray would not be here).
+__device__ __forceinline__ float slab_lo(const Trav& tv) {
+  return tv.best.ref == REF_MISS ? tv.amb : fminf(tv.amb, tv.best.t - (tv.best.hi - tv.best.t));
 }
 
 __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float time) {
@@ -731,15 +738,32 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     missmask = __funnelshift_l(neg, missmask, 1);  // (missmask << 1) | sign bit; child 0 ends in bit 0
   }
   const uint32_t hitmask = ~missmask & 0xFFu;
-  // leaf children (all primitives of one node share a type)
-  const uint32_t leaf = hitmask & ~imask;
-  if (leaf) leaves_fn(leaf, w1.y, w1.z, w1.w);
   // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
   uint32_t ih = hitmask & imask;
   if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);
   if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
   if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
   tv.grp = make_uint2(w1.x, (ih << 8) | imask);
+#ifdef __CUDA_ARCH__
+  if (!ALL_STAGED && sc.prefetch) {
+    // the node the NEXT step will visit (nearest hit child, else the top of the stack) starts its way into L1 now, while
+    // this node's primitives are tested: the traversal of a deep tree waits on exactly this dependent fetch
+    uint2 g = tv.grp;
+    if (!ih && tv.sp > 0) g = stack[tv.sp - 1];
+    if (g.y & 0xFF00u) {
+      const uint32_t pslot = (31u - __clz(g.y >> 8)) ^ octinv;
+      const uint32_t pnode = g.x + __popc(g.y & 0xFFu & ((1u << pslot) - 1u));
+      if (pnode >= n_snodes) {
+        const uint4* pp = sc.nodes + 5 * (size_t)pnode;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 4));
+      }
+    }
+  }
+#endif
+  // leaf children (all primitives of one node share a type)
+  const uint32_t leaf = hitmask & ~imask;
+  if (leaf) leaves_fn(leaf, w1.y, w1.z, w1.w);
   return true;
 }
 
@@ -814,7 +838,7 @@ __device__ __forceinline__ void drain_parked(const DevScene& sc, Trav& tv, float
 // returns the ray's FixKind
 template <bool COUNT, bool ALL_STAGED = false>
 __device__ __forceinline__ uint32_t traverse(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
-                                         float3 o, float3 d, float time, float tmin, Closest& best,
+                                         float3 o, float3 d, float time, float tmin, Closest& best, float& slab_lo_out,
                                          uint32_t& n_nodes_visited, TestCount& n_tests) {
   Trav tv;
   uint2 stack[RTB_STACK];
@@ -822,6 +846,7 @@ __device__ __forceinline__ uint32_t traverse(const DevScene& sc, const uint4* __
   trav_globals<COUNT>(sc, tv, tmin, n_tests);
   while (trav_step_fast<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
+  slab_lo_out = slab_lo(tv);
   return fix_kind(tv);
 }
 
@@ -834,11 +859,14 @@ __device__ __forceinline__ float refine_hit(const DevScene& sc, uint32_t ref, fl
 
 // The exact pass: the same BVH (its conservative boxes cull against the closest exact distance so far), every candidate
 // evaluated by exact_hit(), min t with equal t going to the larger primitive id = HittableList::hit
-// (hittable_list.rs:39-51) in f64.  Nodes come from global memory (n_snodes = 0).
-__device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, float3 d, float time) {
+// (hittable_list.rs:39-51) in f64.  Nodes come from global memory (n_snodes = 0).  [t_lo, t_hi] = the slab handed over by
+// the hot kernel (0, inf = search everything): only the nodes the ray crosses inside it are visited.
+__device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, float3 d, float time, float t_lo = 0.0f, float t_hi = INFINITY) {
   Trav tv;
   uint2 stack[RTB_STACK];
   trav_init(tv, o, d, time);
+  tv.best.hi = fmaf(t_hi, 4.0e-6f, t_hi) + 1.0e-6f;                       // slack: the bounds are f32 themselves
+  const float tmin = fmaxf(fmaf(t_lo, -4.0e-6f, t_lo) - 1.0e-6f, 0.0f);  // (exact_hit applies the real t_min = 0.001)
   double bt = 0.0;
   const ExactTab* tab = sc.xtab;
   auto leaf = [&](uint32_t type, uint32_t idx) {
@@ -856,8 +884,9 @@ __device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, 
   for (uint32_t k = 0; k < sc.n_global; ++k) leaf(sc.global_ref[k] >> REF_TYPE_SHIFT, sc.global_ref[k] & REF_INDEX_MASK);
   if (sc.tree_empty) tv.grp.y = 0u;
   uint32_t nv = 0;
-  while (trav_step<false, false>(sc, nullptr, 0u, 0u, tv, stack, RTB_TMIN, nv,
+  while (trav_step<false, false>(sc, nullptr, 0u, 0u, tv, stack, tmin, nv,
                                  [&](uint32_t lf, uint32_t w1y, uint32_t w1z, uint32_t w1w) { expand_leaves(lf, w1y, w1z, w1w, leaf); })) {}
+  if (tv.best.ref == REF_MISS) tv.best.t = tv.best.hi = INFINITY;
   return tv.best;
 }
 

@@ -62,8 +62,9 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
 
 // a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
 // the one atomic per entry is uncontended in practice)
-__device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind) {
-  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] = slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u);
+__device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind, float lo, float hi) {
+  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] =
+      make_uint4(slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u), __float_as_uint(lo), __float_as_uint(hi), 0u);
 }
 
 // ---- warp-local chunk lists -------------------------------------------------------------------------------------------
@@ -125,7 +126,7 @@ __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint3
 // 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
 #define RTB_EXTEND_MAXREG 80
 struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, t upper bound) after the global primitives
-struct ExtOut { float t; uint32_t ref, slot, redo; };
+struct ExtOut { float t; uint32_t ref, slot, redo; float lo, hi; uint32_t _pad[2]; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
 template <bool COUNT>
@@ -172,7 +173,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
       finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
-      if (h.redo) queue_fix(pool, h.slot, h.redo);
+      if (h.redo) queue_fix(pool, h.slot, h.redo, h.lo, h.hi);
     }
     out_count = 0;
     __syncwarp();
@@ -261,7 +262,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(tv)};
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
       out_count += __popc(done);
       idle |= done;
     }
@@ -317,9 +318,10 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           const float4 ro = pool.ray[2 * slot];
           const float4 rd = pool.ray[2 * slot + 1];
           Closest best;
-          const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, nv, nt);
+          float lo;
+          const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, lo, nv, nt);
           finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-          if (fix) queue_fix(pool, slot, fix);
+          if (fix) queue_fix(pool, slot, fix, lo, best.hi);
         }
       } else {
         // the same traversal with the warp in step: node visits by the lanes that can, primitive tests drained together
@@ -345,9 +347,10 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           if (!active_mask && !parked_mask) break;
         }
         if (valid) {
-          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), tv.best);
           const uint32_t fix = fix_kind(tv);
-          if (fix) queue_fix(pool, slot, fix);
+          const float lo = slab_lo(tv), hi = tv.best.hi;
+          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), tv.best);
+          if (fix) queue_fix(pool, slot, fix, lo, hi);
         }
       }
     }
@@ -867,14 +870,15 @@ __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPoo
   const uint32_t n = c->redo_count;
   uint32_t n_refined = 0;
   for (uint32_t i = blockIdx.x * RTB_FIXUP_THREADS + threadIdx.x; i < n; i += gridDim.x * RTB_FIXUP_THREADS) {
-    const uint32_t entry = pool.redo[i], slot = entry & ~RTB_REDO_REFINE;
+    const uint4 q = pool.redo[i];
+    const uint32_t entry = q.x, slot = entry & ~RTB_REDO_REFINE;
     const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
     if (entry & RTB_REDO_REFINE) {  // certain hit, coarse distance: one f64 evaluation of that primitive
       const float4 h = pool.hit[slot];
       pool.hit[slot].x = refine_hit(sc, __float_as_uint(h.y), xyz(ro), xyz(rd), ro.w, h.x);
       ++n_refined;
     } else {
-      const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w);
+      const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w, __uint_as_float(q.y), __uint_as_float(q.z));
       finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
     }
   }
@@ -1165,7 +1169,7 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (occ2 < 1) occ2 = 1;
   if (getenv("RTB_SHADE_OCC")) occ2 = std::max(1, std::min(occ2, atoi(getenv("RTB_SHADE_OCC"))));
   lc.shade_grid = (uint32_t)(sm_count * occ2);
-  lc.fixup_grid = (uint32_t)std::max(1, sm_count / 2);
+  lc.fixup_grid = (uint32_t)std::max(1, sm_count * 2);
   {  // smallest pool that gives every resident extend warp AND every resident shade warp a whole number of chunks
     uint32_t a = lc.extend_grid * RTB_EXTEND_WARPS, b = lc.shade_grid * RTB_SHADE_WARPS, x = a, y = b;
     while (y) { const uint32_t t = x % y; x = y; y = t; }

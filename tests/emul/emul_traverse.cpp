@@ -29,6 +29,8 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
   return r;
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline int __any_sync(unsigned, int p) { return p; }  // (one 'lane': the warp-cooperative helpers are not run here)
+static inline void __syncwarp() {}
 #undef __forceinline__
 #define __forceinline__ inline
 
@@ -69,10 +71,11 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
     TestCount nt{};
     const float3 ro = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), rd = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
     // the hot path (f32, ambiguity detection), then — as k_fixup does on the device — the exact pass if it asked for one
+    float lo = 0.f;
     const uint32_t fix = traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd,
-                                        time ? time[i] : 0.f, RTB_TMIN, best, nv, nt);
+                                        time ? time[i] : 0.f, RTB_TMIN, best, lo, nv, nt);
     if (fix == FIX_RETRACE) {
-      best = traverse_exact(sc, ro, rd, time ? time[i] : 0.f);
+      best = traverse_exact(sc, ro, rd, time ? time[i] : 0.f, lo, best.hi);
       ++g_exact_rays;
     } else if (fix == FIX_REFINE) {
       best.t = refine_hit(sc, best.ref, ro, rd, time ? time[i] : 0.f, best.t);
