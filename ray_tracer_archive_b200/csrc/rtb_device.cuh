@@ -871,6 +871,14 @@ __device__ __forceinline__ Closest traverse_exact(const DevScene& sc, float3 o, 
   const ExactTab* tab = sc.xtab;
   auto leaf = [&](uint32_t type, uint32_t idx) {
     const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
+    {  // the f32 test first: a CERTAIN miss (most candidates of a long slab) needs no f64 evaluation
+      Closest probe{INFINITY, tv.best.hi, REF_MISS};
+      float probe_amb = INFINITY;
+      uint32_t probe_flags = 0;
+      TestCount none{};
+      intersect_prim<false>(sc, type, idx, tv.o, tv.d, tv.time, RTB_TMIN, probe, probe_amb, probe_flags, none);
+      if (probe.ref == REF_MISS && !(probe_amb < INFINITY)) return;
+    }
     const double tc = exact_hit(tab, ref, tv.o, tv.d, tv.time);
     if (tc < 0.0) return;
     if (tv.best.ref == REF_MISS || tc < bt || (tc == bt && tab_gid(tab, ref) > tab_gid(tab, tv.best.ref))) {

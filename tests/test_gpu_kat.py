@@ -88,7 +88,7 @@ def test_sphere_hit_golden(rtb, ctx):
     for c, a, b in zip(cases, o32, o64):
         exp = c["expect"]
         tmax = c["tmax"] if math.isfinite(c["tmax"]) else 3.0e38
-        st, t, e = int(a[0]), float(w2f(a[1:2])[0]), float(w2f(a[2:3])[0])
+        st, t, e = int(a[0]) & 15, float(w2f(a[1:2])[0]), float(w2f(a[2:3])[0])
         st64, t64 = int(b[0]), float(w2f(b[1:2])[0])
         if exp is None:
             assert st in (0, 2) or t > tmax  # miss, or undecided (grazing) — never a certain hit in range
@@ -123,7 +123,7 @@ def test_sphere_fast_bound_holds_on_random_rays(rtb, orc, ctx):
     d = (tgt - o) * rng.uniform(0.01, 30, n)[:, None]
     rows = np.concatenate([c, r[:, None], o, d, np.full((n, 1), 0.001), np.full((n, 1), 3e38)], axis=1).astype(np.float32)
     out = ctx.kat(F.KAT_SPHERE, rows.view(np.uint32), 3)
-    st, t, e = out[:, 0].astype(int), w2f(out[:, 1]), w2f(out[:, 2])
+    st, coarse, t, e = (out[:, 0] & 15).astype(int), (out[:, 0] & 16) != 0, w2f(out[:, 1]), w2f(out[:, 2])
     # reference on the SAME f32 inputs
     R = rows.astype(np.float64)
     cc, rr, oo, dd = R[:, 0:3], R[:, 3], R[:, 4:7], R[:, 7:10]
@@ -139,11 +139,15 @@ def test_sphere_fast_bound_holds_on_random_rays(rtb, orc, ctx):
     certain_hit, certain_miss = st == 1, st == 0
     assert (certain_hit & ~hit).sum() == 0 and (certain_miss & hit).sum() == 0
     err = np.abs(t[certain_hit] - tref[certain_hit])
-    assert (err <= e[certain_hit] * 1.0 + 1e-30).all(), float((err / np.maximum(e[certain_hit], 1e-30)).max())
-    assert (e[certain_hit] <= 5.0001e-5 * t[certain_hit]).all()
-    assert certain_hit.sum() > 0.2 * n and (st == 2).mean() < 0.35
-    print(f"sphere_fast: {certain_hit.mean():.3f} certain hits, {certain_miss.mean():.3f} certain misses, {(st == 2).mean():.3f} undecided;"
-          f" max err/bound {float((err / np.maximum(e[certain_hit], 1e-30)).max()):.3f}, max rel err {float((err / tref[certain_hit]).max()):.2e}")
+    assert (err <= e[certain_hit] + 1e-30).all(), float((err / np.maximum(e[certain_hit], 1e-30)).max())
+    fine = certain_hit & ~coarse                       # hits whose f32 distance is used as it is
+    rel = np.abs(t[fine] - tref[fine]) / tref[fine]
+    assert (e[fine] <= 4.0001e-4 * t[fine]).all()
+    assert rel.max() <= 1e-5, rel.max()                # ... and it holds the 1e-5 of the parity bar
+    assert certain_hit.sum() > 0.2 * n and (st == 2).mean() < 0.2
+    print(f"sphere_fast: {certain_hit.mean():.3f} certain hits ({(certain_hit & coarse).mean():.3f} coarse -> refined in f64), "
+          f"{certain_miss.mean():.3f} certain misses, {(st == 2).mean():.3f} undecided; max err/bound "
+          f"{float((err / np.maximum(e[certain_hit], 1e-30)).max()):.3f}, max rel err of the fine hits {float(rel.max()):.2e}")
 
 
 def _cornell_scene(rtb, ctx):
