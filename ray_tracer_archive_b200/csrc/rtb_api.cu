@@ -60,9 +60,10 @@ struct Lane {
   DevBuf<uint4> redo;                     // rays queued for the exact pass (slot, distance slab)
   DevBuf<unsigned long long> cursor;      // per-chunk path cursor
   DevBuf<DevCounters> counters;
-  DevCounters* h_counters = nullptr;  // pinned
+  DevCounters* h_counters = nullptr;     // pinned; [0], [1]: the drain check of batch k is read while batch k + 1 runs
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t batch_done[2] = {nullptr, nullptr};
 };
 #define RTB_MAX_LANES 4
 
@@ -129,9 +130,11 @@ static int context_init(rtb_context* c, int device_id) {
   CU(cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters)));
   for (int k = 0; k < RTB_MAX_LANES; ++k) {
     Lane& L = c->lanes[k];
-    CU(cudaMallocHost((void**)&L.h_counters, sizeof(DevCounters)));
+    CU(cudaMallocHost((void**)&L.h_counters, 2 * sizeof(DevCounters)));
     CU(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&L.batch_done[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&L.batch_done[1], cudaEventDisableTiming));
     CU(L.counters.resize(1));
   }
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -172,6 +175,7 @@ void rtb_context_destroy(rtb_context* c) {
     if (L.h_counters) cudaFreeHost(L.h_counters);
     if (L.stream) cudaStreamDestroy(L.stream);
     if (L.done) cudaEventDestroy(L.done);
+    for (cudaEvent_t e : L.batch_done) if (e) cudaEventDestroy(e);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -909,27 +913,33 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const uint32_t present = s->present_materials;
   const uint32_t n_shade = 1 + ((present >> RTB_MAT_LAMBERTIAN) & 1u) + ((present >> RTB_MAT_ISOTROPIC) & 1u) +
                            ((present & ((1u << RTB_MAT_METAL) | (1u << RTB_MAT_DIELECTRIC))) ? 1u : 0u);
+  // The drain check is PIPELINED: batch b + 1 (8 iterations per lane) is queued before the host waits for the counters of
+  // batch b, so the lanes never run dry while the host looks at a counter (a lane that turns out to have drained has
+  // queued one more batch of iterations over an all-dead pool: a few microseconds each).  On any error every lane stream is
+  // synchronised before returning: nothing may still be writing the caller's accumulation buffer.
   const uint32_t check_every = 8;
   size_t ev_used = 0;
   int n_active = n_lanes;
-  while (n_active > 0) {
+  auto sync_all = [&]() { for (int q = 0; q < n_lanes; ++q) cudaStreamSynchronize(c->lanes[q].stream); };
+  auto enqueue_batch = [&](uint32_t b) -> cudaError_t {
+    cudaError_t e = cudaSuccess;
     for (uint32_t it = 0; it < check_every; ++it) {
       for (int k = 0; k < n_lanes; ++k) {  // interleave the lanes' launches so that their phases stay staggered
         if (!run[k].active) continue;
         cudaStream_t ls = c->lanes[k].stream;
         if (time_ext) {
           if (c->ext_events.size() < ev_used + 2) {
-            cudaEvent_t a, b;
-            CU(cudaEventCreate(&a));
-            CU(cudaEventCreate(&b));
-            c->ext_events.push_back(a);
-            c->ext_events.push_back(b);
+            cudaEvent_t a2, b2;
+            if ((e = cudaEventCreate(&a2)) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&b2)) != cudaSuccess) return e;
+            c->ext_events.push_back(a2);
+            c->ext_events.push_back(b2);
           }
-          CU(cudaEventRecord(c->ext_events[ev_used], ls));
+          if ((e = cudaEventRecord(c->ext_events[ev_used], ls)) != cudaSuccess) return e;
         }
         launch_extend(s->lc, s->dev, run[k].pool, run[k].prm, count, ls);
         if (time_ext) {
-          CU(cudaEventRecord(c->ext_events[ev_used + 1], ls));
+          if ((e = cudaEventRecord(c->ext_events[ev_used + 1], ls)) != cudaSuccess) return e;
           ev_used += 2;
         }
         launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // exact pass over the queued rays + counter rotation
@@ -938,23 +948,43 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
         extend_launches += 1;
       }
     }
-    for (int k = 0; k < n_lanes; ++k)
-      if (run[k].active)
-        CU(cudaMemcpyAsync(c->lanes[k].h_counters, c->lanes[k].counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost,
-                           c->lanes[k].stream));
     for (int k = 0; k < n_lanes; ++k) {
       if (!run[k].active) continue;
-      CU(cudaStreamSynchronize(c->lanes[k].stream));
+      Lane& L = c->lanes[k];
+      if ((e = cudaMemcpyAsync(L.h_counters + (b & 1u), L.counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess) return e;
+      if ((e = cudaEventRecord(L.batch_done[b & 1u], L.stream)) != cudaSuccess) return e;
+    }
+    return cudaGetLastError();
+  };
+  auto fail_cuda = [&](cudaError_t e, const char* what) {
+    sync_all();
+    return set_err(RTB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  cudaError_t qe = enqueue_batch(0);
+  if (qe != cudaSuccess) return fail_cuda(qe, "wavefront launch");
+  for (uint32_t b = 0; n_active > 0; ++b) {
+    // (instrumented runs keep the strict order: their per-launch timings must not contain idle iterations)
+    const bool ahead = !(count || time_ext);
+    if (ahead && (qe = enqueue_batch(b + 1)) != cudaSuccess) return fail_cuda(qe, "wavefront launch");
+    for (int k = 0; k < n_lanes; ++k) {
+      if (!run[k].active) continue;
+      if ((qe = cudaEventSynchronize(c->lanes[k].batch_done[b & 1u])) != cudaSuccess) return fail_cuda(qe, "wavefront");
       run[k].iters += check_every;
-      const DevCounters* h = c->lanes[k].h_counters;
+      const DevCounters* h = c->lanes[k].h_counters + (b & 1u);
       if (h->last_rays == 0) {
         run[k].active = false;
         --n_active;
       } else if (run[k].iters > run[k].iter_cap) {
-        for (int q = 0; q < n_lanes; ++q) cudaStreamSynchronize(c->lanes[q].stream);  // nothing may still write d_accum
+        sync_all();
         return set_err(RTB_ERR_CUDA, "wavefront did not drain (internal error)");
       }
     }
+    if (!ahead && n_active > 0 && (qe = enqueue_batch(b + 1)) != cudaSuccess) return fail_cuda(qe, "wavefront launch");
+  }
+  for (int k = 0; k < n_lanes; ++k) {  // final counters (a drained lane may still have an idle batch in flight)
+    Lane& L = c->lanes[k];
+    if ((qe = cudaMemcpyAsync(L.h_counters, L.counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, L.stream)) != cudaSuccess)
+      return fail_cuda(qe, "counter read-back");
   }
   for (int k = 0; k < n_lanes; ++k) {
     CU(cudaEventRecord(c->lanes[k].done, c->lanes[k].stream));
