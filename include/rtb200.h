@@ -233,6 +233,17 @@ int rtb_scene_set_triangles(rtb_scene* s, const float* v0_3, const float* v1_3, 
                             const uint32_t* material, const uint32_t* flags, const uint32_t* prim_id, uint32_t n);
 int rtb_scene_set_media(rtb_scene* s, const rtb_medium* media, uint32_t n);
 
+/* BVH builder quality knobs (README.md:150-152 of the reference asks for an accelerated mesh path; defaults = what the
+ * benchmarks use).  Results never depend on them (closest-hit semantics stay those of the list scan), only speed. */
+typedef struct rtb_build_options {
+  uint32_t max_leaf_triangles;   /* triangles per leaf slot, 1..3 (default 2: halves the node count of large meshes) */
+  uint32_t keep_huge_primitives_out; /* default 1: primitives whose box is >= 80 % of the scene box are tested first for
+                                        every ray instead of coarsening the quantisation grid of the node that holds them */
+  float open_min_extent;         /* default 0.125: the collapse to 8-wide nodes never opens a subtree smaller than this
+                                    fraction of the node's extent (keeps the 7-bit child boxes tight) */
+  uint32_t _reserved;
+} rtb_build_options;
+int rtb_scene_set_build_options(rtb_scene* s, const rtb_build_options* opt);
 /* build the wide BVH (width 8, quantised child boxes) on the host; replaces BVHNode::construct2 (bvh.rs:74-130) */
 int rtb_scene_build_bvh(rtb_scene* s);
 /* build if needed, then upload everything to the device */
@@ -313,6 +324,10 @@ typedef enum rtb_kat_op {
 int rtb_device_kat(rtb_context* ctx, rtb_scene* scene, const rtb_camera* cam, const rtb_params* params, uint32_t op,
                    const uint32_t* in_words, uint32_t n_items, uint32_t in_stride, uint32_t* out_words,
                    uint32_t out_stride);
+
+/* RTB_CHECKED build of the library (make -C csrc checked): failed device-side bounds assertions by kind (traversal stack,
+ * node index, primitive index, pool slot, fix-up queue, chunk list, 2 spare); every entry is 0xFFFFFFFF in a normal build. */
+int rtb_debug_check_failures(rtb_context* ctx, uint32_t* out_8);
 
 /* ---- measurement: the physical bandwidths the extend kernel's roofline is quoted against -------------------------- */
 typedef enum rtb_bw_kind {

@@ -1,25 +1,67 @@
-// Replacement for the render loop raytracer/src/main.rs:720-799.  See INTEGRATION.md.
-let mut b = gpu::SceneBuilder::default();
-let root = world.flatten(&mut b);
-let lights = [RtbLight { ty: 0, _pad: 0, p: [213.0, 343.0, 227.0, 332.0, 554.0] },       // main.rs:670-679
-              RtbLight { ty: 1, _pad: 0, p: [190.0, 90.0, 190.0, 90.0, 0.0] }];          // main.rs:680-684
-unsafe {
-    let (mut ctx, mut sc) = (std::ptr::null_mut(), std::ptr::null_mut());
-    check(rtb_context_create(0, &mut ctx)); check(rtb_scene_create(ctx, &mut sc));
-    check(rtb_scene_set_materials(sc, b.materials.as_ptr(), b.materials.len() as u32));
-    check(rtb_scene_set_textures(sc, b.textures.as_ptr(), b.textures.len() as u32));
-    check(rtb_scene_set_lights(sc, lights.as_ptr(), 2));
-    check(rtb_scene_set_graph(sc, b.nodes.as_ptr(), b.nodes.len() as u32, b.children.as_ptr(), b.children.len() as u32, root));
-    check(rtb_scene_commit(sc));
-    let cam = RtbCamera { lookfrom: [278.0, 278.0, -800.0], lookat: [278.0, 278.0, 0.0], vup: [0.0, 1.0, 0.0],
-                          vfov_deg: 40.0, aspect_ratio: 1.0, aperture: 0.0, focus_dist: 10.0, time0: 0.0, time1: 1.0 };
-    let prm = RtbParams { width: IMAGE_WIDTH, height: IMAGE_HEIGHT, spp: SAMPLES_PER_PIXEL, sample_offset: 0,
-                          total_spp: SAMPLES_PER_PIXEL, max_depth: MAX_DEPTH, rr_start_depth: 0, seed: 1,
-                          background: [0.0; 3], pool_paths: 0, flags: 0 };
-    let mut stats = RtbStats::default();
-    check(rtb_render(ctx, sc, &cam, &prm, std::ptr::null_mut(), &mut stats));
-    let mut rgb = vec![0u8; (IMAGE_WIDTH * IMAGE_HEIGHT * 3) as usize];     // row 0 = top, like img.get_pixel_mut(i, H-1-j)
-    check(rtb_finalize_rgb8(ctx, std::ptr::null(), IMAGE_WIDTH, IMAGE_HEIGHT, SAMPLES_PER_PIXEL, rgb.as_mut_ptr()));
-    // -> image::RgbImage::from_raw(IMAGE_WIDTH, IMAGE_HEIGHT, rgb) -> JPEG exactly as main.rs:791-796
+// raytracer/src/main_render.rs — replaces the render loop of main() (raytracer/src/main.rs:720-784): everything above
+// it (scene construction :668-686, camera constants :688-718, image constants :659-663) stays as it is.  The 18-thread
+// fan-out per pixel (:730-778) and the mpsc reduction (:767-781) become ONE call; the JPEG writer (:785-798) is unchanged.
+// NOT compiled in the build image (no rustc / cargo).
+use crate::flatten_impls::{light_records, FlattenHittable};
+use crate::gpu::{Gpu, RtbCamera, RtbParams, SceneBuilder};
+use crate::hittable_list::HittableList;
+
+pub struct Frame {
+    pub width: u32,
+    pub height: u32,
+    pub samples_per_pixel: u32,
+    pub max_depth: i32,
+    pub background: [f64; 3],
 }
-fn check(rc: c_int) { if rc != 0 { panic!("rtb200: {}", unsafe { CStr::from_ptr(rtb_last_error()) }.to_string_lossy()) } }
+
+/// `world` = cornell_box() (main.rs:337-433) or any other scene function; `lights` = the proxy list of main.rs:669-686;
+/// `devices` = [0] for one B200, [0, 1, .., 7] for the whole box (samples split, one NCCL reduce inside the library).
+/// Returns RGB8 rows from the top — the layout `img.get_pixel_mut(i, IMAGE_HEIGHT - j - 1)` fills at main.rs:733,780.
+pub fn render_gpu(
+    world: &HittableList,
+    lights: (&[&crate::aarect::XzRect], &[&crate::sphere::Sphere]),
+    cam: RtbCamera,
+    frame: &Frame,
+    devices: &[i32],
+) -> Vec<u8> {
+    let mut b = SceneBuilder::default();
+    let root = world.flatten(&mut b);
+    let light_recs = light_records(lights.0, lights.1);
+    let gpu = Gpu::new(devices);
+    let prm = RtbParams {
+        width: frame.width,
+        height: frame.height,
+        spp: frame.samples_per_pixel,
+        sample_offset: 0,
+        total_spp: frame.samples_per_pixel,
+        max_depth: frame.max_depth,
+        rr_start_depth: 0, // Russian roulette off = the reference's behaviour
+        seed: 1,
+        background: [frame.background[0] as f32, frame.background[1] as f32, frame.background[2] as f32],
+        pool_paths: 0,
+        flags: 0,
+    };
+    let (rgb, stats) = gpu.render(&b, root, &light_recs, &cam, &prm);
+    eprintln!(
+        "rtb200: {} paths, {} segments in {:.1} ms on {} GPU(s) ({:.0} Mrays/s; NCCL reduce {:.2} ms)",
+        stats.paths,
+        stats.segments,
+        stats.ms_total,
+        stats.n_devices,
+        stats.segments as f64 / stats.ms_total / 1e3,
+        stats.ms_nccl
+    );
+    rgb
+}
+
+// In main(), after `let cam = Camera::new(...)` (main.rs:711-718):
+//
+//     let frame = Frame { width: IMAGE_WIDTH, height: IMAGE_HEIGHT, samples_per_pixel: SAMPLES_PER_PIXEL, max_depth: MAX_DEPTH,
+//                         background: [background.x(), background.y(), background.z()] };
+//     let rtb_cam = RtbCamera { lookfrom: [lookfrom.x(), lookfrom.y(), lookfrom.z()], lookat: [lookat.x(), lookat.y(), lookat.z()],
+//                               vup: [vup.x(), vup.y(), vup.z()], vfov_deg: vfov, aspect_ratio: ASPECT_RATIO, aperture,
+//                               focus_dist: dist_to_focus, time0: 0.0, time1: 1.0 };
+//     let rgb = render_gpu(&world, (&[&light_rect], &[&glass_sphere]), rtb_cam, &frame, &[0]);
+//     let img: RgbImage = ImageBuffer::from_raw(IMAGE_WIDTH, IMAGE_HEIGHT, rgb).unwrap();
+//
+// and the existing JPEG encode (main.rs:791-796) runs on `img` unchanged.

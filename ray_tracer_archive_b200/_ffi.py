@@ -70,6 +70,11 @@ class Stats(C.Structure):
         return {k: (list(getattr(self, k)) if k == "prims_tested_type" else getattr(self, k)) for k, _ in self._fields_}
 
 
+class BuildOptions(C.Structure):
+    _fields_ = [("max_leaf_triangles", C.c_uint32), ("keep_huge_primitives_out", C.c_uint32),
+                ("open_min_extent", C.c_float), ("_reserved", C.c_uint32)]
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("n_spheres", C.c_uint32), ("n_moving", C.c_uint32), ("n_quads", C.c_uint32),
                 ("n_triangles", C.c_uint32), ("n_media", C.c_uint32), ("n_lights", C.c_uint32),
@@ -108,6 +113,7 @@ SIGNATURES = {
     "rtb_scene_set_quads": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32]),
     "rtb_scene_set_triangles": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32]),
     "rtb_scene_set_media": (_I, [_VP, _VP, _U32]),
+    "rtb_scene_set_build_options": (_I, [_VP, _VP]),
     "rtb_scene_build_bvh": (_I, [_VP]),
     "rtb_scene_commit": (_I, [_VP]),
     "rtb_scene_get_info": (_I, [_VP, C.POINTER(SceneInfo)]),
@@ -120,6 +126,7 @@ SIGNATURES = {
     "rtb_finalize_rgb8": (_I, [_VP, _VP, _U32, _U32, _U32, _VP]),
     "rtb_primary_hits": (_I, [_VP, _VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, C.POINTER(Stats)]),
     "rtb_trace_rays": (_I, [_VP, _VP, _VP, _VP, _VP, _U32, _VP, _VP, C.POINTER(Stats)]),
+    "rtb_debug_check_failures": (_I, [_VP, _VP]),
     "rtb_measure_bandwidth": (_I, [_VP, _U32, _U32, C.POINTER(C.c_double)]),
     "rtb_primary_rays": (_I, [_VP, C.POINTER(Camera), _U32, _U32, _VP, _VP, _VP]),
     "rtb_device_kat": (_I, [_VP, _VP, C.POINTER(Camera), C.POINTER(Params), _U32, _VP, _U32, _U32, _VP, _U32]),

@@ -18,7 +18,9 @@
 #include <future>
 #include <thread>
 #include <cstdlib>
+#if defined(__SSE2__)
 #include <emmintrin.h>
+#endif
 #include <new>
 #include <numeric>
 
@@ -26,6 +28,36 @@
 
 namespace rtb {
 namespace {
+
+// Four floats at a time for the bounds / binning passes: SSE2 on x86-64, a plain array elsewhere (aarch64 hosts such as
+// Grace-based GB200 nodes; the compiler vectorises the loops over the four lanes itself).
+#if defined(__SSE2__)
+typedef __m128 v4f;
+inline v4f v4_set1(float x) { return _mm_set1_ps(x); }
+inline v4f v4_set(float x, float y, float z, float w) { return _mm_set_ps(w, z, y, x); }
+inline v4f v4_load(const float* p) { return _mm_load_ps(p); }
+inline void v4_store(float* p, v4f a) { _mm_store_ps(p, a); }
+inline v4f v4_min(v4f a, v4f b) { return _mm_min_ps(a, b); }
+inline v4f v4_max(v4f a, v4f b) { return _mm_max_ps(a, b); }
+inline v4f v4_add(v4f a, v4f b) { return _mm_add_ps(a, b); }
+inline v4f v4_sub(v4f a, v4f b) { return _mm_sub_ps(a, b); }
+inline v4f v4_mul(v4f a, v4f b) { return _mm_mul_ps(a, b); }
+inline void v4_trunc_store(int32_t* p, v4f a) { _mm_store_si128(reinterpret_cast<__m128i*>(p), _mm_cvttps_epi32(a)); }
+#else
+struct v4f { float v[4]; };
+inline v4f v4_set1(float x) { return v4f{{x, x, x, x}}; }
+inline v4f v4_set(float x, float y, float z, float w) { return v4f{{x, y, z, w}}; }
+inline v4f v4_load(const float* p) { return v4f{{p[0], p[1], p[2], p[3]}}; }
+inline void v4_store(float* p, v4f a) { for (int i = 0; i < 4; ++i) p[i] = a.v[i]; }
+inline v4f v4_min(v4f a, v4f b) { v4f r; for (int i = 0; i < 4; ++i) r.v[i] = b.v[i] < a.v[i] ? b.v[i] : a.v[i]; return r; }
+inline v4f v4_max(v4f a, v4f b) { v4f r; for (int i = 0; i < 4; ++i) r.v[i] = b.v[i] > a.v[i] ? b.v[i] : a.v[i]; return r; }
+inline v4f v4_add(v4f a, v4f b) { v4f r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline v4f v4_sub(v4f a, v4f b) { v4f r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline v4f v4_mul(v4f a, v4f b) { v4f r; for (int i = 0; i < 4; ++i) r.v[i] = a.v[i] * b.v[i]; return r; }
+inline void v4_trunc_store(int32_t* p, v4f a) {  // lane 3 carries an integer bit pattern: any finite-or-not value may appear
+  for (int i = 0; i < 4; ++i) p[i] = (a.v[i] > -2.0e9f && a.v[i] < 2.0e9f) ? (int32_t)a.v[i] : INT32_MIN;
+}
+#endif
 
 struct Box3 {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -63,13 +95,13 @@ static_assert(sizeof(Rec) == 32, "Rec must be two SSE vectors");
 
 // SSE accumulation of bounds: lanes 0-2 = x, y, z; lane 3 carries the record's integer fields and is ignored
 struct Box4 {
-  __m128 lo = _mm_set1_ps(INFINITY), hi = _mm_set1_ps(-INFINITY);
-  void grow(__m128 l, __m128 h) { lo = _mm_min_ps(lo, l); hi = _mm_max_ps(hi, h); }
+  v4f lo = v4_set1(INFINITY), hi = v4_set1(-INFINITY);
+  void grow(v4f l, v4f h) { lo = v4_min(lo, l); hi = v4_max(hi, h); }
   void grow(const Box4& b) { grow(b.lo, b.hi); }
   Box3 box3() const {
     alignas(16) float l[4], h[4];
-    _mm_store_ps(l, lo);
-    _mm_store_ps(h, hi);
+    v4_store(l, lo);
+    v4_store(h, hi);
     Box3 b;
     for (int a = 0; a < 3; ++a) { b.lo[a] = l[a]; b.hi[a] = h[a]; }
     return b;
@@ -92,11 +124,11 @@ struct Builder {
   // bounds of the records [a, b) and of their centroids (SSE: one min + one max per record and box)
   void range_bounds(uint32_t a, uint32_t b, Box3& box, Box3& cbox) const {
     Box4 bx, cb;
-    const __m128 half = _mm_set1_ps(0.5f);
+    const v4f half = v4_set1(0.5f);
     for (uint32_t i = a; i < b; ++i) {
-      const __m128 l = _mm_load_ps(recs[i].lo), h = _mm_load_ps(recs[i].hi);
+      const v4f l = v4_load(recs[i].lo), h = v4_load(recs[i].hi);
       bx.grow(l, h);
-      const __m128 c = _mm_mul_ps(half, _mm_add_ps(l, h));
+      const v4f c = v4_mul(half, v4_add(l, h));
       cb.grow(c, c);
     }
     box = bx.box3();
@@ -109,13 +141,13 @@ struct Builder {
                   uint32_t (&bc)[3][16]) const {
     const int NB = 16;
     Box4 acc[3][NB];
-    const __m128 half = _mm_set1_ps(0.5f);
-    const __m128 lo4 = _mm_set_ps(0.f, lo[2], lo[1], lo[0]), k4 = _mm_set_ps(0.f, k[2], k[1], k[0]);
+    const v4f half = v4_set1(0.5f);
+    const v4f lo4 = v4_set(lo[0], lo[1], lo[2], 0.f), k4 = v4_set(k[0], k[1], k[2], 0.f);
     for (uint32_t i = a; i < b; ++i) {
-      const __m128 l = _mm_load_ps(recs[i].lo), h = _mm_load_ps(recs[i].hi);
-      const __m128 c = _mm_mul_ps(half, _mm_add_ps(l, h));
+      const v4f l = v4_load(recs[i].lo), h = v4_load(recs[i].hi);
+      const v4f c = v4_mul(half, v4_add(l, h));
       alignas(16) int32_t bi[4];
-      _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, lo4), k4)));
+      v4_trunc_store(bi, v4_mul(v4_sub(c, lo4), k4));
       for (int ax = 0; ax < 3; ++ax) {
         if (!valid[ax]) continue;
         int q = bi[ax];
@@ -464,7 +496,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     Box3 scene;
     for (size_t i = 0; i < np; ++i) scene.grow(hs.prims[i].lo, hs.prims[i].hi);
     const float scene_area = scene.area();
-    const bool enabled = !(getenv("RTB_GLOBALS") && atoi(getenv("RTB_GLOBALS")) == 0);
+    const bool enabled = hs.opt_globals != 0 && !(getenv("RTB_GLOBALS") && atoi(getenv("RTB_GLOBALS")) == 0);
     const size_t tiny = getenv("RTB_TINY_SCENE") ? (size_t)atoi(getenv("RTB_TINY_SCENE")) : 16;
     if (enabled && np <= tiny && np <= RTB_MAX_GLOBALS) {
       // a scene this small (the 13-primitive Cornell box) is cheaper to scan than to traverse: one node visit decodes
@@ -497,7 +529,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     Builder* b = new Builder(hs);
     // one primitive per leaf slot: a sphere/quad test costs more than a (quantised) box test and single-primitive
     // leaves fill the 8 slots of a node; triangles keep up to 2 per slot to bound the node count of large meshes
-    b->max_leaf = (t == PT_TRI) ? 2u : 1u;
+    b->max_leaf = (t == PT_TRI) ? std::max(1u, std::min(3u, hs.opt_max_leaf_tris)) : 1u;
     if (const char* e = getenv("RTB_MAX_LEAF")) b->max_leaf = (uint32_t)std::max(1, std::min(3, atoi(e)));
     builders.push_back(b);
     if (type_count[t] == 0) continue;
@@ -579,7 +611,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     queue.push_back(Pending{0, 0, trees[0].root, 1});
   }
 
-  float open_min_rel = 1.0f / 8.0f;
+  float open_min_rel = hs.opt_open_min_rel;
   if (const char* e = getenv("RTB_OPEN_MIN_REL")) open_min_rel = (float)atof(e);
 
   // One wide node: gather up to 8 children of binary node pd.bin_node, assign slots, quantise, append its leaf

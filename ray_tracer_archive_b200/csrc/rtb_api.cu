@@ -488,6 +488,17 @@ int rtb_scene_set_media(rtb_scene* s, const rtb_medium* media, uint32_t n) {
   return RTB_OK;
 }
 
+int rtb_scene_set_build_options(rtb_scene* s, const rtb_build_options* o) {
+  if (!s || !o) return set_err(RTB_ERR_INVALID, "NULL argument");
+  if (o->max_leaf_triangles < 1 || o->max_leaf_triangles > 3) return set_err(RTB_ERR_INVALID, "max_leaf_triangles must be 1..3");
+  if (!(o->open_min_extent >= 0.f && o->open_min_extent <= 1.f)) return set_err(RTB_ERR_INVALID, "open_min_extent must be in [0, 1]");
+  s->hs.opt_max_leaf_tris = o->max_leaf_triangles;
+  s->hs.opt_globals = o->keep_huge_primitives_out ? 1u : 0u;
+  s->hs.opt_open_min_rel = o->open_min_extent;
+  s->built = s->committed = false;
+  return RTB_OK;
+}
+
 // ---- build (host) and commit (upload) ------------------------------------------------------------------------------
 int rtb_scene_build_bvh(rtb_scene* s) {
   if (!s) return set_err(RTB_ERR_INVALID, "scene is NULL");
@@ -615,6 +626,7 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
     CU(cudaStreamSynchronize(0));  // `info` is a temporary
     d.geom[t] = s->d_geom[t].p;
     d.info[t] = s->d_info[t].p;
+    d.n_prims[t] = (uint32_t)(bvh.info[t].size() / 2);
     CU(s->d_exact[t].upload(bvh.exact[t].data(), bvh.exact[t].size()));
   }
   d.coord_max = bvh.coord_max;
@@ -1255,6 +1267,17 @@ int rtb_device_kat(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const rt
   launch_kat(dev, dcam, prm, op, d_in.p, n, in_stride, d_out.p, out_stride, 0);
   CU(cudaMemcpy(out, d_out.p, (size_t)n * out_stride * 4, cudaMemcpyDeviceToHost));
   CU(cudaGetLastError());
+  return RTB_OK;
+}
+
+int rtb_debug_check_failures(rtb_context* c, uint32_t* out8) {
+  if (!c || !out8) return set_err(RTB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  unsigned int v[8];
+  const int e = read_check_failures(v);
+  if (e != 0) return set_err(RTB_ERR_CUDA, cudaGetErrorString((cudaError_t)e));
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
   return RTB_OK;
 }
 

@@ -11,6 +11,21 @@
 
 namespace rtb {
 
+// RTB_CHECKED build (make -C csrc checked -> librtb200_checked.so): bounds assertions on every index the kernels form
+// (traversal stack, node and primitive indices, pool slots, fix-up queue).  compute-sanitizer is closed on the GPU pool, so
+// this build + tests/test_gpu_checked.py take its place; a failed assertion bumps a device counter by kind
+// (rtb_debug_check_failures) instead of trapping, so one run reports everything.
+#ifdef RTB_CHECKED
+__device__ unsigned int g_rtb_check_fail[8];
+enum CheckKind : int { CHK_STACK = 0, CHK_NODE = 1, CHK_PRIM = 2, CHK_SLOT = 3, CHK_QUEUE = 4, CHK_LIST = 5 };
+#define RTB_CHECK(kind, cond)                          \
+  do {                                                 \
+    if (!(cond)) atomicAdd(&g_rtb_check_fail[kind], 1u); \
+  } while (0)
+#else
+#define RTB_CHECK(kind, cond) ((void)0)
+#endif
+
 #define RTB_MAX_LIGHTS 8
 #define RTB_MAX_MEDIA 8
 #define RTB_MAX_TABLES 4
@@ -63,6 +78,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
                         // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
   const float4* geom[PT_COUNT];
   const uint2* info[PT_COUNT];
+  uint32_t n_prims[PT_COUNT];     // leaf entries per type (RTB_CHECKED bounds)
   const ExactTab* xtab;           // tables of the exact path (device memory)
   float coord_max;                // 2 x the largest |coordinate| of the scene box: scale of the plane-test rounding bound
   float eps_ab;                   // rounding bound of a quad's in-plane coordinates (alpha, beta), see intersect_prim
@@ -430,7 +446,7 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
 // decision (disc' sign, root against t_min) is inside its bound.  `coarse` = the bound exceeds RTB_SPHERE_REL_MAX t
 // (measured: the bound is 50-80x the worst actual error, and the reported t must hold 1e-5 relative): such a hit is
 // certain, only its distance wants an f64 recomputation if it ends up the closest.
-#define RTB_SPHERE_REL_MAX 4.0e-4f
+#define RTB_SPHERE_REL_MAX 2.0e-4f
 __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out,
                                            bool& coarse) {
   const float3 oc = o - c;
@@ -492,6 +508,7 @@ template <bool COUNT>
 __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
                                                float time, float tmin, Closest& best, float& amb, uint32_t& flags, TestCount& n_tests) {
   if (COUNT) ++n_tests.n[type];
+  RTB_CHECK(CHK_PRIM, type < PT_COUNT && idx < sc.n_prims[type]);
   const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
   float t, e;
   bool coarse = false;
@@ -684,6 +701,8 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const uint32_t slot = prio ^ octinv;
   const uint32_t gmask = tv.grp.y & 0xFFu;
   const uint32_t node = tv.grp.x + __popc(gmask & ((1u << slot) - 1u));
+  RTB_CHECK(CHK_STACK, !hits || tv.sp < RTB_STACK);
+  RTB_CHECK(CHK_NODE, node < sc.n_nodes);
   if (hits) stack[tv.sp++] = make_uint2(tv.grp.x, (hits << 8) | gmask);
   if (COUNT) ++n_nodes_visited;
   uint4 w0, w1, w2, w3, w4;

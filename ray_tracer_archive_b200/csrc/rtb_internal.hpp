@@ -95,6 +95,10 @@ struct HostScene {
   std::vector<Mesh> meshes;
   std::vector<ExactRec> exact;
   uint32_t n_prim_ids = 0;
+  // BVH builder quality knobs (rtb_scene_set_build_options)
+  uint32_t opt_max_leaf_tris = 2;   // triangles per leaf slot, 1..3
+  uint32_t opt_globals = 1;         // keep scene-dominating primitives out of the tree
+  float opt_open_min_rel = 0.125f;  // collapse: never open a subtree smaller than this fraction of the node's extent
 };
 
 // flatten.cpp

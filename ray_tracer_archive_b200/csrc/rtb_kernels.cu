@@ -56,6 +56,7 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
     minfo = type == PT_MEDIUM ? sc.media[idx].minfo : __ldg(&sc.info[type][idx].y);
     queue = RTB_MINFO_QUEUE(minfo);
   }
+  RTB_CHECK(CHK_SLOT, slot < pool.n);
   pool.hit[slot] = make_float4(best.t, __uint_as_float(best.ref), __uint_as_float(minfo), 0.f);
   pool.cls[slot] = (uint8_t)queue;
 }
@@ -63,7 +64,9 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
 // a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
 // the one atomic per entry is uncontended in practice)
 __device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind, float lo, float hi) {
-  pool.redo[atomicAdd(&pool.c->redo_count, 1u)] =
+  const uint32_t qi = atomicAdd(&pool.c->redo_count, 1u);
+  RTB_CHECK(CHK_QUEUE, qi < pool.n && slot < pool.n);
+  pool.redo[qi] =
       make_uint4(slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u), __float_as_uint(lo), __float_as_uint(hi), 0u);
 }
 
@@ -86,7 +89,10 @@ __device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t
     uint32_t pos = len + incl - cnt;
 #pragma unroll
     for (uint32_t j = 0; j < 8; ++j)
-      if (((j < 4 ? e0 : e1) >> (8 * (j & 3))) & 1u) list[pos++] = (uint8_t)(8u * lane + j);
+      if (((j < 4 ? e0 : e1) >> (8 * (j & 3))) & 1u) {
+        RTB_CHECK(CHK_LIST, pos < RTB_CHUNK);
+        list[pos++] = (uint8_t)(8u * lane + j);
+      }
   }
   return len + total;
 }
@@ -872,6 +878,7 @@ __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPoo
   for (uint32_t i = blockIdx.x * RTB_FIXUP_THREADS + threadIdx.x; i < n; i += gridDim.x * RTB_FIXUP_THREADS) {
     const uint4 q = pool.redo[i];
     const uint32_t entry = q.x, slot = entry & ~RTB_REDO_REFINE;
+    RTB_CHECK(CHK_SLOT, slot < pool.n);
     const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
     if (entry & RTB_REDO_REFINE) {  // certain hit, coarse distance: one f64 evaluation of that primitive
       const float4 h = pool.hit[slot];
@@ -1066,6 +1073,17 @@ __global__ void __launch_bounds__(256) k_bw_shared(uint32_t reps, uint4* __restr
   }
   if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345679u) sink[0] = acc;
 }
+
+#ifdef RTB_CHECKED
+int read_check_failures(unsigned int* out8) {
+  return (int)cudaMemcpyFromSymbol(out8, g_rtb_check_fail, sizeof(unsigned int) * 8);
+}
+#else
+int read_check_failures(unsigned int* out8) {
+  for (int i = 0; i < 8; ++i) out8[i] = 0xFFFFFFFFu;  // not a checked build
+  return 0;
+}
+#endif
 
 // ================================================= launchers ========================================================
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }

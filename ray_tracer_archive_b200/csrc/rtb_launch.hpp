@@ -39,6 +39,7 @@ struct LaunchCfg {
 };
 
 int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
+int read_check_failures(unsigned int* out8);  // RTB_CHECKED build: failed bounds assertions by kind; 0xFFFFFFFF otherwise
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);
 void launch_fixup(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st);

@@ -71,6 +71,12 @@ class Context:
                                         w.shape[1], F.ptr(out), out_stride))
         return out
 
+    def check_failures(self):
+        """RTB_CHECKED build: failed device-side bounds assertions by kind (all 0xFFFFFFFF in a normal build)."""
+        out = np.zeros(8, dtype=np.uint32)
+        F.check(self.lib.rtb_debug_check_failures(self.h, F.ptr(out)))
+        return out
+
     def measure_bandwidth(self, kind: int, repeats: int = 5) -> float:
         """GB/s of a read-only stream: F.BW_L2_READ (48 MB, L2-resident), F.BW_HBM_READ (2 GB), F.BW_SHARED_READ."""
         v = C.c_double()
@@ -130,6 +136,11 @@ class Scene:
         self.set_tables(cs)
         F.check(self.lib.rtb_scene_set_graph(self.h, F.ptr(cs.nodes), len(cs.nodes), F.ptr(cs.child_index),
                                               len(cs.child_index), cs.root))
+
+    def set_build_options(self, max_leaf_triangles=2, keep_huge_primitives_out=True, open_min_extent=0.125):
+        """BVH builder quality knobs (rtb_scene_set_build_options); call before build_bvh() / commit()."""
+        o = F.BuildOptions(max_leaf_triangles, 1 if keep_huge_primitives_out else 0, open_min_extent, 0)
+        F.check(self.lib.rtb_scene_set_build_options(self.h, C.byref(o)))
 
     def build_bvh(self):
         F.check(self.lib.rtb_scene_build_bvh(self.h))

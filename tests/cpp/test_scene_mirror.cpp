@@ -32,7 +32,110 @@ static std::shared_ptr<HittableList> cornell_box() {
   return objects;
 }
 
+// final_scene() (raytracer/src/main.rs:521-649, commented in the reference) with the C++ mirror.  The random numbers of the
+// scene (box heights, the 1000 sphere centres, the Perlin tables) and the earthmap texels come from a file the pytest
+// wrapper writes from the Python mirror's scene, so both sides construct the SAME scene and must emit the same records.
+struct FinalSceneData {
+  std::vector<double> boxes;    // 400 x (x0 y0 z0 x1 y1 z1)
+  std::vector<double> centres;  // 1000 x 3
+  std::vector<double> ranvec;   // 256 x 3
+  std::vector<uint32_t> perm;   // 3 x 256
+  std::vector<uint8_t> earth;   // 512 x 1024 x 3
+};
+static bool read_final_scene_data(const char* path, FinalSceneData& d) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return false;
+  d.boxes.resize(2400); d.centres.resize(3000); d.ranvec.resize(768); d.perm.resize(768); d.earth.resize(512 * 1024 * 3);
+  bool ok = std::fread(d.boxes.data(), 8, 2400, f) == 2400 && std::fread(d.centres.data(), 8, 3000, f) == 3000 &&
+            std::fread(d.ranvec.data(), 8, 768, f) == 768 && std::fread(d.perm.data(), 4, 768, f) == 768 &&
+            std::fread(d.earth.data(), 1, d.earth.size(), f) == d.earth.size();
+  std::fclose(f);
+  return ok;
+}
+static std::shared_ptr<HittableList> final_scene(const FinalSceneData& d) {
+  auto boxes1 = HittableList::new_();
+  auto ground = Lambertian::construct({0.48, 0.83, 0.53});
+  for (int k = 0; k < 400; ++k) {
+    const double* b = &d.boxes[6 * k];
+    boxes1->add(Box::construct({b[0], b[1], b[2]}, {b[3], b[4], b[5]}, ground));
+  }
+  auto objects = HittableList::new_();
+  objects->add(BVHNode::construct2(boxes1, 0.0, 1.0));
+  auto light = DiffuseLight::construct_color({7.0, 7.0, 7.0});
+  objects->add(FlipFace::construct(XzRect::construct(123.0, 423.0, 147.0, 412.0, 554.0, light)));
+  objects->add(MovingSphere::construct({400.0, 400.0, 200.0}, {430.0, 400.0, 200.0}, 0.0, 1.0, 50.0, Lambertian::construct({0.7, 0.3, 0.1})));
+  objects->add(Sphere::construct({260.0, 150.0, 45.0}, 50.0, Dielectric::construct(1.5)));
+  objects->add(Sphere::construct({0.0, 150.0, 145.0}, 50.0, Metal::construct({0.8, 0.8, 0.9}, 1.0)));
+  HittablePtr boundary = Sphere::construct({360.0, 150.0, 145.0}, 70.0, Dielectric::construct(1.5));
+  objects->add(boundary);
+  objects->add(ConstantMedium::construct_color(boundary, 0.2, {0.2, 0.4, 0.9}));
+  HittablePtr boundary2 = Sphere::construct({0.0, 0.0, 0.0}, 5000.0, Dielectric::construct(1.5));
+  objects->add(ConstantMedium::construct_color(boundary2, 0.0001, {1.0, 1.0, 1.0}));
+  objects->add(Sphere::construct({400.0, 200.0, 400.0}, 100.0, Lambertian::construct_texture(ImageTexture::construct(d.earth, 1024, 512))));
+  auto pertext = std::make_shared<NoiseTexture>();
+  pertext->scale = 0.1;
+  pertext->ranvec = d.ranvec;
+  pertext->perm_x.assign(d.perm.begin(), d.perm.begin() + 256);
+  pertext->perm_y.assign(d.perm.begin() + 256, d.perm.begin() + 512);
+  pertext->perm_z.assign(d.perm.begin() + 512, d.perm.end());
+  objects->add(Sphere::construct({220.0, 280.0, 300.0}, 80.0, Lambertian::construct_texture(pertext)));
+  auto boxes2 = HittableList::new_();
+  auto white = Lambertian::construct({0.73, 0.73, 0.73});
+  for (int k = 0; k < 1000; ++k) boxes2->add(Sphere::construct({d.centres[3 * k], d.centres[3 * k + 1], d.centres[3 * k + 2]}, 10.0, white));
+  objects->add(Translate::construct(RotateY::construct(BVHNode::construct2(boxes2, 0.0, 1.0), 15.0), {-100.0, 270.0, 395.0}));
+  return objects;
+}
+
+static void print_records(const SceneRecords& rec) {
+  std::printf("records %zu children %zu root %u\n", rec.nodes.size(), rec.child_index.size(), rec.root);
+  for (const rtb_node& n : rec.nodes) {
+    std::printf("node %u %u %u %u", n.type, n.material, n.first_child, n.n_children);
+    for (double v : n.p) std::printf(" %.17g", v);
+    std::printf("\n");
+  }
+  for (const rtb_material& m : rec.materials) std::printf("material %u %u %.17g\n", m.type, m.texture, m.param);
+  for (const rtb_texture& t : rec.textures)
+    std::printf("texture %u %u %u %u %.17g %.17g %.17g %.17g\n", t.type, t.even, t.odd, t.table, t.rgb[0], t.rgb[1], t.rgb[2], t.scale);
+}
+
 int main(int argc, char** argv) {
+  // "final <data file> [render]": the book-2 final scene through the mirror (records + optional 8-spp GPU render)
+  if (argc > 2 && !std::strcmp(argv[1], "final")) {
+    FinalSceneData d;
+    if (!read_final_scene_data(argv[2], d)) { std::printf("cannot read %s\n", argv[2]); return 2; }
+    auto fworld = final_scene(d);
+    auto flights = HittableList::new_();
+    flights->add(XzRect::construct(123.0, 423.0, 147.0, 412.0, 554.0, DiffuseLight::construct_color({7.0, 7.0, 7.0})));
+    SceneRecords frec;
+    frec.set_world(fworld, flights);
+    print_records(frec);
+    const bool frender = argc > 3 && !std::strcmp(argv[3], "render");
+    rtb_context* fctx = nullptr;
+    if (frender && rtb_context_create(0, &fctx) != 0) { std::printf("context: %s\n", rtb_last_error()); return 2; }
+    rtb_scene* fscene = nullptr;
+    if (rtb_scene_create(fctx, &fscene) != 0) return 3;
+    frec.upload(fscene);
+    if (rtb_scene_build_bvh(fscene) != 0) { std::printf("build: %s\n", rtb_last_error()); return 4; }
+    rtb_scene_info finfo;
+    rtb_scene_get_info(fscene, &finfo);
+    std::printf("final quads %u spheres %u moving %u media %u prims %u lights %u\n", finfo.n_quads, finfo.n_spheres, finfo.n_moving,
+                finfo.n_media, finfo.n_prims, finfo.n_lights);
+    if (frender) {
+      if (rtb_scene_commit(fscene) != 0) { std::printf("commit: %s\n", rtb_last_error()); return 5; }
+      rtb_camera cam{{478, 278, -600}, {278, 278, 0}, {0, 1, 0}, 40.0, 1.0, 0.0, 10.0, 0.0, 1.0};
+      rtb_params prm{};
+      prm.width = 96; prm.height = 96; prm.spp = 8; prm.total_spp = 8; prm.max_depth = 50; prm.seed = 1;
+      rtb_stats st;
+      std::vector<float> acc((size_t)prm.width * prm.height * 4);
+      if (rtb_render(fctx, fscene, &cam, &prm, acc.data(), &st) != 0) { std::printf("render: %s\n", rtb_last_error()); return 6; }
+      double sum = 0;
+      for (float v : acc) sum += v;
+      std::printf("rendered paths %llu segments %llu sum %.9g\n", (unsigned long long)st.paths, (unsigned long long)st.segments, sum);
+    }
+    rtb_scene_destroy(fscene);
+    if (fctx) rtb_context_destroy(fctx);
+    return 0;
+  }
   auto world = cornell_box();
   auto lights = HittableList::new_();
   lights->add(XzRect::construct(213.0, 343.0, 227.0, 332.0, 554.0, DiffuseLight::construct_color({15.0, 15.0, 15.0})));

@@ -21,7 +21,7 @@ def _build():
 
 def _run(*args):
     _build()
-    return subprocess.run([EXE, *args], capture_output=True, text=True, timeout=120)
+    return subprocess.run([EXE, *args], capture_output=True, text=True, timeout=300)
 
 
 def test_cpp_mirror_builds_cornell_and_matches_python_records(rtb):
@@ -38,6 +38,71 @@ def test_cpp_mirror_builds_cornell_and_matches_python_records(rtb):
     for r, n in zip(recs, cs.nodes):
         assert [int(x) for x in r[:4]] == [int(n["type"]), int(n["material"]), int(n["first_child"]), int(n["n_children"])]
         np.testing.assert_array_equal(np.array([float(x) for x in r[4:]]), n["p"])
+
+
+def _final_scene_data(rtb, path):
+    """The random numbers and texels of the Python mirror's final_scene(), for the C++ mirror to build the same scene."""
+    from ray_tracer_archive_b200 import scenes, _ffi as F
+    cfg = scenes.config_final_scene()
+    cs = rtb.compile_scene(cfg.world, cfg.lights)
+    boxes = np.array([n["p"][:6] for n in cs.nodes if int(n["type"]) == F.NODE_BOX], dtype=np.float64)
+    small = np.array([n["p"][:3] for n in cs.nodes if int(n["type"]) == F.NODE_SPHERE and n["p"][3] == 10.0], dtype=np.float64)
+    assert boxes.shape == (400, 6) and small.shape == (1000, 3)
+    pt = cs.perlins[0]
+    with open(path, "wb") as f:
+        f.write(boxes.tobytes())
+        f.write(small.tobytes())
+        f.write(np.ascontiguousarray(pt.ranvec, dtype=np.float64).tobytes())
+        for perm in (pt.perm_x, pt.perm_y, pt.perm_z):
+            f.write(np.ascontiguousarray(perm, dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(cs.images[0], dtype=np.uint8).tobytes())
+    return cfg, cs
+
+
+def _check_final_records(out, cs):
+    lines = out.stdout.strip().splitlines()
+    recs = [l.split()[1:] for l in lines if l.startswith("node ")]
+    assert len(recs) == len(cs.nodes)
+    for r, n in zip(recs, cs.nodes):
+        assert [int(x) for x in r[:4]] == [int(n["type"]), int(n["material"]), int(n["first_child"]), int(n["n_children"])]
+        np.testing.assert_array_equal(np.array([float(x) for x in r[4:]]), n["p"])
+    mats = [l.split()[1:] for l in lines if l.startswith("material ")]
+    assert len(mats) == len(cs.materials)
+    for r, m in zip(mats, cs.materials):
+        assert (int(r[0]), int(r[1]), float(r[2])) == (int(m["type"]), int(m["texture"]), float(m["param"]))
+    texs = [l.split()[1:] for l in lines if l.startswith("texture ")]
+    assert len(texs) == len(cs.textures)
+    for r, t in zip(texs, cs.textures):
+        assert [int(x) for x in r[:4]] == [int(t["type"]), int(t["even"]), int(t["odd"]), int(t["table"])]
+        np.testing.assert_array_equal(np.array([float(x) for x in r[4:7]]), t["rgb"])
+    return lines
+
+
+def test_cpp_mirror_final_scene_records_match_python(rtb, tmp_path):
+    """The book-2 final scene (main.rs:521-649: 400 boxes under a BVHNode, moving sphere, both ConstantMedium, the earthmap
+    and Perlin textures, 1000 spheres under Translate(RotateY(BVHNode))) written with the C++ mirror emits exactly the
+    node / material / texture records the Python mirror emits — the records the Rust shim's flatten() methods emit
+    (integration/rust/src/flatten_impls.rs follows the same post-order, share-by-address rules)."""
+    data = str(tmp_path / "final_scene.bin")
+    cfg, cs = _final_scene_data(rtb, data)
+    out = _run("final", data)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    lines = _check_final_records(out, cs)
+    assert lines[-1] == "final quads 2401 spheres 1005 moving 1 media 2 prims 3409 lights 1"
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_final_scene_renders_like_python(rtb, ctx, tmp_path):
+    """... and rendering those records through the C ABI from C++ gives the image the Python-driven render gives (same
+    seed: same paths; sums equal to f32 summation order)."""
+    data = str(tmp_path / "final_scene.bin")
+    cfg, cs = _final_scene_data(rtb, data)
+    out = _run("final", data, "render")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr
+    last = out.stdout.strip().splitlines()[-1].split()
+    acc, st = rtb.Scene(ctx, cs).render(cfg.camera, rtb.make_params(96, 96, 8, cfg.max_depth, cfg.background, seed=1))
+    assert last[0] == "rendered" and int(last[2]) == st["paths"] == 96 * 96 * 8 and int(last[4]) == st["segments"]
+    assert abs(float(last[6]) / float(acc.astype(np.float64).sum()) - 1.0) < 1e-5
 
 
 @pytest.mark.gpu

@@ -142,7 +142,7 @@ def test_sphere_fast_bound_holds_on_random_rays(rtb, orc, ctx):
     assert (err <= e[certain_hit] + 1e-30).all(), float((err / np.maximum(e[certain_hit], 1e-30)).max())
     fine = certain_hit & ~coarse                       # hits whose f32 distance is used as it is
     rel = np.abs(t[fine] - tref[fine]) / tref[fine]
-    assert (e[fine] <= 4.0001e-4 * t[fine]).all()
+    assert (e[fine] <= 2.0001e-4 * t[fine]).all()
     assert rel.max() <= 1e-5, rel.max()                # ... and it holds the 1e-5 of the parity bar
     assert certain_hit.sum() > 0.2 * n and (st == 2).mean() < 0.2
     print(f"sphere_fast: {certain_hit.mean():.3f} certain hits ({(certain_hit & coarse).mean():.3f} coarse -> refined in f64), "

@@ -209,3 +209,29 @@ def test_parallel_subtree_collapse_large_mesh(rtb, orc, emul, monkeypatch):
             continue
         assert int(nd["child_base"][i]) == nxt, i
         nxt += k
+
+
+def test_build_options_change_the_tree_not_the_hits(rtb, orc, emul):
+    """rtb_scene_set_build_options (f2: builder quality knobs): different leaf sizes / collapse thresholds / no global
+    primitives give different trees and the same closest hits."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_mesh(nx=60, nz=30)
+    cs = rtb.compile_scene(cfg.world, cfg.lights)
+    o, d = H.primary_rays(cfg.camera, 120, 68)
+    o32, d32 = o.astype(np.float32), d.astype(np.float32)
+    ref, nodes = None, set()
+    for kw in ({}, {"max_leaf_triangles": 1}, {"max_leaf_triangles": 3, "open_min_extent": 0.0},
+               {"keep_huge_primitives_out": False, "open_min_extent": 0.5}):
+        hs = rtb.Scene(None)
+        hs.set_compiled(cs)
+        hs.set_build_options(**kw)
+        hs.build_bvh()
+        nodes.add(hs.info()["n_bvh_nodes"])
+        ids, ts, _, _ = H.emul_trace(emul, hs, o32, d32)
+        if ref is None:
+            ref = (ids, ts)
+        else:
+            assert np.array_equal(ids, ref[0]) and np.allclose(ts, ref[1], rtol=1e-6)
+    assert len(nodes) >= 3
+    with pytest.raises(rtb.RtbError):
+        rtb.Scene(None).set_build_options(max_leaf_triangles=7)
