@@ -57,7 +57,7 @@ struct Lane {
   uint32_t pool_n = 0;
   DevBuf<float4> ray, st, hit;
   DevBuf<uint8_t> cls;                    // per-slot shade class
-  DevBuf<uint4> redo;                     // rays queued for the exact pass (slot, distance slab)
+  DevBuf<uint4> redo[2];                  // rays queued for the exact pass (slot, distance slab), double-buffered
   DevBuf<unsigned long long> cursor;      // per-chunk path cursor
   DevBuf<DevCounters> counters;
   DevCounters* h_counters = nullptr;     // pinned; [0], [1]: the drain check of batch k is read while batch k + 1 runs
@@ -108,6 +108,7 @@ struct rtb_scene {
   DevBuf<uint2> d_info[PT_COUNT];
   DevBuf<double> d_exact[PT_COUNT];
   DevBuf<ExactTab> d_xtab;
+  DevBuf<DevScene> d_self;
   DevBuf<float4> d_materials;
   DevBuf<DevTexture> d_textures;
   DevBuf<float4> d_perlin_vec[RTB_MAX_TABLES];
@@ -697,6 +698,9 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
     CU(cudaStreamSynchronize(0));  // `xt` is a temporary
     d.xtab = s->d_xtab.p;
   }
+  CU(s->d_self.resize(1));
+  d.self = s->d_self.p;
+  CU(cudaMemcpy(s->d_self.p, &d, sizeof(DevScene), cudaMemcpyHostToDevice));  // (after every other field is final)
   int e = configure_launch(s->lc, d.n_nodes, s->ctx->prop.multiProcessorCount);
   if (e != 0) return set_err(RTB_ERR_CUDA, std::string("configure_launch: ") + cudaGetErrorString((cudaError_t)e));
   CU(cudaStreamSynchronize(0));
@@ -817,7 +821,7 @@ static int ensure_pool(Lane& c, uint32_t n) {
   CU(c.ray.resize((size_t)n * 2)); CU(c.st.resize((size_t)n * 2)); CU(c.hit.resize(n));
   const size_t chunks = ((size_t)n + RTB_CHUNK - 1) / RTB_CHUNK;
   CU(c.cls.resize(chunks * RTB_CHUNK)); CU(c.cursor.resize(chunks));
-  CU(c.redo.resize(n));
+  CU(c.redo[0].resize(n)); CU(c.redo[1].resize(n));
   c.pool_n = n;
   return RTB_OK;
 }
@@ -827,7 +831,7 @@ static DevPool lane_pool(Lane& L, uint32_t n) {
   p.n = n;
   p.n_chunks = (n + RTB_CHUNK - 1) / RTB_CHUNK;
   p.ray = L.ray.p; p.st = L.st.p; p.hit = L.hit.p;
-  p.cls = L.cls.p; p.redo = L.redo.p; p.cursor = L.cursor.p;
+  p.cls = L.cls.p; p.redo[0] = L.redo[0].p; p.redo[1] = L.redo[1].p; p.cursor = L.cursor.p;
   p.c = L.counters.p;
   return p;
 }
@@ -897,10 +901,12 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     for (int a = 0; a < 3; ++a) prm.bg[a] = p->background[a];
     prm.pix_order = c->pix_order.p;
     prm.inv_npix = 1.0 / (double)npix;
-    // leaf-test parking (rtb_device.cuh: drain_parked): on for the dynamic-fetch kernel of deep trees (C4 +7 %), off for
-    // the one-ray-per-thread kernel (C1 / C3 -13 %): profiles/r3_ab.md.  RTB_OPT overrides (experiments).
     static const char* env_opt = getenv("RTB_OPT");
-    prm.opt = env_opt ? (uint32_t)atoi(env_opt) : (s->lc.dynamic_fetch ? (14u << RTB_OPT_PARK_SHIFT) : 0u);
+    // per-scene scheduling of the extend kernel (profiles/r3_ab.md): deep trees (dynamic fetch) park their leaf tests,
+    // trees that do not fit the shared-memory stage order each chunk's rays by direction octant, small staged trees do
+    // neither.  RTB_OPT overrides (experiments).
+    prm.opt = env_opt ? (uint32_t)atoi(env_opt)
+                      : (s->lc.dynamic_fetch ? (14u << RTB_OPT_PARK_SHIFT) : (s->lc.all_staged ? 0u : 2u /* RTB_OPT_OCTANT_SORT */));
     prm.inv_wm1 = (float)(1.0 / (double)(p->width - 1));
     prm.inv_hm1 = (float)(1.0 / (double)(p->height - 1));
     prm.accum = (float4*)d_accum;
@@ -919,7 +925,7 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     CU(cudaStreamWaitEvent(ls, c->ev_fork, 0));
     launch_init_pool(run[k].pool, run[k].total, ls);
     launch_generate(s->lc, run[k].pool, run[k].prm, dcam, ls);
-    launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // nothing queued yet: rotates the counters
+    launch_rotate(run[k].pool, ls);
     launches += 3;
   }
   const uint32_t present = s->present_materials;
@@ -954,9 +960,8 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
           if ((e = cudaEventRecord(c->ext_events[ev_used + 1], ls)) != cudaSuccess) return e;
           ev_used += 2;
         }
-        launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // exact pass over the queued rays + counter rotation
         launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls);
-        launches += 2 + n_shade;
+        launches += 1 + n_shade;
         extend_launches += 1;
       }
     }

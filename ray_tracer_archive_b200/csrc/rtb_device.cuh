@@ -80,6 +80,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   const uint2* info[PT_COUNT];
   uint32_t n_prims[PT_COUNT];     // leaf entries per type (RTB_CHECKED bounds)
   const ExactTab* xtab;           // tables of the exact path (device memory)
+  const DevScene* self;           // this struct in device memory: the out-of-line exact pass takes ONE pointer
   float coord_max;                // 2 x the largest |coordinate| of the scene box: scale of the plane-test rounding bound
   float eps_ab;                   // rounding bound of a quad's in-plane coordinates (alpha, beta), see intersect_prim
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
@@ -101,8 +102,11 @@ struct DevCounters {
   uint32_t last_rays;   // ... in the previous iteration: 0 = the pool has drained (host check)
   uint32_t iter;
   uint32_t ext_cursor;  // next unclaimed slot batch (dynamic ray fetch)
-  uint32_t redo_count;  // rays of this iteration that need the exact pass (k_fixup)
-  uint32_t fix_ticket;  // CTAs of k_fixup that have finished (the last one rotates the counters)
+  uint32_t redo_count[2];  // fix-up queue lengths: [redo_sel] is being filled by this extend launch, [redo_sel ^ 1] was
+                           // filled by the previous one and is consumed by this launch's prologue
+  uint32_t redo_sel;
+  uint32_t iter_fixed;  // queue entries the current launch's prologue processed (they were shaded one iteration late)
+  uint32_t ext_ticket;  // CTAs of the extend launch that have finished (the last one rotates the counters)
   unsigned long long redone;  // total rays re-traced exactly
   unsigned long long refined; // total hits whose distance was recomputed in f64
   unsigned long long total_paths;
@@ -119,7 +123,11 @@ struct DevCounters {
 // 32-path blocks, so no kernel issues a contended global atomic (the queue-compacting version spent 77 % of
 // k_shade_terminal's stall samples on two same-address atomics per warp, profiles/r2_ab.md §3).
 #define RTB_CHUNK 256u
-enum SlotClass : uint32_t { CLS_NEW = 6, CLS_DEAD = 7 };  // 0..4 = Queue of the slot's current hit
+// 0..4 = Queue of the slot's current hit; CLS_WAIT: the hit is queued for the exact pass (not shaded this iteration).
+// Class byte: bits 0-2 class, bits 3-5 direction octant of the slot's ray (written by the shade kernels), bit 6: the hit
+// was (re)written by the exact pass of THIS iteration — the shade kernels shade it, extend's list building skips it.
+enum SlotClass : uint32_t { CLS_WAIT = 5, CLS_NEW = 6, CLS_DEAD = 7 };
+#define RTB_CLS_FIXED 0x40u
 struct DevPool {
   uint32_t n;         // slots
   uint32_t n_chunks;  // ceil(n / RTB_CHUNK)
@@ -127,7 +135,7 @@ struct DevPool {
   float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
   float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
   uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
-  uint4* redo;        // [n] rays for k_fixup: (slot | RTB_REDO_REFINE, slab lower bound, slab upper bound, -), filled by extend
+  uint4* redo[2];     // [n] each: rays for the exact pass, (slot | RTB_REDO_REFINE, slab lower bound, upper bound, -)
   unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence
   DevCounters* c;
 };
@@ -234,8 +242,8 @@ __device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint
 // re-traced by traverse_exact(): the same BVH, every candidate evaluated with the reference's literal f64 arithmetic
 // (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176; same operation order, no FMA contraction) on the
 // constructor's own f64 arguments, equal t going to the larger primitive id (hittable_list.rs:44-47).  That happens
-// for 0.03-0.3 % of the rays and runs in a separate small kernel (k_fixup), so the hot loop contains no call and no
-// f64.  On identical rays the device therefore returns the primitive id the reference's f64 linear scan returns.
+// for 0.01-0.2 % of the rays, in the prologue of the NEXT extend launch (fix_one(), out of line, one queue entry per
+// lane), so the hot loop contains no call and no f64 and the exact pass hides among the launch's other warps.  On identical rays the device therefore returns the primitive id the reference's f64 linear scan returns.
 struct Closest {
   float t;        // f32 distance of `ref` (closest_so_far, hittable_list.rs:42)
   float hi;       // upper bound of the exact distance of the closest hit (t + error bound): the traversal's t_max

@@ -18,6 +18,10 @@
 namespace rtb {
 
 // ---- helpers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ray_octant(float3 d) {
+  return (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
@@ -64,19 +68,96 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
 // a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
 // the one atomic per entry is uncontended in practice)
 __device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind, float lo, float hi) {
-  const uint32_t qi = atomicAdd(&pool.c->redo_count, 1u);
+  const uint32_t sel = pool.c->redo_sel;
+  const uint32_t qi = atomicAdd(&pool.c->redo_count[sel], 1u);
   RTB_CHECK(CHK_QUEUE, qi < pool.n && slot < pool.n);
-  pool.redo[qi] =
+  pool.cls[slot] = (uint8_t)CLS_WAIT;  // not shaded until the exact pass (next launch's prologue) has rewritten the hit
+  pool.redo[sel][qi] =
       make_uint4(slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u), __float_as_uint(lo), __float_as_uint(hi), 0u);
+}
+
+// ---- the exact pass (out of line: it must not cost the hot kernels a register) -----------------------------------------
+// One queue entry: FIX_RETRACE = the ray is traced again with traverse_exact() inside the slab the hot kernel handed
+// over; FIX_REFINE = the (certain) hit's distance is recomputed in f64.  The hit record is rewritten and the slot's class
+// becomes its shade queue | RTB_CLS_FIXED: the shade kernels of this iteration shade it, extend leaves it alone.
+// `dsc` is the scene struct in DEVICE memory (DevScene::self): passing the kernel parameter by reference would force the
+// compiler to copy the whole parameter block into every thread's local memory.
+__device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t slot,
+                                           float3 o, float3 d, Closest best);
+static __device__ __noinline__ void fix_one(const DevScene* __restrict__ dsc, float4* ray, float4* st, float4* hit, uint8_t* cls,
+                                            DevCounters* c, uint4 q, uint32_t seed, uint32_t opt) {
+  const DevScene& sc = *dsc;
+  DevPool pool;
+  pool.n = 0xFFFFFFFFu; pool.n_chunks = 0;
+  pool.ray = ray; pool.st = st; pool.hit = hit; pool.cls = cls;
+  pool.redo[0] = pool.redo[1] = nullptr; pool.cursor = nullptr; pool.c = c;
+  DevParams prm;
+  prm.seed = seed; prm.opt = opt;
+  const uint32_t slot = q.x & ~RTB_REDO_REFINE;
+  const float4 ro = ray[2 * slot], rd = ray[2 * slot + 1];
+  if (q.x & RTB_REDO_REFINE) {
+    const float4 h = hit[slot];
+    hit[slot].x = refine_hit(sc, __float_as_uint(h.y), xyz(ro), xyz(rd), ro.w, h.x);
+    cls[slot] = (uint8_t)(RTB_MINFO_QUEUE(__float_as_uint(h.z)) | RTB_CLS_FIXED);
+    atomicAdd(&c->refined, 1ull);
+  } else {
+    const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w, __uint_as_float(q.y), __uint_as_float(q.z));
+    finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+    cls[slot] |= (uint8_t)RTB_CLS_FIXED;
+  }
+  atomicAdd(&c->redone, 1ull);
+}
+
+// Prologue of every extend launch: the entries the PREVIOUS launch queued, one per lane, spread over all warps of the grid.
+// Returns how many entries this thread handled.
+__device__ __forceinline__ uint32_t fix_prologue(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t warp_in_grid,
+                                                 uint32_t n_warps_in_grid, uint32_t lane) {
+  const uint32_t prev = pool.c->redo_sel ^ 1u, n = pool.c->redo_count[prev];
+  uint32_t done = 0;
+  for (uint32_t i = warp_in_grid * 32u + lane; i < n; i += n_warps_in_grid * 32u) {
+    fix_one(sc.self, pool.ray, pool.st, pool.hit, pool.cls, pool.c, pool.redo[prev][i], prm.seed, prm.opt);
+    ++done;
+  }
+  return done;
+}
+
+// End of every extend launch: the last CTA to finish rotates the iteration counters (what a separate one-thread kernel did).
+// Must be reached by all threads of the CTA.
+__device__ __forceinline__ void rotate_counters(const DevPool& pool) {
+  DevCounters* c = pool.c;
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&c->ext_ticket, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t sel = c->redo_sel;
+    c->segments += c->iter_rays;
+    // anything extended, fixed or still waiting for its exact pass = the pool has not drained
+    c->last_rays = c->iter_rays + c->iter_fixed + c->redo_count[sel];
+    c->iter_rays = 0;
+    c->iter_fixed = 0;
+    c->ext_cursor = 0;
+    c->redo_count[sel ^ 1u] = 0;  // consumed by this launch's prologue
+    c->redo_sel = sel ^ 1u;
+    c->ext_ticket = 0;
+    c->iter += 1;
+  }
 }
 
 // ---- warp-local chunk lists -------------------------------------------------------------------------------------------
 // A warp owns RTB_CHUNK consecutive slots; lane l holds the class bytes of slots 8l..8l+7 (`cw`).  append_class() appends
 // the chunk-relative indices of the slots whose class is `key` to the warp's shared-memory list (ascending slot order)
 // and returns the new list length.  Must be executed by all 32 lanes.
-__device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t* list, uint32_t len, uint32_t lane) {
+// `mask`: 0x07 per byte = match on the class alone (the shade kernels); 0x47 = ... and not yet handled this iteration
+// (extend: a hit the exact pass just rewrote carries RTB_CLS_FIXED and must not be traced again before it is shaded).
+__device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t* list, uint32_t len, uint32_t lane,
+                                                 uint32_t mask = 0x07070707u) {
   // bytes equal to key -> 0xFF (SIMD-in-a-word compare), one bit per matching slot
-  const uint32_t e0 = __vcmpeq4(cw.x, key * 0x01010101u), e1 = __vcmpeq4(cw.y, key * 0x01010101u);
+  const uint32_t e0 = __vcmpeq4(cw.x & mask, key * 0x01010101u), e1 = __vcmpeq4(cw.y & mask, key * 0x01010101u);
   const uint32_t cnt = (__popc(e0) + __popc(e1)) >> 3;
   uint32_t incl = cnt;
 #pragma unroll
@@ -104,15 +185,57 @@ __device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t
 __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint32_t chunk, uint8_t* list, uint32_t lane) {
   const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + chunk * RTB_CHUNK + 8u * lane);
   uint32_t len = 0;
-  len = append_class(cw, CLS_NEW, list, len, lane);
-  len = append_class(cw, Q_TERMINAL, list, len, lane);
-  len = append_class(cw, Q_LAMBERT, list, len, lane);
-  len = append_class(cw, Q_METAL, list, len, lane);
-  len = append_class(cw, Q_DIELECTRIC, list, len, lane);
-  len = append_class(cw, Q_ISOTROPIC, list, len, lane);
+  len = append_class(cw, CLS_NEW, list, len, lane, 0x47474747u);
+  len = append_class(cw, Q_TERMINAL, list, len, lane, 0x47474747u);
+  len = append_class(cw, Q_LAMBERT, list, len, lane, 0x47474747u);
+  len = append_class(cw, Q_METAL, list, len, lane, 0x47474747u);
+  len = append_class(cw, Q_DIELECTRIC, list, len, lane, 0x47474747u);
+  len = append_class(cw, Q_ISOTROPIC, list, len, lane, 0x47474747u);
   __syncwarp();
   return len;
 }
+
+// The same list ordered by (ray kind, direction octant): a counting sort over 6 x 8 buckets in shared memory.  Rays of one
+// octant descend the tree in the same child order (slot ^ octant), so a warp's lanes visit the same nodes for longer and
+// their node / primitive fetches hit the same cache lines (bounce rays of one chunk start from neighbouring surfaces but
+// scatter in all directions).  `cnt` = 64 per-warp counters.
+__device__ __forceinline__ uint32_t build_extend_list_sorted(const DevPool& pool, uint32_t chunk, uint8_t* list, uint32_t* cnt, uint32_t lane) {
+  const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + chunk * RTB_CHUNK + 8u * lane);
+  cnt[lane] = 0u;
+  cnt[lane + 32u] = 0u;
+  __syncwarp();
+  uint32_t key[8], rank[8];
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j) {
+    const uint32_t b = ((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, cls = b & 7u;
+    // kind rank: restarted camera rays first (coherent), then the bounce kinds; dead slots are skipped
+    key[j] = (cls == CLS_DEAD || cls == CLS_WAIT || (b & RTB_CLS_FIXED)) ? 64u : ((cls == CLS_NEW ? 0u : cls + 1u) << 3) | ((b >> 3) & 7u);
+    rank[j] = key[j] < 64u ? atomicAdd(&cnt[key[j]], 1u) : 0u;
+  }
+  __syncwarp();
+  // exclusive scan of the 48 bucket counts (lane l: buckets l and 32 + l)
+  const uint32_t v0 = cnt[lane], v1 = lane < 16u ? cnt[32u + lane] : 0u;
+  uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+  for (uint32_t d = 1; d < 32; d <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, i0, d), b2 = __shfl_up_sync(0xffffffffu, i1, d);
+    if (lane >= d) { i0 += a; i1 += b2; }
+  }
+  const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31), total = t0 + __shfl_sync(0xffffffffu, i1, 15);
+  __syncwarp();
+  cnt[lane] = i0 - v0;
+  if (lane < 16u) cnt[32u + lane] = t0 + i1 - v1;
+  __syncwarp();
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j)
+    if (key[j] < 64u) {
+      RTB_CHECK(CHK_LIST, cnt[key[j]] + rank[j] < RTB_CHUNK);
+      list[cnt[key[j]] + rank[j]] = (uint8_t)(8u * lane + j);
+    }
+  __syncwarp();
+  return total;
+}
+#define RTB_OPT_OCTANT_SORT 2u  /* DevParams::opt bit: order each chunk's rays by (kind, octant) */
 
 // ---- extend ------------------------------------------------------------------------------------------------------
 // Dynamic-fetch variant (deep trees).  Persistent warps: every lane owns one in-flight ray and advances it by ONE node
@@ -143,12 +266,14 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   __shared__ ExtOut s_out[RTB_EXTEND_WARPS][32];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
+  __shared__ uint32_t s_cnt[RTB_EXTEND_WARPS][64];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const bool octant_sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;
   const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
   uint4* park = &s_park[warp][lane];
   uint32_t parked_mask = 0;  // warp-uniform: lanes with parked leaf primitives
@@ -168,6 +293,11 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   // idle lanes are refilled when at least this many wait (or nobody runs): a swap costs the whole warp ~40 issue slots
   // however few lanes take part (C4 ext_ms: 1 -> 21.6, 4 -> 21.2, 8 -> 21.1, 16 -> 21.7; profiles/r2_ab.md §7)
   const uint32_t refill_min = 8u;
+  {
+    const uint32_t fixed = fix_prologue(sc, pool, prm, blockIdx.x * RTB_EXTEND_WARPS + warp, gridDim.x * RTB_EXTEND_WARPS, lane);
+    if (fixed) atomicAdd(&c->iter_fixed, fixed);
+    __syncwarp();
+  }
 
   auto flush = [&]() {  // executed by the whole warp
     __syncwarp();
@@ -199,7 +329,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
             break;
           }
           chunk_base = ch * RTB_CHUNK;
-          list_len = build_extend_list(pool, ch, list, lane);
+          list_len = octant_sort ? build_extend_list_sorted(pool, ch, list, s_cnt[warp], lane) : build_extend_list(pool, ch, list, lane);
           list_pos = 0;
           n_rays += list_len;
           if (list_len == 0) continue;
@@ -289,6 +419,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
+  rotate_counters(pool);
 }
 
 // One ray per thread to completion (small trees: all lanes start at the root together, so root-level work stays
@@ -301,20 +432,27 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
+  __shared__ uint32_t s_cnt[RTB_EXTEND_WARPS][64];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool octant_sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;
   uint8_t* list = s_list[warp];
   const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
   uint4* park = &s_park[warp][lane];
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
   uint32_t n_rays = 0, nv = 0;
   TestCount nt{};
+  {
+    const uint32_t fixed = fix_prologue(sc, pool, prm, blockIdx.x * RTB_EXTEND_WARPS + warp, n_warps, lane);
+    if (fixed) atomicAdd(&c->iter_fixed, fixed);
+    __syncwarp();
+  }
   for (uint32_t chunk = blockIdx.x * RTB_EXTEND_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
     const uint32_t base = chunk * RTB_CHUNK;
-    const uint32_t total = build_extend_list(pool, chunk, list, lane);
+    const uint32_t total = octant_sort ? build_extend_list_sorted(pool, chunk, list, s_cnt[warp], lane) : build_extend_list(pool, chunk, list, lane);
     n_rays += total;
     for (uint32_t r = 0; r < total; r += 32) {
       if (r + 32 + lane < total) prefetch_l1(pool.ray + 2 * (size_t)(base + list[r + 32 + lane]));
@@ -378,6 +516,7 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
+  rotate_counters(pool);
 }
 
 // ---- surface reconstruction in the shade kernels -------------------------------------------------------------------
@@ -619,6 +758,8 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
     else io.beta = rcp_fast(qv) * io.beta;
   }
   if (alive) {
+    // the slot keeps its class; bits 3-5 carry the new ray's direction octant for extend's ordering
+    pool.cls[io.slot] = (uint8_t)(RTB_MINFO_QUEUE(io.minfo) | ray_octant(nd) << 3);
     pool.ray[2 * io.slot] = make_float4(no.x, no.y, no.z, ntime);
     pool.ray[2 * io.slot + 1] = make_float4(nd.x, nd.y, nd.z, 0.f);
     pool.st[2 * io.slot] = make_float4(io.beta.x, io.beta.y, io.beta.z, __uint_as_float(io.pixel));
@@ -666,6 +807,7 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
   float3 o, d;
   float time;
   camera_ray(cam, prm, pixel, sample, o, d, time);
+  pool.cls[slot] = (uint8_t)(CLS_NEW | ray_octant(d) << 3);
   pool.ray[2 * slot] = make_float4(o.x, o.y, o.z, time);
   pool.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, 0.f);
   pool.st[2 * slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
@@ -842,7 +984,6 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, De
       const unsigned long long path = chunk_path(m, chunk, pool.n_chunks);
       if (path < total) {
         start_path(pool, prm, cam, base + m, path);
-        pool.cls[base + m] = (uint8_t)CLS_NEW;
       }
     }
     if (lane == 0) pool.cursor[chunk] = cnt;
@@ -858,7 +999,9 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
     c->iter_rays = c->last_rays = 0;
     c->iter = 0;
     c->ext_cursor = 0;
-    c->redo_count = c->fix_ticket = 0;
+    c->redo_count[0] = c->redo_count[1] = 0;
+    c->redo_sel = 0;
+    c->iter_fixed = c->ext_ticket = 0;
     c->redone = c->refined = 0;
     c->total_paths = total_paths;
     c->segments = c->rejected = 0;
@@ -867,49 +1010,32 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
   }
 }
 
-// ---- the exact pass + iteration bookkeeping (runs after extend, before the shade kernels) ---------------------------
-// Every ray `extend` queued (its closest hit was undecidable in f32) is re-traced with traverse_exact() and its hit
-// record rewritten; the last CTA to finish then rotates the iteration counters (what a one-thread kernel did before).
+// ---- stand-alone exact pass: the parity probes (one extend launch, no further iteration) ------------------------------
+// Processes the queue the last extend launch filled (what the next launch's prologue would do) and empties it.
 #define RTB_FIXUP_THREADS 128
 __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPool pool, DevParams prm) {
   DevCounters* c = pool.c;
-  const uint32_t n = c->redo_count;
-  uint32_t n_refined = 0;
-  for (uint32_t i = blockIdx.x * RTB_FIXUP_THREADS + threadIdx.x; i < n; i += gridDim.x * RTB_FIXUP_THREADS) {
-    const uint4 q = pool.redo[i];
-    const uint32_t entry = q.x, slot = entry & ~RTB_REDO_REFINE;
-    RTB_CHECK(CHK_SLOT, slot < pool.n);
-    const float4 ro = pool.ray[2 * slot], rd = pool.ray[2 * slot + 1];
-    if (entry & RTB_REDO_REFINE) {  // certain hit, coarse distance: one f64 evaluation of that primitive
-      const float4 h = pool.hit[slot];
-      pool.hit[slot].x = refine_hit(sc, __float_as_uint(h.y), xyz(ro), xyz(rd), ro.w, h.x);
-      ++n_refined;
-    } else {
-      const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w, __uint_as_float(q.y), __uint_as_float(q.z));
-      finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-    }
-  }
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = RTB_FIXUP_THREADS / 32u;
+  fix_prologue(sc, pool, prm, blockIdx.x * warps + (threadIdx.x >> 5), gridDim.x * warps, lane);
   __shared__ bool last;
-  if (n) {
-    n_refined = __reduce_add_sync(0xffffffffu, n_refined);
-    if ((threadIdx.x & 31u) == 0 && n_refined) atomicAdd(&c->refined, (unsigned long long)n_refined);
-  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    last = atomicAdd(&c->fix_ticket, 1u) == gridDim.x - 1u;
+    last = atomicAdd(&c->ext_ticket, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
-    c->segments += c->iter_rays;
-    c->redone += n;  // (retraces + refinements; the retraces are redone - refined)
-    c->last_rays = c->iter_rays;
-    c->iter_rays = 0;
-    c->ext_cursor = 0;
-    c->redo_count = 0;
-    c->fix_ticket = 0;
-    c->iter += 1;
+    c->redo_count[c->redo_sel ^ 1u] = 0;
+    c->ext_ticket = 0;
   }
+}
+
+// the very first "iteration" of a render has no extend launch yet: only the counters rotate
+__global__ void k_rotate(DevPool pool) {
+  DevCounters* c = pool.c;
+  c->last_rays = 1;  // paths were just started
+  c->iter += 1;
 }
 
 // ---- write_color, main.rs:141-169 ----------------------------------------------------------------------------------
@@ -1097,6 +1223,7 @@ void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& 
 void launch_fixup(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st) {
   k_fixup<<<lc.fixup_grid, RTB_FIXUP_THREADS, 0, st>>>(sc, pool, prm);
 }
+void launch_rotate(const DevPool& pool, cudaStream_t st) { k_rotate<<<1, 1, 0, st>>>(pool); }
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st) {
   // one-ray-per-thread wins on small trees (all lanes start at the root together); dynamic fetch wins on deep trees

@@ -43,6 +43,7 @@ int read_check_failures(unsigned int* out8);  // RTB_CHECKED build: failed bound
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);
 void launch_fixup(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, cudaStream_t st);
+void launch_rotate(const DevPool& pool, cudaStream_t st);
 void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm, bool count,
                    cudaStream_t st);
 void launch_shade(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool, const DevParams& prm,
