@@ -960,8 +960,9 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
           if ((e = cudaEventRecord(c->ext_events[ev_used + 1], ls)) != cudaSuccess) return e;
           ev_used += 2;
         }
+        launch_fixup(s->lc, s->dev, run[k].pool, run[k].prm, ls);  // exact pass over the rays this launch queued
         launch_shade(s->lc, s->dev, run[k].pool, run[k].prm, dcam, present, ls);
-        launches += 1 + n_shade;
+        launches += 2 + n_shade;
         extend_launches += 1;
       }
     }

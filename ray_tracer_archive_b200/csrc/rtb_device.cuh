@@ -123,11 +123,9 @@ struct DevCounters {
 // 32-path blocks, so no kernel issues a contended global atomic (the queue-compacting version spent 77 % of
 // k_shade_terminal's stall samples on two same-address atomics per warp, profiles/r2_ab.md §3).
 #define RTB_CHUNK 256u
-// 0..4 = Queue of the slot's current hit; CLS_WAIT: the hit is queued for the exact pass (not shaded this iteration).
-// Class byte: bits 0-2 class, bits 3-5 direction octant of the slot's ray (written by the shade kernels), bit 6: the hit
-// was (re)written by the exact pass of THIS iteration — the shade kernels shade it, extend's list building skips it.
-enum SlotClass : uint32_t { CLS_WAIT = 5, CLS_NEW = 6, CLS_DEAD = 7 };
-#define RTB_CLS_FIXED 0x40u
+// 0..4 = Queue of the slot's current hit.  Class byte: bits 0-2 class; bits 3-5 direction octant of the slot's ray (written
+// by the shade kernels when octant ordering is on).
+enum SlotClass : uint32_t { CLS_NEW = 6, CLS_DEAD = 7 };
 struct DevPool {
   uint32_t n;         // slots
   uint32_t n_chunks;  // ceil(n / RTB_CHUNK)
@@ -242,8 +240,8 @@ __device__ __forceinline__ float4 philox_u(uint32_t pixel, uint32_t sample, uint
 // re-traced by traverse_exact(): the same BVH, every candidate evaluated with the reference's literal f64 arithmetic
 // (sphere.rs:41-65, aarect.rs:31-48, hittable.rs:76-85,147-176; same operation order, no FMA contraction) on the
 // constructor's own f64 arguments, equal t going to the larger primitive id (hittable_list.rs:44-47).  That happens
-// for 0.01-0.2 % of the rays, in the prologue of the NEXT extend launch (fix_one(), out of line, one queue entry per
-// lane), so the hot loop contains no call and no f64 and the exact pass hides among the launch's other warps.  On identical rays the device therefore returns the primitive id the reference's f64 linear scan returns.
+// for 0.01-0.2 % of the rays, in a small kernel of its own between extend and shade (k_fixup -> fix_one(), one queue entry
+// per thread), so the hot loop contains no call and no f64.  On identical rays the device therefore returns the primitive id the reference's f64 linear scan returns.
 struct Closest {
   float t;        // f32 distance of `ref` (closest_so_far, hittable_list.rs:42)
   float hi;       // upper bound of the exact distance of the closest hit (t + error bound): the traversal's t_max

@@ -71,21 +71,20 @@ __device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, ui
   const uint32_t sel = pool.c->redo_sel;
   const uint32_t qi = atomicAdd(&pool.c->redo_count[sel], 1u);
   RTB_CHECK(CHK_QUEUE, qi < pool.n && slot < pool.n);
-  pool.cls[slot] = (uint8_t)CLS_WAIT;  // not shaded until the exact pass (next launch's prologue) has rewritten the hit
   pool.redo[sel][qi] =
       make_uint4(slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u), __float_as_uint(lo), __float_as_uint(hi), 0u);
 }
 
 // ---- the exact pass (out of line: it must not cost the hot kernels a register) -----------------------------------------
 // One queue entry: FIX_RETRACE = the ray is traced again with traverse_exact() inside the slab the hot kernel handed
-// over; FIX_REFINE = the (certain) hit's distance is recomputed in f64.  The hit record is rewritten and the slot's class
-// becomes its shade queue | RTB_CLS_FIXED: the shade kernels of this iteration shade it, extend leaves it alone.
+// over; FIX_REFINE = the (certain) hit's distance is recomputed in f64 (returns 1).  The hit record and the slot's class
+// are rewritten before the shade kernels of the iteration run.
 // `dsc` is the scene struct in DEVICE memory (DevScene::self): passing the kernel parameter by reference would force the
 // compiler to copy the whole parameter block into every thread's local memory.
 __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t slot,
                                            float3 o, float3 d, Closest best);
-static __device__ __noinline__ void fix_one(const DevScene* __restrict__ dsc, float4* ray, float4* st, float4* hit, uint8_t* cls,
-                                            DevCounters* c, uint4 q, uint32_t seed, uint32_t opt) {
+static __device__ __noinline__ uint32_t fix_one(const DevScene* __restrict__ dsc, float4* ray, float4* st, float4* hit, uint8_t* cls,
+                                                DevCounters* c, uint4 q, uint32_t seed, uint32_t opt) {
   const DevScene& sc = *dsc;
   DevPool pool;
   pool.n = 0xFFFFFFFFu; pool.n_chunks = 0;
@@ -98,25 +97,25 @@ static __device__ __noinline__ void fix_one(const DevScene* __restrict__ dsc, fl
   if (q.x & RTB_REDO_REFINE) {
     const float4 h = hit[slot];
     hit[slot].x = refine_hit(sc, __float_as_uint(h.y), xyz(ro), xyz(rd), ro.w, h.x);
-    cls[slot] = (uint8_t)(RTB_MINFO_QUEUE(__float_as_uint(h.z)) | RTB_CLS_FIXED);
-    atomicAdd(&c->refined, 1ull);
-  } else {
-    const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w, __uint_as_float(q.y), __uint_as_float(q.z));
-    finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-    cls[slot] |= (uint8_t)RTB_CLS_FIXED;
+    return 1u;
   }
-  atomicAdd(&c->redone, 1ull);
+  const Closest best = traverse_exact(sc, xyz(ro), xyz(rd), ro.w, __uint_as_float(q.y), __uint_as_float(q.z));
+  finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+  return 0u;
 }
 
-// Prologue of every extend launch: the entries the PREVIOUS launch queued, one per lane, spread over all warps of the grid.
-// Returns how many entries this thread handled.
-__device__ __forceinline__ uint32_t fix_prologue(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t warp_in_grid,
-                                                 uint32_t n_warps_in_grid, uint32_t lane) {
+// The entries the last extend launch queued (after its counter rotation they sit in redo[redo_sel ^ 1]), one per lane, spread
+// over all warps of the grid.  Returns (entries handled, of which refinements) of this thread.
+// (Measured and not kept: running this as the PROLOGUE of the next extend launch instead of its own kernel — the queued
+// hits are then shaded one iteration late (C1 217 -> 257 iterations) and a 20 us single-lane exact trace stalls a warp
+// whose chunks are statically assigned: C1 7997 -> 7390, C3 3711 -> 3438 Mrays/s, profiles/r3_ab.md.)
+__device__ __forceinline__ uint2 fix_prologue(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t warp_in_grid,
+                                              uint32_t n_warps_in_grid, uint32_t lane) {
   const uint32_t prev = pool.c->redo_sel ^ 1u, n = pool.c->redo_count[prev];
-  uint32_t done = 0;
+  uint2 done = make_uint2(0u, 0u);
   for (uint32_t i = warp_in_grid * 32u + lane; i < n; i += n_warps_in_grid * 32u) {
-    fix_one(sc.self, pool.ray, pool.st, pool.hit, pool.cls, pool.c, pool.redo[prev][i], prm.seed, prm.opt);
-    ++done;
+    done.y += fix_one(sc.self, pool.ray, pool.st, pool.hit, pool.cls, pool.c, pool.redo[prev][i], prm.seed, prm.opt);
+    ++done.x;
   }
   return done;
 }
@@ -152,12 +151,10 @@ __device__ __forceinline__ void rotate_counters(const DevPool& pool) {
 // A warp owns RTB_CHUNK consecutive slots; lane l holds the class bytes of slots 8l..8l+7 (`cw`).  append_class() appends
 // the chunk-relative indices of the slots whose class is `key` to the warp's shared-memory list (ascending slot order)
 // and returns the new list length.  Must be executed by all 32 lanes.
-// `mask`: 0x07 per byte = match on the class alone (the shade kernels); 0x47 = ... and not yet handled this iteration
-// (extend: a hit the exact pass just rewrote carries RTB_CLS_FIXED and must not be traced again before it is shaded).
-__device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t* list, uint32_t len, uint32_t lane,
-                                                 uint32_t mask = 0x07070707u) {
+__device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t* list, uint32_t len, uint32_t lane) {
   // bytes equal to key -> 0xFF (SIMD-in-a-word compare), one bit per matching slot
-  const uint32_t e0 = __vcmpeq4(cw.x & mask, key * 0x01010101u), e1 = __vcmpeq4(cw.y & mask, key * 0x01010101u);
+  // (bits 0-2 of a class byte = the class; bits 3-5 = the direction octant of the slot's ray when octant ordering is on)
+  const uint32_t e0 = __vcmpeq4(cw.x & 0x07070707u, key * 0x01010101u), e1 = __vcmpeq4(cw.y & 0x07070707u, key * 0x01010101u);
   const uint32_t cnt = (__popc(e0) + __popc(e1)) >> 3;
   uint32_t incl = cnt;
 #pragma unroll
@@ -185,12 +182,12 @@ __device__ __forceinline__ uint32_t append_class(uint2 cw, uint32_t key, uint8_t
 __device__ __forceinline__ uint32_t build_extend_list(const DevPool& pool, uint32_t chunk, uint8_t* list, uint32_t lane) {
   const uint2 cw = *reinterpret_cast<const uint2*>(pool.cls + chunk * RTB_CHUNK + 8u * lane);
   uint32_t len = 0;
-  len = append_class(cw, CLS_NEW, list, len, lane, 0x47474747u);
-  len = append_class(cw, Q_TERMINAL, list, len, lane, 0x47474747u);
-  len = append_class(cw, Q_LAMBERT, list, len, lane, 0x47474747u);
-  len = append_class(cw, Q_METAL, list, len, lane, 0x47474747u);
-  len = append_class(cw, Q_DIELECTRIC, list, len, lane, 0x47474747u);
-  len = append_class(cw, Q_ISOTROPIC, list, len, lane, 0x47474747u);
+  len = append_class(cw, CLS_NEW, list, len, lane);
+  len = append_class(cw, Q_TERMINAL, list, len, lane);
+  len = append_class(cw, Q_LAMBERT, list, len, lane);
+  len = append_class(cw, Q_METAL, list, len, lane);
+  len = append_class(cw, Q_DIELECTRIC, list, len, lane);
+  len = append_class(cw, Q_ISOTROPIC, list, len, lane);
   __syncwarp();
   return len;
 }
@@ -209,7 +206,7 @@ __device__ __forceinline__ uint32_t build_extend_list_sorted(const DevPool& pool
   for (uint32_t j = 0; j < 8; ++j) {
     const uint32_t b = ((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xFFu, cls = b & 7u;
     // kind rank: restarted camera rays first (coherent), then the bounce kinds; dead slots are skipped
-    key[j] = (cls == CLS_DEAD || cls == CLS_WAIT || (b & RTB_CLS_FIXED)) ? 64u : ((cls == CLS_NEW ? 0u : cls + 1u) << 3) | ((b >> 3) & 7u);
+    key[j] = cls == CLS_DEAD ? 64u : ((cls == CLS_NEW ? 0u : cls + 1u) << 3) | ((b >> 3) & 7u);
     rank[j] = key[j] < 64u ? atomicAdd(&cnt[key[j]], 1u) : 0u;
   }
   __syncwarp();
@@ -235,7 +232,6 @@ __device__ __forceinline__ uint32_t build_extend_list_sorted(const DevPool& pool
   __syncwarp();
   return total;
 }
-#define RTB_OPT_OCTANT_SORT 2u  /* DevParams::opt bit: order each chunk's rays by (kind, octant) */
 
 // ---- extend ------------------------------------------------------------------------------------------------------
 // Dynamic-fetch variant (deep trees).  Persistent warps: every lane owns one in-flight ray and advances it by ONE node
@@ -293,12 +289,6 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   // idle lanes are refilled when at least this many wait (or nobody runs): a swap costs the whole warp ~40 issue slots
   // however few lanes take part (C4 ext_ms: 1 -> 21.6, 4 -> 21.2, 8 -> 21.1, 16 -> 21.7; profiles/r2_ab.md §7)
   const uint32_t refill_min = 8u;
-  {
-    const uint32_t fixed = fix_prologue(sc, pool, prm, blockIdx.x * RTB_EXTEND_WARPS + warp, gridDim.x * RTB_EXTEND_WARPS, lane);
-    if (fixed) atomicAdd(&c->iter_fixed, fixed);
-    __syncwarp();
-  }
-
   auto flush = [&]() {  // executed by the whole warp
     __syncwarp();
     if (lane < out_count) {
@@ -445,11 +435,6 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
   uint32_t n_rays = 0, nv = 0;
   TestCount nt{};
-  {
-    const uint32_t fixed = fix_prologue(sc, pool, prm, blockIdx.x * RTB_EXTEND_WARPS + warp, n_warps, lane);
-    if (fixed) atomicAdd(&c->iter_fixed, fixed);
-    __syncwarp();
-  }
   for (uint32_t chunk = blockIdx.x * RTB_EXTEND_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
     const uint32_t base = chunk * RTB_CHUNK;
     const uint32_t total = octant_sort ? build_extend_list_sorted(pool, chunk, list, s_cnt[warp], lane) : build_extend_list(pool, chunk, list, lane);
@@ -758,8 +743,8 @@ __device__ __forceinline__ bool finish_bounce(const DevPool& pool, const DevPara
     else io.beta = rcp_fast(qv) * io.beta;
   }
   if (alive) {
-    // the slot keeps its class; bits 3-5 carry the new ray's direction octant for extend's ordering
-    pool.cls[io.slot] = (uint8_t)(RTB_MINFO_QUEUE(io.minfo) | ray_octant(nd) << 3);
+    // the slot keeps its class; with octant ordering on, bits 3-5 carry the new ray's direction octant for extend
+    if (prm.opt & RTB_OPT_OCTANT_SORT) pool.cls[io.slot] = (uint8_t)(RTB_MINFO_QUEUE(io.minfo) | ray_octant(nd) << 3);
     pool.ray[2 * io.slot] = make_float4(no.x, no.y, no.z, ntime);
     pool.ray[2 * io.slot + 1] = make_float4(nd.x, nd.y, nd.z, 0.f);
     pool.st[2 * io.slot] = make_float4(io.beta.x, io.beta.y, io.beta.z, __uint_as_float(io.pixel));
@@ -807,7 +792,7 @@ __device__ __forceinline__ void start_path(const DevPool& pool, const DevParams&
   float3 o, d;
   float time;
   camera_ray(cam, prm, pixel, sample, o, d, time);
-  pool.cls[slot] = (uint8_t)(CLS_NEW | ray_octant(d) << 3);
+  if (prm.opt & RTB_OPT_OCTANT_SORT) pool.cls[slot] = (uint8_t)(CLS_NEW | ray_octant(d) << 3);
   pool.ray[2 * slot] = make_float4(o.x, o.y, o.z, time);
   pool.ray[2 * slot + 1] = make_float4(d.x, d.y, d.z, 0.f);
   pool.st[2 * slot] = make_float4(1.f, 1.f, 1.f, __uint_as_float(pixel));
@@ -984,6 +969,7 @@ __global__ void __launch_bounds__(RTB_SHADE_THREADS) k_generate(DevPool pool, De
       const unsigned long long path = chunk_path(m, chunk, pool.n_chunks);
       if (path < total) {
         start_path(pool, prm, cam, base + m, path);
+        if (!(prm.opt & RTB_OPT_OCTANT_SORT)) pool.cls[base + m] = (uint8_t)CLS_NEW;
       }
     }
     if (lane == 0) pool.cursor[chunk] = cnt;
@@ -1010,14 +996,23 @@ __global__ void k_init_pool(DevPool pool, unsigned long long total_paths) {
   }
 }
 
-// ---- stand-alone exact pass: the parity probes (one extend launch, no further iteration) ------------------------------
-// Processes the queue the last extend launch filled (what the next launch's prologue would do) and empties it.
+// ---- the exact pass: runs right after every extend launch, before the shade kernels (and after the probes' single launch) ---
+// Processes the queue that launch filled and empties it.  On its own stream position it overlaps the extend / shade kernels
+// of the other wavefront lanes; what it costs is latency on this lane only (one queue entry = one thread).
 #define RTB_FIXUP_THREADS 128
 __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPool pool, DevParams prm) {
   DevCounters* c = pool.c;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = RTB_FIXUP_THREADS / 32u;
-  fix_prologue(sc, pool, prm, blockIdx.x * warps + (threadIdx.x >> 5), gridDim.x * warps, lane);
+  uint2 done = fix_prologue(sc, pool, prm, blockIdx.x * warps + (threadIdx.x >> 5), gridDim.x * warps, lane);
+  if (c->redo_count[c->redo_sel ^ 1u]) {  // (uniform) one pair of atomics per warp, not per entry
+    done.x = __reduce_add_sync(0xffffffffu, done.x);
+    done.y = __reduce_add_sync(0xffffffffu, done.y);
+    if (lane == 0 && done.x) {
+      atomicAdd(&c->redone, (unsigned long long)done.x);
+      if (done.y) atomicAdd(&c->refined, (unsigned long long)done.y);
+    }
+  }
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {

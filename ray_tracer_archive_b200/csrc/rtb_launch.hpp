@@ -14,6 +14,7 @@
 #define RTB_OPT_PROBE 1u  /* DevParams::opt bit: parity probe (media sampled at xi = 0.5 instead of the path's stream) */
 /* DevParams::opt bits 8-13: leaf-test parking threshold of the extend kernels (lanes that must have parked primitives before
    the warp drains them together); 0 = test leaves inline at the node visit */
+#define RTB_OPT_OCTANT_SORT 2u  /* DevParams::opt bit: extend orders each chunk's rays by (kind, direction octant) */
 #define RTB_OPT_PARK_SHIFT 8
 #define RTB_OPT_PARK_MASK 63u
 
