@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the workload's spp is SPLIT across the ranks (BASELINE config C5) instead of "
                          "rendered by every rank (weak, default)")
-    ap.add_argument("--strong-spp", type=int, default=512,
+    ap.add_argument("--strong-spp", type=int, default=2048,
                     help="total spp of the C5 strong-scaling sub-record (split across the ranks); 0 = skip it")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -821,7 +821,7 @@ static int ensure_pool(Lane& c, uint32_t n) {
   CU(c.ray.resize((size_t)n * 2)); CU(c.st.resize((size_t)n * 2)); CU(c.hit.resize(n));
   const size_t chunks = ((size_t)n + RTB_CHUNK - 1) / RTB_CHUNK;
   CU(c.cls.resize(chunks * RTB_CHUNK)); CU(c.cursor.resize(chunks));
-  CU(c.redo[0].resize(n)); CU(c.redo[1].resize(n));
+  CU(c.redo[0].resize(n));
   c.pool_n = n;
   return RTB_OK;
 }

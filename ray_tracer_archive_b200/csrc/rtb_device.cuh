@@ -102,11 +102,9 @@ struct DevCounters {
   uint32_t last_rays;   // ... in the previous iteration: 0 = the pool has drained (host check)
   uint32_t iter;
   uint32_t ext_cursor;  // next unclaimed slot batch (dynamic ray fetch)
-  uint32_t redo_count[2];  // fix-up queue lengths: [redo_sel] is being filled by this extend launch, [redo_sel ^ 1] was
-                           // filled by the previous one and is consumed by this launch's prologue
-  uint32_t redo_sel;
-  uint32_t iter_fixed;  // queue entries the current launch's prologue processed (they were shaded one iteration late)
-  uint32_t ext_ticket;  // CTAs of the extend launch that have finished (the last one rotates the counters)
+  uint32_t redo_count[2];  // [0]: length of the fix-up queue this extend launch fills and k_fixup then empties
+  uint32_t redo_sel, iter_fixed;  // (spare)
+  uint32_t ext_ticket;  // CTAs of k_fixup that have finished (the last one rotates the counters)
   unsigned long long redone;  // total rays re-traced exactly
   unsigned long long refined; // total hits whose distance was recomputed in f64
   unsigned long long total_paths;
@@ -133,7 +131,7 @@ struct DevPool {
   float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
   float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
   uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
-  uint4* redo[2];     // [n] each: rays for the exact pass, (slot | RTB_REDO_REFINE, slab lower bound, upper bound, -)
+  uint4* redo[2];     // [0]: [n] rays for the exact pass, (slot | RTB_REDO_REFINE, slab lower bound, upper bound, -)
   unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence
   DevCounters* c;
 };

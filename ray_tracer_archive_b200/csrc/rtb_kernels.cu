@@ -68,10 +68,9 @@ __device__ __forceinline__ void finish_ray(const DevScene& sc, const DevPool& po
 // a ray whose closest hit the f32 tests could not decide: queued for the exact pass (rare: 0.03-0.3 % of the rays, so
 // the one atomic per entry is uncontended in practice)
 __device__ __forceinline__ void queue_fix(const DevPool& pool, uint32_t slot, uint32_t kind, float lo, float hi) {
-  const uint32_t sel = pool.c->redo_sel;
-  const uint32_t qi = atomicAdd(&pool.c->redo_count[sel], 1u);
+  const uint32_t qi = atomicAdd(&pool.c->redo_count[0], 1u);
   RTB_CHECK(CHK_QUEUE, qi < pool.n && slot < pool.n);
-  pool.redo[sel][qi] =
+  pool.redo[0][qi] =
       make_uint4(slot | (kind == FIX_REFINE ? RTB_REDO_REFINE : 0u), __float_as_uint(lo), __float_as_uint(hi), 0u);
 }
 
@@ -104,47 +103,20 @@ static __device__ __noinline__ uint32_t fix_one(const DevScene* __restrict__ dsc
   return 0u;
 }
 
-// The entries the last extend launch queued (after its counter rotation they sit in redo[redo_sel ^ 1]), one per lane, spread
-// over all warps of the grid.  Returns (entries handled, of which refinements) of this thread.
+// The entries the last extend launch queued, one per lane, spread over all warps of the grid.  Returns (entries handled, of
+// which refinements) of this thread.
 // (Measured and not kept: running this as the PROLOGUE of the next extend launch instead of its own kernel — the queued
 // hits are then shaded one iteration late (C1 217 -> 257 iterations) and a 20 us single-lane exact trace stalls a warp
 // whose chunks are statically assigned: C1 7997 -> 7390, C3 3711 -> 3438 Mrays/s, profiles/r3_ab.md.)
 __device__ __forceinline__ uint2 fix_prologue(const DevScene& sc, const DevPool& pool, const DevParams& prm, uint32_t warp_in_grid,
                                               uint32_t n_warps_in_grid, uint32_t lane) {
-  const uint32_t prev = pool.c->redo_sel ^ 1u, n = pool.c->redo_count[prev];
+  const uint32_t n = pool.c->redo_count[0];
   uint2 done = make_uint2(0u, 0u);
   for (uint32_t i = warp_in_grid * 32u + lane; i < n; i += n_warps_in_grid * 32u) {
-    done.y += fix_one(sc.self, pool.ray, pool.st, pool.hit, pool.cls, pool.c, pool.redo[prev][i], prm.seed, prm.opt);
+    done.y += fix_one(sc.self, pool.ray, pool.st, pool.hit, pool.cls, pool.c, pool.redo[0][i], prm.seed, prm.opt);
     ++done.x;
   }
   return done;
-}
-
-// End of every extend launch: the last CTA to finish rotates the iteration counters (what a separate one-thread kernel did).
-// Must be reached by all threads of the CTA.
-__device__ __forceinline__ void rotate_counters(const DevPool& pool) {
-  DevCounters* c = pool.c;
-  __shared__ bool s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = atomicAdd(&c->ext_ticket, 1u) == gridDim.x - 1u;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t sel = c->redo_sel;
-    c->segments += c->iter_rays;
-    // anything extended, fixed or still waiting for its exact pass = the pool has not drained
-    c->last_rays = c->iter_rays + c->iter_fixed + c->redo_count[sel];
-    c->iter_rays = 0;
-    c->iter_fixed = 0;
-    c->ext_cursor = 0;
-    c->redo_count[sel ^ 1u] = 0;  // consumed by this launch's prologue
-    c->redo_sel = sel ^ 1u;
-    c->ext_ticket = 0;
-    c->iter += 1;
-  }
 }
 
 // ---- warp-local chunk lists -------------------------------------------------------------------------------------------
@@ -254,6 +226,8 @@ struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, gro
 struct ExtOut { float t; uint32_t ref, slot, redo; float lo, hi; uint32_t _pad[2]; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
 
+// Leaf primitives are always PARKED here (drain_parked; threshold = DevParams::opt bits 8-13, default 14 lanes): testing
+// them at the node visit instead costs 7 % on the 1 M-triangle mesh (profiles/r3_ab.md §2).
 template <bool COUNT>
 __global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
@@ -262,15 +236,13 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   __shared__ ExtOut s_out[RTB_EXTEND_WARPS][32];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
   __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
-  __shared__ uint32_t s_cnt[RTB_EXTEND_WARPS][64];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const bool octant_sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;
-  const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
+  const uint32_t park_min = max(1u, (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK);  // lanes that must wait before a drain
   uint4* park = &s_park[warp][lane];
   uint32_t parked_mask = 0;  // warp-uniform: lanes with parked leaf primitives
   ExtIn* in = s_in[warp];
@@ -319,7 +291,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
             break;
           }
           chunk_base = ch * RTB_CHUNK;
-          list_len = octant_sort ? build_extend_list_sorted(pool, ch, list, s_cnt[warp], lane) : build_extend_list(pool, ch, list, lane);
+          list_len = build_extend_list(pool, ch, list, lane);
           list_pos = 0;
           n_rays += list_len;
           if (list_len == 0) continue;
@@ -371,9 +343,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
     // ---- one node visit (or pop) per running lane -------------------------------------------------------------------
     bool finished = false;
-    if (park_min == 0u) {
-      if (!((idle >> lane) & 1u)) finished = !trav_step_fast<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, nt);
-    } else {
+    {
       bool parked = (parked_mask >> lane) & 1u;
       if (!(((idle | parked_mask) >> lane) & 1u))
         finished = !trav_step_park<COUNT>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, park, parked);
@@ -409,78 +379,46 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
-  rotate_counters(pool);
 }
 
 // One ray per thread to completion (small trees: all lanes start at the root together, so root-level work stays
 // converged).  Slot-stable pool: a warp takes one chunk of RTB_CHUNK slots at a time, orders its live slots by ray kind
 // (build_extend_list) and traces them 32 at a time; the next round's ray sectors are prefetched into L1 during the
 // current traversal.  No queue, no atomics apart from one ray-count add per warp at the end.
-template <bool COUNT, bool ALL_STAGED>
+// SORT: each chunk's rays are ordered by (ray kind, direction octant) instead of by kind alone (trees that do not fit the
+// stage: C3 +6 %; fully staged trees lose 3 %, the dynamic kernel is indifferent — profiles/r3_ab.md §4).  Parking the
+// leaf tests (as the dynamic kernel does) costs this kernel 13 %: with one ray per thread the lanes that wait for a drain
+// are simply idle.  Both are compile-time choices so that each variant's loop carries only its own path.
+template <bool COUNT, bool ALL_STAGED, bool SORT>
 __global__ void __maxnreg__(RTB_EXTEND_MAXREG)
 k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ uint8_t s_list[RTB_EXTEND_WARPS][RTB_CHUNK];
-  __shared__ uint4 s_park[RTB_EXTEND_WARPS][32];
-  __shared__ uint32_t s_cnt[RTB_EXTEND_WARPS][64];
+  __shared__ uint32_t s_cnt[SORT ? RTB_EXTEND_WARPS : 1][64];
   DevCounters* c = pool.c;
   stage_nodes(sc, snodes, n_snodes);
   uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));  // opaque: keep it in a register instead of re-deriving it per node visit
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const bool octant_sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;
   uint8_t* list = s_list[warp];
-  const uint32_t park_min = (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK;  // 0: leaves are tested at the node visit
-  uint4* park = &s_park[warp][lane];
   const uint32_t n_warps = gridDim.x * RTB_EXTEND_WARPS;
   uint32_t n_rays = 0, nv = 0;
   TestCount nt{};
   for (uint32_t chunk = blockIdx.x * RTB_EXTEND_WARPS + warp; chunk < pool.n_chunks; chunk += n_warps) {
     const uint32_t base = chunk * RTB_CHUNK;
-    const uint32_t total = octant_sort ? build_extend_list_sorted(pool, chunk, list, s_cnt[warp], lane) : build_extend_list(pool, chunk, list, lane);
+    const uint32_t total = SORT ? build_extend_list_sorted(pool, chunk, list, s_cnt[SORT ? warp : 0], lane) : build_extend_list(pool, chunk, list, lane);
     n_rays += total;
     for (uint32_t r = 0; r < total; r += 32) {
       if (r + 32 + lane < total) prefetch_l1(pool.ray + 2 * (size_t)(base + list[r + 32 + lane]));
-      if (park_min == 0u) {
-        if (r + lane < total) {
-          const uint32_t slot = base + list[r + lane];
-          const float4 ro = pool.ray[2 * slot];
-          const float4 rd = pool.ray[2 * slot + 1];
-          Closest best;
-          float lo;
-          const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, lo, nv, nt);
-          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
-          if (fix) queue_fix(pool, slot, fix, lo, best.hi);
-        }
-      } else {
-        // the same traversal with the warp in step: node visits by the lanes that can, primitive tests drained together
-        const bool valid = r + lane < total;
-        const uint32_t slot = base + (valid ? list[r + lane] : 0u);
-        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(1.f, 0.f, 0.f, 0.f);
-        if (valid) { ro = pool.ray[2 * slot]; rd = pool.ray[2 * slot + 1]; }
-        Trav tv;
-        uint2 stack[RTB_STACK];
-        trav_init(tv, xyz(ro), xyz(rd), ro.w);
-        if (valid) trav_globals<COUNT>(sc, tv, RTB_TMIN, nt);
-        bool active = valid, parked = false;
-        uint32_t parked_mask = 0;
-        for (;;) {
-          if (active && !parked) active = trav_step_park<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, RTB_TMIN, nv, park, parked);
-          parked_mask = __ballot_sync(0xffffffffu, parked);
-          const uint32_t active_mask = __ballot_sync(0xffffffffu, active);
-          if (parked_mask && ((uint32_t)__popc(parked_mask) >= park_min || (active_mask & ~parked_mask) == 0u)) {
-            drain_parked<COUNT>(sc, tv, RTB_TMIN, park, parked, nt);
-            parked = false;
-            parked_mask = 0;
-          }
-          if (!active_mask && !parked_mask) break;
-        }
-        if (valid) {
-          const uint32_t fix = fix_kind(tv);
-          const float lo = slab_lo(tv), hi = tv.best.hi;
-          finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), tv.best);
-          if (fix) queue_fix(pool, slot, fix, lo, hi);
-        }
+      if (r + lane < total) {
+        const uint32_t slot = base + list[r + lane];
+        const float4 ro = pool.ray[2 * slot];
+        const float4 rd = pool.ray[2 * slot + 1];
+        Closest best;
+        float lo;
+        const uint32_t fix = traverse<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, lo, nv, nt);
+        finish_ray(sc, pool, prm, slot, xyz(ro), xyz(rd), best);
+        if (fix) queue_fix(pool, slot, fix, lo, best.hi);
       }
     }
     __syncwarp();  // the list is rewritten for the next chunk
@@ -501,7 +439,6 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
     }
   }
-  rotate_counters(pool);
 }
 
 // ---- surface reconstruction in the shade kernels -------------------------------------------------------------------
@@ -1005,7 +942,7 @@ __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPoo
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = RTB_FIXUP_THREADS / 32u;
   uint2 done = fix_prologue(sc, pool, prm, blockIdx.x * warps + (threadIdx.x >> 5), gridDim.x * warps, lane);
-  if (c->redo_count[c->redo_sel ^ 1u]) {  // (uniform) one pair of atomics per warp, not per entry
+  if (c->redo_count[0]) {  // (uniform) one pair of atomics per warp, not per entry
     done.x = __reduce_add_sync(0xffffffffu, done.x);
     done.y = __reduce_add_sync(0xffffffffu, done.y);
     if (lane == 0 && done.x) {
@@ -1020,9 +957,14 @@ __global__ void __launch_bounds__(RTB_FIXUP_THREADS) k_fixup(DevScene sc, DevPoo
     last = atomicAdd(&c->ext_ticket, 1u) == gridDim.x - 1u;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    c->redo_count[c->redo_sel ^ 1u] = 0;
+  if (last && threadIdx.x == 0) {  // the last CTA rotates the iteration counters (what a one-thread kernel did in round 1)
+    c->segments += c->iter_rays;
+    c->last_rays = c->iter_rays;
+    c->iter_rays = 0;
+    c->ext_cursor = 0;
+    c->redo_count[0] = 0;
     c->ext_ticket = 0;
+    c->iter += 1;
   }
 }
 
@@ -1226,9 +1168,17 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
   static const char* mode = getenv("RTB_EXTEND_MODE");
   const bool use_static = mode ? !strcmp(mode, "static") : !lc.dynamic_fetch;
   if (use_static) {
-    if (count) k_extend_static<true, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
-    else if (lc.all_staged) k_extend_static<false, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
-    else k_extend_static<false, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    const bool sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;  // (the shade kernels write the octant bits under the same flag)
+    if (count) {
+      if (sort) k_extend_static<true, false, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+      else k_extend_static<true, false, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    } else if (lc.all_staged) {
+      if (sort) k_extend_static<false, true, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+      else k_extend_static<false, true, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    } else {
+      if (sort) k_extend_static<false, false, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+      else k_extend_static<false, false, false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    }
     return;
   }
   if (count) k_extend<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
@@ -1288,12 +1238,12 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_extend_static<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_extend_static<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_extend_static<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-  if (e != cudaSuccess) return (int)e;
+  for (const void* fn : {(const void*)k_extend_static<true, false, false>, (const void*)k_extend_static<true, false, true>,
+                         (const void*)k_extend_static<false, true, false>, (const void*)k_extend_static<false, true, true>,
+                         (const void*)k_extend_static<false, false, false>, (const void*)k_extend_static<false, false, true>}) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e != cudaSuccess) return (int)e;
+  }
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
