@@ -235,13 +235,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    reduce_ms_list = []
+    reduce_ms_list, wait_ms_list = [], []
 
     def step(flags=0):
         flush.zero_()  # flush L2 between steps
         # render + (N > 1) the library's ncclReduce of the float4 accumulation buffer onto rank 0, on this stream
         st = scene.render_device(cfg.camera, params(flags | reduce_flag), accum.data_ptr(), stream.cuda_stream)
         reduce_ms_list.append(st["ms_nccl"])
+        wait_ms_list.append(st["ms_nccl_wait"])
         return st
 
     # clocks / throttle reasons are sampled from the first warm-up step to the last e2e step (everything under load)
@@ -253,6 +254,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reduce_ms_list.clear()
+    wait_ms_list.clear()
     e0.record(stream)
     segs = launches = 0
     for _ in range(args.steps):
@@ -263,6 +265,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     reduce_ms = sum(reduce_ms_list) / max(len(reduce_ms_list), 1)
+    wait_ms = sum(wait_ms_list) / max(len(wait_ms_list), 1)
     tot = torch.tensor([ms, float(segs), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = tot.clone()
@@ -348,7 +351,7 @@ def main():
         strong = {"workload": c5.name, "width": c5.width, "height": c5.height, "total_spp": c5.spp, "spp_per_gpu": cnt5,
                   "scaling": "strong", "value": t5[1].item() / (m5[0].item() * 1e-3) / 1e6, "unit": "Mrays/s",
                   "ms_per_step": m5[0].item(), "ms_render_slowest_rank": m5[2].item(), "ms_render_fastest_rank": mn5[2].item(),
-                  "reduce_bytes": c5.width * c5.height * 16, "reduce_ms_rank0": st5["ms_nccl"],
+                  "reduce_bytes": c5.width * c5.height * 16, "reduce_ms_rank0": st5["ms_nccl"], "ms_rank0_waited_for_the_slowest_rank": st5["ms_nccl_wait"],
                   "reduce_frac_of_step": st5["ms_nccl"] / m5[0].item(), "segments": t5[1].item(),
                   "note": "efficiency = value(N) / (N x value(1)) across the per-N lines; what limits it is the wavefront drain "
                           "tail of each rank's shorter render (fewer samples per pixel to refill the path pool from), not the collective"}
@@ -447,7 +450,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(all_launches),
             "reduce": {"collective": "ncclReduce(sum) of W*H float4 onto rank 0, issued by librtb200 (RTB_RENDER_REDUCE)" if world > 1 else "none (1 GPU)",
-                       "bytes": npix * 16, "ms_per_step_rank0": reduce_ms, "frac_of_step": reduce_ms / (ms / args.steps)},
+                       "bytes": npix * 16, "ms_per_step_rank0": reduce_ms, "frac_of_step": reduce_ms / (ms / args.steps),
+                       "ms_rank0_waited_for_the_slowest_rank": wait_ms},
             "strong_scaling": strong,
             "clocks": clk,
             "roofline": roofline,

@@ -177,6 +177,7 @@ typedef struct rtb_stats {
   uint32_t n_devices;      /* GPUs that took part in this call */
   uint32_t _pad;
   uint64_t prims_tested_type[4]; /* prims_tested per type: sphere, moving sphere, quad, triangle */
+  double ms_nccl_wait;     /* one process per GPU: time this rank waited for the others to arrive at the reduce (render skew) */
 } rtb_stats;
 
 typedef struct rtb_context rtb_context;

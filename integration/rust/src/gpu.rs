@@ -121,6 +121,7 @@ pub struct RtbStats {
     pub n_devices: u32,
     pub _pad: u32,
     pub prims_tested_type: [u64; 4],
+    pub ms_nccl_wait: f64,
 }
 pub enum RtbContext {}
 pub enum RtbScene {}

@@ -64,7 +64,7 @@ class Stats(C.Structure):
                 ("ms_total", C.c_double), ("ms_extend", C.c_double), ("nodes_visited", C.c_uint64),
                 ("prims_tested", C.c_uint64), ("exact_rays", C.c_uint64), ("refined_rays", C.c_uint64),
                 ("ms_nccl", C.c_double), ("ms_render", C.c_double), ("n_devices", C.c_uint32), ("_pad", C.c_uint32),
-                ("prims_tested_type", C.c_uint64 * 4)]
+                ("prims_tested_type", C.c_uint64 * 4), ("ms_nccl_wait", C.c_double)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k == "prims_tested_type" else getattr(self, k)) for k, _ in self._fields_}

@@ -90,7 +90,8 @@ struct rtb_context {
   std::vector<rtb_context*> peers;
   NcclComm comm = nullptr;
   int rank = 0, n_ranks = 1;
-  cudaEvent_t ev_n0 = nullptr, ev_n1 = nullptr;
+  cudaEvent_t ev_n0 = nullptr, ev_n1 = nullptr, ev_w0 = nullptr;
+  DevBuf<float> comm_scratch;  // 1 float: the arrival barrier in front of the timed reduce
 };
 
 struct rtb_scene {
@@ -143,6 +144,8 @@ static int context_init(rtb_context* c, int device_id) {
   CU(cudaEventCreate(&c->ev1));
   CU(cudaEventCreate(&c->ev_n0));
   CU(cudaEventCreate(&c->ev_n1));
+  CU(cudaEventCreate(&c->ev_w0));
+  CU(c->comm_scratch.resize(1));
   CU(c->counters.resize(1));
   return RTB_OK;
 }
@@ -183,6 +186,7 @@ void rtb_context_destroy(rtb_context* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_n0) cudaEventDestroy(c->ev_n0);
   if (c->ev_n1) cudaEventDestroy(c->ev_n1);
+  if (c->ev_w0) cudaEventDestroy(c->ev_w0);
   for (cudaEvent_t e : c->ext_events) cudaEventDestroy(e);
   delete c;
 }
@@ -221,6 +225,20 @@ int rtb_context_create_multi(const int* device_ids, int n_devices, rtb_context**
     NCCLCHECK(api.CommInitAll(comms.data(), n_devices, device_ids));  // one communicator per device, ranks = list order
     root->comm = comms[0];
     for (int k = 1; k < n_devices; ++k) root->peers[(size_t)k - 1]->comm = comms[(size_t)k];
+    // one-float reduce now: NCCL sets its NVLink connections up on first use (~0.3 s), which must not land in a frame
+    NCCLCHECK(api.GroupStart());
+    for (int k = 0; k < n_devices; ++k) {
+      rtb_context* ck = k == 0 ? root : root->peers[(size_t)k - 1];
+      CU(cudaSetDevice(ck->device));
+      NCCLCHECK(api.Reduce(ck->comm_scratch.p, ck->comm_scratch.p, 1, kNcclFloat32, kNcclSum, 0, ck->comm, (cudaStream_t)0));
+    }
+    NCCLCHECK(api.GroupEnd());
+    for (int k = 0; k < n_devices; ++k) {
+      rtb_context* ck = k == 0 ? root : root->peers[(size_t)k - 1];
+      CU(cudaSetDevice(ck->device));
+      CU(cudaStreamSynchronize(0));
+    }
+    CU(cudaSetDevice(root->device));
   }
   *out = guard.release();
   return RTB_OK;
@@ -247,6 +265,9 @@ int rtb_context_comm_init(rtb_context* c, const uint8_t* id128, int rank, int n_
   NCCLCHECK(api.CommInitRank(&c->comm, n_ranks, id, rank));
   c->rank = rank;
   c->n_ranks = n_ranks;
+  // one-float reduce now (collective: every rank is here): connection set-up must not land in the first frame
+  NCCLCHECK(api.Reduce(c->comm_scratch.p, c->comm_scratch.p, 1, kNcclFloat32, kNcclSum, 0, c->comm, (cudaStream_t)0));
+  CU(cudaStreamSynchronize(0));
   return RTB_OK;
 }
 
@@ -1009,16 +1030,21 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     CU(cudaStreamWaitEvent(st, c->lanes[k].done, 0));
   }
   CU(cudaEventRecord(c->ev1, st));
-  float ms_nccl = 0.f;
+  float ms_nccl = 0.f, ms_wait = 0.f;
   if ((p->flags & RTB_RENDER_REDUCE) && c->n_ranks > 1) {
-    // one ncclReduce(float32, 4 W H, sum, root 0) per frame, in place, on the caller's stream
+    // one ncclReduce(float32, 4 W H, sum, root 0) per frame, in place, on the caller's stream.  A one-float
+    // reduce in front of it is the arrival barrier: ranks finish rendering a few ms apart, and that skew is waiting,
+    // not collective time (ms_nccl_wait vs ms_nccl).
     if (!c->comm) return set_err(RTB_ERR_STATE, "RTB_RENDER_REDUCE needs a communicator (rtb_context_comm_init)");
+    CU(cudaEventRecord(c->ev_w0, st));
+    int r = nccl_api().Reduce(c->comm_scratch.p, c->comm_scratch.p, 1, kNcclFloat32, kNcclSum, 0, c->comm, st);
     CU(cudaEventRecord(c->ev_n0, st));
-    const int r = nccl_api().Reduce(d_accum, d_accum, npix * 4, kNcclFloat32, kNcclSum, 0, c->comm, st);
+    if (r == kNcclSuccess) r = nccl_api().Reduce(d_accum, d_accum, npix * 4, kNcclFloat32, kNcclSum, 0, c->comm, st);
     if (r != kNcclSuccess) return set_err(RTB_ERR_CUDA, std::string("ncclReduce: ") + nccl_api().GetErrorString(r));
     CU(cudaEventRecord(c->ev_n1, st));
     CU(cudaEventSynchronize(c->ev_n1));
     cudaEventElapsedTime(&ms_nccl, c->ev_n0, c->ev_n1);
+    cudaEventElapsedTime(&ms_wait, c->ev_w0, c->ev_n0);
   }
   CU(cudaEventSynchronize(c->ev1));
   CU(cudaGetLastError());
@@ -1027,9 +1053,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     stats->ms_nccl = ms_nccl;
+    stats->ms_nccl_wait = ms_wait;
     stats->ms_render = ms;
     stats->n_devices = 1;
-    ms += ms_nccl;
+    ms += ms_nccl + ms_wait;
     for (int k = 0; k < n_lanes; ++k) {
       const DevCounters* h = c->lanes[k].h_counters;
       stats->paths += run[k].total;  // a render always runs to completion: every path number was started exactly once

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header(rtb):
     F = rtb._ffi
     assert C.sizeof(F.Camera) == 15 * 8
     assert C.sizeof(F.Params) == 13 * 4
-    assert C.sizeof(F.Stats) == 19 * 8
+    assert C.sizeof(F.Stats) == 20 * 8
     assert F.NODE_DTYPE.itemsize == 112 and F.LIGHT_DTYPE.itemsize == 48
 
 
