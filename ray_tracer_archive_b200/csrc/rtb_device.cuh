@@ -114,8 +114,10 @@ struct DevCounters {
 };
 
 // Path pool of one wavefront instance ("lane").  SLOT-STABLE: a path lives in slot i until it terminates, and slot i is
-// then restarted in place with a new camera path.  There are NO global work queues: `extend` walks the slots in order
-// (coalesced ray loads), writes the hit record and the slot's shade class; every per-material shade kernel walks the
+// then restarted in place with a new camera path.  There are NO global work queues: `extend` walks the pool one
+// RTB_CHUNK-slot chunk per warp, orders the chunk's live slots by the kind (and, for trees outside the stage, direction
+// octant) of the ray they hold, traces them and writes the hit record and the slot's shade class (the few rays f32 cannot
+// decide go to the small fix-up queue of k_fixup); every per-material shade kernel walks the
 // class bytes in chunks of RTB_CHUNK slots per warp and compacts the matching slots warp-locally (ballot/scan into a
 // shared-memory list).  Path numbers for restarted slots come from a per-chunk cursor over the chunk's own sequence of
 // 32-path blocks, so no kernel issues a contended global atomic (the queue-compacting version spent 77 % of
