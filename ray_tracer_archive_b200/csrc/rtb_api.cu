@@ -635,10 +635,7 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
   d.tree_empty = (d.n_global == (uint32_t)hs.prims.size()) ? 1u : 0u;
   for (uint32_t k = 0; k < d.n_global; ++k) d.global_ref[k] = bvh.global_refs[k];
   d.global_f64 = d.tree_empty ? 0u : bvh.global_f64;
-  {
-    static const char* pf = getenv("RTB_PREFETCH");
-    d.prefetch = pf ? (uint32_t)atoi(pf) : 0u;
-  }
+  d._reserved0 = 0u;
   for (uint32_t t = 0; t < PT_COUNT; ++t) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(bvh.geom[t].data()), bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
@@ -722,7 +719,7 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
   CU(s->d_self.resize(1));
   d.self = s->d_self.p;
   CU(cudaMemcpy(s->d_self.p, &d, sizeof(DevScene), cudaMemcpyHostToDevice));  // (after every other field is final)
-  int e = configure_launch(s->lc, d.n_nodes, s->ctx->prop.multiProcessorCount);
+  int e = configure_launch(s->lc, d.n_nodes, s->bvh.max_depth, s->ctx->prop.multiProcessorCount);
   if (e != 0) return set_err(RTB_ERR_CUDA, std::string("configure_launch: ") + cudaGetErrorString((cudaError_t)e));
   CU(cudaStreamSynchronize(0));
   s->committed = true;
@@ -927,7 +924,9 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
     // trees that do not fit the shared-memory stage order each chunk's rays by direction octant, small staged trees do
     // neither.  RTB_OPT overrides (experiments).
     prm.opt = env_opt ? (uint32_t)atoi(env_opt)
-                      : (s->lc.dynamic_fetch ? (14u << RTB_OPT_PARK_SHIFT) : (s->lc.all_staged ? 0u : 2u /* RTB_OPT_OCTANT_SORT */));
+              : s->lc.mode == EXTEND_WQ ? ((24u << RTB_OPT_PARK_SHIFT) | (2u << 16))  // serve queues of >= 24 rays, 2 tests per ray and round
+              : s->lc.mode == EXTEND_DYNAMIC ? (14u << RTB_OPT_PARK_SHIFT)
+                                             : (s->lc.all_staged ? 0u : 2u /* RTB_OPT_OCTANT_SORT */);
     prm.inv_wm1 = (float)(1.0 / (double)(p->width - 1));
     prm.inv_hm1 = (float)(1.0 / (double)(p->height - 1));
     prm.accum = (float4*)d_accum;

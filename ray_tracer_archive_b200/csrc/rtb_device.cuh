@@ -72,7 +72,7 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   uint32_t prmt_magic;  // = 0x43000000, see q2f()
   uint32_t n_global;    // primitives tested for every ray before the traversal (kept out of the tree)
   uint32_t tree_empty;  // all primitives are global (tiny scene): skip the traversal
-  uint32_t prefetch;    // prefetch the next node to be visited into L1 before the leaf tests of the current one (deep trees)
+  uint32_t _reserved0;
   uint32_t global_ref[RTB_MAX_GLOBALS];
   uint32_t global_f64;  // bit k: global k is a sphere so large next to the rest of the scene (radius >= 16 scene
                         // extents) that the f32 test can never be trusted for a hit: go to the f64 form directly
@@ -510,19 +510,21 @@ __device__ __forceinline__ bool sphere_roots(float3 o, float3 d, float3 c, float
   return true;
 }
 
+// One f32 primitive test as a PURE function of (ray, primitive): HIT_MISS, HIT_CERTAIN (t, bound e on |t - t_exact|,
+// `coarse`) or HIT_AMBIGUOUS (t = a lower bound of the distance at which the undecided candidate may lie).  `tmax_hi` is
+// only an early-out (a candidate certainly beyond it is reported as a miss); apply_result() re-checks against the ray's
+// current bound, so a stale (larger) tmax_hi changes nothing — which lets the warp-queue extend kernel run the tests of
+// many rays side by side and merge afterwards.
 template <bool COUNT>
-__device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
-                                               float time, float tmin, Closest& best, float& amb, uint32_t& flags, TestCount& n_tests) {
+__device__ __forceinline__ int prim_test(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d, float time, float tmin,
+                                         float tmax_hi, float& t, float& e, bool& coarse, TestCount& n_tests) {
   if (COUNT) ++n_tests.n[type];
   RTB_CHECK(CHK_PRIM, type < PT_COUNT && idx < sc.n_prims[type]);
-  const uint32_t ref = (type << REF_TYPE_SHIFT) | idx;
-  float t, e;
-  bool coarse = false;
+  coarse = false;
+  e = 0.0f;
   if (type == PT_SPHERE) {
     const float4 s = __ldg(sc.geom[PT_SPHERE] + idx);
-    const int st = sphere_fast(o, d, xyz(s), s.w, tmin, best.hi, t, e, coarse);
-    if (st == HIT_MISS) return;
-    if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
+    return sphere_fast(o, d, xyz(s), s.w, tmin, tmax_hi, t, e, coarse);
   } else if (type == PT_QUAD) {
     // aarect.rs:31-48 generalised: t = (n.Q - n.o)/(n.d); in-plane coordinates must lie in the CLOSED unit square.
     // Numerator error <= 2^-22 (|o|_1 + coord_max) (three FMAs on |n_i| <= 1, the stored n.Q); denominator error <=
@@ -532,9 +534,9 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float inv = rcp_fast(nd);
     t = (w0.w - dot(xyz(w0), o)) * inv;
     e = fmaf(fabsf(inv), fmaf(RTB_U22 * abs1(d), fabsf(t), RTB_U22 * (abs1(o) + sc.coord_max)), RTB_U21 * fabsf(t));
-    if (!(t - e <= best.hi)) return;  // also rejects NaN
+    if (!(t - e <= tmax_hi)) return HIT_MISS;  // also rejects NaN
     const int st = tmin_status(t, e, tmin);
-    if (st == HIT_MISS) return;
+    if (st == HIT_MISS) return HIT_MISS;
     const float4 w1 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 1);
     const float4 w2 = __ldg(sc.geom[PT_QUAD] + 3 * idx + 2);
     const float3 p = fma3(t, d, o);
@@ -543,8 +545,9 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     const float ea = fmaf(e, fabsf(dot(xyz(w1), d)), fmaf(RTB_U20, fabsf(alpha), sc.eps_ab));
     const float eb = fmaf(e, fabsf(dot(xyz(w2), d)), fmaf(RTB_U20, fabsf(beta), sc.eps_ab));
     const float ma = fminf(alpha, 1.0f - alpha), mb = fminf(beta, 1.0f - beta);
-    if (ma < -ea || mb < -eb) return;
-    if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { undecided(best, amb, fmaxf(t - e, 0.0f)); return; }
+    if (ma < -ea || mb < -eb) return HIT_MISS;
+    if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { t = fmaxf(t - e, 0.0f); return HIT_AMBIGUOUS; }
+    return HIT_CERTAIN;
   } else if (type == PT_TRI) {
     // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
     // Watertight edge functions (Woop, Benthin, Wald 2013): vertices are translated to the ray origin and sheared so
@@ -582,31 +585,43 @@ __device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type
     // the subtraction: 2^-24), so an edge function (two products of one exact and one perturbed factor pair) by <= m
     const float m = (1.25f * RTB_U22 * amax) * (fabsf(Ax) + fabsf(Ay) + fabsf(Bx) + fabsf(By) + fabsf(Cx) + fabsf(Cy));
     const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
-    if (mn < -m && mx > m) return;  // certainly outside
+    if (mn < -m && mx > m) return HIT_MISS;  // certainly outside
     const float det = U + V + W;
     const float idet = rcp_fast(det), za = Sz * A.z, zb = Sz * B.z, zc = Sz * C.z;
     const float zlo = fminf(fminf(za, zb), zc), zhi = fmaxf(fmaxf(za, zb), zc);
     if (!(mn > m || mx < -m)) {  // on an edge / vertex / edge-on: any hit lies within the triangle's depth range
-      if (zhi >= tmin) undecided(best, amb, fmaxf(zlo - RTB_U20 * fabsf(zlo), 0.0f));
-      return;
+      if (!(zhi >= tmin)) return HIT_MISS;
+      t = fmaxf(zlo - RTB_U20 * fabsf(zlo), 0.0f);
+      return HIT_AMBIGUOUS;
     }
     t = (U * za + V * zb + W * zc) * idet;
     // t is the (U, V, W)-weighted mean of the vertex depths: the weights' error m/|det| moves it by at most the depth
     // spread of the triangle
     e = fmaf(RTB_U20, fabsf(t), 4.0f * m * fabsf(idet) * (zhi - zlo));
-    if (!(t - e <= best.hi)) return;
+    if (!(t - e <= tmax_hi)) return HIT_MISS;
     const int st = tmin_status(t, e, tmin);
-    if (st == HIT_MISS) return;
-    if (st == HIT_AMBIGUOUS) { undecided(best, amb, fmaxf(t - e, 0.0f)); return; }
+    if (st == HIT_AMBIGUOUS) t = fmaxf(t - e, 0.0f);
+    return st;
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
     const float4 b = __ldg(sc.geom[PT_MOVING] + 2 * idx + 1);
     const float3 c = fma3(time, xyz(b), xyz(a));
-    const int st = sphere_fast(o, d, c, a.w, tmin, best.hi, t, e, coarse);
-    if (st == HIT_MISS) return;
-    if (st == HIT_AMBIGUOUS) { undecided(best, amb, t); return; }
+    return sphere_fast(o, d, c, a.w, tmin, tmax_hi, t, e, coarse);
   }
-  consider(best, amb, flags, t, e, ref, coarse);
+}
+// the closest-hit update of one test result (hittable_list.rs:42-48 with the certainty bookkeeping)
+__device__ __forceinline__ void apply_result(Closest& best, float& amb, uint32_t& flags, int st, float t, float e, uint32_t ref,
+                                             bool coarse) {
+  if (st == HIT_CERTAIN) consider(best, amb, flags, t, e, ref, coarse);
+  else if (st == HIT_AMBIGUOUS) undecided(best, amb, t);
+}
+template <bool COUNT>
+__device__ __forceinline__ void intersect_prim(const DevScene& sc, uint32_t type, uint32_t idx, float3 o, float3 d,
+                                               float time, float tmin, Closest& best, float& amb, uint32_t& flags, TestCount& n_tests) {
+  float t, e;
+  bool coarse;
+  const int st = prim_test<COUNT>(sc, type, idx, o, d, time, tmin, best.hi, t, e, coarse, n_tests);
+  apply_result(best, amb, flags, st, t, e, (type << REF_TYPE_SHIFT) | idx, coarse);
 }
 
 __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel) {
@@ -692,13 +707,15 @@ __device__ __forceinline__ void expand_leaves(uint32_t leaf, uint32_t w1y, uint3
 
 // `leaves(leaf mask, w1y, w1z, w1w)` receives the hit leaf children of the visited node: the hot kernels test them at once
 // (intersect_prim) or park them to test many lanes' primitives together; the exact pass runs exact_hit on them.
-template <bool COUNT, bool ALL_STAGED, class Leaves>
+// STRIDE: distance (in entries) between consecutive levels of the ray's stack (1 = a private array; the warp-queue kernel
+// keeps the stacks of a warp's rays interleaved in shared memory).
+template <bool COUNT, bool ALL_STAGED, int STRIDE = 1, class Leaves>
 __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __restrict__ snodes, uint32_t sbase, uint32_t n_snodes,
                                           Trav& tv, uint2* __restrict__ stack, float tmin,
                                           uint32_t& n_nodes_visited, Leaves&& leaves_fn) {
   if (!(tv.grp.y & 0xFF00u)) {  // group exhausted: pop (stack entries always have hits left) and visit in the same step
     if (tv.sp == 0) return false;
-    tv.grp = stack[--tv.sp];
+    tv.grp = stack[(--tv.sp) * STRIDE];
   }
   const uint32_t octinv = tv.octinv & 7u;
   uint32_t hits = tv.grp.y >> 8;
@@ -709,7 +726,7 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   const uint32_t node = tv.grp.x + __popc(gmask & ((1u << slot) - 1u));
   RTB_CHECK(CHK_STACK, !hits || tv.sp < RTB_STACK);
   RTB_CHECK(CHK_NODE, node < sc.n_nodes);
-  if (hits) stack[tv.sp++] = make_uint2(tv.grp.x, (hits << 8) | gmask);
+  if (hits) stack[(tv.sp++) * STRIDE] = make_uint2(tv.grp.x, (hits << 8) | gmask);
   if (COUNT) ++n_nodes_visited;
   uint4 w0, w1, w2, w3, w4;
   if (ALL_STAGED || node < n_snodes) {
@@ -769,23 +786,8 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
   if (octinv & 2u) ih = ((ih & 0x33u) << 2) | ((ih & 0xCCu) >> 2);
   if (octinv & 4u) ih = ((ih & 0x0Fu) << 4) | ((ih & 0xF0u) >> 4);
   tv.grp = make_uint2(w1.x, (ih << 8) | imask);
-#ifdef __CUDA_ARCH__
-  if (!ALL_STAGED && sc.prefetch) {
-    // the node the NEXT step will visit (nearest hit child, else the top of the stack) starts its way into L1 now, while
-    // this node's primitives are tested: the traversal of a deep tree waits on exactly this dependent fetch
-    uint2 g = tv.grp;
-    if (!ih && tv.sp > 0) g = stack[tv.sp - 1];
-    if (g.y & 0xFF00u) {
-      const uint32_t pslot = (31u - __clz(g.y >> 8)) ^ octinv;
-      const uint32_t pnode = g.x + __popc(g.y & 0xFFu & ((1u << pslot) - 1u));
-      if (pnode >= n_snodes) {
-        const uint4* pp = sc.nodes + 5 * (size_t)pnode;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 4));
-      }
-    }
-  }
-#endif
+  // (measured and removed: prefetching the next step's node into L1 here, -4 % — and even switched off the dormant path
+  //  cost the deep-tree kernels 2-3 %, profiles/r3_ab.md §3)
   // leaf children (all primitives of one node share a type)
   const uint32_t leaf = hitmask & ~imask;
   if (leaf) leaves_fn(leaf, w1.y, w1.z, w1.w);

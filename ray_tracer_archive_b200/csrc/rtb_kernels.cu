@@ -23,6 +23,7 @@ __device__ __forceinline__ uint32_t ray_octant(float3 d) {
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -36,6 +37,13 @@ __device__ __forceinline__ void deposit(const DevParams& prm, DevCounters* c, ui
   }
   const float Y = 0.2126f * L.x + 0.7152f * L.y + 0.0722f * L.z;
   red_add_v4(prm.accum + pixel, L.x, L.y, L.z, Y * Y);
+}
+
+// the ray records of a chunk (8 KB, contiguous) start their way from HBM to L2 when a warp claims the chunk (+1 %)
+__device__ __forceinline__ void prefetch_chunk_rays(const DevPool& pool, uint32_t chunk_base, uint32_t lane) {
+  const char* rp = reinterpret_cast<const char*>(pool.ray + 2 * (size_t)chunk_base);
+  prefetch_l2(rp + 128u * lane);
+  prefetch_l2(rp + 128u * (lane + 32u));
 }
 
 // ---- stage the top of the BVH in shared memory -------------------------------------------------------------------
@@ -362,6 +370,258 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
       out_count += __popc(done);
       idle |= done;
     }
+  }
+  if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
+  if (COUNT) {
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    uint32_t tot = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < PT_COUNT; ++t) {
+      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
+      tot += nt.n[t];
+    }
+    if (lane == 0) {
+      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+      atomicAdd(&c->prims_tested, (unsigned long long)tot);
+      for (uint32_t t = 0; t < PT_COUNT; ++t)
+        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
+    }
+  }
+}
+
+// ---- warp-queue extend (deep trees) ----------------------------------------------------------------------------------
+// The per-line profile of the kernels above on trees outside the stage (profiles/r3g_lines.md): node visits run with
+// 13-17 of 32 lanes (lanes whose ray waits for a refill or for its leaf tests) and the primitive tests with 3-4 of 32 (the
+// few lanes whose node happened to have a leaf hit) — a third of all issued warp instructions at a tenth of the width.
+// Here the WARP, not the lane, owns the rays: RTB_WQ_RAYS rays per warp live entirely in shared memory (ray, closest hit,
+// traversal group AND stack), and any lane can advance any of them:
+//   * a node step takes (up to) 32 READY rays — lane j the j-th of them — through one node visit each;
+//   * a node visit that hits leaves does not test them: the ray goes to the queue of its leaf's primitive class (sphere /
+//     quad / triangle) and waits; a queue is served by all lanes, 32 rays at a time, a bounded number of primitives per ray
+//     and round (same per-ray order of tests as everywhere else, hence the same hits and counters);
+//   * each loop iteration does whichever has more lanes' worth of work (node step / serving the fullest queue);
+//   * finished rays are pushed to the per-warp result buffer and written out 32 at a time, free table entries take new rays
+//     straight from the chunk list.
+// All scheduling state (free / ready masks, queue heads) is warp-uniform registers.
+#define RTB_WQ_RAYS 48u
+#define RTB_WQ_STACK 12u  /* levels: configure_launch() uses this kernel only for trees of at most this depth */
+struct WqWarp {
+  float4 o_time[RTB_WQ_RAYS];
+  float4 d_slot[RTB_WQ_RAYS];
+  float4 idir_oct[RTB_WQ_RAYS];
+  float4 best[RTB_WQ_RAYS];      // t, ref, upper bound of the exact t, ambiguity horizon
+  uint4 trav[RTB_WQ_RAYS];       // current group (x, y), stack depth, flags (RTB_TRAV_COARSE)
+  uint4 rec[RTB_WQ_RAYS];        // the leaf record of the last node visit (x = leaf mask | next primitive << 8) while the ray waits
+  uint2 stack[RTB_WQ_STACK][RTB_WQ_RAYS];  // level-major: the lanes of a node step touch consecutive words
+  ExtOut out[32];
+  uint8_t list[RTB_CHUNK];
+  uint8_t q[3][64];              // per class: ring of waiting rays (a ray waits in at most one queue: never overflows)
+  uint8_t ready[64];             // the ready rays of the current node step, compacted
+};
+
+template <bool COUNT>
+__global__ void __maxnreg__(RTB_EXTEND_MAXREG)
+k_extend_wq(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
+  extern __shared__ uint4 snodes[];
+  DevCounters* c = pool.c;
+  stage_nodes(sc, snodes, n_snodes);
+  uint32_t sbase = (uint32_t)__cvta_generic_to_shared(snodes);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  WqWarp& W = reinterpret_cast<WqWarp*>(snodes + 5u * n_snodes)[warp];
+  // warp-uniform scheduling state: rays 0-31 in the *_lo masks, 32-47 in *_hi
+  uint32_t free_lo = 0xffffffffu, free_hi = (1u << (RTB_WQ_RAYS - 32u)) - 1u, rdy_lo = 0u, rdy_hi = 0u;
+  uint32_t qh0 = 0, qh1 = 0, qh2 = 0, qn0 = 0, qn1 = 0, qn2 = 0;  // ring head / length per class
+  uint32_t out_count = 0, flip = 0;
+  uint32_t chunk_base = 0, list_pos = 0, list_len = 0;
+  bool exhausted = false;
+  uint32_t n_rays = 0;
+  uint32_t nv = 0;
+  TestCount nt{};
+  const uint32_t refill_min = 8u;
+  // a queue is served before a node step when it holds at least this many rays (or more rays than lanes could step)
+  const uint32_t serve_min = max(1u, (prm.opt >> RTB_OPT_PARK_SHIFT) & RTB_OPT_PARK_MASK);
+  const uint32_t serve_tests = max(1u, (prm.opt >> 16) & 15u);  // primitive tests per ray and serving round
+  auto flush = [&]() {
+    __syncwarp();
+    if (lane < out_count) {
+      const ExtOut h = W.out[lane];
+      float3 o = f3(0.f, 0.f, 0.f), d = o;
+      if (sc.n_media) {
+        o = xyz(pool.ray[2 * h.slot]);
+        d = xyz(pool.ray[2 * h.slot + 1]);
+      }
+      finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
+      if (h.redo) queue_fix(pool, h.slot, h.redo, h.lo, h.hi);
+    }
+    out_count = 0;
+    __syncwarp();
+  };
+
+  for (;;) {
+    const uint32_t n_ready = __popc(rdy_lo) + __popc(rdy_hi);
+    const uint32_t n_free = __popc(free_lo) + __popc(free_hi);
+    const bool more_rays = !(exhausted && list_pos == list_len);
+    const uint32_t q_max = max(qn0, max(qn1, qn2));
+    // ---- free table entries take new rays ---------------------------------------------------------------------------
+    if (more_rays && n_free && (n_free >= refill_min || (n_ready == 0u && q_max == 0u))) {
+      uint32_t left = n_free;
+      while (left) {
+        if (list_pos == list_len) {
+          uint32_t ch = 0;
+          if (lane == 0) ch = atomicAdd(&c->ext_cursor, 1u);
+          ch = __shfl_sync(0xffffffffu, ch, 0);
+          if (ch >= pool.n_chunks) {
+            exhausted = true;
+            break;
+          }
+          __syncwarp();
+          chunk_base = ch * RTB_CHUNK;
+          prefetch_chunk_rays(pool, chunk_base, lane);
+          list_len = build_extend_list(pool, ch, W.list, lane);
+          list_pos = 0;
+          n_rays += list_len;
+          if (list_len == 0) continue;
+        }
+        const uint32_t n = min(left, list_len - list_pos);
+        const uint32_t base_hi = __popc(free_lo);
+#pragma unroll 1
+        for (uint32_t w = 0; w < 2u; ++w) {  // lane l fills table entry l, then entry 32 + l
+          const uint32_t fm = w ? free_hi : free_lo;
+          const uint32_t rank = (w ? base_hi : 0u) + __popc(fm & lt_mask);
+          const bool take = ((fm >> lane) & 1u) && rank < n;
+          if (take) {
+            const uint32_t sl = chunk_base + W.list[list_pos + rank];
+            const float4 ro = pool.ray[2 * sl], rd = pool.ray[2 * sl + 1];
+            Trav t0;
+            trav_init(t0, xyz(ro), xyz(rd), ro.w);
+            trav_globals<COUNT>(sc, t0, RTB_TMIN, nt);
+            const uint32_t r = w * 32u + lane;
+            W.o_time[r] = ro;
+            W.d_slot[r] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(sl));
+            W.idir_oct[r] = make_float4(t0.idx, t0.idy, t0.idz, __uint_as_float(t0.octinv & 7u));
+            W.best[r] = make_float4(t0.best.t, __uint_as_float(t0.best.ref), t0.best.hi, t0.amb);
+            W.trav[r] = make_uint4(0u, t0.grp.y, 0u, t0.octinv & RTB_TRAV_COARSE);
+          }
+          const uint32_t took = __ballot_sync(0xffffffffu, take);
+          if (w) { free_hi &= ~took; rdy_hi |= took; } else { free_lo &= ~took; rdy_lo |= took; }
+        }
+        list_pos += n;
+        left -= n;
+      }
+      __syncwarp();
+      continue;
+    }
+    if (n_ready == 0u && q_max == 0u) {  // nothing in flight and nothing left to take
+      if (out_count) flush();
+      break;
+    }
+    if (q_max >= serve_min || q_max > n_ready) {
+      // ---- serve the fullest queue: lane j runs leaf tests of the j-th waiting ray ---------------------------------------
+      const uint32_t cls = qn0 == q_max ? 0u : (qn1 == q_max ? 1u : 2u);
+      const uint32_t head = cls == 0u ? qh0 : (cls == 1u ? qh1 : qh2);
+      const uint32_t n = min(32u, q_max);
+      uint32_t r = 64u;
+      bool again = false;  // primitives left in the record: the ray goes back to the end of the queue
+      if (lane < n) {
+        r = W.q[cls][(head + lane) & 63u];
+        RTB_CHECK(CHK_QUEUE, r < RTB_WQ_RAYS);
+        const float4 ro = W.o_time[r], rd = W.d_slot[r], b = W.best[r];
+        const uint4 rc = W.rec[r];
+        Closest best{b.x, b.z, __float_as_uint(b.y)};
+        float amb = b.w;
+        uint32_t flags = W.trav[r].w;
+        // at most `serve_tests` primitives per ray and round, so that the lanes of a round stay together (a ray that grazes a
+        // row of leaves has 6+ primitives to test, most have 1-2)
+        uint32_t leaf = rc.x & 0xFFu, k = rc.x >> 8;
+        const uint32_t ptype = rc.y >> REF_TYPE_SHIFT, pbase = rc.y & REF_INDEX_MASK;
+        for (uint32_t it = 0; it < serve_tests && leaf; ++it) {
+          const uint32_t sl = __ffs(leaf) - 1;
+          const uint32_t m = ((sl < 4 ? rc.z : rc.w) >> (8 * (sl & 3))) & 0xFFu;
+          intersect_prim<COUNT>(sc, ptype, pbase + (m & 31u) + k, xyz(ro), xyz(rd), ro.w, RTB_TMIN, best, amb, flags, nt);
+          if (++k >= (m >> 5)) { k = 0; leaf &= leaf - 1; }
+        }
+        W.best[r] = make_float4(best.t, __uint_as_float(best.ref), best.hi, amb);
+        W.trav[r].w = flags;
+        again = leaf != 0u;
+        if (again) W.rec[r].x = leaf | (k << 8);
+      }
+      const uint32_t again_mask = __ballot_sync(0xffffffffu, again);
+      rdy_lo |= __reduce_or_sync(0xffffffffu, !again && r < 32u ? 1u << r : 0u);
+      rdy_hi |= __reduce_or_sync(0xffffffffu, !again && (r & 32u) ? 1u << (r & 31u) : 0u);
+      __syncwarp();
+      if (again) W.q[cls][(head + q_max + __popc(again_mask & lt_mask)) & 63u] = (uint8_t)r;  // (n <= 32 entries were read above)
+      const uint32_t delta = __popc(again_mask) - n;
+      if (cls == 0u) { qh0 += n; qn0 += delta; } else if (cls == 1u) { qh1 += n; qn1 += delta; } else { qh2 += n; qn2 += delta; }
+      __syncwarp();
+      continue;
+    }
+    // ---- one node visit (or pop) of up to 32 ready rays: lane j takes the j-th ------------------------------------------
+    if ((rdy_lo >> lane) & 1u) W.ready[__popc(rdy_lo & lt_mask)] = (uint8_t)lane;
+    if ((rdy_hi >> lane) & 1u) W.ready[__popc(rdy_lo) + __popc(rdy_hi & lt_mask)] = (uint8_t)(32u + lane);
+    __syncwarp();
+    flip ^= 1u;
+    bool finished = false, leafed = false;
+    uint32_t cls = 3u, r = 64u;
+    if (lane < n_ready) {
+      r = W.ready[lane + (flip && n_ready > 32u ? n_ready - 32u : 0u)];  // (more than 32 ready: alternate which end waits)
+      Trav tv;
+      const float4 ro = W.o_time[r], id = W.idir_oct[r];
+      const uint4 tr = W.trav[r];
+      tv.o = xyz(ro);
+      tv.idx = id.x; tv.idy = id.y; tv.idz = id.z;
+      tv.octinv = __float_as_uint(id.w);
+      tv.grp = make_uint2(tr.x, tr.y);
+      tv.sp = (int)tr.z;
+      tv.best.hi = W.best[r].z;
+      finished = !trav_step<COUNT, false, (int)RTB_WQ_RAYS>(sc, snodes, sbase, n_snodes, tv, &W.stack[0][r], RTB_TMIN, nv,
+                                                            [&](uint32_t leaf, uint32_t w1y, uint32_t w1z, uint32_t w1w) {
+                                                              W.rec[r] = make_uint4(leaf, w1y, w1z, w1w);
+                                                              const uint32_t type = w1y >> REF_TYPE_SHIFT;
+                                                              cls = type <= PT_MOVING ? 0u : type - 1u;
+                                                              leafed = true;
+                                                            });
+      RTB_CHECK(CHK_STACK, tv.sp <= (int)RTB_WQ_STACK);
+      if (!finished) {
+        *reinterpret_cast<uint2*>(&W.trav[r]) = tv.grp;
+        W.trav[r].z = (uint32_t)tv.sp;
+      }
+    }
+    const uint32_t done = __ballot_sync(0xffffffffu, finished);
+    const uint32_t leafs = __ballot_sync(0xffffffffu, leafed);
+    if (done | leafs) {
+      const uint32_t bit_lo = r < 32u ? 1u << r : 0u, bit_hi = (r & 32u) ? 1u << (r & 31u) : 0u;
+      rdy_lo &= ~__reduce_or_sync(0xffffffffu, finished || leafed ? bit_lo : 0u);
+      rdy_hi &= ~__reduce_or_sync(0xffffffffu, finished || leafed ? bit_hi : 0u);
+      // ---- rays with leaf hits queue up by class ----------------------------------------------------------------------------
+      if (leafs) {
+        const uint32_t m0 = __ballot_sync(0xffffffffu, cls == 0u), m1 = __ballot_sync(0xffffffffu, cls == 1u), m2 = leafs & ~(m0 | m1);
+        if (leafed) {
+          const uint32_t mine = cls == 0u ? m0 : (cls == 1u ? m1 : m2);
+          const uint32_t end = cls == 0u ? qh0 + qn0 : (cls == 1u ? qh1 + qn1 : qh2 + qn2);
+          W.q[cls][(end + __popc(mine & lt_mask)) & 63u] = (uint8_t)r;
+        }
+        qn0 += __popc(m0); qn1 += __popc(m1); qn2 += __popc(m2);
+      }
+      // ---- finished rays push their result ------------------------------------------------------------------------------
+      if (done) {
+        free_lo |= __reduce_or_sync(0xffffffffu, finished ? bit_lo : 0u);
+        free_hi |= __reduce_or_sync(0xffffffffu, finished ? bit_hi : 0u);
+        if (out_count + __popc(done) > 32u) flush();
+        if (finished) {
+          const float4 b = W.best[r];
+          Trav tv;
+          tv.best = Closest{b.x, b.z, __float_as_uint(b.y)};
+          tv.amb = b.w;
+          tv.octinv = W.trav[r].w;
+          W.out[out_count + __popc(done & lt_mask)] =
+              ExtOut{tv.best.t, tv.best.ref, __float_as_uint(W.d_slot[r].w), fix_kind(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
+        }
+        out_count += __popc(done);
+      }
+    }
+    __syncwarp();
   }
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
   if (COUNT) {
@@ -1165,9 +1425,12 @@ void launch_extend(const LaunchCfg& lc, const DevScene& sc, const DevPool& pool,
                    cudaStream_t st) {
   // one-ray-per-thread wins on small trees (all lanes start at the root together); dynamic fetch wins on deep trees
   // where the number of node visits per ray varies widely (measured: profiles/r1_ab_extend.md)
-  static const char* mode = getenv("RTB_EXTEND_MODE");
-  const bool use_static = mode ? !strcmp(mode, "static") : !lc.dynamic_fetch;
-  if (use_static) {
+  if (lc.mode == EXTEND_WQ) {
+    if (count) k_extend_wq<true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    else k_extend_wq<false><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
+    return;
+  }
+  if (lc.mode == EXTEND_STATIC) {
     const bool sort = (prm.opt & RTB_OPT_OCTANT_SORT) != 0u;  // (the shade kernels write the octant bits under the same flag)
     if (count) {
       if (sort) k_extend_static<true, false, true><<<lc.extend_grid, RTB_EXTEND_THREADS, lc.extend_smem, st>>>(sc, pool, prm, lc.n_snodes);
@@ -1218,7 +1481,7 @@ void launch_primary_rays(const DevCameraF64& cam, uint32_t W, uint32_t H, float*
   k_primary_rays<<<cdiv(W * H, 256), 256, 0, st>>>(cam, W, H, org, dir, time);
 }
 
-int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
+int configure_launch(LaunchCfg& lc, uint32_t n_nodes, uint32_t max_depth, int sm_count) {
   // stage as much of the (breadth-first ordered) node array as fits the shared-memory budget
   // extend runs 2 CTAs per SM: 2 x (stage + 2 KB list [+ 20 KB of per-warp ray/result buffers, dynamic fetch]) must fit
   // the 227 KB of an SM beside one 3 KB shade CTA
@@ -1234,7 +1497,25 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
   lc.n_snodes = n_s;
   lc.all_staged = n_s == n_nodes && !(getenv("RTB_ALL_STAGED") && atoi(getenv("RTB_ALL_STAGED")) == 0);
   lc.extend_smem = n_s * 80;
-  cudaError_t e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+  // which scheduler: one ray per thread for small trees, the warp-queue kernel for trees outside the stage
+  // (RTB_EXTEND_MODE = static | dynamic | wq overrides; profiles/r3_ab.md)
+  const char* mode = getenv("RTB_EXTEND_MODE");
+  lc.mode = lc.dynamic_fetch ? EXTEND_DYNAMIC : EXTEND_STATIC;
+  if (mode) lc.mode = !strcmp(mode, "static") ? EXTEND_STATIC : (!strcmp(mode, "wq") ? EXTEND_WQ : EXTEND_DYNAMIC);
+  if (lc.mode == EXTEND_WQ && (lc.all_staged || max_depth + 2u > RTB_WQ_STACK))  // (pushes <= internal levels on a path)
+    lc.mode = lc.dynamic_fetch ? EXTEND_DYNAMIC : EXTEND_STATIC;
+  cudaError_t e;
+  const void* extend_fn = (const void*)k_extend<false>;
+  if (lc.mode == EXTEND_WQ) {
+    const uint32_t wq_bytes = RTB_EXTEND_WARPS * (uint32_t)sizeof(WqWarp);
+    lc.extend_smem += wq_bytes;
+    extend_fn = (const void*)k_extend_wq<false>;
+    for (const void* fn : {(const void*)k_extend_wq<false>, (const void*)k_extend_wq<true>}) {
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + wq_bytes));
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  e = cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
   if (e != cudaSuccess) return (int)e;
@@ -1245,7 +1526,7 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count) {
     if (e != cudaSuccess) return (int)e;
   }
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, RTB_EXTEND_THREADS, lc.extend_smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, extend_fn, RTB_EXTEND_THREADS, lc.extend_smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) occ = 1;
   // two extend CTAs per SM (of the three that fit): leaves a third of the register file to the shade kernels of the

@@ -31,7 +31,9 @@ struct DevCameraF64 {  // camera.rs:6-17 in f64, for the parity probe's primary 
   double time0;
 };
 
+enum ExtendMode : uint32_t { EXTEND_STATIC = 0, EXTEND_DYNAMIC = 1, EXTEND_WQ = 2 };
 struct LaunchCfg {
+  uint32_t mode = EXTEND_STATIC;  // which extend scheduler (configure_launch)
   uint32_t extend_grid = 0, shade_grid = 0, fixup_grid = 0, extend_smem = 0, n_snodes = 0;
   bool dynamic_fetch = false;
   bool all_staged = false;  // every BVH node fits the shared-memory stage: the kernel without a global node path is used
@@ -39,7 +41,8 @@ struct LaunchCfg {
   uint32_t pool_unit = 0;
 };
 
-int configure_launch(LaunchCfg& lc, uint32_t n_nodes, int sm_count);
+// max_depth: levels of the tree (the warp-queue kernel keeps fixed-depth stacks in shared memory)
+int configure_launch(LaunchCfg& lc, uint32_t n_nodes, uint32_t max_depth, int sm_count);
 int read_check_failures(unsigned int* out8);  // RTB_CHECKED build: failed bounds assertions by kind; 0xFFFFFFFF otherwise
 void launch_init_pool(const DevPool& pool, unsigned long long total_paths, cudaStream_t st);
 void launch_generate(const LaunchCfg& lc, const DevPool& pool, const DevParams& prm, const DevCamera& cam, cudaStream_t st);

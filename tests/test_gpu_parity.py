@@ -92,6 +92,34 @@ def test_p1_mesh_small(rtb, orc, ctx):
     _p1(rtb, orc, ctx, cfg, 320, 180)
 
 
+@pytest.mark.parametrize("which", ["final_scene", "mesh"])
+def test_extend_schedulers_agree(rtb, ctx, monkeypatch, which):
+    """The three extend schedulers (one ray per thread / dynamic fetch with parked leaf tests / warp queue with the rays
+    in shared memory) run the same per-ray sequence of node visits and primitive tests: identical hits, distances, work
+    counters and exact-pass sets on identical rays, and the same image from the same seed."""
+    from ray_tracer_archive_b200 import scenes
+    cfg = scenes.config_final_scene() if which == "final_scene" else scenes.config_mesh(nx=200, nz=100)
+    cs = rtb.compile_scene(cfg.world, cfg.lights)
+    W, Hh = 400, 300
+    out = {}
+    for mode in ("static", "dynamic", "wq"):
+        monkeypatch.setenv("RTB_EXTEND_MODE", mode)  # read when the scene is committed (configure_launch)
+        dev = rtb.Scene(ctx, cs)
+        ids, ts, st = dev.primary_hits(cfg.camera, W, Hh)
+        acc, rst = dev.render(cfg.camera, rtb.make_params(W, Hh, 8, cfg.max_depth, cfg.background, seed=5))
+        out[mode] = (ids, ts, st, np.asarray(acc, dtype=np.float64), rst)
+        dev.close()
+    ids0, ts0, st0, acc0, rst0 = out["static"]
+    for mode in ("dynamic", "wq"):
+        ids, ts, st, acc, rst = out[mode]
+        assert np.array_equal(ids, ids0) and np.array_equal(ts, ts0), mode
+        for k in ("nodes_visited", "prims_tested", "exact_rays", "refined_rays"):
+            assert st[k] == st0[k], (mode, k, st[k], st0[k])
+        assert rst["segments"] == rst0["segments"], mode
+        # same paths; only the order of the float atomics into the accumulator differs
+        assert np.allclose(acc[..., :3], acc0[..., :3], rtol=1e-4, atol=1e-5), mode
+
+
 def test_p1_other_scenes(rtb, orc, ctx):
     from ray_tracer_archive_b200 import scenes
     base = scenes.config_cornell()
