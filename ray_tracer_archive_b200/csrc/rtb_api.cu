@@ -65,7 +65,7 @@ struct Lane {
   cudaEvent_t done = nullptr;
   cudaEvent_t batch_done[2] = {nullptr, nullptr};
 };
-#define RTB_MAX_LANES 4
+#define RTB_MAX_LANES 8
 
 struct rtb_context {
   int device = 0;
@@ -883,10 +883,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   const bool count = (p->flags & RTB_RENDER_COUNT) != 0, time_ext = (p->flags & RTB_RENDER_TIME_EXTEND) != 0;
   // lanes: concurrent wavefront instances on disjoint sample ranges (instrumented runs use one lane so that the
   // per-launch timings / counters describe the kernel alone)
-  // 4 lanes for trees that use the static extend scheduler, 3 for deep trees (dynamic fetch): C1 7696 -> 7882, C3 +2.6 %
-  // with 4; C4 +0.9 % only, not worth a fourth 147 MB pool (profiles/r2_ab.md)
+  // 4 lanes: C1 7696 -> 7882, C3 +2.6 % against 3; the dynamic-fetch kernel at 64 registers co-schedules the extend CTAs of
+  // four lanes on an SM: C4 3915 (3 lanes) -> 4096 (4), 5 / 6 lanes add nothing (profiles/r3_ab.md §9)
   static const int env_lanes = getenv("RTB_LANES") ? atoi(getenv("RTB_LANES")) : 0;
-  const int want_lanes = env_lanes > 0 ? env_lanes : (s->lc.dynamic_fetch ? 3 : 4);
+  const int want_lanes = env_lanes > 0 ? env_lanes : 4;
   int n_lanes = (count || time_ext) ? 1 : std::max(1, std::min(want_lanes, RTB_MAX_LANES));
   if ((uint32_t)n_lanes > p->spp) n_lanes = (int)p->spp;
   uint32_t pool_total = p->pool_paths ? p->pool_paths : (1u << 22);  // all lanes together; 112 B per slot

@@ -638,6 +638,10 @@ __device__ __forceinline__ float q2f(uint32_t word, uint32_t magic, uint32_t sel
 // The traversal is split into trav_init / trav_step (ONE node visit or one stack pop per call) so that the extend
 // kernel can keep all 32 lanes of a warp busy by swapping finished rays for new ones between steps.
 // Every step is exactly one node visit: lanes never spend an iteration on bookkeeping while others decode a node.
+#if !defined(__CUDA_ARCH__) && defined(RTB_EMUL_STATS)
+inline unsigned long long g_emul_stats[8];  // host build only (tools/emul_stats.py)
+inline float g_emul_tmax0 = INFINITY;       // ... initial t_max of the next traversal ("what if the hit distance were known")
+#endif
 struct Trav {
   float3 o, d;
   float idx, idy, idz, time;
@@ -672,6 +676,9 @@ __device__ __forceinline__ void trav_init(Trav& tv, float3 o, float3 d, float ti
   tv.grp = make_uint2(0u, (1u << (tv.octinv + 8)) | 1u);  // virtual group whose slot 0 is the root node
   tv.sp = 0;
   tv.best = Closest{INFINITY, INFINITY, REF_MISS};
+#if !defined(__CUDA_ARCH__) && defined(RTB_EMUL_STATS)
+  tv.best.hi = g_emul_tmax0;
+#endif
   tv.amb = INFINITY;
 }
 
@@ -780,6 +787,12 @@ __device__ __forceinline__ bool trav_step(const DevScene& sc, const uint4* __res
     missmask = __funnelshift_l(neg, missmask, 1);  // (missmask << 1) | sign bit; child 0 ends in bit 0
   }
   const uint32_t hitmask = ~missmask & 0xFFu;
+#if !defined(__CUDA_ARCH__) && defined(RTB_EMUL_STATS)
+  ++g_emul_stats[0];                    // node visits
+  if (!hitmask) ++g_emul_stats[1];      // ... that found no child to continue with (stale stack entries, loose boxes)
+  g_emul_stats[2] += __builtin_popcount(hitmask & imask);   // internal children hit
+  g_emul_stats[3] += __builtin_popcount(hitmask & ~imask);  // leaf children hit
+#endif
   // internal children: slot mask -> priority mask (bit p = slot ^ octinv)
   uint32_t ih = hitmask & imask;
   if (octinv & 1u) ih = ((ih & 0x55u) << 1) | ((ih & 0xAAu) >> 1);

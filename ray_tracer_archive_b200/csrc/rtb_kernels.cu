@@ -226,10 +226,18 @@ __device__ __forceinline__ uint32_t build_extend_list_sorted(const DevPool& pool
 // ray kind (build_extend_list) and handed out 32 at a time.
 // COUNT = true: the instrumented build used for the roofline's algorithmic work (nodes visited / primitives tested per
 // segment); the timed path runs COUNT = false.
-// extend runs 2 CTAs/SM (configure_launch) with at most 80 registers: 2 x 256 x 80 = 41 K of the 64 K registers, so a
-// 256-thread shade CTA of another lane fits beside them.  Measured (C1, Mrays/s): cap 72: 4476, 80: 4497, 88: 4326,
-// 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
+// Register caps.  The one-ray-per-thread kernels run 2 CTAs/SM (configure_launch) with at most 80 registers: 2 x 256 x 80 =
+// 41 K of the 64 K registers, so a 256-thread shade CTA of another lane fits beside them.  Measured (C1, Mrays/s): cap 72:
+// 4476, 80: 4497, 88: 4326, 96: 3947 — the extend kernel alone is fastest at 88+, the overlapped pipeline at 80.
+// The dynamic-fetch kernel (deep trees) is latency-bound on its dependent node -> primitive fetches and wants WARPS: at 64
+// registers (no spills) four extend CTAs — of four wavefront lanes — share an SM, 32 warps instead of 24: C4 3706 -> 4096
+// Mrays/s (profiles/r3_ab.md §9).
+#ifndef RTB_EXTEND_MAXREG
 #define RTB_EXTEND_MAXREG 80
+#endif
+#ifndef RTB_EXTEND_DYN_MAXREG
+#define RTB_EXTEND_DYN_MAXREG 64
+#endif
 struct ExtIn { float4 o_time, d_slot, idir_oct, best; };  // best = (t, ref, group word, t upper bound) after the global primitives
 struct ExtOut { float t; uint32_t ref, slot, redo; float lo, hi; uint32_t _pad[2]; };
 #define RTB_EXTEND_WARPS (RTB_EXTEND_THREADS / 32)
@@ -237,7 +245,7 @@ struct ExtOut { float t; uint32_t ref, slot, redo; float lo, hi; uint32_t _pad[2
 // Leaf primitives are always PARKED here (drain_parked; threshold = DevParams::opt bits 8-13, default 14 lanes): testing
 // them at the node visit instead costs 7 % on the 1 M-triangle mesh (profiles/r3_ab.md §2).
 template <bool COUNT>
-__global__ void __maxnreg__(RTB_EXTEND_MAXREG)
+__global__ void __maxnreg__(RTB_EXTEND_DYN_MAXREG)
 k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
   extern __shared__ uint4 snodes[];
   __shared__ ExtIn s_in[RTB_EXTEND_WARPS][32];
@@ -1490,7 +1498,9 @@ int configure_launch(LaunchCfg& lc, uint32_t n_nodes, uint32_t max_depth, int sm
   // one-lane ext_ms C3 66.3 at 12 KB vs 68.5 at 56 KB, C4 20.8 vs 21.1) and cost the multi-lane pipeline its overlap —
   // with <= ~62 KB per CTA a third extend CTA (of another lane) fits an SM: C4 2748 -> 3268 Mrays/s, C3 3585 -> 3694
   // (profiles/r2_ab.md §9).
-  uint32_t budget = (getenv("RTB_STAGE_KB") ? (uint32_t)atoi(getenv("RTB_STAGE_KB")) : 12u) * 1024u;
+  // Deep trees (dynamic fetch, four extend CTAs of four lanes per SM): 6 KB — the root and its children's children; what the
+  // stage does not hold comes from an L1 that is 24 KB larger (C4 4075 -> 4108 Mrays/s).
+  uint32_t budget = (getenv("RTB_STAGE_KB") ? (uint32_t)atoi(getenv("RTB_STAGE_KB")) : (lc.dynamic_fetch ? 6u : 12u)) * 1024u;
   budget = std::min(budget, (lc.dynamic_fetch ? 84u : 104u) * 1024u);
   uint32_t n_s = n_nodes;
   if ((size_t)n_s * 80 > budget) n_s = budget / 80;

@@ -39,6 +39,9 @@ static inline void __syncwarp() {}
 using namespace rtb;
 static unsigned long long g_exact_rays = 0, g_refined_rays = 0;
 
+#ifdef RTB_EMUL_STATS
+static const float* g_tmax0 = nullptr;
+#endif
 extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom0, const uint32_t* info0,
                           const float* geom1, const uint32_t* info1, const float* geom2, const uint32_t* info2,
                           const float* geom3, const uint32_t* info3, const double* exact0, const double* exact1,
@@ -72,6 +75,9 @@ extern "C" int emul_trace(const void* nodes, uint32_t n_nodes, const float* geom
     const float3 ro = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), rd = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
     // the hot path (f32, ambiguity detection), then — as k_fixup does on the device — the exact pass if it asked for one
     float lo = 0.f;
+#ifdef RTB_EMUL_STATS
+    rtb::g_emul_tmax0 = g_tmax0 ? g_tmax0[i] : INFINITY;
+#endif
     const uint32_t fix = traverse<true>(sc, (const uint4*)nodes, 0u, n_snodes < n_nodes ? n_snodes : n_nodes, ro, rd,
                                         time ? time[i] : 0.f, RTB_TMIN, best, lo, nv, nt);
     if (fix == FIX_RETRACE) {
@@ -106,3 +112,10 @@ extern "C" unsigned long long emul_refined_rays() {
 extern "C" unsigned long long emul_chunk_path(unsigned long long m, uint32_t chunk, uint32_t n_chunks) {
   return chunk_path(m, chunk, n_chunks);
 }
+
+#ifdef RTB_EMUL_STATS
+extern "C" void emul_set_tmax0(const float* per_ray) { g_tmax0 = per_ray; }
+extern "C" void emul_stats(unsigned long long* out8, int reset) {
+  for (int i = 0; i < 8; ++i) { out8[i] = rtb::g_emul_stats[i]; if (reset) rtb::g_emul_stats[i] = 0; }
+}
+#endif
