@@ -512,6 +512,32 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
       }
       std::sort(big.begin(), big.end());
       for (size_t k = 0; k < big.size() && k < 4; ++k) is_global[big[k].second] = 1;
+      // A handful of LARGE primitives of a type of their own (the six walls around the 1 M-triangle height field: their
+      // boxes add up to twice the scene box, nearly every ray reaches one anyway): in the tree they cost a typed subtree
+      // whose leaf tests split every leaf-test round of the deep-tree extend kernel in two (one type at a time); out of
+      // it they cost a few full-width quad tests per ray.  C4: 4120 -> 4400 Mrays/s, one node visit less per segment.
+      // (A SMALL lone primitive — the one moving sphere of the final scene — stays in the tree: testing it for every ray
+      // costs 3 %.)
+      if (!(getenv("RTB_GLOBAL_MINORITY") && atoi(getenv("RTB_GLOBAL_MINORITY")) == 0)) {
+        size_t cnt[PT_COUNT] = {0, 0, 0, 0};
+        float area[PT_COUNT] = {0.f, 0.f, 0.f, 0.f};
+        for (size_t i = 0; i < np; ++i)
+          if (hs.prims[i].type < PT_COUNT && !is_global[i]) {
+            Box3 b;
+            b.grow(hs.prims[i].lo, hs.prims[i].hi);
+            cnt[hs.prims[i].type]++;
+            area[hs.prims[i].type] += b.area();
+          }
+        size_t n_glob = 0, n_types = 0;
+        for (size_t i = 0; i < np; ++i) n_glob += is_global[i];
+        for (uint32_t t = 0; t < PT_COUNT; ++t) n_types += cnt[t] ? 1u : 0u;
+        for (uint32_t t = 0; t < PT_COUNT && n_types > 1; ++t)
+          if (cnt[t] && cnt[t] <= 8 && area[t] >= scene_area && n_glob + cnt[t] <= RTB_MAX_GLOBALS) {
+            for (size_t i = 0; i < np; ++i)
+              if (hs.prims[i].type == t && !is_global[i]) { is_global[i] = 1; ++n_glob; }
+            --n_types;
+          }
+      }
     }
   }
 
@@ -581,13 +607,35 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   const bool joined = trees.size() > 1;
   out.nodes.emplace_back();
   if (joined) {
-    // root joins the typed subtree roots (each forced to be an internal node)
-    WideChild ch[8];
+    // The root joins the typed trees.  Its children are all internal nodes and may come from different trees (only the LEAF
+    // children of a node share a type), so the typed roots are opened — largest box first — until the eight slots are used:
+    // a ray does not spend one visit on a 2-3-child join node plus one per typed root before it reaches real branching
+    // (final scene: 5.6 -> 4.x node visits per segment).  RTB_JOIN_OPEN=0: the plain join of round 1.
+    struct Cand { int tree, bin; };
+    Cand cand[8];
     int nch = (int)trees.size();
+    for (int i = 0; i < nch; ++i) cand[i] = Cand{i, trees[i].root};
+    const bool open_join = !(getenv("RTB_JOIN_OPEN") && atoi(getenv("RTB_JOIN_OPEN")) == 0);
+    while (open_join && nch < 8) {
+      int best = -1;
+      float best_area = -1.f;
+      for (int i = 0; i < nch; ++i) {
+        const BinNode& c = trees[cand[i].tree].b->bin[cand[i].bin];
+        if (c.left < 0) continue;
+        const float a = c.box.area();
+        if (a > best_area) { best_area = a; best = i; }
+      }
+      if (best < 0) break;
+      const Cand o = cand[best];
+      const BinNode& ob = trees[o.tree].b->bin[o.bin];
+      cand[best] = Cand{o.tree, ob.left};
+      cand[nch++] = Cand{o.tree, ob.right};
+    }
+    WideChild ch[8];
     uint32_t base = (uint32_t)out.nodes.size();
     for (int i = 0; i < nch; ++i) {
-      ch[i].box = trees[i].b->bin[trees[i].root].box;
-      ch[i].leaf = false;
+      ch[i].box = trees[cand[i].tree].b->bin[cand[i].bin].box;
+      ch[i].leaf = false;  // (a one-primitive tree becomes a node with one leaf child, process())
       out.nodes.emplace_back();
     }
     int slot_of[8];
@@ -604,7 +652,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
     for (int k = 0; k < nch; ++k) {
       int i = idx[k];
       n.imask |= (uint8_t)(1u << slot_of[i]);
-      queue.push_back(Pending{base + (uint32_t)k, i, trees[i].root, 2});
+      queue.push_back(Pending{base + (uint32_t)k, cand[i].tree, cand[i].bin, 2});
     }
     out.nodes[0] = n;
   } else {
