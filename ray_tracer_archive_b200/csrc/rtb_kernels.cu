@@ -213,6 +213,23 @@ __device__ __forceinline__ uint32_t build_extend_list_sorted(const DevPool& pool
   return total;
 }
 
+// instrumented build (COUNT): a warp's node visits / primitive tests per type go to the lane's counters
+__device__ __forceinline__ void report_counts(DevCounters* c, uint32_t nv, TestCount nt, uint32_t lane) {
+  nv = __reduce_add_sync(0xffffffffu, nv);
+  uint32_t tot = 0;
+#pragma unroll
+  for (uint32_t t = 0; t < PT_COUNT; ++t) {
+    nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
+    tot += nt.n[t];
+  }
+  if (lane == 0) {
+    atomicAdd(&c->nodes_visited, (unsigned long long)nv);
+    atomicAdd(&c->prims_tested, (unsigned long long)tot);
+    for (uint32_t t = 0; t < PT_COUNT; ++t)
+      if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
+  }
+}
+
 // ---- extend ------------------------------------------------------------------------------------------------------
 // Dynamic-fetch variant (deep trees).  Persistent warps: every lane owns one in-flight ray and advances it by ONE node
 // visit per loop iteration, so the 32 lanes execute the node-decode code together.  Rays finish after different
@@ -380,21 +397,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     }
   }
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
-  if (COUNT) {
-    nv = __reduce_add_sync(0xffffffffu, nv);
-    uint32_t tot = 0;
-#pragma unroll
-    for (uint32_t t = 0; t < PT_COUNT; ++t) {
-      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
-      tot += nt.n[t];
-    }
-    if (lane == 0) {
-      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-      atomicAdd(&c->prims_tested, (unsigned long long)tot);
-      for (uint32_t t = 0; t < PT_COUNT; ++t)
-        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
-    }
-  }
+  if (COUNT) report_counts(c, nv, nt, lane);
 }
 
 // ---- warp-queue extend (deep trees) ----------------------------------------------------------------------------------
@@ -632,21 +635,7 @@ k_extend_wq(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     __syncwarp();
   }
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
-  if (COUNT) {
-    nv = __reduce_add_sync(0xffffffffu, nv);
-    uint32_t tot = 0;
-#pragma unroll
-    for (uint32_t t = 0; t < PT_COUNT; ++t) {
-      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
-      tot += nt.n[t];
-    }
-    if (lane == 0) {
-      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-      atomicAdd(&c->prims_tested, (unsigned long long)tot);
-      for (uint32_t t = 0; t < PT_COUNT; ++t)
-        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
-    }
-  }
+  if (COUNT) report_counts(c, nv, nt, lane);
 }
 
 // One ray per thread to completion (small trees: all lanes start at the root together, so root-level work stays
@@ -692,21 +681,7 @@ k_extend_static(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     __syncwarp();  // the list is rewritten for the next chunk
   }
   if (lane == 0 && n_rays) atomicAdd(&c->iter_rays, n_rays);
-  if (COUNT) {
-    nv = __reduce_add_sync(0xffffffffu, nv);
-    uint32_t tot = 0;
-#pragma unroll
-    for (uint32_t t = 0; t < PT_COUNT; ++t) {
-      nt.n[t] = __reduce_add_sync(0xffffffffu, nt.n[t]);
-      tot += nt.n[t];
-    }
-    if (lane == 0) {
-      atomicAdd(&c->nodes_visited, (unsigned long long)nv);
-      atomicAdd(&c->prims_tested, (unsigned long long)tot);
-      for (uint32_t t = 0; t < PT_COUNT; ++t)
-        if (nt.n[t]) atomicAdd(&c->prims_tested_type[t], (unsigned long long)nt.n[t]);
-    }
-  }
+  if (COUNT) report_counts(c, nv, nt, lane);
 }
 
 // ---- surface reconstruction in the shade kernels -------------------------------------------------------------------
