@@ -111,7 +111,9 @@ typedef struct rtb_texture {
 
 /* ---- flat records ---------------------------------------------------------------------------------------- */
 #define RTB_PRIM_FLIP_FACE   1u /* FlipFace: front_face toggled, normal untouched         hittable.rs:195-201 */
-#define RTB_PRIM_FORCE_FRONT 2u /* wrapped by Translate/RotateY: front_face = true        hittable.rs:82-83,173 */
+#define RTB_PRIM_FORCE_FRONT 2u /* wrapped by a Translate: front_face = true                 hittable.rs:82-83
+                                   (the flat API has no rotation record: RotateY's object-ray / world-normal
+                                   front_face, hittable.rs:173, is reproduced for scene-graph input only) */
 
 typedef enum rtb_light_type { RTB_LIGHT_XZ_RECT = 0, RTB_LIGHT_SPHERE = 1 } rtb_light_type;
 /* the only two Hittables with pdf_value/random (aarect.rs:107-125, sphere.rs:75-90) */

@@ -31,22 +31,43 @@ struct Xform {           // world = Ry(angle) * p + t   (the reference only has 
   }
 };
 
-// front_face rewriting by wrappers, composed outer∘inner while walking down
-uint32_t compose_face(uint32_t outer, uint32_t inner_wrapper) {
-  // value of outer(inner(x)) where inner_wrapper ∈ {FLIPPED (FlipFace), TRUE (Translate/RotateY)}
-  if (inner_wrapper == FACE_TRUE) {
-    switch (outer) {
-      case FACE_NATURAL: return FACE_TRUE;
-      case FACE_FLIPPED: return FACE_FALSE;
-      default: return outer;
+// front_face / normal rewriting by the wrappers between the root and a primitive, evaluated the way the reference
+// does per hit, innermost first (`wr` is stored outermost first):
+//   primitive        set_face_normal(ray, outward): normal n against the ray, front = natural
+//   FlipFace         front = !front                                                     (hittable.rs:197-201)
+//   Translate        set_face_normal(moved ray, normal): the normal is re-oriented against the ray,
+//                    front = "the incoming normal already was"                           (hittable.rs:82-83)
+//   RotateY          set_face_normal(OBJECT-space ray, WORLD-space normal): q = dot(R^T d, n) < 0;
+//                    front = q (or !q if the incoming normal was mis-oriented), normal = q ? n : -n   (hittable.rs:173)
+// One RotateY gives a closed form in q (FACE_Q / FACE_NOT_Q / FACE_BARE); with two the outer one's q depends on the inner
+// one's and the chain falls back to "front = true" for transforms (what round 1 did for every chain).
+enum : uint8_t { WR_TRANSLATE = 1, WR_ROTATE = 2, WR_FLIP = 3 };
+uint32_t eval_face(const uint8_t* wr, int n) {
+  enum { F0, NF0, T, F, Q, NQ } front = F0;
+  bool sign_q = false;  // the normal is q ? n : -n instead of n
+  int n_rot = 0;
+  auto neg = [](decltype(front) f) { return f == F0 ? NF0 : f == NF0 ? F0 : f == T ? F : f == F ? T : f == Q ? NQ : Q; };
+  for (int i = n - 1; i >= 0; --i) {
+    if (wr[i] == WR_FLIP) {
+      front = neg(front);
+    } else if (wr[i] == WR_TRANSLATE || n_rot >= 1) {
+      if (wr[i] == WR_ROTATE) ++n_rot;
+      front = sign_q ? Q : T;
+      sign_q = false;
+    } else {  // the chain's first (innermost) RotateY
+      ++n_rot;
+      front = Q;  // (the incoming normal is correctly oriented: nothing before it can have flipped it)
+      sign_q = true;
     }
   }
-  // inner is a flip
-  switch (outer) {
-    case FACE_NATURAL: return FACE_FLIPPED;
-    case FACE_FLIPPED: return FACE_NATURAL;
-    default: return outer;
-  }
+  const uint32_t base = front == F0 ? FACE_NATURAL : front == NF0 ? FACE_FLIPPED : front == T ? FACE_TRUE
+                        : front == F ? FACE_FALSE : front == Q ? FACE_Q : FACE_NOT_Q;
+  return base | (sign_q ? FACE_BARE : 0u);
+}
+// triangles carry no rotation record on the device: q is taken as true (the round-1 behaviour)
+uint32_t face_without_q(uint32_t fm) {
+  const uint32_t b = fm & 7u;
+  return b == FACE_Q ? FACE_TRUE : b == FACE_NOT_Q ? FACE_FALSE : b;
 }
 
 void set_bounds(HostPrim& p, const double lo[3], const double hi[3]) {
@@ -64,6 +85,13 @@ void set_bounds(HostPrim& p, const double lo[3], const double hi[3]) {
 struct Chain {
   ExactXform x;
   bool canonical = true;
+  uint8_t wr[32];  // wrapper kinds from the root down to here (eval_face)
+  int n_wr = 0;
+  Chain with(uint8_t kind) const {
+    Chain c = *this;
+    if (c.n_wr < 32) c.wr[c.n_wr++] = kind;
+    return c;
+  }
 };
 
 struct Walker {
@@ -185,7 +213,7 @@ struct Walker {
         double pf[9], a[3], b[3], c[3];
         for (int q = 0; q < 9; ++q) pf[q] = (double)(float)p[q];
         x.point(pf, a); x.point(pf + 3, b); x.point(pf + 6, c);
-        HostPrim& pr = emit(PT_TRI, n.material, fm);
+        HostPrim& pr = emit(PT_TRI, n.material, face_without_q(fm));
         pack_tri(pr, a, b, c);
         break;
       }
@@ -227,7 +255,7 @@ struct Walker {
             pr.type = PT_TRI;
             pr.prim_id = id0 + (uint32_t)t;
             pr.material = material;
-            pr.face_mode = fm;
+            pr.face_mode = face_without_q(fm);
             pr.exact = RTB_NONE;
             pack_tri(pr, v[0], v[1], v[2]);
           }
@@ -253,14 +281,14 @@ struct Walker {
         double off[3];
         x.vec(p, off);
         for (int a = 0; a < 3; ++a) y.t[a] += off[a];
-        Chain c2 = ch;
+        Chain c2 = ch.with(WR_TRANSLATE);
         if (ch.canonical && ch.x.flags == 0) {
           c2.x.flags = EX_TRANSLATE;
           for (int a = 0; a < 3; ++a) c2.x.off[a] = p[a];
         } else {
           c2.canonical = false;  // Translate inside RotateY / inside another Translate
         }
-        ok = walk(c, y, compose_face(fm, FACE_TRUE), c2);
+        ok = walk(c, y, eval_face(c2.wr, c2.n_wr), c2);
         break;
       }
       case RTB_NODE_ROTATE_Y: {
@@ -271,7 +299,7 @@ struct Walker {
         double rad = y.angle_deg * kPi / 180.0;  // hittable.rs:108
         y.c = std::cos(rad); y.s = std::sin(rad);
         y.identity_rot = false;
-        Chain c2 = ch;
+        Chain c2 = ch.with(WR_ROTATE);
         if (ch.canonical && !(ch.x.flags & EX_ROTATE)) {
           const double r1 = p[0] * kPi / 180.0;  // hittable.rs:108
           c2.x.flags |= EX_ROTATE;
@@ -279,13 +307,14 @@ struct Walker {
         } else {
           c2.canonical = false;
         }
-        ok = walk(c, y, compose_face(fm, FACE_TRUE), c2);
+        ok = walk(c, y, eval_face(c2.wr, c2.n_wr), c2);
         break;
       }
       case RTB_NODE_FLIP_FACE: {
         uint32_t c;
         if (!child(0, c)) { ok = false; break; }
-        ok = walk(c, x, compose_face(fm, FACE_FLIPPED), ch);
+        const Chain c2 = ch.with(WR_FLIP);
+        ok = walk(c, x, eval_face(c2.wr, c2.n_wr), c2);
         break;
       }
       case RTB_NODE_CONSTANT_MEDIUM: {

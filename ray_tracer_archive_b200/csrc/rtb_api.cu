@@ -640,7 +640,7 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
     CU(s->d_geom[t].upload(reinterpret_cast<const float4*>(bvh.geom[t].data()), bvh.geom[t].size() / 4));
     // device copy of the info words carries the shade queue of the primitive's material (RTB_MINFO_QUEUE)
     std::vector<uint32_t> info = bvh.info[t];
-    for (size_t i = 1; i < info.size(); i += 2) info[i] |= queue_of_material(hs, info[i] & 0xFFFFFFu) << 26;
+    for (size_t i = 1; i < info.size(); i += 2) info[i] |= queue_of_material(hs, info[i] & 0xFFFFFFu) << 28;
     CU(s->d_info[t].upload(reinterpret_cast<const uint2*>(info.data()), info.size() / 2));
     CU(cudaStreamSynchronize(0));  // `info` is a temporary
     d.geom[t] = s->d_geom[t].p;
@@ -699,7 +699,7 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
     const HostMedium& m = hs.media[i];
     DevMedium& o = d.media[i];
     o.boundary_type = m.boundary_type; o.material = m.material; o.prim_id = m.prim_id;
-    o.minfo = (m.material & 0xFFFFFFu) | (FACE_TRUE << 24) | (queue_of_material(hs, m.material) << 26);
+    o.minfo = (m.material & 0xFFFFFFu) | (FACE_TRUE << 24) | (queue_of_material(hs, m.material) << 28);
     o.neg_inv_density = m.neg_inv_density;
     for (int k = 0; k < 6; ++k) o.p[k] = m.p[k];
     o.sin_t = m.sin_t; o.cos_t = m.cos_t;

@@ -34,12 +34,12 @@ enum CheckKind : int { CHK_STACK = 0, CHK_NODE = 1, CHK_PRIM = 2, CHK_SLOT = 3, 
 #define RTB_PI 3.14159265358979323846f
 
 enum Queue : uint32_t { Q_TERMINAL = 0, Q_LAMBERT = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_ISOTROPIC = 4, Q_COUNT = 5 };
-// per-primitive info word y (device copy): material (24 bits) | face mode << 24 (2 bits) | shade queue << 26 (3 bits).
+// per-primitive info word y (device copy): material (24 bits) | face mode << 24 (4 bits, FaceMode) | shade queue << 28 (3 bits).
 // The queue is resolved from the material type on the host at commit, so `extend` classifies a hit without touching
 // the material table (one dependent load less on its tail).
 #define RTB_MINFO_MAT(m) ((m) & 0xFFFFFFu)
-#define RTB_MINFO_FACE(m) (((m) >> 24) & 3u)
-#define RTB_MINFO_QUEUE(m) (((m) >> 26) & 7u)
+#define RTB_MINFO_FACE(m) (((m) >> 24) & 15u)
+#define RTB_MINFO_QUEUE(m) (((m) >> 28) & 7u)
 
 struct DevTexture {  // 32 bytes
   uint32_t type, even, odd, table;
@@ -52,7 +52,7 @@ struct DevMedium {
   float p[6];
   float sin_t, cos_t;
   float off[3];
-  uint32_t minfo;  // hit-record word of this medium: material | FACE_TRUE << 24 | queue << 26
+  uint32_t minfo;  // hit-record word of this medium: material | FACE_TRUE << 24 | queue << 28
 };
 struct DevImage { const uint8_t* data; uint32_t w, h; };
 
@@ -131,7 +131,7 @@ struct DevPool {
   uint32_t n_chunks;  // ceil(n / RTB_CHUNK)
   float4* ray;        // [2s] origin xyz, time ; [2s+1] direction xyz (un-normalised, ray.rs), 0   — one 32-byte sector
   float4* st;         // [2s] throughput rgb, pixel index bits ; [2s+1] radiance rgb, (sample << 8 | segments) bits
-  float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 26) bits, 0
+  float4* hit;        // t, ref bits, (material | face mode << 24 | shade queue << 28) bits, 0
   uint8_t* cls;       // [n_chunks * RTB_CHUNK] SlotClass / Queue per slot; padding slots are CLS_DEAD
   uint4* redo[2];     // [0]: [n] rays for the exact pass, (slot | RTB_REDO_REFINE, slab lower bound, upper bound, -)
   unsigned long long* cursor;  // [n_chunks] path numbers consumed so far from the chunk's sequence

@@ -17,7 +17,11 @@ static const uint32_t REF_MISS = 0xFFFFFFFFu;
 #define RTB_MAX_GLOBALS 16
 
 // face-orientation modes: how Translate/RotateY/FlipFace wrappers rewrite front_face (hittable.rs:82-83,173,199)
-enum FaceMode : uint32_t { FACE_NATURAL = 0, FACE_FLIPPED = 1, FACE_TRUE = 2, FACE_FALSE = 3 };
+// front_face of the hit record as the reference's wrapper chain leaves it (flatten.cpp: eval_face).  q = the value
+// RotateY::hit computes by testing the OBJECT-space ray against the WORLD-space normal (hittable.rs:173);
+// FACE_BARE: no Translate outside that RotateY re-oriented the normal, so the normal itself is q ? n : -n.
+enum FaceMode : uint32_t { FACE_NATURAL = 0, FACE_FLIPPED = 1, FACE_TRUE = 2, FACE_FALSE = 3, FACE_Q = 4, FACE_NOT_Q = 5,
+                           FACE_BARE = 8 };
 
 struct Float3 { float x, y, z; };
 

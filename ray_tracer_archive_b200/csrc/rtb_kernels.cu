@@ -718,8 +718,17 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uin
   s.mat = RTB_MINFO_MAT(minfo);
   bool ff = dot(d, s.outward) < 0.0f;
   s.n = ff ? s.outward : -s.outward;
-  const uint32_t mode = RTB_MINFO_FACE(minfo);  // wrappers rewrite front_face but leave the oriented normal (hittable.rs:82-83,173,199)
-  s.front = mode == FACE_NATURAL ? ff : mode == FACE_FLIPPED ? !ff : mode == FACE_TRUE;
+  // wrappers rewrite front_face (hittable.rs:82-83,173,199; flatten.cpp eval_face has the algebra)
+  const uint32_t mode = RTB_MINFO_FACE(minfo), base = mode & 7u;
+  if (mode >= FACE_Q) {  // under a RotateY: q = RotateY::hit's test of the OBJECT-space ray against the WORLD-space normal
+    const double* ex = sc.xtab->exact[type == PT_MOVING ? 1 : (type == PT_QUAD ? 2 : 0)] + (size_t)idx * RTB_EXACT_STRIDE;
+    const float sn = (float)ex[4], cs = (float)ex[5];
+    const bool q = dot(f3(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z), s.n) < 0.0f;
+    s.front = base == FACE_Q ? q : base == FACE_NOT_Q ? !q : base == FACE_NATURAL ? ff : base == FACE_FLIPPED ? !ff : base == FACE_TRUE;
+    if ((mode & FACE_BARE) && !q) s.n = -s.n;  // no Translate outside the RotateY re-oriented the normal
+  } else {
+    s.front = base == FACE_NATURAL ? ff : base == FACE_FLIPPED ? !ff : base == FACE_TRUE;
+  }
   return s;
 }
 

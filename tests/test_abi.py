@@ -90,9 +90,29 @@ def test_flatten_ids_and_face_modes(rtb):
     assert ids == list(range(12))
     mode = {int(i): int(m >> 24) for i, m in quad_info}
     assert mode[2] == 1                       # FlipFace(light): front_face toggled (hittable.rs:195-201)
-    assert all(mode[i] == 2 for i in range(6, 12))  # Translate(RotateY(Box)): front_face forced true (hittable.rs:82-83)
+    # Translate(RotateY(Box)): front_face = q, RotateY's object-ray / world-normal test; the Translate re-orients the normal
+    # (hittable.rs:173 then 82-83) -> FaceMode Q = 4
+    assert all(mode[i] == 4 for i in range(6, 12))
     assert all(mode[i] == 0 for i in (0, 1, 3, 4, 5))
     assert int(prims[0][1][0]) == 12          # the glass sphere is the last object
+
+
+def test_face_modes_of_wrapper_chains(rtb):
+    """flatten.cpp eval_face: the reference's per-hit front_face / normal rewriting (hittable.rs:82-83,173,197-201)
+    evaluated symbolically per wrapper chain.  FaceMode: 0 natural, 1 flipped, 2 true, 3 false, 4 q, 5 !q, +8 bare."""
+    from ray_tracer_archive_b200 import scene as S
+    m = S.Lambertian.construct((0.5, 0.5, 0.5))
+    r = lambda: S.XzRect.construct(0.0, 1.0, 0.0, 1.0, 0.0, m)
+    T, R, Fl = (lambda x: S.Translate.construct(x, (1.0, 0.0, 0.0))), (lambda x: S.RotateY.construct(x, 30.0)), S.FlipFace.construct
+    chains = [(r(), 0), (Fl(r()), 1), (T(r()), 2), (Fl(T(r())), 3), (T(Fl(r())), 2),
+              (T(R(r())), 4), (T(R(Fl(r()))), 4), (Fl(T(R(r()))), 5), (R(r()), 12), (Fl(R(r())), 13), (R(T(r())), 12),
+              (T(T(R(r()))), 2),          # the second Translate sees a correctly oriented normal: front = true
+              (T(R(R(r()))), 2)]          # two rotations: documented fall-back
+    world = S.HittableList([c for c, _ in chains])
+    s = rtb.Scene(None, rtb.compile_scene(world, None))
+    _, prims = s.export_bvh()
+    mode = {int(i): int(w >> 24) & 15 for i, w in prims[2][1].reshape(-1, 2)}
+    assert [mode[k] for k in range(len(chains))] == [want for _, want in chains]
 
 
 def test_obj_loader_and_ppm_writer(rtb, tmp_path):

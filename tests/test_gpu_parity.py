@@ -443,6 +443,36 @@ def test_rotated_image_textured_sphere(rtb, orc, ctx):
     _p2(rtb, orc, ctx, cfg, 48, 32, spp=1024)
 
 
+def test_front_face_under_rotate_y(rtb, orc, ctx):
+    """H8: RotateY::hit calls set_face_normal with the OBJECT-space ray and the WORLD-space normal (hittable.rs:173), so
+    under a RotateY `front_face` is q = dot(R^T d, n) < 0 — whatever side was hit — and a BARE RotateY also leaves the
+    normal mis-oriented where q is false; a Translate outside re-orients the normal but keeps q as front_face
+    (hittable.rs:82-83).  Dielectric (material.rs:127-132) and DiffuseLight (material.rs:183-189) read front_face: a
+    strongly rotated emissive panel and rotated glass boxes, in every wrapper arrangement, against the literal oracle."""
+    from ray_tracer_archive_b200 import scenes, scene as S
+    white = S.Lambertian.construct((0.73, 0.73, 0.73))
+    glass = S.Dielectric.construct(1.5)
+    lamp = S.DiffuseLight.construct_color((6.0, 5.0, 4.0))
+    lamp2 = S.DiffuseLight.construct_color((3.0, 5.0, 7.0))
+    world = S.HittableList([
+        S.XzRect.construct(-30.0, 30.0, -30.0, 30.0, 0.0, white),                                   # floor
+        # emissive panels: Translate(RotateY(FlipFace(rect))), bare RotateY(rect), FlipFace(Translate(RotateY(rect)))
+        S.Translate.construct(S.RotateY.construct(S.FlipFace.construct(S.XzRect.construct(-3.0, 3.0, -2.0, 2.0, 0.0, lamp)), 50.0), (-4.0, 7.0, 0.0)),
+        S.RotateY.construct(S.XyRect.construct(2.0, 7.0, 1.0, 5.0, -6.0, lamp2), -40.0),
+        S.FlipFace.construct(S.Translate.construct(S.RotateY.construct(S.YzRect.construct(1.0, 4.0, -2.0, 2.0, 0.0, lamp), 35.0), (8.0, 0.0, 3.0))),
+        # glass boxes: Translate(RotateY(box)) as in the reference's scenes, and a bare RotateY(box)
+        S.Translate.construct(S.RotateY.construct(S.Box.construct((0.0, 0.0, 0.0), (2.5, 3.0, 2.5), glass), 30.0), (-2.0, 0.01, 1.0)),
+        S.RotateY.construct(S.Box.construct((2.0, 0.01, -1.0), (4.0, 2.5, 1.0), glass), -25.0),
+        # a glass sphere under RotateY(Translate(.)) — a Translate INSIDE the rotation
+        S.RotateY.construct(S.Translate.construct(S.Sphere.construct((0.0, 0.0, 0.0), 1.2, glass), (-5.0, 1.3, 4.0)), 20.0),
+    ])
+    cfg = scenes.config_cornell()
+    cfg.world, cfg.lights, cfg.name, cfg.background = world, None, "front_face under RotateY", (0.02, 0.02, 0.03)
+    cfg.camera = rtb.Camera.new((3.0, 9.0, 22.0), (0.0, 2.5, 0.0), (0, 1, 0), 38.0, 1.5, 0.0, 10.0)
+    _p1(rtb, orc, ctx, cfg, 240, 160)
+    _p2(rtb, orc, ctx, cfg, 60, 40, spp=4096)
+
+
 def test_obj_mesh_parity(rtb, orc, ctx, tmp_path):
     """f2: a mesh read by the OBJ loader (io.load_obj -> rtb_scene_set_mesh), transformed, inside the Cornell walls:
     P1 on identical rays + P2 against the oracle."""
