@@ -112,9 +112,10 @@ struct rtb_scene {
   DevBuf<DevScene> d_self;
   DevBuf<float4> d_materials;
   DevBuf<DevTexture> d_textures;
-  DevBuf<float4> d_perlin_vec[RTB_MAX_TABLES];
-  DevBuf<uint8_t> d_perlin_perm[RTB_MAX_TABLES];
-  DevBuf<uint8_t> d_images[RTB_MAX_TABLES];
+  DevBuf<float4> d_perlin_vec;   // all perlin tables, 256 vectors each
+  DevBuf<uint8_t> d_perlin_perm; // all perlin tables, 768 bytes each
+  DevBuf<uint8_t> d_image_data;  // all images, packed
+  DevBuf<DevImage> d_images;     // their descriptors
   DevScene dev;
   LaunchCfg lc;
 };
@@ -675,19 +676,39 @@ static int upload_scene(rtb_scene* s, const rtb_scene* host) {
   }
   CU(s->d_textures.upload(texs.data(), texs.size()));
   d.textures = s->d_textures.p;
-  for (size_t i = 0; i < hs.perlins.size() && i < RTB_MAX_TABLES; ++i) {
-    if (!hs.perlins[i].set) continue;
-    CU(s->d_perlin_vec[i].upload(reinterpret_cast<const float4*>(hs.perlins[i].ranvec.data()), 256));
-    CU(s->d_perlin_perm[i].upload(hs.perlins[i].perm.data(), 768));
-    d.perlin_vec[i] = s->d_perlin_vec[i].p;
-    d.perlin_perm[i] = s->d_perlin_perm[i].p;
-  }
-  for (size_t i = 0; i < hs.images.size() && i < RTB_MAX_TABLES; ++i) {
-    if (hs.images[i].rgb.empty()) continue;
-    CU(s->d_images[i].upload(hs.images[i].rgb.data(), hs.images[i].rgb.size()));
-    d.images[i].data = s->d_images[i].p;
-    d.images[i].w = hs.images[i].w;
-    d.images[i].h = hs.images[i].h;
+  {  // perlin tables and images: any number of them, packed into one buffer each (an unset perlin table stays zero)
+    const size_t np = hs.perlins.size();
+    std::vector<float> vec(np * 1024, 0.f);
+    std::vector<uint8_t> perm(np * 768, 0);
+    for (size_t i = 0; i < np; ++i) {
+      if (!hs.perlins[i].set) continue;
+      std::copy(hs.perlins[i].ranvec.begin(), hs.perlins[i].ranvec.end(), vec.begin() + i * 1024);
+      std::copy(hs.perlins[i].perm.begin(), hs.perlins[i].perm.end(), perm.begin() + i * 768);
+    }
+    CU(s->d_perlin_vec.upload(reinterpret_cast<const float4*>(vec.data()), np * 256));
+    CU(s->d_perlin_perm.upload(perm.data(), perm.size()));
+    d.perlin_vec = s->d_perlin_vec.p;
+    d.perlin_perm = s->d_perlin_perm.p;
+    d.n_perlin = (uint32_t)np;
+    const size_t ni = hs.images.size();
+    size_t total = 0;
+    for (size_t i = 0; i < ni; ++i) total += (hs.images[i].rgb.size() + 15) & ~(size_t)15;
+    std::vector<uint8_t> data(total, 0);
+    std::vector<DevImage> desc(ni);
+    CU(s->d_image_data.resize(total));
+    size_t off = 0;
+    for (size_t i = 0; i < ni; ++i) {
+      desc[i].data = hs.images[i].rgb.empty() ? nullptr : s->d_image_data.p + off;
+      desc[i].w = hs.images[i].w;
+      desc[i].h = hs.images[i].h;
+      std::copy(hs.images[i].rgb.begin(), hs.images[i].rgb.end(), data.begin() + off);
+      off += (hs.images[i].rgb.size() + 15) & ~(size_t)15;
+    }
+    CU(s->d_image_data.upload(data.data(), total));
+    CU(s->d_images.upload(desc.data(), ni));
+    CU(cudaStreamSynchronize(0));  // the staging vectors are temporaries
+    d.images = s->d_images.p;
+    d.n_images = (uint32_t)ni;
   }
   d.n_lights = (uint32_t)hs.lights.size();
   for (size_t i = 0; i < hs.lights.size(); ++i) {

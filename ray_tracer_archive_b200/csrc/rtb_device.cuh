@@ -28,7 +28,7 @@ enum CheckKind : int { CHK_STACK = 0, CHK_NODE = 1, CHK_PRIM = 2, CHK_SLOT = 3, 
 
 #define RTB_MAX_LIGHTS 8
 #define RTB_MAX_MEDIA 8
-#define RTB_MAX_TABLES 4
+#define RTB_MAX_TABLES 4096  /* sanity cap on perlin / image ids (the tables live in device memory, not in DevScene) */
 #define RTB_STACK 32
 #define RTB_TMIN 0.001f  // main.rs:74
 #define RTB_PI 3.14159265358979323846f
@@ -85,9 +85,10 @@ struct DevScene {  // passed by value as a kernel parameter (constant bank)
   float eps_ab;                   // rounding bound of a quad's in-plane coordinates (alpha, beta), see intersect_prim
   const float4* materials;   // [2m] (type bits, texture bits, param, texture-type bits) ; [2m+1] solid albedo rgb, 0
   const DevTexture* textures;
-  const float4* perlin_vec[RTB_MAX_TABLES];
-  const uint8_t* perlin_perm[RTB_MAX_TABLES];
-  DevImage images[RTB_MAX_TABLES];
+  const float4* perlin_vec;   // n_perlin tables x 256 unit vectors
+  const uint8_t* perlin_perm; // n_perlin tables x 3 x 256 permutation bytes
+  const DevImage* images;     // n_images descriptors (data = nullptr: never set, renders cyan like texture.rs:119-121)
+  uint32_t n_perlin, n_images;
   DevLight lights[RTB_MAX_LIGHTS];
   DevMedium media[RTB_MAX_MEDIA];
 };

@@ -800,12 +800,13 @@ __device__ float3 tex_value_slow(const DevScene& sc, uint32_t tex, const Surf& s
     t = sc.textures[sines < 0.f ? t.odd : t.even];
   }
   if (t.type == RTB_TEX_NOISE) {  // texture.rs:90-96
-    const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * perlin_turb(sc.perlin_vec[t.table], sc.perlin_perm[t.table], s.p)));
+    const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * perlin_turb(sc.perlin_vec + 256u * t.table, sc.perlin_perm + 768u * t.table, s.p)));
     return f3(g, g, g);
   }
   if (t.type == RTB_TEX_IMAGE) {  // texture.rs:118-140: nearest texel, v flipped
-    if (t.table >= RTB_MAX_TABLES || sc.images[t.table].data == nullptr) return f3(0.f, 1.f, 1.f);
+    if (t.table >= sc.n_images) return f3(0.f, 1.f, 1.f);
     const DevImage im = sc.images[t.table];
+    if (im.data == nullptr) return f3(0.f, 1.f, 1.f);
     float u, v;
     surface_uv(sc, s, u, v);
     u = fminf(fmaxf(u, 0.f), 1.f);
@@ -1314,8 +1315,8 @@ __global__ void k_kat(DevScene sc, DevCamera cam, DevParams prm, uint32_t op, co
     }
     case RTB_KAT_LIGHTS_PDF: put(0, lights_pdf(sc, V(0), V(3))); break;                      // (o, v) -> pdf over sc.lights
     case RTB_KAT_LIGHTS_RANDOM: put3(0, lights_random(sc, V(0), F(3), F(4), F(5))); break;   // (o, pick, r1, r2) -> direction
-    case RTB_KAT_PERLIN_NOISE: put(0, perlin_noise(sc.perlin_vec[a[0]], sc.perlin_perm[a[0]], V(1))); break;  // (table, p)
-    case RTB_KAT_PERLIN_TURB: put(0, perlin_turb(sc.perlin_vec[a[0]], sc.perlin_perm[a[0]], V(1))); break;
+    case RTB_KAT_PERLIN_NOISE: put(0, perlin_noise(sc.perlin_vec + 256u * a[0], sc.perlin_perm + 768u * a[0], V(1))); break;  // (table, p)
+    case RTB_KAT_PERLIN_TURB: put(0, perlin_turb(sc.perlin_vec + 256u * a[0], sc.perlin_perm + 768u * a[0], V(1))); break;
     case RTB_KAT_Q2F: put(0, q2f(a[0], sc.prmt_magic, 0x7044u | ((a[1] & 3u) << 8))); break;  // (plane word, byte) -> 128 + q
     case RTB_KAT_ONB: { const Onb b(V(0)); put3(0, b.u); put3(3, b.v); put3(6, b.w); break; }
     case RTB_KAT_REFLECT: put3(0, reflect3(V(0), V(3))); break;
