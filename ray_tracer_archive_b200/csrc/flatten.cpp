@@ -64,12 +64,6 @@ uint32_t eval_face(const uint8_t* wr, int n) {
                         : front == F ? FACE_FALSE : front == Q ? FACE_Q : FACE_NOT_Q;
   return base | (sign_q ? FACE_BARE : 0u);
 }
-// triangles carry no rotation record on the device: q is taken as true (the round-1 behaviour)
-uint32_t face_without_q(uint32_t fm) {
-  const uint32_t b = fm & 7u;
-  return b == FACE_Q ? FACE_TRUE : b == FACE_NOT_Q ? FACE_FALSE : b;
-}
-
 void set_bounds(HostPrim& p, const double lo[3], const double hi[3]) {
   for (int a = 0; a < 3; ++a) {
     double m = std::fmax(std::fabs(lo[a]), std::fabs(hi[a]));
@@ -213,8 +207,9 @@ struct Walker {
         double pf[9], a[3], b[3], c[3];
         for (int q = 0; q < 9; ++q) pf[q] = (double)(float)p[q];
         x.point(pf, a); x.point(pf + 3, b); x.point(pf + 6, c);
-        HostPrim& pr = emit(PT_TRI, n.material, face_without_q(fm));
+        HostPrim& pr = emit(PT_TRI, n.material, fm);
         pack_tri(pr, a, b, c);
+        pr.g[3] = (float)x.s; pr.g[7] = (float)x.c;  // the chain's rotation, for RotateY's front_face test (surface_at)
         break;
       }
       case RTB_NODE_QUAD: {
@@ -255,9 +250,10 @@ struct Walker {
             pr.type = PT_TRI;
             pr.prim_id = id0 + (uint32_t)t;
             pr.material = material;
-            pr.face_mode = face_without_q(fm);
+            pr.face_mode = fm;
             pr.exact = RTB_NONE;
             pack_tri(pr, v[0], v[1], v[2]);
+            pr.g[3] = (float)x.s; pr.g[7] = (float)x.c;
           }
         };
         unsigned n_thr = ntri >= 100000 ? std::max(1u, std::min(std::thread::hardware_concurrency(), 16u)) : 1u;
@@ -468,7 +464,7 @@ void pack_tri(HostPrim& p, const double v0[3], const double v1[3], const double 
     lo[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
     hi[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
   }
-  p.g[3] = p.g[7] = p.g[11] = 0.f;
+  p.g[3] = 0.f; p.g[7] = 1.f; p.g[11] = 0.f;  // (sin, cos) of the wrapper chain's rotation: identity unless the caller sets it
   set_bounds(p, lo, hi);
 }
 

@@ -452,7 +452,9 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
 // term is the grazing amplification.  HIT_AMBIGUOUS (t_out = a lower bound of the possible hit distance) when a
 // decision (disc' sign, root against t_min) is inside its bound.  `coarse` = the bound exceeds RTB_SPHERE_REL_MAX t
 // (measured: the bound is 50-80x the worst actual error, and the reported t must hold 1e-5 relative): such a hit is
-// certain, only its distance wants an f64 recomputation if it ends up the closest.
+// certain, only its distance wants an f64 recomputation if it ends up the closest.  The same threshold marks the hits of
+// rays nearly parallel to a quad's plane / edge-on to a triangle (found by the random scene-graph tests: n.d = 3e-4 |d|,
+// bound 3e-3 t, actual error 5e-5 t).
 #define RTB_SPHERE_REL_MAX 2.0e-4f
 __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out,
                                            bool& coarse) {
@@ -548,6 +550,7 @@ __device__ __forceinline__ int prim_test(const DevScene& sc, uint32_t type, uint
     const float ma = fminf(alpha, 1.0f - alpha), mb = fminf(beta, 1.0f - beta);
     if (ma < -ea || mb < -eb) return HIT_MISS;
     if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { t = fmaxf(t - e, 0.0f); return HIT_AMBIGUOUS; }
+    coarse = e > RTB_SPHERE_REL_MAX * t;  // a ray nearly parallel to the plane (n.d -> 0): certain hit, distance refined in f64
     return HIT_CERTAIN;
   } else if (type == PT_TRI) {
     // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
@@ -602,6 +605,7 @@ __device__ __forceinline__ int prim_test(const DevScene& sc, uint32_t type, uint
     if (!(t - e <= tmax_hi)) return HIT_MISS;
     const int st = tmin_status(t, e, tmin);
     if (st == HIT_AMBIGUOUS) t = fmaxf(t - e, 0.0f);
+    else coarse = e > RTB_SPHERE_REL_MAX * t;  // (an edge-on triangle)
     return st;
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
@@ -657,8 +661,34 @@ __device__ __forceinline__ bool needs_exact(const Closest& best, float amb) { re
 // what k_fixup has to do for a finished ray: 0 nothing, 1 exact re-trace, 2 recompute the distance of its (certain) hit
 enum FixKind : uint32_t { FIX_NONE = 0, FIX_RETRACE = 1, FIX_REFINE = 2 };
 #define RTB_REDO_REFINE 0x80000000u  /* redo-queue entry: slot | this bit = FIX_REFINE */
-__device__ __forceinline__ uint32_t fix_kind(const Trav& tv) {
-  return needs_exact(tv.best, tv.amb) ? FIX_RETRACE : ((tv.octinv & RTB_TRAV_COARSE) && tv.best.ref != REF_MISS ? FIX_REFINE : FIX_NONE);
+// prim_test() marks a quad / triangle hit coarse from its cheap, loose error bound (for a quad it takes |o|_1 + coord_max
+// as the magnitude of the plane equation's terms, which flags 2-4 % of the rays of a box-shaped scene: every origin within
+// a unit or two of a wall).  Before such a ray is sent to k_fixup the CONDITIONING of its hit is looked at once: t =
+// (n.Q - n.o) / (n.d) loses bits only by cancellation, about 3 x 2^-24 x (sum of the terms' magnitudes / |result|) — so
+// 1e-5 needs a cancellation factor below ~64 in the numerator and in the denominator.  An axis-aligned plane has none (one
+// exact product, and the difference of two nearby floats is exact).
+__device__ __forceinline__ bool quad_distance_is_coarse(const DevScene& sc, uint32_t idx, float3 o, float3 d) {
+  const float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
+  if ((w0.x == 0.0f) + (w0.y == 0.0f) + (w0.z == 0.0f) == 2) return false;
+  const float mag_num = fabsf(w0.w) + fabsf(w0.x * o.x) + fabsf(w0.y * o.y) + fabsf(w0.z * o.z);
+  const float mag_den = fabsf(w0.x * d.x) + fabsf(w0.y * d.y) + fabsf(w0.z * d.z);
+  return 64.0f * fabsf(dot(xyz(w0), d)) < mag_den || 64.0f * fabsf(w0.w - dot(xyz(w0), o)) < mag_num;
+}
+__device__ __forceinline__ bool tri_distance_is_coarse(const DevScene& sc, uint32_t idx, float3 o, float3 d) {
+  const float3 v0 = xyz(__ldg(sc.geom[PT_TRI] + 3 * idx));
+  const float3 n = cross(xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 1)) - v0, xyz(__ldg(sc.geom[PT_TRI] + 3 * idx + 2)) - v0);
+  const float3 r = v0 - o;  // (the test translates the vertices to the ray origin: magnitudes are local)
+  const float mag_num = fabsf(n.x * r.x) + fabsf(n.y * r.y) + fabsf(n.z * r.z);
+  const float mag_den = fabsf(n.x * d.x) + fabsf(n.y * d.y) + fabsf(n.z * d.z);
+  return 64.0f * fabsf(dot(n, d)) < mag_den || 64.0f * fabsf(dot(n, r)) < mag_num;
+}
+__device__ __forceinline__ uint32_t fix_kind(const DevScene& sc, const Trav& tv) {
+  if (needs_exact(tv.best, tv.amb)) return FIX_RETRACE;
+  if (!(tv.octinv & RTB_TRAV_COARSE) || tv.best.ref == REF_MISS) return FIX_NONE;
+  const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT, idx = tv.best.ref & REF_INDEX_MASK;
+  if (type == PT_QUAD && !quad_distance_is_coarse(sc, idx, tv.o, tv.d)) return FIX_NONE;
+  if (type == PT_TRI && !tri_distance_is_coarse(sc, idx, tv.o, tv.d)) return FIX_NONE;
+  return FIX_REFINE;
 }
 // The distance slab the exact pass has to search: every candidate f32 left open lies at or beyond `amb`, the closest
 // certain hit within [2t - hi, hi], and whatever the traversal culled lies beyond hi.  Nothing closer than the slab can be
@@ -888,7 +918,7 @@ __device__ __forceinline__ uint32_t traverse(const DevScene& sc, const uint4* __
   while (trav_step_fast<COUNT, ALL_STAGED>(sc, snodes, sbase, n_snodes, tv, stack, tmin, n_nodes_visited, n_tests)) {}
   best = tv.best;
   slab_lo_out = slab_lo(tv);
-  return fix_kind(tv);
+  return fix_kind(sc, tv);
 }
 
 // FIX_REFINE: the hit is certain, its distance is recomputed with the reference's arithmetic

@@ -391,7 +391,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(sc, tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
       out_count += __popc(done);
       idle |= done;
     }
@@ -626,8 +626,10 @@ k_extend_wq(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.best = Closest{b.x, b.z, __float_as_uint(b.y)};
           tv.amb = b.w;
           tv.octinv = W.trav[r].w;
+          tv.o = xyz(W.o_time[r]);
+          tv.d = xyz(W.d_slot[r]);
           W.out[out_count + __popc(done & lt_mask)] =
-              ExtOut{tv.best.t, tv.best.ref, __float_as_uint(W.d_slot[r].w), fix_kind(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
+              ExtOut{tv.best.t, tv.best.ref, __float_as_uint(W.d_slot[r].w), fix_kind(sc, tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
         }
         out_count += __popc(done);
       }
@@ -721,8 +723,14 @@ __device__ __forceinline__ Surf surface_at(const DevScene& sc, uint32_t ref, uin
   // wrappers rewrite front_face (hittable.rs:82-83,173,199; flatten.cpp eval_face has the algebra)
   const uint32_t mode = RTB_MINFO_FACE(minfo), base = mode & 7u;
   if (mode >= FACE_Q) {  // under a RotateY: q = RotateY::hit's test of the OBJECT-space ray against the WORLD-space normal
-    const double* ex = sc.xtab->exact[type == PT_MOVING ? 1 : (type == PT_QUAD ? 2 : 0)] + (size_t)idx * RTB_EXACT_STRIDE;
-    const float sn = (float)ex[4], cs = (float)ex[5];
+    float sn, cs;  // the chain's rotation: in the exact record, for a triangle in the spare words of its vertices
+    if (type == PT_TRI) {
+      sn = __ldg(sc.geom[PT_TRI] + 3 * idx).w;
+      cs = __ldg(sc.geom[PT_TRI] + 3 * idx + 1).w;
+    } else {
+      const double* ex = sc.xtab->exact[type] + (size_t)idx * RTB_EXACT_STRIDE;
+      sn = (float)ex[4]; cs = (float)ex[5];
+    }
     const bool q = dot(f3(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z), s.n) < 0.0f;
     s.front = base == FACE_Q ? q : base == FACE_NOT_Q ? !q : base == FACE_NATURAL ? ff : base == FACE_FLIPPED ? !ff : base == FACE_TRUE;
     if ((mode & FACE_BARE) && !q) s.n = -s.n;  // no Translate outside the RotateY re-oriented the normal

@@ -16,7 +16,7 @@ from test_gpu_parity import _p1, _p2
 pytestmark = pytest.mark.gpu
 
 
-def _random_scene(seed, S, scenes, dim=False):
+def _random_scene(seed, S, scenes, dim=False, extended=False):
     rng = np.random.default_rng(1000 + seed)
     u = lambda a, b: float(rng.uniform(a, b))
     col = lambda lo=0.2, hi=0.9: (u(lo, hi), u(lo, hi), u(lo, hi))
@@ -39,7 +39,7 @@ def _random_scene(seed, S, scenes, dim=False):
         return S.DiffuseLight.construct_color((u(2, 6), u(2, 6), u(2, 6)))
 
     def primitive():
-        k = rng.integers(0, 6)
+        k = rng.integers(0, 8 if extended else 6)
         m = material()
         c = (u(-5, 5), u(0.5, 4), u(-5, 5))
         if k == 0:
@@ -52,7 +52,13 @@ def _random_scene(seed, S, scenes, dim=False):
             return S.XzRect.construct(c[0], c[0] + u(1, 3), c[2], c[2] + u(1, 3), c[1], m)
         if k == 4:
             return S.YzRect.construct(c[1], c[1] + u(1, 3), c[2], c[2] + u(1, 3), c[0], m)
-        return S.Box.construct(c, (c[0] + u(0.8, 2.5), c[1] + u(0.8, 2.5), c[2] + u(0.8, 2.5)), m)
+        if k == 5:
+            return S.Box.construct(c, (c[0] + u(0.8, 2.5), c[1] + u(0.8, 2.5), c[2] + u(0.8, 2.5)), m)
+        # the primitives that have no reference counterpart: general quad, triangle
+        e1, e2 = (u(0.8, 2.5), u(-0.5, 0.5), u(-0.5, 0.5)), (u(-0.5, 0.5), u(0.8, 2.5), u(-0.8, 0.8))
+        if k == 6:
+            return S.Quad(c, e1, e2, m)
+        return S.Triangle(c, tuple(a + b for a, b in zip(c, e1)), tuple(a + b for a, b in zip(c, e2)), m)
 
     def wrapped(obj, rotations_left=1, depth=0):
         """0-3 random wrappers around obj (at most one RotateY per chain)."""
@@ -91,17 +97,22 @@ def _random_scene(seed, S, scenes, dim=False):
     return S.HittableList(list(objs)), lights
 
 
-@pytest.mark.parametrize("seed", range(24))
+import os
+_SEEDS = range(int(os.environ.get("RTB_FUZZ_FIRST", "0")), int(os.environ.get("RTB_FUZZ_LAST", "24")))  # (one-off sweeps: more seeds)
+
+
+@pytest.mark.parametrize("seed", _SEEDS)
 def test_random_scene_graph(rtb, orc, ctx, seed):
     from ray_tracer_archive_b200 import scenes, scene as S
-    dim = seed >= 12  # second half: almost all light comes from emitters (front_face-sensitive) instead of the sky
-    world, lights = _random_scene(seed, S, scenes, dim)
+    dim = seed % 24 >= 12  # second half: almost all light comes from emitters (front_face-sensitive) instead of the sky
+    extended = seed % 2 == 1  # odd seeds: + general quads and triangles, a thin lens, Russian roulette
+    world, lights = _random_scene(seed, S, scenes, dim, extended)
     cfg = scenes.config_cornell()
     cfg.world, cfg.lights, cfg.name = world, lights, f"random scene graph {seed}"
     cfg.background = (0.03, 0.04, 0.06) if dim else (0.55, 0.65, 0.85)
-    cfg.camera = rtb.Camera.new((2.0, 7.0, 19.0), (0.0, 2.0, 0.0), (0, 1, 0), 40.0, 1.5, 0.0, 10.0, 0.0, 1.0)
+    cfg.camera = rtb.Camera.new((2.0, 7.0, 19.0), (0.0, 2.0, 0.0), (0, 1, 0), 40.0, 1.5, 0.3 if extended else 0.0, 19.0, 0.0, 1.0)
     _p1(rtb, orc, ctx, cfg, 192, 128)
-    _p2(rtb, orc, ctx, cfg, 48, 32, spp=4096 if dim else 1024)
+    _p2(rtb, orc, ctx, cfg, 48, 32, spp=4096 if dim else 1024, rr=4 if extended and seed % 4 == 1 else 0)
 
 
 def test_many_image_and_noise_textures(rtb, orc, ctx):
