@@ -582,7 +582,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
       const uint32_t idx = (uint32_t)(out.info[p.type].size() / 2);
       for (uint32_t w = 0; w < geom_words(p.type); ++w) out.geom[p.type].push_back(p.g[w]);
       out.info[p.type].push_back(p.prim_id);
-      out.info[p.type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
+      out.info[p.type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24) | (p.type == PT_QUAD && p.plane_exact ? 0x80000000u : 0u));
       out.global_refs.push_back((p.type << REF_TYPE_SHIFT) | idx);
     }
   };
@@ -738,7 +738,7 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
           const HostPrim& p = hs.prims[b.recs[lf.first + q].prim()];
           for (uint32_t w = 0; w < gw; ++w) sk.geom[type].push_back(p.g[w]);
           sk.info[type].push_back(p.prim_id);
-          sk.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24));
+          sk.info[type].push_back((p.material & 0xFFFFFFu) | (p.face_mode << 24) | (p.type == PT_QUAD && p.plane_exact ? 0x80000000u : 0u));
         }
         off += lf.count;
       } else {

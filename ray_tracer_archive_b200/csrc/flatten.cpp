@@ -444,6 +444,11 @@ void pack_quad(HostPrim& p, const double Q[3], const double U[3], const double V
   }
   for (int a = 0; a < 3; ++a) { p.g[a] = (float)nh[a]; p.g[4 + a] = (float)wa[a]; p.g[8 + a] = (float)wb[a]; }
   p.g[3] = (float)dot3(nh, Q);
+  {  // an axis-aligned plane whose constant is a float (555, 0, 213 ...): t = (k - o_a) / d_a carries no rounding but its own
+    const double nq = dot3(nh, Q);
+    const int zeros = (p.g[0] == 0.f) + (p.g[1] == 0.f) + (p.g[2] == 0.f);
+    p.plane_exact = zeros == 2 && (double)p.g[3] == nq && std::fabs(p.g[0] + p.g[1] + p.g[2]) == 1.0f;
+  }
   p.g[7] = (float)dot3(wa, Q);
   p.g[11] = (float)dot3(wb, Q);
   double lo[3], hi[3];

@@ -34,7 +34,7 @@ enum CheckKind : int { CHK_STACK = 0, CHK_NODE = 1, CHK_PRIM = 2, CHK_SLOT = 3, 
 #define RTB_PI 3.14159265358979323846f
 
 enum Queue : uint32_t { Q_TERMINAL = 0, Q_LAMBERT = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_ISOTROPIC = 4, Q_COUNT = 5 };
-// per-primitive info word y (device copy): material (24 bits) | face mode << 24 (4 bits, FaceMode) | shade queue << 28 (3 bits).
+// per-primitive info word y (device copy): material (24 bits) | face mode << 24 (4 bits, FaceMode) | shade queue << 28 (3 bits) | bit 31: quad with an exact plane.
 // The queue is resolved from the material type on the host at commit, so `extend` classifies a hit without touching
 // the material table (one dependent load less on its tail).
 #define RTB_MINFO_MAT(m) ((m) & 0xFFFFFFu)
@@ -665,11 +665,11 @@ enum FixKind : uint32_t { FIX_NONE = 0, FIX_RETRACE = 1, FIX_REFINE = 2 };
 // as the magnitude of the plane equation's terms, which flags 2-4 % of the rays of a box-shaped scene: every origin within
 // a unit or two of a wall).  Before such a ray is sent to k_fixup the CONDITIONING of its hit is looked at once: t =
 // (n.Q - n.o) / (n.d) loses bits only by cancellation, about 3 x 2^-24 x (sum of the terms' magnitudes / |result|) — so
-// 1e-5 needs a cancellation factor below ~64 in the numerator and in the denominator.  An axis-aligned plane has none (one
-// exact product, and the difference of two nearby floats is exact).
+// 1e-5 needs a cancellation factor below ~64 in the numerator and in the denominator.  An axis-aligned plane whose constant
+// is exactly a float (555, 0, 213 ...) has none: one exact product, and the difference of two nearby floats is exact.
 __device__ __forceinline__ bool quad_distance_is_coarse(const DevScene& sc, uint32_t idx, float3 o, float3 d) {
   const float4 w0 = __ldg(sc.geom[PT_QUAD] + 3 * idx);
-  if ((w0.x == 0.0f) + (w0.y == 0.0f) + (w0.z == 0.0f) == 2) return false;
+  if (__ldg(&sc.info[PT_QUAD][idx].y) >> 31) return false;  // axis-aligned, plane constant exactly a float (flatten.cpp pack_quad)
   const float mag_num = fabsf(w0.w) + fabsf(w0.x * o.x) + fabsf(w0.y * o.y) + fabsf(w0.z * o.z);
   const float mag_den = fabsf(w0.x * d.x) + fabsf(w0.y * d.y) + fabsf(w0.z * d.z);
   return 64.0f * fabsf(dot(xyz(w0), d)) < mag_den || 64.0f * fabsf(w0.w - dot(xyz(w0), o)) < mag_num;

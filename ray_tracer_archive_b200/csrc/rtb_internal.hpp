@@ -33,6 +33,7 @@ struct HostPrim {      // one flattened primitive, any type
   float g[12];         // device geometry words: sphere (c,r); moving (A,r)(B,0); quad plane form; triangle v0,v1,v2
   float lo[3], hi[3];  // bounds (padded)
   uint32_t exact;      // index into HostScene::exact (RTB_NONE for triangles: their f32 vertices ARE the exact record)
+  uint32_t plane_exact;  // quad: axis-aligned and its plane constant is exactly a float (info word bit 31)
 };
 
 // Reference-exact record of one sphere / moving sphere / quad: the constructor's own f64 arguments in OBJECT space plus

@@ -88,7 +88,7 @@ def test_flatten_ids_and_face_modes(rtb):
     quad_info = prims[2][1].reshape(-1, 2)
     ids = sorted(quad_info[:, 0].tolist())
     assert ids == list(range(12))
-    mode = {int(i): int(m >> 24) for i, m in quad_info}
+    mode = {int(i): int(m >> 24) & 15 for i, m in quad_info}  # (bit 31: exact axis-aligned plane)
     assert mode[2] == 1                       # FlipFace(light): front_face toggled (hittable.rs:195-201)
     # Translate(RotateY(Box)): front_face = q, RotateY's object-ray / world-normal test; the Translate re-orients the normal
     # (hittable.rs:173 then 82-83) -> FaceMode Q = 4

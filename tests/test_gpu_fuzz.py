@@ -11,7 +11,8 @@ Dielectric and DiffuseLight, and each scene has to pass
 import numpy as np
 import pytest
 
-from test_gpu_parity import _p1, _p2
+import helpers as H
+from test_gpu_parity import _p1, _p2, _scene_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -93,6 +94,10 @@ def _random_scene(seed, S, scenes, dim=False, extended=False):
         objs.append(S.FlipFace.construct(S.XzRect.construct(-2.0, 2.0, -2.0, 2.0, 9.0, lamp)))
         lights = S.HittableList.new()
         lights.add(S.XzRect.construct(-2.0, 2.0, -2.0, 2.0, 9.0, lamp))
+        if rng.random() < 0.5:  # a second, spherical entry in the light list (sphere.rs:75-90), like main.rs:682-686
+            ball = S.Sphere.construct((u(-4, 4), u(4, 6), u(-4, 4)), u(0.5, 1.0), lamp if rng.random() < 0.5 else S.Dielectric.construct(1.5))
+            objs.append(ball)
+            lights.add(ball)
     rng.shuffle(objs)
     return S.HittableList(list(objs)), lights
 
@@ -112,7 +117,41 @@ def test_random_scene_graph(rtb, orc, ctx, seed):
     cfg.background = (0.03, 0.04, 0.06) if dim else (0.55, 0.65, 0.85)
     cfg.camera = rtb.Camera.new((2.0, 7.0, 19.0), (0.0, 2.0, 0.0), (0, 1, 0), 40.0, 1.5, 0.3 if extended else 0.0, 19.0, 0.0, 1.0)
     _p1(rtb, orc, ctx, cfg, 192, 128)
+    _random_rays(rtb, orc, ctx, cfg, seed)
     _p2(rtb, orc, ctx, cfg, 48, 32, spp=4096 if dim else 1024, rr=4 if extended and seed % 4 == 1 else 0)
+
+
+def _random_rays(rtb, orc, ctx, cfg, seed, n=20000):
+    """Closest hit of rays no camera produces: origins anywhere in the scene's volume (also inside boxes, spheres and
+    media), directions uniform on the sphere, un-normalised lengths 0.01-100, random times; and bounce-like rays that
+    start ON a surface (the oracle's hit point of the first set).  Ids equal; the second set tolerates the documented
+    self-intersection band of rays skimming their own surface (t against t_min is decided in f32)."""
+    from test_host_bvh import _media_ids
+    dev, osc, cs = _scene_pair(rtb, orc, ctx, cfg)
+    rng = np.random.default_rng(7000 + seed)
+    o = rng.uniform([-9, 0.05, -9], [9, 9, 9], (n, 3)).astype(np.float32)
+    d = rng.normal(0, 1, (n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True) * np.exp(rng.uniform(np.log(0.01), np.log(100.0), (n, 1)))).astype(np.float32)
+    tm = rng.random(n).astype(np.float32)
+    mid = _media_ids(cs) if dev.info()["n_media"] else []
+    for label, tol in (("free-space", 0), ("on-surface", 4e-4)):
+        ids, ts, _ = dev.trace_rays(o, d, tm)
+        oid, ot = osc.trace_rays(o.astype(np.float64), d.astype(np.float64), tm.astype(np.float64))
+        surf = ~(np.isin(oid, mid) | np.isin(ids, mid))
+        mism = (ids != oid) & surf
+        hit = surf & ~mism & (oid != H.NONE)
+        rel = np.abs(ts[hit].astype(np.float64) - ot[hit]) / ot[hit]
+        print(f"{cfg.name}: {label} rays: {int(mism.sum())} id mismatches of {n}, max t err {rel.max() if hit.any() else 0:.2e}")
+        assert mism.sum() <= tol * n, (label, np.argwhere(mism)[:5].ravel())
+        assert not hit.any() or np.quantile(rel, 0.999) <= 1e-5
+        # next: from the oracle's hit points, new random directions
+        p = (o[hit].astype(np.float64) + ot[hit, None] * d[hit].astype(np.float64)).astype(np.float32)
+        nd = rng.normal(0, 1, p.shape)
+        o, d = p, (nd / np.linalg.norm(nd, axis=1, keepdims=True)).astype(np.float32)
+        tm = rng.random(len(p)).astype(np.float32)
+        n = len(p)
+        if n == 0:
+            break
 
 
 def test_many_image_and_noise_textures(rtb, orc, ctx):
