@@ -456,6 +456,13 @@ static __device__ __noinline__ int sphere_roots_f64(float3 o, float3 d, float3 c
 // rays nearly parallel to a quad's plane / edge-on to a triangle (found by the random scene-graph tests: n.d = 3e-4 |d|,
 // bound 3e-3 t, actual error 5e-5 t).
 #define RTB_SPHERE_REL_MAX 2.0e-4f
+// quads / triangles: their bounds are within 2-60x of the actual error, so anything that may exceed 1e-5 is nominated and
+// the (cheap, once per ray) conditioning test of fix_kind() decides
+#define RTB_FLAT_REL_MAX 1.0e-5f
+// (a triangle's bound carries the distance to its vertices, not its size: far, well-conditioned hits sit at 1e-5 t with an
+//  actual error of 1e-7 t, while an origin a hair from the plane gives >= 3e-4 t — nominating at 1e-5 sends a third of the
+//  mesh hits through the conditioning test, 3 % of C4)
+#define RTB_TRI_REL_MAX 1.0e-4f
 __device__ __forceinline__ int sphere_fast(float3 o, float3 d, float3 c, float r, float tmin, float tmax_hi, float& t_out, float& e_out,
                                            bool& coarse) {
   const float3 oc = o - c;
@@ -550,7 +557,6 @@ __device__ __forceinline__ int prim_test(const DevScene& sc, uint32_t type, uint
     const float ma = fminf(alpha, 1.0f - alpha), mb = fminf(beta, 1.0f - beta);
     if (ma < -ea || mb < -eb) return HIT_MISS;
     if (st == HIT_AMBIGUOUS || !(ma > ea && mb > eb)) { t = fmaxf(t - e, 0.0f); return HIT_AMBIGUOUS; }
-    coarse = e > RTB_SPHERE_REL_MAX * t;  // a ray nearly parallel to the plane (n.d -> 0): certain hit, distance refined in f64
     return HIT_CERTAIN;
   } else if (type == PT_TRI) {
     // Triangle (no reference counterpart): closed edges and closed t-range like aarect.rs:33,38.
@@ -600,12 +606,12 @@ __device__ __forceinline__ int prim_test(const DevScene& sc, uint32_t type, uint
     }
     t = (U * za + V * zb + W * zc) * idet;
     // t is the (U, V, W)-weighted mean of the vertex depths: the weights' error m/|det| moves it by at most the depth
-    // spread of the triangle
+    // spread of the triangle (which also covers the rounding of the sum itself: for depths of mixed sign the spread is at
+    // least their largest magnitude, for depths of one sign the sum rounds by 2^-22 t)
     e = fmaf(RTB_U20, fabsf(t), 4.0f * m * fabsf(idet) * (zhi - zlo));
     if (!(t - e <= tmax_hi)) return HIT_MISS;
     const int st = tmin_status(t, e, tmin);
     if (st == HIT_AMBIGUOUS) t = fmaxf(t - e, 0.0f);
-    else coarse = e > RTB_SPHERE_REL_MAX * t;  // (an edge-on triangle)
     return st;
   } else {  // PT_MOVING: MovingSphere::hit, moving_sphere.rs:43-66, centre = A + time*B
     const float4 a = __ldg(sc.geom[PT_MOVING] + 2 * idx);
@@ -661,9 +667,9 @@ __device__ __forceinline__ bool needs_exact(const Closest& best, float amb) { re
 // what k_fixup has to do for a finished ray: 0 nothing, 1 exact re-trace, 2 recompute the distance of its (certain) hit
 enum FixKind : uint32_t { FIX_NONE = 0, FIX_RETRACE = 1, FIX_REFINE = 2 };
 #define RTB_REDO_REFINE 0x80000000u  /* redo-queue entry: slot | this bit = FIX_REFINE */
-// prim_test() marks a quad / triangle hit coarse from its cheap, loose error bound (for a quad it takes |o|_1 + coord_max
-// as the magnitude of the plane equation's terms, which flags 2-4 % of the rays of a box-shaped scene: every origin within
-// a unit or two of a wall).  Before such a ray is sent to k_fixup the CONDITIONING of its hit is looked at once: t =
+// A quad / triangle hit whose error interval (the cheap, loose bound of prim_test(): for a quad it takes |o|_1 + coord_max as
+// the magnitude of the plane equation's terms, which would send 2-4 % of the rays of a box-shaped scene to k_fixup — every
+// origin within a unit or two of a wall) exceeds RTB_FLAT_REL_MAX t is only NOMINATED; the CONDITIONING of the hit decides: t =
 // (n.Q - n.o) / (n.d) loses bits only by cancellation, about 3 x 2^-24 x (sum of the terms' magnitudes / |result|) — so
 // 1e-5 needs a cancellation factor below ~64 in the numerator and in the denominator.  An axis-aligned plane whose constant
 // is exactly a float (555, 0, 213 ...) has none: one exact product, and the difference of two nearby floats is exact.
@@ -682,13 +688,27 @@ __device__ __forceinline__ bool tri_distance_is_coarse(const DevScene& sc, uint3
   const float mag_den = fabsf(n.x * d.x) + fabsf(n.y * d.y) + fabsf(n.z * d.z);
   return 64.0f * fabsf(dot(n, d)) < mag_den || 64.0f * fabsf(dot(n, r)) < mag_num;
 }
-__device__ __forceinline__ uint32_t fix_kind(const DevScene& sc, const Trav& tv) {
+// fix_kind_cheap(): what can be said without touching memory — FIX_NOMINATED = a quad / triangle hit whose error interval
+// (hi - t; no per-test work) exceeds RTB_FLAT_REL_MAX t; resolve_nominated() then looks at the conditioning of that hit.
+// The dynamic-fetch kernels resolve in their full-warp result flush, outside the traversal loop (inside it the extra code
+// costs the 64-register kernel 4 %).
+#define FIX_NOMINATED 3u
+__device__ __forceinline__ uint32_t fix_kind_cheap(const Trav& tv) {
   if (needs_exact(tv.best, tv.amb)) return FIX_RETRACE;
-  if (!(tv.octinv & RTB_TRAV_COARSE) || tv.best.ref == REF_MISS) return FIX_NONE;
-  const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT, idx = tv.best.ref & REF_INDEX_MASK;
-  if (type == PT_QUAD && !quad_distance_is_coarse(sc, idx, tv.o, tv.d)) return FIX_NONE;
-  if (type == PT_TRI && !tri_distance_is_coarse(sc, idx, tv.o, tv.d)) return FIX_NONE;
-  return FIX_REFINE;
+  if (tv.best.ref == REF_MISS) return FIX_NONE;
+  const uint32_t type = tv.best.ref >> REF_TYPE_SHIFT;
+  if (type == PT_QUAD || type == PT_TRI)
+    return tv.best.hi - tv.best.t > (type == PT_QUAD ? RTB_FLAT_REL_MAX : RTB_TRI_REL_MAX) * tv.best.t ? FIX_NOMINATED : FIX_NONE;
+  return (tv.octinv & RTB_TRAV_COARSE) ? FIX_REFINE : FIX_NONE;
+}
+__device__ __forceinline__ uint32_t resolve_nominated(const DevScene& sc, uint32_t ref, float3 o, float3 d) {
+  const uint32_t type = ref >> REF_TYPE_SHIFT, idx = ref & REF_INDEX_MASK;
+  const bool coarse = type == PT_QUAD ? quad_distance_is_coarse(sc, idx, o, d) : tri_distance_is_coarse(sc, idx, o, d);
+  return coarse ? FIX_REFINE : FIX_NONE;
+}
+__device__ __forceinline__ uint32_t fix_kind(const DevScene& sc, const Trav& tv) {
+  const uint32_t k = fix_kind_cheap(tv);
+  return k == FIX_NOMINATED ? resolve_nominated(sc, tv.best.ref, tv.o, tv.d) : k;
 }
 // The distance slab the exact pass has to search: every candidate f32 left open lies at or beyond `amb`, the closest
 // certain hit within [2t - hi, hi], and whatever the traversal culled lies beyond hi.  Nothing closer than the slab can be

@@ -304,7 +304,9 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
       finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
-      if (h.redo) queue_fix(pool, h.slot, h.redo, h.lo, h.hi);
+      uint32_t redo = h.redo;
+      if (redo == FIX_NOMINATED) redo = resolve_nominated(sc, h.ref, xyz(pool.ray[2 * h.slot]), xyz(pool.ray[2 * h.slot + 1]));
+      if (redo) queue_fix(pool, h.slot, redo, h.lo, h.hi);
     }
     out_count = 0;
     __syncwarp();
@@ -391,7 +393,7 @@ k_extend(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
     const uint32_t done = __ballot_sync(0xffffffffu, finished);
     if (done) {
       if (out_count + __popc(done) > 32u) flush();
-      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind(sc, tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
+      if (finished) out[out_count + __popc(done & lt_mask)] = ExtOut{tv.best.t, tv.best.ref, slot, fix_kind_cheap(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
       out_count += __popc(done);
       idle |= done;
     }
@@ -464,7 +466,9 @@ k_extend_wq(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
         d = xyz(pool.ray[2 * h.slot + 1]);
       }
       finish_ray(sc, pool, prm, h.slot, o, d, Closest{h.t, h.t, h.ref});
-      if (h.redo) queue_fix(pool, h.slot, h.redo, h.lo, h.hi);
+      uint32_t redo = h.redo;
+      if (redo == FIX_NOMINATED) redo = resolve_nominated(sc, h.ref, xyz(pool.ray[2 * h.slot]), xyz(pool.ray[2 * h.slot + 1]));
+      if (redo) queue_fix(pool, h.slot, redo, h.lo, h.hi);
     }
     out_count = 0;
     __syncwarp();
@@ -626,10 +630,8 @@ k_extend_wq(DevScene sc, DevPool pool, DevParams prm, uint32_t n_snodes) {
           tv.best = Closest{b.x, b.z, __float_as_uint(b.y)};
           tv.amb = b.w;
           tv.octinv = W.trav[r].w;
-          tv.o = xyz(W.o_time[r]);
-          tv.d = xyz(W.d_slot[r]);
           W.out[out_count + __popc(done & lt_mask)] =
-              ExtOut{tv.best.t, tv.best.ref, __float_as_uint(W.d_slot[r].w), fix_kind(sc, tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
+              ExtOut{tv.best.t, tv.best.ref, __float_as_uint(W.d_slot[r].w), fix_kind_cheap(tv), slab_lo(tv), tv.best.hi, {0u, 0u}};
         }
         out_count += __popc(done);
       }

@@ -17,7 +17,7 @@ from test_gpu_parity import _p1, _p2, _scene_pair
 pytestmark = pytest.mark.gpu
 
 
-def _random_scene(seed, S, scenes, dim=False, extended=False):
+def _random_scene(seed, S, scenes, dim=False, extended=False, n_objs=None):
     rng = np.random.default_rng(1000 + seed)
     u = lambda a, b: float(rng.uniform(a, b))
     col = lambda lo=0.2, hi=0.9: (u(lo, hi), u(lo, hi), u(lo, hi))
@@ -80,7 +80,7 @@ def _random_scene(seed, S, scenes, dim=False, extended=False):
         return obj
 
     objs = [S.XzRect.construct(-40.0, 40.0, -40.0, 40.0, 0.0, S.Lambertian.construct(col(0.4, 0.8)))]  # floor
-    for _ in range(int(rng.integers(6, 14))):
+    for _ in range(n_objs if n_objs else int(rng.integers(6, 14))):
         objs.append(wrapped(primitive()))
     if rng.random() < 0.6:  # a participating medium bounded by a (possibly transformed) sphere or box
         b = S.Sphere.construct((u(-3, 3), u(1.5, 3), u(-3, 3)), u(1.0, 2.0), S.Dielectric.construct(1.5)) if rng.random() < 0.5 else \
@@ -119,6 +119,28 @@ def test_random_scene_graph(rtb, orc, ctx, seed):
     _p1(rtb, orc, ctx, cfg, 192, 128)
     _random_rays(rtb, orc, ctx, cfg, seed)
     _p2(rtb, orc, ctx, cfg, 48, 32, spp=4096 if dim else 1024, rr=4 if extended and seed % 4 == 1 else 0)
+    _same_seed(rtb, orc, ctx, cfg)
+
+
+def _same_seed(rtb, orc, ctx, cfg, W=96, Hh=64, spp=32):
+    """GPU and oracle trace the SAME paths from the same seed (shared Philox keying): the per-pixel means of a 32-sample
+    render agree far inside the Monte-Carlo error — in every combination of material, texture, medium and light list the
+    generator comes up with.  A sampler that draws its uniforms in a different order anywhere shows up here."""
+    dev, osc, _ = _scene_pair(rtb, orc, ctx, cfg)
+    acc, st = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=77))
+    oacc, oseg, _ = osc.render(cfg.camera, rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=77))
+    acc2, _ = dev.render(cfg.camera, rtb.make_params(W, Hh, spp, cfg.max_depth, cfg.background, seed=78))
+    mg, vg = H.image_stats(acc, spp)
+    mr, vr = H.image_stats(oacc, spp)
+    m2, _ = H.image_stats(acc2, spp)
+    sigma = np.sqrt((vg + vr) / spp) + 1e-6
+    same, indep = np.abs(mg - mr) / sigma, np.abs(m2 - mr) / sigma
+    close = (np.abs(mg - mr) <= 2e-3 * (np.abs(mr) + 1e-3)).mean()
+    print(f"{cfg.name}: same seed {W}x{Hh}x{spp}: {100 * close:.1f}% of pixels within 0.2%, mean |d|/sigma {same.mean():.3f} "
+          f"(independent seeds: {indep.mean():.3f}), segments gpu/oracle {st['segments'] / oseg:.5f}")
+    assert same.mean() < 0.25 * indep.mean()
+    assert close > 0.5
+    assert abs(st["segments"] / oseg - 1) < 5e-3
 
 
 def _random_rays(rtb, orc, ctx, cfg, seed, n=20000):
@@ -134,6 +156,7 @@ def _random_rays(rtb, orc, ctx, cfg, seed, n=20000):
     d = (d / np.linalg.norm(d, axis=1, keepdims=True) * np.exp(rng.uniform(np.log(0.01), np.log(100.0), (n, 1)))).astype(np.float32)
     tm = rng.random(n).astype(np.float32)
     mid = _media_ids(cs) if dev.info()["n_media"] else []
+    tri_ids = dev.export_bvh()[1][3][1].reshape(-1, 2)[:, 0]
     for label, tol in (("free-space", 0), ("on-surface", 4e-4)):
         ids, ts, _ = dev.trace_rays(o, d, tm)
         oid, ot = osc.trace_rays(o.astype(np.float64), d.astype(np.float64), tm.astype(np.float64))
@@ -141,9 +164,13 @@ def _random_rays(rtb, orc, ctx, cfg, seed, n=20000):
         mism = (ids != oid) & surf
         hit = surf & ~mism & (oid != H.NONE)
         rel = np.abs(ts[hit].astype(np.float64) - ot[hit]) / ot[hit]
+        # a triangle under Translate / RotateY has the transform baked into its f32 vertices: its distances carry
+        # the rounding of the world-space vertex, an ABSOLUTE 2^-24 of the coordinate, which is more than 1e-5 of a hit 0.01 away
+        dist = ot[hit] * np.linalg.norm(d[hit].astype(np.float64), axis=1)
+        floor = np.where(np.isin(oid[hit], tri_ids), 3e-6 / np.maximum(dist, 1e-30), 0.0)
         print(f"{cfg.name}: {label} rays: {int(mism.sum())} id mismatches of {n}, max t err {rel.max() if hit.any() else 0:.2e}")
         assert mism.sum() <= tol * n, (label, np.argwhere(mism)[:5].ravel())
-        assert not hit.any() or np.quantile(rel, 0.999) <= 1e-5
+        assert not hit.any() or np.quantile(np.maximum(rel - floor, 0.0), 0.999) <= 1e-5
         # next: from the oracle's hit points, new random directions
         p = (o[hit].astype(np.float64) + ot[hit, None] * d[hit].astype(np.float64)).astype(np.float32)
         nd = rng.normal(0, 1, p.shape)
@@ -173,3 +200,18 @@ def test_many_image_and_noise_textures(rtb, orc, ctx):
     _p1(rtb, orc, ctx, cfg, 192, 128)
     acc, oacc, _ = _p2(rtb, orc, ctx, cfg, 48, 32, spp=1024)
     assert oacc[..., :3].std() > 0.05
+
+
+@pytest.mark.parametrize("seed,n_objs", [(200, 300), (201, 1500), (202, 4000)])
+def test_random_scene_graph_large(rtb, orc, ctx, seed, n_objs):
+    """The same generator with hundreds to thousands of objects (lists, boxes and wrappers included: up to ~4x as many
+    primitives): the BVH8 builder's typed trees, their opened join, the global-primitive rules and the three extend
+    schedulers' thresholds on scenes nobody tuned them for.  P1 on camera rays and on random rays."""
+    from ray_tracer_archive_b200 import scenes, scene as S
+    world, lights = _random_scene(seed, S, scenes, False, True, n_objs)
+    cfg = scenes.config_cornell()
+    cfg.world, cfg.lights, cfg.name, cfg.background = world, lights, f"random scene graph {seed} ({n_objs} objects)", (0.55, 0.65, 0.85)
+    cfg.camera = rtb.Camera.new((2.0, 7.0, 19.0), (0.0, 2.0, 0.0), (0, 1, 0), 40.0, 1.5, 0.0, 19.0, 0.0, 1.0)
+    _p1(rtb, orc, ctx, cfg, 192, 128)
+    _random_rays(rtb, orc, ctx, cfg, seed, n=8000)
+    _same_seed(rtb, orc, ctx, cfg, 48, 32, 16)
