@@ -324,10 +324,21 @@ int rtb_scene_set_textures(rtb_scene* s, const rtb_texture* tex, uint32_t n) {
     if (tex[i].type > RTB_TEX_IMAGE) return set_err(RTB_ERR_INVALID, "unknown texture type");
     if (tex[i].type == RTB_TEX_CHECKER && (tex[i].even >= n || tex[i].odd >= n))
       return set_err(RTB_ERR_INVALID, "checker child out of range");
-    // the reference's Arc<dyn Texture> children can nest (texture.rs:41-45) but only solid colours are ever constructed
-    // (:52-57); the device resolves ONE checker level, so a checker under a checker is refused instead of rendered black
-    if (tex[i].type == RTB_TEX_CHECKER && (tex[tex[i].even].type == RTB_TEX_CHECKER || tex[tex[i].odd].type == RTB_TEX_CHECKER))
-      return set_err(RTB_ERR_UNSUPPORTED, "a checker texture's children must not be checker textures");
+    // the reference's Arc<dyn Texture> children can nest (texture.rs:41-45): followed on the device up to
+    // RTB_MAX_CHECKER_DEPTH levels, so deeper chains (and cycles, which Arc cannot express) are refused here
+    if (tex[i].type == RTB_TEX_CHECKER) {
+      for (int side = 0; side < 2; ++side) {
+        uint32_t c = side ? tex[i].odd : tex[i].even;
+        int depth = 1;
+        while (tex[c].type == RTB_TEX_CHECKER && depth <= RTB_MAX_CHECKER_DEPTH) {
+          const uint32_t nx = side ? tex[c].odd : tex[c].even;
+          if (nx >= n) return set_err(RTB_ERR_INVALID, "checker child out of range");
+          c = nx;
+          ++depth;
+        }
+        if (depth > RTB_MAX_CHECKER_DEPTH) return set_err(RTB_ERR_UNSUPPORTED, "checker textures nested deeper than 8 levels (or cyclic)");
+      }
+    }
     if (tex[i].type == RTB_TEX_NOISE && tex[i].table >= RTB_MAX_TABLES) return set_err(RTB_ERR_INVALID, "perlin table id too large");
   }
   s->hs.textures.assign(tex, tex + n);

@@ -28,6 +28,7 @@ enum CheckKind : int { CHK_STACK = 0, CHK_NODE = 1, CHK_PRIM = 2, CHK_SLOT = 3, 
 
 #define RTB_MAX_LIGHTS 8
 #define RTB_MAX_MEDIA 8
+#define RTB_MAX_CHECKER_DEPTH 8  /* checker textures nested in checker textures (texture.rs:41-45: Arc<dyn Texture> children) */
 #define RTB_MAX_TABLES 4096  /* sanity cap on perlin / image ids (the tables live in device memory, not in DevScene) */
 #define RTB_STACK 32
 #define RTB_TMIN 0.001f  // main.rs:74

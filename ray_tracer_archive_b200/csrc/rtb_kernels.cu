@@ -806,8 +806,9 @@ __device__ float perlin_turb(const float4* __restrict__ vec, const uint8_t* __re
 __device__ float3 tex_value_slow(const DevScene& sc, uint32_t tex, const Surf& s) {
   DevTexture t = sc.textures[tex];
   if (t.type == RTB_TEX_CHECKER) {  // texture.rs:60-69, on the world-space point
+    // (children are Arc<dyn Texture>: a checker of checkers evaluates the same sign at every level; the host bounds the depth)
     const float sines = sinf(10.f * s.p.x) * sinf(10.f * s.p.y) * sinf(10.f * s.p.z);
-    t = sc.textures[sines < 0.f ? t.odd : t.even];
+    for (int level = 0; level < RTB_MAX_CHECKER_DEPTH && t.type == RTB_TEX_CHECKER; ++level) t = sc.textures[sines < 0.f ? t.odd : t.even];
   }
   if (t.type == RTB_TEX_NOISE) {  // texture.rs:90-96
     const float g = 0.5f * (1.0f + sinf(t.scale * s.p.z + 10.f * perlin_turb(sc.perlin_vec + 256u * t.table, sc.perlin_perm + 768u * t.table, s.p)));

@@ -28,13 +28,17 @@ class SolidColor(Texture):  # texture.rs:12-38
 
 
 @dataclass(eq=False)
-class CheckerTexture(Texture):  # texture.rs:40-69 (construct_color: two solid colours)
-    even: Sequence[float]
-    odd: Sequence[float]
+class CheckerTexture(Texture):  # texture.rs:40-69 (construct_color: two solid colours; construct: any two textures, :46-51)
+    even: object  # colour triple or Texture
+    odd: object
 
     @classmethod
     def construct_color(cls, c1, c2):
         return cls(c1, c2)
+
+    @classmethod
+    def construct(cls, ev: "Texture", od: "Texture"):
+        return cls(ev, od)
 
 
 @dataclass(eq=False)
@@ -315,8 +319,8 @@ class _Compiler:
             rec["rgb"] = tuple(t.color)
         elif isinstance(t, CheckerTexture):
             rec["type"] = F.TEX_CHECKER
-            rec["even"] = self.tex(SolidColor(tuple(t.even)))
-            rec["odd"] = self.tex(SolidColor(tuple(t.odd)))
+            rec["even"] = self.tex(t.even if isinstance(t.even, Texture) else SolidColor(tuple(t.even)))
+            rec["odd"] = self.tex(t.odd if isinstance(t.odd, Texture) else SolidColor(tuple(t.odd)))
         elif isinstance(t, NoiseTexture):
             rec["type"] = F.TEX_NOISE
             rec["scale"] = t.scale

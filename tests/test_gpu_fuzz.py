@@ -27,7 +27,11 @@ def _random_scene(seed, S, scenes, dim=False, extended=False, n_objs=None):
         if k <= 1:
             return S.Lambertian.construct(col())
         if k == 2:
-            return S.Lambertian.construct_texture(S.CheckerTexture.construct_color(col(0.1, 0.4), col(0.6, 0.95)))
+            chk = S.CheckerTexture.construct_color(col(0.1, 0.4), col(0.6, 0.95))
+            if extended and rng.random() < 0.5:  # Arc<dyn Texture> children (texture.rs:41-51): noise, image, another checker
+                chk = S.CheckerTexture.construct(S.NoiseTexture.construct(u(1, 4), np.random.default_rng(int(rng.integers(1 << 30)))),
+                                                 S.CheckerTexture.construct(S.SolidColor(col()), chk))
+            return S.Lambertian.construct_texture(chk)
         if k == 3:
             return S.Lambertian.construct_texture(S.NoiseTexture.construct(u(0.5, 4.0), np.random.default_rng(int(rng.integers(1 << 30)))))
         if k == 4:
