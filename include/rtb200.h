@@ -220,6 +220,11 @@ int rtb_scene_set_perlin(rtb_scene* s, uint32_t table_id, const double* ranvec_2
 int rtb_scene_set_mesh(rtb_scene* s, uint32_t mesh_id, const float* vertices_xyz, uint32_t n_vertices,
                        const uint32_t* indices, uint32_t n_triangles);
 int rtb_scene_set_lights(rtb_scene* s, const rtb_light* lights, uint32_t n);
+/* Limits (RTB_ERR_UNSUPPORTED beyond them): at most 8 entries in the light list and 8 ConstantMedium objects per scene (both
+ * live in the kernels' constant bank: every shaded hit walks the light list, every ray tests every medium boundary; the
+ * reference's scenes have <= 2 of each); a ConstantMedium's boundary is a Sphere or a Box, optionally under
+ * Translate / RotateY; checker textures nest at most 8 deep.  Any number of image / perlin tables, textures, materials,
+ * primitives (per type < 2^29) and wrapper levels (< 256). */
 
 /* ---- scene: geometry, way 1 (graph records; replaces the reference's trait-object world, main.rs:668) ------ */
 int rtb_scene_set_graph(rtb_scene* s, const rtb_node* nodes, uint32_t n_nodes, const uint32_t* child_index,
