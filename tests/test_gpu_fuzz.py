@@ -84,8 +84,20 @@ def _random_scene(seed, S, scenes, dim=False, extended=False, n_objs=None):
         return obj
 
     objs = [S.XzRect.construct(-40.0, 40.0, -40.0, 40.0, 0.0, S.Lambertian.construct(col(0.4, 0.8)))]  # floor
+    import copy
     for _ in range(n_objs if n_objs else int(rng.integers(6, 14))):
-        objs.append(wrapped(primitive()))
+        prim = primitive()
+        objs.append(wrapped(prim))
+        if extended and rng.random() < 0.15 and not isinstance(prim, S.MovingSphere):
+            # an exact duplicate with another material, and a coplanar / concentric sibling: equal-t ties go to the LATER
+            # object of the list (hittable_list.rs:44-47 with sphere.rs:52 / aarect.rs:33), whatever the traversal order
+            twin = copy.copy(prim)
+            twin.mat = material()
+            objs.append(twin)
+            if isinstance(prim, (S.XyRect, S.XzRect, S.YzRect)):
+                sib = copy.copy(prim)
+                sib.a0, sib.a1, sib.mat = prim.a0 + 0.4 * (prim.a1 - prim.a0), prim.a1 + 0.7, material()
+                objs.append(sib)
     if rng.random() < 0.6:  # a participating medium bounded by a (possibly transformed) sphere or box
         b = S.Sphere.construct((u(-3, 3), u(1.5, 3), u(-3, 3)), u(1.0, 2.0), S.Dielectric.construct(1.5)) if rng.random() < 0.5 else \
             S.Box.construct((-1.0, 0.2, -1.0), (1.5, 2.5, 1.2), S.Lambertian.construct(col()))
