@@ -486,6 +486,17 @@ int build_bvh8(const HostScene& hs, HostBvh& out, std::string& err) {
   out.max_depth = 0;
   out.global_refs.clear();
   const size_t np = hs.prims.size();
+  // malformed input (NaN / inf / 1e308 constructor arguments) must come back as an error, not as a builder that sorts NaNs
+  for (size_t i = 0; i < np; ++i) {
+    const HostPrim& p = hs.prims[i];
+    bool ok = p.type < PT_COUNT;
+    for (int a = 0; a < 3 && ok; ++a) ok = std::isfinite(p.lo[a]) && std::isfinite(p.hi[a]) && p.lo[a] <= p.hi[a] && std::fabs(p.lo[a]) < 1e30f && std::fabs(p.hi[a]) < 1e30f;
+    for (int w = 0; w < 12 && ok; ++w) ok = std::isfinite(p.g[w]);
+    if (!ok) {
+      err = "primitive " + std::to_string(p.prim_id) + " has non-finite or out-of-range geometry";
+      return RTB_ERR_INVALID;
+    }
+  }
 
   // --- "global" primitives: a primitive whose box is (nearly) the whole scene box (the r=1000 ground sphere of
   // book 1) cannot be culled by any node and only coarsens the quantisation grid of the node that holds
