@@ -927,6 +927,10 @@ int rtb_render_device(rtb_context* c, rtb_scene* s, const rtb_camera* cam, const
   DevCamera dcam;
   DevCameraF64 dcam64;
   camera_basis(*cam, dcam, dcam64);
+  for (int a = 0; a < 3; ++a)  // lookfrom == lookat, vup parallel to the view direction, NaN / inf arguments
+    if (!std::isfinite(dcam.origin[a]) || !std::isfinite(dcam.lmo[a]) || !std::isfinite(dcam.horizontal[a]) || !std::isfinite(dcam.vertical[a]) ||
+        !std::isfinite(dcam.u[a]) || !std::isfinite(dcam.v[a]))
+      return set_err(RTB_ERR_INVALID, "degenerate camera (non-finite basis: lookfrom == lookat, vup along the view direction, or non-finite arguments)");
 
   struct LaneRun { DevPool pool; DevParams prm; unsigned long long total; bool active; uint64_t iters, iter_cap; };
   LaneRun run[RTB_MAX_LANES];

@@ -657,5 +657,11 @@ def test_abi_state_errors(rtb, ctx):
         s.render(cfg.camera, rtb.make_params(8, 8, 1, max_depth=0))
     acc, st = s.render(cfg.camera, rtb.make_params(8, 8, 2))
     assert st["paths"] == 128 and np.isfinite(acc).all()
+    for bad in (rtb.Camera.new((1, 2, 3), (1, 2, 3), (0, 1, 0), 40.0, 1.0, 0.0, 10.0),          # lookfrom == lookat
+                rtb.Camera.new((0, 0, 0), (0, 5, 0), (0, 1, 0), 40.0, 1.0, 0.0, 10.0),          # vup along the view direction
+                rtb.Camera.new((0, 0, 0), (0, 0, -1), (0, 1, 0), float("nan"), 1.0, 0.0, 10.0)):
+        with pytest.raises(rtb.RtbError) as e:
+            s.render(bad, rtb.make_params(8, 8, 1))
+        assert e.value.code == -1
     info = ctx.device_info()
     assert info["sm_count"] > 0
