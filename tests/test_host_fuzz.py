@@ -51,3 +51,24 @@ def test_random_scene_graph_closest_hits(rtb, orc, emul, seed):
         nd = rng.normal(0, 1, p.shape)
         o32, d32 = p, (nd / np.linalg.norm(nd, axis=1, keepdims=True)).astype(np.float32)
         tm = rng.random(len(p)).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [5, 63])
+def test_oracle_bvh_culling_equals_its_linear_scan_on_random_graphs(rtb, orc, seed):
+    """The fuzz tests above let the oracle cull candidates with the shipped BVH8 (the per-primitive arithmetic stays the
+    reference's): on random scene graphs that must return bit-identical (id, t) to the oracle's own linear HittableList scan."""
+    from ray_tracer_archive_b200 import scenes, scene as S
+    from test_gpu_fuzz import _random_scene
+    world, lights = _random_scene(seed, S, scenes, False, True, None)
+    cs = rtb.compile_scene(world, lights)
+    hs = rtb.Scene(None, cs)
+    lin, acc = orc.OracleScene(cs), orc.OracleScene(cs)
+    acc.attach_bvh(hs)
+    rng = np.random.default_rng(seed)
+    n = 6000
+    o = rng.uniform([-9, 0.05, -9], [9, 9, 9], (n, 3))
+    d = rng.normal(0, 1, (n, 3))
+    tm = rng.random(n)
+    i1, t1 = lin.trace_rays(o, d, tm)
+    i2, t2 = acc.trace_rays(o, d, tm)
+    assert np.array_equal(i1, i2) and np.array_equal(t1, t2)
